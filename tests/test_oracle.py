@@ -1,0 +1,141 @@
+"""CPU: pins the oracle (oracle/ppo_oracle.py, oracle/oracle.c) against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py).  The reference itself ships no tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+from oracle import c_oracle as C
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+GAE_CASES = ["kat1", "kat2", "rand_small", "rand_ragged", "rand_mid", "t1", "both_masks"]
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def test_gae_kats_hand_checkable():
+    g = _load("gae.npz")
+    # SURVEY §8c KAT 1: sum_k (gamma*lambda)^k
+    gl = 0.99 * 0.95
+    expect = [sum(gl ** k for k in range(n)) for n in range(8, 0, -1)]
+    np.testing.assert_allclose(g["kat1.advantages"][:, 0], expect, rtol=1e-6)
+    np.testing.assert_allclose(g["kat2.advantages"],
+                               [[9.069237, 2.950250, 4.812440], [7.006100, 0.5, 2.48], [4.812440] * 3, [2.48] * 3], rtol=1e-6)
+
+
+@pytest.mark.parametrize("case", GAE_CASES)
+@pytest.mark.parametrize("tag,gam,lam", [("", 0.99, 0.95), (".g9l8", 0.9, 0.8)])
+def test_gae_oracles_bit_exact(case, tag, gam, lam):
+    g = _load("gae.npz")
+    args = [g[f"{case}.{k}"] for k in ("rewards", "terminations", "truncations", "values", "next_values")]
+    ref = g[f"{case}{tag}.advantages"]
+    np.testing.assert_array_equal(O.gae(*args, gam, lam), ref)           # numpy restatement: bit-exact
+    adv, ret = C.gae(*args, gam, lam)
+    np.testing.assert_array_equal(adv, ref)                                # C restatement: bit-exact
+    if tag == "":
+        np.testing.assert_array_equal(ret, g[f"{case}.returns"])
+
+
+@pytest.mark.parametrize("case", [c for c in GAE_CASES if c != "t1"])
+def test_adv_norm(case):
+    g = _load("gae.npz")
+    ret, an = O.returns_and_normalise(g[f"{case}.values"], g[f"{case}.advantages"], True)
+    np.testing.assert_array_equal(ret, g[f"{case}.returns"])
+    ref = g[f"{case}.adv_norm"]
+    assert np.abs(an - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_permutation_oracles_bit_exact():
+    g = _load("perm.npz")
+    for seed, n in ((42, 1024), (123, 1024), (0, 1), (0, 2), (7, 1000)):
+        p = O.legacy_permutation(O.MT19937(seed), n)
+        np.testing.assert_array_equal(p, g[f"s{seed}_n{n}.full"])
+    for seed, n in ((42, 1024), (42, 524288), (123, 1024), (0, 1), (0, 2), (7, 1000), (5, 65537)):
+        mt = C.MT(seed)
+        p = mt.permutation(n)
+        np.testing.assert_array_equal(p[:32], g[f"s{seed}_n{n}.head"])
+        np.testing.assert_array_equal(p[-32:], g[f"s{seed}_n{n}.tail"])
+        assert int((p * np.arange(1, n + 1)).sum()) == int(g[f"s{seed}_n{n}.checksum"])
+        assert sorted(p.tolist()) == list(range(n)) if n <= 65537 else True
+        assert mt.next_u32() == int(g[f"s{seed}_n{n}.next_u32"])        # stream position after the call
+    mt = C.MT(123)
+    np.testing.assert_array_equal(mt.permutation(4096), g["s123_n4096_x2.first"])
+    np.testing.assert_array_equal(mt.permutation(4096), g["s123_n4096_x2.second"])
+    # and against the live numpy in this image
+    np.random.seed(99)
+    np.testing.assert_array_equal(C.MT(99).permutation(5000), np.random.permutation(5000))
+
+
+def _run_learn(name, epochs_tag, extra=None):
+    g = _load(f"learn_{name}.npz")
+    D, act, H, N, T, E, MB, cont = (int(x) for x in g["meta"])
+    cont = bool(cont)
+    names = O.CONTINUOUS_PARAM_NAMES if cont else O.DISCRETE_PARAM_NAMES
+    p = {n: torch.as_tensor(g[f"init.{n}"]).clone() for n in names}
+    state = O.new_adam_state(p, names)
+    epochs = int(epochs_tag[1:])
+    cfg = O.default_cfg(num_epochs=epochs, num_minibatches=MB, **(extra or {}))
+    mt = C.MT(123)
+    perms = np.stack([mt.permutation(T * N) for _ in range(epochs)])
+    losses, inter = O.learn(p, state, g["obs"], g["next_obs"], g["actions"], g["rewards"], g["terminations"],
+                            g["truncations"], cfg, perms, continuous=cont)
+    return g, p, state, losses, inter, names
+
+
+@pytest.mark.parametrize("name", ["C", "L", "Ssmall", "Pn", "Pn3"])
+def test_learn_oracle_one_epoch(name):
+    g, p, state, losses, inter, names = _run_learn(name, "e1")
+    np.testing.assert_array_equal(inter["advantages"], g["gae.advantages"])
+    np.testing.assert_allclose(inter["values"], g["gae.values"], rtol=1e-5, atol=1e-6)
+    ref_l = g["e1.losses"]
+    got = np.array([[l[k] for k in ("policy", "value", "entropy", "total")] for l in losses])
+    np.testing.assert_allclose(got, ref_l, rtol=1e-4, atol=2e-6)
+    for n in names:
+        ref = g[f"e1.params.{n}"]
+        err = np.abs(p[n].numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        assert err <= 1e-5, (n, err)
+    if f"e1.exp_avg.{names[0]}" in g:
+        for n in names:
+            np.testing.assert_allclose(state["exp_avg"][n].numpy(), g[f"e1.exp_avg.{n}"], rtol=1e-4, atol=1e-8)
+            np.testing.assert_allclose(state["exp_avg_sq"][n].numpy(), g[f"e1.exp_avg_sq.{n}"], rtol=1e-4, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["C", "Pn"])
+def test_learn_oracle_four_epochs(name):
+    g, p, state, losses, inter, names = _run_learn(name, "e4")
+    got = np.array([[l[k] for k in ("policy", "value", "entropy", "total")] for l in losses])
+    np.testing.assert_allclose(got, g["e4.losses"], rtol=2e-4, atol=5e-6)
+    for n in names:
+        ref = g[f"e4.params.{n}"]
+        err = np.abs(p[n].numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        assert err <= 1e-4, (n, err)
+
+
+def test_learn_oracle_nondefault_cfg_and_lr_decay():
+    extra = dict(advantage_norm=False, ppo_clip=0.1, value_loss_weight=0.5, entropy_beta=0.02, grad_norm_clip=0.3,
+                 gamma=0.97, gae_lambda=0.9)
+    g, p, state, losses, inter, names = _run_learn("Cdecay", "e1", extra)
+    got = np.array([[l[k] for k in ("policy", "value", "entropy", "total")] for l in losses])
+    np.testing.assert_allclose(got, g["e1.losses"], rtol=1e-4, atol=2e-6)
+    for n in names:
+        ref = g[f"e1.params.{n}"]
+        assert np.abs(p[n].numpy() - ref).max() / max(np.abs(ref).max(), 1e-12) <= 1e-5
+    # LinearLR after one learn(): total_iters = total_steps // (N*T) = 10, end factor 0.05 (ppo.py:137-142,287)
+    assert abs(3e-4 * O.linear_lr_factor(1, 10, 1.0, 0.05) - float(g["e1.lr_after"])) < 1e-12
+
+
+def test_gru_restatement_matches_nn_gru():
+    torch.manual_seed(0)
+    gru = torch.nn.GRU(6, 5)
+    p = {f"gru.{k}": v.detach() for k, v in gru.named_parameters()}
+    x = torch.randn(7, 3, 6)
+    h0 = torch.randn(3, 5)
+    dones = torch.zeros(7, 3, dtype=torch.bool)
+    out, h = O.gru_forward(p, x, h0, dones)
+    ref_out, ref_h = gru(x, h0.unsqueeze(0))
+    np.testing.assert_allclose(out.numpy(), ref_out.detach().numpy(), atol=1e-6)
+    np.testing.assert_allclose(h.numpy(), ref_h[0].detach().numpy(), atol=1e-6)
