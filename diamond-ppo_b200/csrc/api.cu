@@ -1,0 +1,248 @@
+// C-ABI entry points that orchestrate the per-layer kernels: context, parameter layout,
+// forward pass (diamond/ppo.py:91-96, 235-238) and one minibatch of the PPO update (ppo.py:258-283).
+#include "common.cuh"
+#include "heads.cuh"
+#include "optim.cuh"
+
+char g_dppo_create_error[512] = "";
+
+extern "C" int dppo_version(void) { return DPPO_VERSION; }
+
+extern "C" const char* dppo_last_error(dppo_ctx* ctx) { return ctx ? ctx->err : g_dppo_create_error; }
+
+extern "C" int dppo_create(dppo_ctx** out, int device)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        snprintf(g_dppo_create_error, sizeof(g_dppo_create_error),
+                 "dppo_create: no CUDA device (%s); libdppo has no CPU fallback", cudaGetErrorString(e));
+        return 2;
+    }
+    if (device < 0 || device >= count) {
+        snprintf(g_dppo_create_error, sizeof(g_dppo_create_error), "dppo_create: device %d out of range (%d devices)", device, count);
+        return 3;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        snprintf(g_dppo_create_error, sizeof(g_dppo_create_error), "dppo_create: %s", cudaGetErrorString(e));
+        return 4;
+    }
+    if (prop.major != 10) {
+        snprintf(g_dppo_create_error, sizeof(g_dppo_create_error),
+                 "dppo_create: device %d is sm_%d%d; libdppo embeds sm_100a code only (B200) and has no fallback", device,
+                 prop.major, prop.minor);
+        return 5;
+    }
+    dppo_ctx* c = new dppo_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->err[0] = 0;
+    *out = c;
+    return 0;
+}
+
+extern "C" int dppo_destroy(dppo_ctx* ctx)
+{
+    delete ctx;
+    return 0;
+}
+
+extern "C" int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
+{
+    if (!ctx) return 1;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    return 0;
+}
+
+extern "C" int dppo_mlp_layout_compute(const dppo_mlp_desc* d, dppo_mlp_layout* L)
+{
+    if (!d || !L || d->obs_dim < 1 || d->hidden < 1 || d->act_dim < 1) return 1;
+    const int64_t D = d->obs_dim, H = d->hidden, A = d->act_dim;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { const int64_t at = o; o += align_up(n, 4); return at; };
+    L->w1 = take(H * D); L->b1 = take(H);
+    L->w2 = take(H * H); L->b2 = take(H);
+    L->w3 = take(2 * H * H); L->b3 = take(2 * H);
+    L->wa = take(A * H); L->ba = take(A);
+    L->wc = take(H); L->bc = take(1);
+    L->log_std = d->continuous ? take(A) : -1;
+    L->total = o;
+    return 0;
+}
+
+namespace {
+
+struct TrainWs {
+    float *h1, *h2, *h3, *d3, *d2, *d1;
+    float *p3, *p2, *p1, *c2, *c1, *hp;
+    int s3, s2, s1, tiles2, tiles1, head_blocks, head_stride;
+    int64_t bytes;
+};
+
+// Carves the training workspace for M rows.  sm_count fixes the split-K / head grid sizes.
+TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
+{
+    dppo_ctx fake; fake.sm_count = sm_count;
+    const int64_t D = d->obs_dim, H = d->hidden, A = d->act_dim;
+    TrainWs w;
+    int64_t o = 0;
+    auto take = [&](int64_t floats) { float* p = reinterpret_cast<float*>(base + o); o += align_up(floats * 4, 256); return p; };
+    w.h1 = take(M * H); w.h2 = take(M * H); w.h3 = take(M * 2 * H);
+    w.d3 = take(M * 2 * H); w.d2 = take(M * H); w.d1 = take(M * H);
+    w.s3 = dppo_wgrad_splits(&fake, M, (int)(2 * H), (int)H);
+    w.s2 = dppo_wgrad_splits(&fake, M, (int)H, (int)H);
+    w.s1 = dppo_wgrad_splits(&fake, M, (int)H, (int)D);
+    w.p3 = take((int64_t)w.s3 * 2 * H * H);
+    w.p2 = take((int64_t)w.s2 * H * H);
+    w.p1 = take((int64_t)w.s1 * H * D);
+    w.tiles2 = dppo_gemm_row_tiles(M, (int)H);
+    w.tiles1 = dppo_gemm_row_tiles(M, (int)H);
+    w.c2 = take((int64_t)w.tiles2 * H);
+    w.c1 = take((int64_t)w.tiles1 * H);
+    w.head_blocks = head_train_blocks(&fake, M);
+    w.head_stride = (int)align_up(head_partial_floats((int)H, (int)A), 4);
+    w.hp = take((int64_t)w.head_blocks * w.head_stride);
+    w.bytes = o;
+    return w;
+}
+
+int current_sm_count()
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+}  // namespace
+
+extern "C" int64_t dppo_mlp_workspace_bytes(const dppo_mlp_desc* d, int64_t rows, int training)
+{
+    if (!d || rows <= 0) return 0;
+    const int64_t H = d->hidden;
+    if (!training) return align_up(rows * H * 4, 256) * 2 + align_up(rows * 2 * H * 4, 256);
+    // sized for the B200's 148 SMs or the current device, whichever is larger
+    int sms = current_sm_count();
+    if (sms < 148) sms = 148;
+    return carve_train(d, rows, sms, nullptr).bytes;
+}
+
+extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const float* params, const float* obs,
+                                const int32_t* idx, int64_t rows, int heads, float* head_out, float* values, void* ws,
+                                int64_t ws_bytes, void* stream)
+{
+    if (!ctx) return 1;
+    if (!d || !params || !obs || rows <= 0) DPPO_FAIL(ctx, "mlp_forward: bad arguments");
+    if ((heads & 3) == 0) DPPO_FAIL(ctx, "mlp_forward: heads mask selects nothing");
+    if ((heads & 1) && !head_out) DPPO_FAIL(ctx, "mlp_forward: head_out is null");
+    if ((heads & 2) && !values) DPPO_FAIL(ctx, "mlp_forward: values is null");
+    dppo_mlp_layout L;
+    if (dppo_mlp_layout_compute(d, &L)) DPPO_FAIL(ctx, "mlp_forward: bad descriptor");
+    const int D = d->obs_dim, H = d->hidden, A = d->act_dim;
+    cudaStream_t st = (cudaStream_t)stream;
+    // chunk the rows so that h1 | h2 | h3 fit the workspace
+    const int64_t per_row = (int64_t)4 * H * 4;
+    int64_t chunk = (ws_bytes - 3 * 256) / per_row;
+    if (chunk > rows) chunk = rows;
+    if (chunk < 1) DPPO_FAIL(ctx, "mlp_forward: workspace too small (%lld bytes, need >= %lld per row)", (long long)ws_bytes, (long long)per_row);
+    char* base = (char*)ws;
+    float* h1 = (float*)base;
+    float* h2 = (float*)(base + align_up(chunk * H * 4, 256));
+    float* h3 = (float*)(base + 2 * align_up(chunk * H * 4, 256));
+    const bool actor = heads & 1, critic = heads & 2;
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int64_t n = rows - r0 < chunk ? rows - r0 : chunk;
+        const float* x = idx ? obs : obs + r0 * D;
+        const int32_t* rowsel = idx ? idx + r0 : nullptr;
+        if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
+        if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
+        // first head layers: both (one [2H,H] product) or only the requested half
+        const int64_t w3off = actor ? 0 : (int64_t)H * H;
+        const int b3off = actor ? 0 : H;
+        const int n3 = (actor && critic) ? 2 * H : H;
+        if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
+        const float* ha = actor ? h3 : nullptr;
+        const float* hc = critic ? (actor ? h3 + H : h3) : nullptr;
+        if (launch_head_eval(ctx, ha, hc, n3, params + L.wa, params + L.ba, params + L.wc, params + L.bc,
+                             head_out ? head_out + r0 * A : nullptr, values ? values + r0 : nullptr, n, H, A, st)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, const float* params, float* grads,
+                                       const float* obs, const void* actions, const float* old_log_probs, const float* adv,
+                                       const float* returns, const double* adv_stats, const int32_t* idx, int64_t M,
+                                       const dppo_hyper* hy, float* losses, void* ws, int64_t ws_bytes, void* stream)
+{
+    if (!ctx) return 1;
+    if (!d || !params || !grads || !obs || !actions || !old_log_probs || !adv || !returns || !hy || !ws)
+        DPPO_FAIL(ctx, "mlp_grad_minibatch: null argument");
+    if (M <= 0) DPPO_FAIL(ctx, "mlp_grad_minibatch: empty minibatch");
+    if (hy->advantage_norm && (!adv_stats || hy->adv_count < 2)) DPPO_FAIL(ctx, "mlp_grad_minibatch: advantage_norm needs adv_stats and adv_count >= 2");
+    dppo_mlp_layout L;
+    if (dppo_mlp_layout_compute(d, &L)) DPPO_FAIL(ctx, "mlp_grad_minibatch: bad descriptor");
+    const int D = d->obs_dim, H = d->hidden, A = d->act_dim;
+    TrainWs w = carve_train(d, M, ctx->sm_count, (char*)ws);
+    if (w.bytes > ws_bytes) DPPO_FAIL(ctx, "mlp_grad_minibatch: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float inv_m = 1.0f / (float)(hy->loss_denominator > 0 ? hy->loss_denominator : M);
+
+    // forward (ppo.py:261), activations kept for the backward pass
+    if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, obs, D, idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
+    if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
+    if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
+
+    // heads + loss (ppo.py:264-280) + backward into the first head layers
+    HeadTrainArgs ha;
+    ha.h3 = w.h3; ha.d3 = w.d3;
+    ha.wa = params + L.wa; ha.ba = params + L.ba; ha.wc = params + L.wc; ha.bc = params + L.bc;
+    ha.log_std = d->continuous ? params + L.log_std : nullptr;
+    ha.idx = idx;
+    ha.actions_i = d->continuous ? nullptr : (const int32_t*)actions;
+    ha.actions_f = d->continuous ? (const float*)actions : nullptr;
+    ha.old_logp = old_log_probs; ha.adv = adv; ha.ret = returns;
+    ha.adv_stats = adv_stats; ha.adv_count = hy->adv_count; ha.advantage_norm = hy->advantage_norm;
+    ha.M = M; ha.H = H; ha.A = A;
+    ha.clip = hy->ppo_clip; ha.vw = hy->value_loss_weight; ha.beta = hy->entropy_beta; ha.inv_m = inv_m;
+    ha.partials = w.hp; ha.partial_stride = w.head_stride;
+    if (launch_head_train_kernel(ctx, ha, d->continuous, w.head_blocks, st)) return 1;
+
+    // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused
+    if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+    if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+    // weight gradients: deterministic split-K partials
+    if (dppo_wgrad(ctx, w.d3, 2 * H, w.h2, H, nullptr, w.p3, w.s3, M, 2 * H, H, st)) return 1;
+    if (dppo_wgrad(ctx, w.d2, H, w.h1, H, nullptr, w.p2, w.s2, M, H, H, st)) return 1;
+    if (dppo_wgrad(ctx, w.d1, H, obs, D, idx, w.p1, w.s1, M, H, D, st)) return 1;
+
+    // assemble the flat gradient
+    GradSegTable tab;
+    int n = 0;
+    auto seg = [&](int64_t dst, int64_t count, const float* src, int64_t stride, int nparts) {
+        tab.seg[n].dst = dst; tab.seg[n].count = count; tab.seg[n].src = src; tab.seg[n].stride = stride;
+        tab.seg[n].nparts = nparts; tab.seg[n].pad = 0; ++n;
+    };
+    seg(L.w1, (int64_t)H * D, w.p1, (int64_t)H * D, w.s1);
+    seg(L.b1, H, w.c1, H, w.tiles1);
+    seg(L.w2, (int64_t)H * H, w.p2, (int64_t)H * H, w.s2);
+    seg(L.b2, H, w.c2, H, w.tiles2);
+    seg(L.w3, (int64_t)2 * H * H, w.p3, (int64_t)2 * H * H, w.s3);
+    const int off_dba = A * H, off_dwc = A * H + A, off_dbc = off_dwc + H, off_dls = off_dbc + 1, off_b3 = off_dls + A,
+              off_loss = off_b3 + 2 * H;
+    seg(L.b3, 2 * H, w.hp + off_b3, w.head_stride, w.head_blocks);
+    seg(L.wa, (int64_t)A * H, w.hp, w.head_stride, w.head_blocks);
+    seg(L.ba, A, w.hp + off_dba, w.head_stride, w.head_blocks);
+    seg(L.wc, H, w.hp + off_dwc, w.head_stride, w.head_blocks);
+    seg(L.bc, 1, w.hp + off_dbc, w.head_stride, w.head_blocks);
+    if (d->continuous) seg(L.log_std, A, w.hp + off_dls, w.head_stride, w.head_blocks);
+    tab.nseg = n;
+    return launch_grad_reduce(ctx, tab, grads, L.total, w.hp + off_loss, w.head_blocks, w.head_stride, hy->value_loss_weight,
+                              hy->entropy_beta, inv_m, losses, st);
+}

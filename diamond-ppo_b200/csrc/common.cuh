@@ -1,0 +1,63 @@
+// Shared declarations for libdppo's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "dppo.h"
+
+struct dppo_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    char err[512];
+};
+
+extern char g_dppo_create_error[512];
+
+#define DPPO_FAIL(ctx, ...)                                   \
+    do {                                                      \
+        if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+        return 1;                                             \
+    } while (0)
+
+#define DPPO_CHECK_LAUNCH(ctx, what)                                                        \
+    do {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess) DPPO_FAIL(ctx, "%s: %s", what, cudaGetErrorString(e_));      \
+    } while (0)
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- internal launchers shared between translation units ----------------------------------
+// C[M,N] = epi(A[M,K] * op(B)); see gemm_simt.cu
+enum { DPPO_EPI_BIAS = 0, DPPO_EPI_BIAS_TANH = 1, DPPO_EPI_TANH_BWD = 2 };
+// NT: B is [N,K] row-major (a torch Linear weight used in the forward direction)
+int dppo_gemm_nt(dppo_ctx* ctx, int epi, const float* A, int lda, const int32_t* a_rows, const float* B, int ldb,
+                 const float* bias, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st);
+// NN: B is [K,N] row-major (a Linear weight used in the backward/dgrad direction);
+// C = (A*B) .* (1 - Hact^2); colsum (optional) receives per-row-tile column sums of C: [tiles_m, N]
+int dppo_gemm_nn_tanh_bwd(dppo_ctx* ctx, const float* A, int lda, const float* B, int ldb, const float* Hact, int ldh,
+                          float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);
+int dppo_gemm_row_tiles(int64_t M, int N);     // number of row tiles the NN kernel uses (colsum partial count)
+// TN split-K weight gradient: partials[s][n1][n2] = sum over the rows of split s of A[m,n1]*B[m,n2]
+int dppo_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2);
+int dppo_wgrad(dppo_ctx* ctx, const float* A, int lda, const float* B, int ldb, const int32_t* b_rows,
+               float* partials, int splits, int64_t M, int N1, int N2, cudaStream_t st);

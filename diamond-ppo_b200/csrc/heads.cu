@@ -1,0 +1,528 @@
+// Output heads, PPO loss and its gradient (diamond/ppo.py:261-280, continuous_ppo.py:273-292).
+//
+// One warp owns one minibatch row at a time.  The two head products (actor [A,H], critic [1,H])
+// are far too thin for a GEMM tile (A <= 32), so the warp keeps the row's two H-wide activations in
+// registers (lane k owns columns k, k+32, ...), forms the A+1 dot products with shuffles, evaluates
+// the distribution with lane a <-> action a, and immediately back-propagates into the
+// pre-activation gradient of the first head layers (the tanh' factor is applied here).  Weight /
+// bias gradients of the heads, the bias gradient of the first head layers and the three loss sums
+// are accumulated per CTA and written as one partial per CTA (summed in fixed order later).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "heads.cuh"
+
+namespace {
+
+struct RowTerms {
+    float policy;      // max(-A r, -A clamp(r))
+    float dlogp;       // d(loss)/d(new_log_prob), already scaled by 1/M
+};
+
+// ppo.py:266-270 and the gradient torch autograd assigns (see oracle/ppo_oracle.py loss_and_grads)
+__device__ __forceinline__ RowTerms policy_terms(float new_lp, float old_lp, float adv, float clip, float inv_m)
+{
+    const float ratio = expf(new_lp - old_lp);
+    const float lo = 1.0f - clip, hi = 1.0f + clip;
+    const float s1 = -adv * ratio;
+    const float s2 = -adv * fminf(fmaxf(ratio, lo), hi);
+    const bool in_range = ratio >= lo && ratio <= hi;
+    const float w1 = in_range ? 1.0f : (s1 > s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f));
+    RowTerms t;
+    t.policy = fmaxf(s1, s2);
+    t.dlogp = (-adv * w1 * inv_m) * ratio;
+    return t;
+}
+
+__device__ __forceinline__ void adv_norm_consts(const double* stats, int64_t count, int enabled, float& mean, float& denom)
+{
+    mean = 0.f; denom = 1.f;
+    if (enabled) {
+        const double mu = stats[0] / (double)count;
+        double var = (stats[1] - stats[0] * mu) / (double)(count - 1);
+        var = var > 0.0 ? var : 0.0;
+        mean = (float)mu;
+        denom = (float)sqrt(var) + 1e-6f;                 // ppo.py:243
+    }
+}
+
+// Distribution evaluation with lane a <-> action a.  z: this lane's head output (logit / mean).
+// Returns new_log_prob and entropy (warp-uniform); dz_scale_* let the caller form d(loss)/dz.
+template <bool CONT>
+struct Dist {
+    float new_lp, entropy;
+    float p, lsm;          // discrete: softmax prob / normalised logit of this lane
+    float diff, var;       // gaussian: (a - mu), sigma^2 of this lane
+};
+
+template <bool CONT>
+__device__ __forceinline__ Dist<CONT> eval_dist(float z, int lane, int A, int act_i, float act_f, float log_std)
+{
+    Dist<CONT> d;
+    const bool on = lane < A;
+    if (!CONT) {
+        // torch/distributions/categorical.py:78 (logits - logsumexp), :151-163 (log_prob, entropy)
+        const float zz = on ? z : -CUDART_INF_F;
+        const float mx = warp_max(zz);
+        const float e = on ? expf(zz - mx) : 0.f;
+        const float s = warp_sum(e);
+        const float lse = mx + logf(s);
+        d.lsm = on ? z - lse : 0.f;
+        d.p = on ? expf(d.lsm) : 0.f;
+        d.entropy = -warp_sum(on ? d.p * d.lsm : 0.f);
+        d.new_lp = __shfl_sync(0xffffffffu, d.lsm, act_i);
+        d.diff = d.var = 0.f;
+    } else {
+        // torch/distributions/normal.py:87-102, :114-115, summed over dims (continuous_ppo.py:40-47)
+        const float sigma = expf(log_std);
+        const float log_scale = logf(sigma);
+        d.var = sigma * sigma;
+        d.diff = act_f - z;
+        const float lp = on ? (-(d.diff * d.diff) / (2.0f * d.var) - log_scale - 0.91893853320467274178f) : 0.f;
+        d.new_lp = warp_sum(lp);
+        d.entropy = warp_sum(on ? (0.5f + 0.91893853320467274178f + log_scale) : 0.f);
+        d.p = d.lsm = 0.f;
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Training kernel: heads forward + loss + backward into the first head layers.
+// ---------------------------------------------------------------------------------------------
+template <bool CONT, int KPL>
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+head_train_kernel(HeadTrainArgs a)
+{
+    extern __shared__ float smem[];
+    const int H = a.H, A = a.A;
+    float* s_wa = smem;                         // [A][H]
+    float* s_wc = s_wa + A * H;                 // [H]
+    float* s_acc = s_wc + H;                    // [HEAD_WARPS][(A+1)][H]  per-warp dWa | dWc
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = a.wa[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_wc[i] = a.wc[i];
+    float* acc = s_acc + (size_t)warp * (A + 1) * H;
+    for (int i = lane; i < (A + 1) * H; i += 32) acc[i] = 0.f;
+    __syncthreads();
+
+    float mean, denom;
+    adv_norm_consts(a.adv_stats, a.adv_count, a.advantage_norm, mean, denom);
+    const float bias_a = lane < A ? a.ba[lane] : 0.f;
+    const float bias_c = a.bc[0];
+    const float log_std = (CONT && lane < A) ? a.log_std[lane] : 0.f;
+
+    float acc_b3[2 * KPL];
+#pragma unroll
+    for (int i = 0; i < 2 * KPL; ++i) acc_b3[i] = 0.f;
+    float acc_dba = 0.f, acc_dbc = 0.f, acc_dls = 0.f;
+    float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+
+    const int64_t warp_global = (int64_t)blockIdx.x * HEAD_WARPS + warp;
+    const int64_t warp_stride = (int64_t)gridDim.x * HEAD_WARPS;
+    for (int64_t m = warp_global; m < a.M; m += warp_stride) {
+        const int64_t src = a.idx ? (int64_t)a.idx[m] : m;
+        const float* h3 = a.h3 + m * (int64_t)(2 * H);
+        float ha[KPL], hc[KPL];
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            ha[i] = k < H ? __ldg(h3 + k) : 0.f;
+            hc[i] = k < H ? __ldg(h3 + H + k) : 0.f;
+        }
+        const float old_lp = __ldg(a.old_logp + src);
+        float adv = __ldg(a.adv + src);
+        adv = (adv - mean) / denom;
+        const float ret = __ldg(a.ret + src);
+        int act_i = 0;
+        float act_f = 0.f;
+        if (CONT) act_f = lane < A ? __ldg(a.actions_f + src * A + lane) : 0.f;
+        else act_i = __ldg(a.actions_i + src);
+
+        // head products
+        float z = 0.f;
+        for (int j = 0; j < A; ++j) {
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                if (k < H) part = fmaf(ha[i], s_wa[j * H + k], part);
+            }
+            part = warp_sum(part);
+            if (lane == j) z = part;
+        }
+        z += bias_a;
+        float vpart = 0.f;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            if (k < H) vpart = fmaf(hc[i], s_wc[k], vpart);
+        }
+        const float v = warp_sum(vpart) + bias_c;
+
+        const Dist<CONT> d = eval_dist<CONT>(z, lane, A, act_i, act_f, log_std);
+        const RowTerms t = policy_terms(d.new_lp, old_lp, adv, a.clip, a.inv_m);
+        float dz = 0.f;
+        if (lane < A) {
+            if (!CONT) {
+                dz = t.dlogp * ((lane == act_i ? 1.0f : 0.0f) - d.p) + (a.beta * a.inv_m) * d.p * (d.lsm + d.entropy);
+            } else {
+                dz = t.dlogp * d.diff / d.var;
+                acc_dls += t.dlogp * (d.diff * d.diff / d.var - 1.0f) - a.beta * a.inv_m;
+            }
+        }
+        const float verr = v - ret;
+        const float dv = a.vw * verr * a.inv_m;
+        l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
+        acc_dba += dz;
+        acc_dbc += dv;
+
+        // backward into the first head layers (+ head weight gradients)
+        float ga[KPL];
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) ga[i] = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float dzj = __shfl_sync(0xffffffffu, dz, j);
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) {
+                const int k = lane + 32 * i;
+                if (k < H) {
+                    ga[i] = fmaf(dzj, s_wa[j * H + k], ga[i]);
+                    acc[j * H + k] = fmaf(dzj, ha[i], acc[j * H + k]);
+                }
+            }
+        }
+        float* d3 = a.d3 + m * (int64_t)(2 * H);
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+            const int k = lane + 32 * i;
+            if (k < H) {
+                const float da = ga[i] * (1.0f - ha[i] * ha[i]);
+                const float dc = dv * s_wc[k] * (1.0f - hc[i] * hc[i]);
+                d3[k] = da;
+                d3[H + k] = dc;
+                acc_b3[i] += da;
+                acc_b3[KPL + i] += dc;
+                acc[A * H + k] = fmaf(dv, hc[i], acc[A * H + k]);
+            }
+        }
+    }
+
+    // ---- per-CTA partial: [dWa A*H | dba A | dWc H | dbc 1 | dlog_std A | db3 2H | losses 4] ----
+    __syncthreads();
+    float* out = a.partials + (int64_t)blockIdx.x * a.partial_stride;
+    for (int i = threadIdx.x; i < (A + 1) * H; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < HEAD_WARPS; ++w) s += s_acc[(size_t)w * (A + 1) * H + i];
+        if (i < A * H) out[i] = s; else out[A * H + A + (i - A * H)] = s;
+    }
+    __syncthreads();
+    // reuse s_acc as scratch for the small per-warp vectors
+    float* scratch = s_acc;                    // [HEAD_WARPS][2H + 3*32 + 4]
+    const int sw = 2 * H + 100;
+    float* mine = scratch + warp * sw;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        if (k < H) { mine[k] = acc_b3[i]; mine[H + k] = acc_b3[KPL + i]; }
+    }
+    mine[2 * H + lane] = acc_dba;
+    mine[2 * H + 32 + lane] = acc_dls;
+    if (lane == 0) {
+        mine[2 * H + 64] = acc_dbc; mine[2 * H + 65] = l_pol; mine[2 * H + 66] = l_val; mine[2 * H + 67] = l_ent;
+    }
+    __syncthreads();
+    const int off_dba = A * H, off_dbc = A * H + A + H, off_dls = off_dbc + 1, off_b3 = off_dls + A, off_loss = off_b3 + 2 * H;
+    for (int i = threadIdx.x; i < 2 * H + 68; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < HEAD_WARPS; ++w) s += scratch[w * sw + i];
+        if (i < 2 * H) out[off_b3 + i] = s;
+        else if (i < 2 * H + 32) { if (i - 2 * H < A) out[off_dba + (i - 2 * H)] = s; }
+        else if (i < 2 * H + 64) { if (i - 2 * H - 32 < A) out[off_dls + (i - 2 * H - 32)] = s; }
+        else if (i == 2 * H + 64) out[off_dbc] = s;
+        else out[off_loss + (i - 2 * H - 65)] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inference: head outputs (+ log-prob of given actions) for the pre-update pass and get_actions.
+// ha/hc point at the first-head-layer activations (row stride ld); either may be null.
+// ---------------------------------------------------------------------------------------------
+template <int KPL>
+__global__ void __launch_bounds__(256)
+head_eval_kernel(const float* __restrict__ ha_base, const float* __restrict__ hc_base, int ld, const float* __restrict__ wa,
+                 const float* __restrict__ ba, const float* __restrict__ wc, const float* __restrict__ bc,
+                 float* __restrict__ head_out, float* __restrict__ values, int64_t rows, int H, int A)
+{
+    extern __shared__ float smem[];
+    float* s_wa = smem;
+    float* s_wc = smem + A * H;
+    if (ha_base) for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = wa[i];
+    if (hc_base) for (int i = threadIdx.x; i < H; i += blockDim.x) s_wc[i] = wc[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t ws = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = w0; m < rows; m += ws) {
+        if (ha_base) {
+            float h[KPL];
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) { const int k = lane + 32 * i; h[i] = k < H ? __ldg(ha_base + m * ld + k) : 0.f; }
+            float z = 0.f;
+            for (int j = 0; j < A; ++j) {
+                float part = 0.f;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) { const int k = lane + 32 * i; if (k < H) part = fmaf(h[i], s_wa[j * H + k], part); }
+                part = warp_sum(part);
+                if (lane == j) z = part;
+            }
+            if (lane < A) head_out[m * A + lane] = z + ba[lane];
+        }
+        if (hc_base) {
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) { const int k = lane + 32 * i; if (k < H) part = fmaf(__ldg(hc_base + m * ld + k), s_wc[k], part); }
+            part = warp_sum(part);
+            if (lane == 0) values[m] = part + bc[0];
+        }
+    }
+}
+
+__global__ void logprob_categorical_kernel(const float* __restrict__ logits, const int32_t* __restrict__ actions,
+                                           float* __restrict__ out, int64_t rows, int A)
+{
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += (int64_t)gridDim.x * blockDim.x) {
+        const float* z = logits + m * A;
+        float mx = -CUDART_INF_F;
+        for (int j = 0; j < A; ++j) mx = fmaxf(mx, z[j]);
+        float s = 0.f;
+        for (int j = 0; j < A; ++j) s += expf(z[j] - mx);
+        out[m] = z[actions[m]] - (mx + logf(s));
+    }
+}
+
+__global__ void logprob_gaussian_kernel(const float* __restrict__ mean, const float* __restrict__ log_std,
+                                        const float* __restrict__ actions, float* __restrict__ out, int64_t rows, int A)
+{
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += (int64_t)gridDim.x * blockDim.x) {
+        float lp = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float sigma = expf(log_std[j]);
+            const float diff = actions[m * A + j] - mean[m * A + j];
+            lp += -(diff * diff) / (2.0f * sigma * sigma) - logf(sigma) - 0.91893853320467274178f;
+        }
+        out[m] = lp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standalone loss forward+backward on already-gathered rows (custom network_cls path).
+// One warp per row, lane a <-> action a.  Per-CTA partial: [policy, value, entropy, pad, dlog_std A]
+// ---------------------------------------------------------------------------------------------
+template <bool CONT>
+__global__ void __launch_bounds__(256)
+loss_rows_kernel(const float* __restrict__ head, const float* __restrict__ log_std_p, int64_t ls_stride, const float* __restrict__ values,
+                 const int32_t* __restrict__ actions_i, const float* __restrict__ actions_f, const float* __restrict__ old_logp,
+                 const float* __restrict__ adv_p, const float* __restrict__ ret_p, int64_t M, int A, float clip, float vw,
+                 float beta, float inv_m, float* __restrict__ dhead, float* __restrict__ dls_rows, float* __restrict__ dvalues,
+                 float* __restrict__ partials)
+{
+    __shared__ float s_red[8][36];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float log_std = (CONT && lane < A && ls_stride == 0) ? log_std_p[lane] : 0.f;
+    float l_pol = 0.f, l_val = 0.f, l_ent = 0.f, acc_dls = 0.f;
+    const int64_t w0 = (int64_t)blockIdx.x * 8 + warp, wstride = (int64_t)gridDim.x * 8;
+    for (int64_t m = w0; m < M; m += wstride) {
+        const float z = lane < A ? head[m * A + lane] : 0.f;
+        int act_i = 0; float act_f = 0.f;
+        if (CONT) act_f = lane < A ? actions_f[m * A + lane] : 0.f; else act_i = actions_i[m];
+        if (CONT && ls_stride != 0) log_std = lane < A ? log_std_p[m * ls_stride + lane] : 0.f;
+        const Dist<CONT> d = eval_dist<CONT>(z, lane, A, act_i, act_f, log_std);
+        const RowTerms t = policy_terms(d.new_lp, old_logp[m], adv_p[m], clip, inv_m);
+        if (lane < A) {
+            float dz;
+            if (!CONT) dz = t.dlogp * ((lane == act_i ? 1.0f : 0.0f) - d.p) + (beta * inv_m) * d.p * (d.lsm + d.entropy);
+            else {
+                dz = t.dlogp * d.diff / d.var;
+                const float dls = t.dlogp * (d.diff * d.diff / d.var - 1.0f) - beta * inv_m;
+                acc_dls += dls;
+                if (ls_stride != 0) dls_rows[m * A + lane] = dls;
+            }
+            dhead[m * A + lane] = dz;
+        }
+        const float verr = values[m] - ret_p[m];
+        if (lane == 0) dvalues[m] = vw * verr * inv_m;
+        l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
+    }
+    s_red[warp][lane] = acc_dls;
+    if (lane == 0) { s_red[warp][32] = l_pol; s_red[warp][33] = l_val; s_red[warp][34] = l_ent; }
+    __syncthreads();
+    if (threadIdx.x < 35) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+        float* out = partials + (int64_t)blockIdx.x * 40;
+        if (threadIdx.x < 32) out[4 + threadIdx.x] = s; else out[threadIdx.x - 32] = s;
+    }
+}
+
+__global__ void loss_finalize_kernel(const float* __restrict__ partials, int nparts, int A, float vw, float beta, float inv_m,
+                                     float* __restrict__ losses, float* __restrict__ dlog_std)
+{
+    __shared__ float l[3];
+    const int i = threadIdx.x;
+    if (i < 35) {
+        float s = 0.f;
+        for (int p = 0; p < nparts; ++p) s += partials[(int64_t)p * 40 + (i < 3 ? i : i + 1)];
+        if (i < 3) l[i] = s;
+        if (i >= 3 && dlog_std && i - 3 < A) dlog_std[i - 3] = s;
+    }
+    __syncthreads();
+    if (i == 0) {
+        const float pol = l[0] * inv_m, val = 0.5f * l[1] * inv_m, ent = l[2] * inv_m;
+        losses[0] = pol; losses[1] = val; losses[2] = ent; losses[3] = pol + vw * val + -beta * ent;
+    }
+}
+
+template <int KPL>
+int launch_head_train(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int blocks, size_t smem, cudaStream_t st)
+{
+    if (continuous) {
+        cudaFuncSetAttribute(head_train_kernel<true, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        head_train_kernel<true, KPL><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(head_train_kernel<false, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        head_train_kernel<false, KPL><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
+    }
+    DPPO_CHECK_LAUNCH(ctx, "head_train_kernel");
+    return 0;
+}
+
+}  // namespace
+
+int head_partial_floats(int H, int A) { return A * H + A + H + 1 + A + 2 * H + 4; }
+
+int head_train_blocks(dppo_ctx* ctx, int64_t M)
+{
+    int64_t want = (M + HEAD_WARPS - 1) / HEAD_WARPS;
+    int64_t cap = 2 * (int64_t)ctx->sm_count;
+    return (int)(want < cap ? want : cap);
+}
+
+int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int blocks, cudaStream_t st)
+{
+    const int H = a.H, A = a.A;
+    if (A < 1 || A > DPPO_MAX_ACT) DPPO_FAIL(ctx, "head kernel supports 1..%d actions/action dims, got %d", DPPO_MAX_ACT, A);
+    if (H < 1 || H > 512) DPPO_FAIL(ctx, "head kernel supports hidden <= 512, got %d", H);
+    size_t accf = (size_t)HEAD_WARPS * (A + 1) * H;
+    const size_t scratchf = (size_t)HEAD_WARPS * (2 * H + 100);
+    if (accf < scratchf) accf = scratchf;
+    const size_t smem = ((size_t)(A + 1) * H + accf) * sizeof(float);
+    if (smem > 200 * 1024) DPPO_FAIL(ctx, "head kernel: (A+1)*H = %d too large for shared memory", (A + 1) * H);
+    if (H <= 64) return launch_head_train<2>(ctx, a, continuous, blocks, smem, st);
+    if (H <= 128) return launch_head_train<4>(ctx, a, continuous, blocks, smem, st);
+    if (H <= 256) return launch_head_train<8>(ctx, a, continuous, blocks, smem, st);
+    return launch_head_train<16>(ctx, a, continuous, blocks, smem, st);
+}
+
+int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, const float* wa, const float* ba, const float* wc,
+                     const float* bc, float* head_out, float* values, int64_t rows, int H, int A, cudaStream_t st)
+{
+    if (A < 1 || A > DPPO_MAX_ACT) DPPO_FAIL(ctx, "head kernel supports 1..%d actions/action dims, got %d", DPPO_MAX_ACT, A);
+    if (H < 1 || H > 512) DPPO_FAIL(ctx, "head kernel supports hidden <= 512, got %d", H);
+    const size_t smem = (size_t)(A + 1) * H * sizeof(float);
+    int64_t want = (rows + 7) / 8;
+    int blocks = (int)(want < 4 * (int64_t)ctx->sm_count ? want : 4 * (int64_t)ctx->sm_count);
+#define HE(KPL)                                                                                                   \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(head_eval_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        head_eval_kernel<KPL><<<blocks, 256, smem, st>>>(ha, hc, ld, wa, ba, wc, bc, head_out, values, rows, H, A); \
+    } while (0)
+    if (H <= 64) HE(2); else if (H <= 128) HE(4); else if (H <= 256) HE(8); else HE(16);
+#undef HE
+    DPPO_CHECK_LAUNCH(ctx, "head_eval_kernel");
+    return 0;
+}
+
+extern "C" int dppo_logprob_categorical(dppo_ctx* ctx, const float* logits, const int32_t* actions, float* log_probs,
+                                        int64_t rows, int A, void* stream)
+{
+    if (!ctx) return 1;
+    if (rows <= 0) return 0;
+    int blocks = (int)((rows + 255) / 256);
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    logprob_categorical_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, actions, log_probs, rows, A);
+    DPPO_CHECK_LAUNCH(ctx, "logprob_categorical_kernel");
+    return 0;
+}
+
+extern "C" int dppo_logprob_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, const float* actions,
+                                     float* log_probs, int64_t rows, int A, void* stream)
+{
+    if (!ctx) return 1;
+    if (rows <= 0) return 0;
+    int blocks = (int)((rows + 255) / 256);
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    logprob_gaussian_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mean, log_std, actions, log_probs, rows, A);
+    DPPO_CHECK_LAUNCH(ctx, "logprob_gaussian_kernel");
+    return 0;
+}
+
+static int loss_blocks(dppo_ctx* ctx, int64_t M)
+{
+    int64_t want = (M + 7) / 8;
+    int64_t cap = 2 * (int64_t)ctx->sm_count;
+    return (int)(want < cap ? want : cap);
+}
+
+extern "C" int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A)
+{
+    (void)A;
+    int64_t blocks = (M + 7) / 8;
+    if (blocks > 2 * 256) blocks = 2 * 256;            // upper bound on 2*SMs
+    return blocks * 40 * (int64_t)sizeof(float);
+}
+
+static int ppo_loss_common(dppo_ctx* ctx, bool cont, const float* head, const float* log_std, int64_t ls_stride, const float* values,
+                           const int32_t* actions_i, const float* actions_f, const float* old_lp, const float* adv,
+                           const float* ret, int64_t M, int A, const dppo_hyper* h, float* losses, float* dhead,
+                           float* dlog_std, float* dvalues, void* ws, int64_t ws_bytes, cudaStream_t st)
+{
+    if (!ctx) return 1;
+    if (M <= 0) DPPO_FAIL(ctx, "ppo_loss: empty minibatch");
+    if (A < 1 || A > DPPO_MAX_ACT) DPPO_FAIL(ctx, "ppo_loss supports 1..%d actions/action dims, got %d", DPPO_MAX_ACT, A);
+    const int blocks = loss_blocks(ctx, M);
+    if (ws_bytes < (int64_t)blocks * 40 * (int64_t)sizeof(float)) DPPO_FAIL(ctx, "ppo_loss: workspace too small");
+    const float inv_m = 1.0f / (float)(h->loss_denominator > 0 ? h->loss_denominator : M);
+    float* partials = (float*)ws;
+    if (cont)
+        loss_rows_kernel<true><<<blocks, 256, 0, st>>>(head, log_std, ls_stride, values, actions_i, actions_f, old_lp, adv, ret, M, A,
+                                                       h->ppo_clip, h->value_loss_weight, h->entropy_beta, inv_m, dhead,
+                                                       ls_stride ? dlog_std : nullptr, dvalues, partials);
+    else
+        loss_rows_kernel<false><<<blocks, 256, 0, st>>>(head, log_std, 0, values, actions_i, actions_f, old_lp, adv, ret, M, A,
+                                                        h->ppo_clip, h->value_loss_weight, h->entropy_beta, inv_m, dhead, nullptr, dvalues, partials);
+    DPPO_CHECK_LAUNCH(ctx, "loss_rows_kernel");
+    loss_finalize_kernel<<<1, 64, 0, st>>>(partials, blocks, A, h->value_loss_weight, h->entropy_beta, inv_m, losses,
+                                           ls_stride ? nullptr : dlog_std);
+    DPPO_CHECK_LAUNCH(ctx, "loss_finalize_kernel");
+    return 0;
+}
+
+extern "C" int dppo_ppo_loss_discrete(dppo_ctx* ctx, const float* logits, const float* values, const int32_t* actions,
+                                      const float* old_log_probs, const float* adv, const float* returns, int64_t M, int A,
+                                      const dppo_hyper* hyper, float* losses, float* dlogits, float* dvalues, void* ws,
+                                      int64_t ws_bytes, void* stream)
+{
+    return ppo_loss_common(ctx, false, logits, nullptr, 0, values, actions, nullptr, old_log_probs, adv, returns, M, A, hyper,
+                           losses, dlogits, nullptr, dvalues, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dppo_ppo_loss_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, int64_t log_std_row_stride, const float* values,
+                                      const float* actions, const float* old_log_probs, const float* adv, const float* returns,
+                                      int64_t M, int A, const dppo_hyper* hyper, float* losses, float* dmean, float* dlog_std,
+                                      float* dvalues, void* ws, int64_t ws_bytes, void* stream)
+{
+    return ppo_loss_common(ctx, true, mean, log_std, log_std_row_stride, values, nullptr, actions, old_log_probs, adv, returns, M, A, hyper, losses,
+                           dmean, dlog_std, dvalues, ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,208 @@
+#include <math.h>
+// Gradient assembly, clip_grad_norm_ (diamond/ppo.py:284) and Adam (ppo.py:285) over flat buffers.
+#include "optim.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, const float* __restrict__ loss_partials,
+                   int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* __restrict__ losses)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < tab.nseg; ++g) {
+            const GradSeg& sg = tab.seg[g];
+            if (i >= sg.dst && i < sg.dst + sg.count) {
+                const float* p = sg.src + (i - sg.dst);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int q = 0;
+                for (; q + 3 < sg.nparts; q += 4) {
+                    s0 += __ldg(p + (int64_t)q * sg.stride);
+                    s1 += __ldg(p + (int64_t)(q + 1) * sg.stride);
+                    s2 += __ldg(p + (int64_t)(q + 2) * sg.stride);
+                    s3 += __ldg(p + (int64_t)(q + 3) * sg.stride);
+                }
+                for (; q < sg.nparts; ++q) s0 += __ldg(p + (int64_t)q * sg.stride);
+                s = (s0 + s1) + (s2 + s3);
+                break;
+            }
+        }
+        grads[i] = s;
+    }
+    if (blockIdx.x == 0 && losses != nullptr) {
+        __shared__ float l[3];
+        if (threadIdx.x < 3) {
+            float s = 0.f;
+            for (int p = 0; p < loss_nparts; ++p) s += loss_partials[(int64_t)p * loss_stride + threadIdx.x];
+            l[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float pol = l[0] * inv_m, val = 0.5f * l[1] * inv_m, ent = l[2] * inv_m;    // ppo.py:270-274
+            losses[0] = pol; losses[1] = val; losses[2] = ent;
+            losses[3] = pol + vw * val + -beta * ent;                                          // ppo.py:276-280
+        }
+    }
+}
+
+constexpr int SUMSQ_THREADS = 256;
+
+__global__ void __launch_bounds__(SUMSQ_THREADS)
+sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partials)
+{
+    __shared__ double red[SUMSQ_THREADS / 32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = g[i];
+        s += (double)x * (double)x;
+    }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < SUMSQ_THREADS / 32 ? red[threadIdx.x] : 0.0;
+        s = warp_sum_d(s);
+        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    }
+}
+
+// torch/nn/utils/clip_grad.py:165-182 then torch/optim/adam.py single-tensor path (:457,:476,:531-547).
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                 const double* __restrict__ norm_partials, int nparts, float max_norm, float w1, float beta2, float w2,
+                 float bc2_sqrt, float eps, float neg_step_size, float* __restrict__ grad_norm_out)
+{
+    __shared__ float s_coef;
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += 32) s += norm_partials[i];
+        s = warp_sum_d(s);
+        if (threadIdx.x == 0) {
+            const float total = (float)sqrt(s);
+            float coef = max_norm / (total + 1e-6f);
+            s_coef = coef > 1.0f ? 1.0f : coef;
+            if (blockIdx.x == 0 && grad_norm_out) *grad_norm_out = total;
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = __fmul_rn(g[i], coef);                                   // grads are always scaled
+        float mi = m[i], vi = v[i];
+        mi = fmaf(w1, gi - mi, mi);                                               // exp_avg.lerp_(grad, 1-beta1)
+        vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(w2, gi), gi));   // mul_(beta2).addcmul_(g, g, 1-beta2)
+        const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+        p[i] = __fadd_rn(p[i], __fmul_rn(neg_step_size, __fdiv_rn(mi, denom)));   // addcdiv_(m, denom, -step_size)
+        g[i] = gi; m[i] = mi; v[i] = vi;
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                   int64_t rows, int row_floats)
+{
+    const int64_t total = rows * row_floats;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / row_floats;
+        const int c = (int)(i - r * row_floats);
+        dst[i] = __ldg(src + (int64_t)idx[r] * row_floats + c);
+    }
+}
+
+// 16 independent 3-register FFMA chains per thread (acc = x*y + acc, the form a GEMM inner loop issues):
+// the FP32 FMA-pipe ceiling of this GPU at its current clocks.  iters FMAs per thread (multiple of 16).
+__global__ void __launch_bounds__(256)
+fma_peak_kernel(float* __restrict__ sink, int64_t iters)
+{
+    float x[4], y[4], acc[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        x[i] = sink[(threadIdx.x + i) & 63] * 1e-6f;
+        y[i] = sink[(threadIdx.x + 4 + i) & 63] * 1e-6f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int64_t it = 0; it < iters; it += 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i * 4 + j] = fmaf(x[i], y[j], acc[i * 4 + j]);
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r += acc[i];
+    if (r == 123.456f) sink[64] = r;
+}
+
+}  // namespace
+
+int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int64_t total, const float* loss_partials,
+                       int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* losses, cudaStream_t st)
+{
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
+    if (blocks < 1) blocks = 1;
+    grad_reduce_kernel<<<blocks, 256, 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses);
+    DPPO_CHECK_LAUNCH(ctx, "grad_reduce_kernel");
+    return 0;
+}
+
+static int sumsq_blocks(int64_t n)
+{
+    int64_t b = (n + SUMSQ_THREADS * 4 - 1) / (SUMSQ_THREADS * 4);
+    if (b > 256) b = 256;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int64_t dppo_clip_adam_workspace_bytes(int64_t n) { return (int64_t)sumsq_blocks(n) * (int64_t)sizeof(double); }
+
+extern "C" int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                   const dppo_hyper* h, float* grad_norm_out, void* ws, int64_t ws_bytes, void* stream)
+{
+    if (!ctx) return 1;
+    if (n <= 0) DPPO_FAIL(ctx, "clip_adam: empty parameter buffer");
+    if (h->step < 1) DPPO_FAIL(ctx, "clip_adam: step must be >= 1 (got %lld)", (long long)h->step);
+    const int nb = sumsq_blocks(n);
+    if (ws_bytes < (int64_t)nb * (int64_t)sizeof(double)) DPPO_FAIL(ctx, "clip_adam: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(ws) & 7u) != 0) DPPO_FAIL(ctx, "clip_adam: workspace must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* partials = (double*)ws;
+    sumsq_kernel<<<nb, SUMSQ_THREADS, 0, st>>>(grads, n, partials);
+    DPPO_CHECK_LAUNCH(ctx, "sumsq_kernel");
+    // bias corrections in double on the host exactly as torch does with python floats (adam.py:531-547)
+    const double bc1 = 1.0 - pow(h->beta1, (double)h->step);
+    const double bc2 = 1.0 - pow(h->beta2, (double)h->step);
+    const double step_size = h->lr / bc1;
+    const double bc2_sqrt = sqrt(bc2);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
+    clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, nb, h->grad_norm_clip,
+                                             (float)(1.0 - h->beta1), (float)h->beta2, (float)(1.0 - h->beta2), (float)bc2_sqrt,
+                                             h->adam_eps, (float)(-step_size), grad_norm_out);
+    DPPO_CHECK_LAUNCH(ctx, "clip_adam_kernel");
+    return 0;
+}
+
+extern "C" int dppo_gather_rows_f32(dppo_ctx* ctx, const float* src, const int32_t* idx, float* dst, int64_t rows,
+                                    int row_floats, void* stream)
+{
+    if (!ctx) return 1;
+    if (rows <= 0 || row_floats <= 0) return 0;
+    const int64_t total = rows * row_floats;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, dst, rows, row_floats);
+    DPPO_CHECK_LAUNCH(ctx, "gather_rows_kernel");
+    return 0;
+}
+
+extern "C" int dppo_fma_peak_kernel(dppo_ctx* ctx, float* sink, int64_t iters, int* blocks_out, int* threads_out, void* stream)
+{
+    if (!ctx) return 1;
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters);
+    DPPO_CHECK_LAUNCH(ctx, "fma_peak_kernel");
+    if (blocks_out) *blocks_out = blocks;
+    if (threads_out) *threads_out = threads;
+    return 0;
+}

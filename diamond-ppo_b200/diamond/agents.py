@@ -1,0 +1,651 @@
+"""PPO and ContinuousPPO agents with the reference's constructor, attributes and methods
+(diamond/ppo.py:111-312, diamond/continuous_ppo.py:124-324), running the hot path — rollout
+storage, action sampling, pre-update pass, GAE, permutation/gather, MLP forward/backward + loss,
+clip + Adam — in libdppo's sm_100a kernels.
+
+Two engines sit behind the same agent API:
+  * FusedMlpEngine   — the default networks: every step of learn() is a libdppo kernel over flat
+                       parameter buffers (no torch ops, no autograd, no host sync in the loop).
+  * AutogradEngine   — a user `network_cls` (readme.md:89-111): the module runs under PyTorch autograd
+                       on the GPU; buffer, GAE, gather, loss (+ its gradient) and clip+Adam stay on
+                       libdppo kernels.
+Env-sharded data parallelism (one process per GPU, torch.distributed/NCCL) is enabled by passing
+`process_group=` or by initialising torch.distributed before constructing the agent with `dp=True`.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from math import sqrt
+from typing import Any, Callable
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .config import PPOConfig, ContinuousPPOConfig
+from .flat import FlatMlp
+from .networks import ActorCriticNetwork, ContinuousActorCriticNetwork, network_parameter_init_
+from .utils import Ticker, Logger, Timer, Checkpointer
+
+try:                                    # the real package when present, else the in-repo shim
+    import gymnasium as gym             # noqa: F401
+except ImportError:                     # pragma: no cover - the GPU image has no gymnasium
+    from . import envs as gym
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise N.NativeError("diamond (B200 build) needs a CUDA device: the hot path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-resident rollout buffer (replaces the Python list of NumPy arrays, ppo.py:155-172)
+# ------------------------------------------------------------------------------------------------
+class RolloutBuffer:
+    """Time-major [T, N, ...] device tensors filled one vector step at a time.
+
+    Behaves like the reference's `experience` list (len, iteration, indexing give the six NumPy
+    arrays of a step) so user code that inspects `agent.rollout()` keeps working, while
+    `agent.learn()` consumes the device tensors directly with no bulk host->device copy."""
+
+    def __init__(self, ctx: N.Context, T: int, N_: int, D: int, A: int, continuous: bool, device: torch.device):
+        self.ctx, self.T, self.N, self.D, self.A, self.continuous, self.device = ctx, T, N_, D, A, continuous, device
+        f = dict(dtype=torch.float32, device=device)
+        self.obs = torch.empty(T, N_, D, **f)
+        self.next_obs = torch.empty(T, N_, D, **f)
+        self.actions = torch.empty((T, N_, A), **f) if continuous else torch.empty(T, N_, dtype=torch.int32, device=device)
+        self.rewards = torch.empty(T, N_, **f)
+        self.terminations = torch.empty(T, N_, **f)
+        self.truncations = torch.empty(T, N_, **f)
+        self.rec_bytes = ctx.step_record_bytes(N_, D, A, continuous)
+        padded = (self.rec_bytes + 7) // 8 * 8
+        self._pinned = [torch.empty(padded, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._events = [None, None]
+        self._dev_rec = torch.empty(padded, dtype=torch.uint8, device=device)
+        self._views = [self._carve(p.numpy()) for p in self._pinned]
+        self.h2d_bytes = 0
+        self.filled = 0
+
+    def _carve(self, raw: np.ndarray):
+        nd = self.N * self.D
+        o = 0
+        obs = raw[o:o + nd * 4].view(np.float32).reshape(self.N, self.D); o += nd * 4
+        nobs = raw[o:o + nd * 4].view(np.float32).reshape(self.N, self.D); o += nd * 4 + 4 * (nd & 1)
+        rew = raw[o:o + self.N * 8].view(np.float64); o += self.N * 8
+        if self.continuous:
+            act = raw[o:o + self.N * self.A * 4].view(np.float32).reshape(self.N, self.A); o += self.N * self.A * 4
+        else:
+            act = raw[o:o + self.N * 8].view(np.int64); o += self.N * 8
+        term = raw[o:o + self.N]; o += self.N
+        trunc = raw[o:o + self.N]; o += self.N
+        assert o == self.rec_bytes
+        return obs, nobs, rew, act, term, trunc
+
+    def store(self, t: int, obs, next_obs, actions, rewards, terminations, truncations) -> None:
+        """One packed record -> one H2D copy -> one unpack/cast kernel (dppo_buffer_store_step)."""
+        slot = t & 1
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()               # the copy that last read this slot has finished
+        v_obs, v_nobs, v_rew, v_act, v_term, v_trunc = self._views[slot]
+        np.copyto(v_obs, np.asarray(obs, dtype=np.float32).reshape(self.N, self.D))
+        np.copyto(v_nobs, np.asarray(next_obs, dtype=np.float32).reshape(self.N, self.D))
+        np.copyto(v_rew, np.asarray(rewards, dtype=np.float64))
+        if self.continuous:
+            np.copyto(v_act, np.asarray(actions, dtype=np.float32).reshape(self.N, self.A))
+        else:
+            np.copyto(v_act, np.asarray(actions, dtype=np.int64))
+        np.copyto(v_term, np.asarray(terminations, dtype=bool).view(np.uint8))
+        np.copyto(v_trunc, np.asarray(truncations, dtype=bool).view(np.uint8))
+        self._dev_rec.copy_(self._pinned[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+        self.ctx.buffer_store_step(self._dev_rec, t, self.N, self.D, self.A, self.continuous, self.obs, self.next_obs,
+                                   self.actions, self.rewards, self.terminations, self.truncations)
+        self.h2d_bytes += self.rec_bytes
+        self.filled = max(self.filled, t + 1)
+
+    @classmethod
+    def from_lists(cls, ctx, experience, continuous: bool, device) -> "RolloutBuffer":
+        """Reference-style experience (list of [obs, next_obs, actions, rewards, term, trunc] NumPy
+        arrays, ppo.py:165-172) -> device buffer, with the casts of ppo.py:227-232."""
+        obs, nobs, act, rew, term, trunc = (np.asarray(x) for x in zip(*experience))
+        T, N_ = rew.shape[:2]
+        D = int(np.prod(obs.shape[2:]))
+        A = int(np.prod(act.shape[2:])) if continuous else 1
+        buf = cls.__new__(cls)
+        buf.ctx, buf.T, buf.N, buf.D, buf.A, buf.continuous, buf.device = ctx, T, N_, D, A, continuous, device
+
+        def up(x, dtype):
+            t = torch.as_tensor(np.ascontiguousarray(x)).to(dtype)
+            return t.pin_memory().to(device, non_blocking=True).contiguous()
+        buf.obs = up(obs.reshape(T, N_, D), torch.float32)
+        buf.next_obs = up(nobs.reshape(T, N_, D), torch.float32)
+        buf.actions = up(act.reshape(T, N_, A), torch.float32) if continuous else up(act, torch.int32)
+        buf.rewards, buf.terminations, buf.truncations = up(rew, torch.float32), up(term, torch.float32), up(trunc, torch.float32)
+        buf.h2d_bytes = sum(t.numel() * t.element_size() for t in (buf.obs, buf.next_obs, buf.actions, buf.rewards,
+                                                                    buf.terminations, buf.truncations))
+        buf.filled = T
+        return buf
+
+    # ---- list-like view for user code ---------------------------------------------------------
+    def __len__(self) -> int:
+        return self.filled
+
+    def __getitem__(self, t: int):
+        if not -self.filled <= t < self.filled:
+            raise IndexError(t)
+        act = self.actions[t].cpu().numpy()
+        return [self.obs[t].cpu().numpy(), self.next_obs[t].cpu().numpy(),
+                act if self.continuous else act.astype(np.int64),
+                self.rewards[t].cpu().numpy().astype(np.float64), self.terminations[t].cpu().numpy() != 0,
+                self.truncations[t].cpu().numpy() != 0]
+
+    def __iter__(self):
+        return (self[t] for t in range(self.filled))
+
+
+# ------------------------------------------------------------------------------------------------
+# Data-parallel plumbing: env-sharded, one process per GPU
+# ------------------------------------------------------------------------------------------------
+class _Dist:
+    def __init__(self, group=None, enabled=False):
+        import torch.distributed as dist
+        self.dist = dist
+        self.enabled = bool(enabled or group is not None) and dist.is_available() and dist.is_initialized()
+        self.group = group
+        self.world = dist.get_world_size(group) if self.enabled else 1
+        self.rank = dist.get_rank(group) if self.enabled else 0
+        if self.world == 1:
+            self.enabled = False
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        if self.enabled:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class _PermWorker(threading.Thread):
+    """Generates the E minibatch permutations of one learn() (ppo.py:252-255) on a host thread while
+    the GPU runs the pre-update pass / previous epoch.  Bit-exact continuation of numpy's global
+    legacy stream (dppo_permutation_mt19937); under data parallelism each global permutation is
+    also filtered down to this rank's env shard and re-indexed to local flat indices."""
+
+    def __init__(self, B_global, E, MB, outs, shard=None):
+        super().__init__(daemon=True)
+        st = np.random.get_state(legacy=True)
+        self.state_tail = (st[3], st[4])
+        self.key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+        self.pos = int(st[2])
+        self.B, self.E, self.MB, self.outs, self.shard = B_global, E, MB, outs, shard
+        self.ready = [threading.Event() for _ in range(E)]
+        self.counts = [None] * E
+        self.error = None
+        self.scratch = np.empty(B_global, np.int32) if shard is not None else None
+
+    def run(self):
+        try:
+            M = self.B // self.MB
+            for e in range(self.E):
+                if self.shard is None:
+                    _, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.outs[e])
+                else:
+                    n_global, lo, n_local = self.shard
+                    perm, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.scratch)
+                    t, env = np.divmod(perm, n_global)
+                    mine = (env >= lo) & (env < lo + n_local)
+                    local = (t * n_local + (env - lo)).astype(np.int32)
+                    counts, o = [], 0
+                    for k in range(self.MB):
+                        sel = local[k * M:(k + 1) * M][mine[k * M:(k + 1) * M]]
+                        self.outs[e][o:o + sel.size] = sel
+                        counts.append((o, int(sel.size)))
+                        o += sel.size
+                    self.counts[e] = counts
+                self.ready[e].set()
+        except BaseException as ex:      # surfaced by wait()
+            self.error = ex
+            for ev in self.ready:
+                ev.set()
+
+    def wait(self, e):
+        self.ready[e].wait()
+        if self.error is not None:
+            raise self.error
+
+    def finish(self):
+        self.join()
+        if self.error is not None:
+            raise self.error
+        np.random.set_state(("MT19937", self.key, self.pos) + self.state_tail)
+
+
+# ------------------------------------------------------------------------------------------------
+# Engines
+# ------------------------------------------------------------------------------------------------
+class _EngineBase:
+    """State shared by both engines: flat P/G/M/V buffers aliased by the module's parameters."""
+
+    def _adopt(self, network: nn.Module, named_offsets: dict[str, tuple[int, tuple]], total: int):
+        dev = self.device
+        self.P = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.G = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.M = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.V = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.param_list = []
+        with torch.no_grad():
+            for name, p in network.named_parameters():
+                off, shape = named_offsets[name]
+                n = p.numel()
+                view = self.P[off:off + n].view(*shape)
+                view.copy_(p.detach().to(dev, torch.float32).reshape(shape))
+                p.data = view                                            # parameters alias the flat buffer
+                p.grad = self.G[off:off + n].view(*shape)
+                self.param_list.append((name, p, off, n, shape))
+        self.adam_ws = torch.empty(self.ctx.clip_adam_workspace_bytes(total) // 8 + 1, dtype=torch.float64, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.adam_step = 0
+
+    def bind_optimizer(self, optimizer: torch.optim.Optimizer):
+        """Expose the kernel-side Adam moments through optimizer.state so `optimizer.state_dict()`
+        (Checkpointer, utils.py:584-600) reflects them."""
+        self.optimizer = optimizer
+        for name, p, off, n, shape in self.param_list:
+            optimizer.state[p] = {"step": torch.tensor(float(self.adam_step)),
+                                  "exp_avg": self.M[off:off + n].view(*shape),
+                                  "exp_avg_sq": self.V[off:off + n].view(*shape)}
+        optimizer._opt_called = True      # the kernels are the optimiser step; silences LinearLR's ordering warning
+
+    def _resync_optimizer(self):
+        """If user code replaced optimizer state / parameter storage (load_state_dict), pull it back
+        into the flat buffers and re-alias."""
+        for name, p, off, n, shape in self.param_list:
+            if p.data_ptr() != self.P[off:off + n].data_ptr():
+                self.P[off:off + n].view(*shape).copy_(p.detach())
+                p.data = self.P[off:off + n].view(*shape)
+            if p.grad is None or p.grad.data_ptr() != self.G[off:off + n].data_ptr():
+                p.grad = self.G[off:off + n].view(*shape)
+            st = self.optimizer.state.get(p)
+            if st and st["exp_avg"].data_ptr() != self.M[off:off + n].data_ptr():
+                self.M[off:off + n].view(*shape).copy_(st["exp_avg"])
+                self.V[off:off + n].view(*shape).copy_(st["exp_avg_sq"])
+                self.adam_step = int(float(st["step"]))
+                st["exp_avg"], st["exp_avg_sq"] = self.M[off:off + n].view(*shape), self.V[off:off + n].view(*shape)
+
+    def _publish_steps(self):
+        for _, p, *_ in self.param_list:
+            self.optimizer.state[p]["step"] = torch.tensor(float(self.adam_step))
+
+    def _hyper(self, cfg, M_global, B_global) -> N.Hyper:
+        h = N.Hyper()
+        h.ppo_clip, h.value_loss_weight, h.entropy_beta = cfg.ppo_clip, cfg.value_loss_weight, cfg.entropy_beta
+        h.grad_norm_clip, h.adam_eps = cfg.grad_norm_clip, cfg.adam_eps
+        h.beta1, h.beta2 = self.optimizer.param_groups[0]["betas"]
+        h.lr = self.optimizer.param_groups[0]["lr"]
+        h.advantage_norm, h.adv_count, h.loss_denominator = int(cfg.advantage_norm), B_global, M_global
+        return h
+
+
+class FusedMlpEngine(_EngineBase):
+    """learn() for the default MLP networks: libdppo kernels only."""
+
+    def __init__(self, ctx, network, cfg, obs_dim, act_dim, continuous, device, dist: _Dist):
+        self.ctx, self.cfg, self.device, self.dist, self.continuous = ctx, cfg, device, dist, continuous
+        self.network = network
+        self.fm = FlatMlp(obs_dim, cfg.network_hidden_dim, act_dim, continuous)
+        self._adopt(network, self.fm.slices, self.fm.total)
+        self.D, self.A = obs_dim, act_dim
+        self.fwd_rows = 65536
+        self.fwd_ws = torch.empty(ctx.mlp_workspace_bytes(self.fm.desc, self.fwd_rows, False) // 4 + 256, device=device)
+        self._train_ws = None
+        self._bufs = {}
+        self.draws = 0
+        self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        self._act_stage = {}
+        self.last_losses = None
+        self.timing = {}
+
+    # ---- rollout side: fused forward + sampling (ppo.py:73-82) -----------------------------------
+    def sample_actions(self, observations: np.ndarray) -> np.ndarray:
+        n = observations.shape[0]
+        st = self._act_stage.get(n)
+        if st is None:
+            st = dict(h_obs=torch.empty(n, self.D, dtype=torch.float32).pin_memory(),
+                      d_obs=torch.empty(n, self.D, dtype=torch.float32, device=self.device),
+                      head=torch.empty(n, self.A, dtype=torch.float32, device=self.device),
+                      d_act=(torch.empty(n, self.A, dtype=torch.float32, device=self.device) if self.continuous
+                             else torch.empty(n, dtype=torch.int64, device=self.device)))
+            st["h_act"] = torch.empty(st["d_act"].shape, dtype=st["d_act"].dtype).pin_memory()
+            self._act_stage[n] = st
+        np.copyto(st["h_obs"].numpy(), np.asarray(observations, dtype=np.float32).reshape(n, self.D))
+        st["d_obs"].copy_(st["h_obs"], non_blocking=True)
+        self.ctx.mlp_forward(self.fm.desc, self.P, st["d_obs"], n, 1, st["head"], None, self.fwd_ws)
+        env_offset = self.dist.rank * n
+        if self.continuous:
+            lay = self.fm.layout
+            self.ctx.sample_gaussian(st["head"], self.P[lay.log_std:lay.log_std + self.A], self.seed, self.draws, env_offset, st["d_act"])
+        else:
+            self.ctx.sample_categorical(st["head"], self.seed, self.draws, env_offset, st["d_act"])
+        self.draws += 1
+        st["h_act"].copy_(st["d_act"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return st["h_act"].numpy().copy()
+
+    # ---- learn (ppo.py:224-287) ---------------------------------------------------------------------
+    def _alloc(self, T, N_, E, MB):
+        key = (T, N_, E, MB)
+        if key in self._bufs:
+            return self._bufs[key]
+        dev, B = self.device, T * N_
+        B_global = B * self.dist.world
+        f = dict(dtype=torch.float32, device=dev)
+        b = dict(head=torch.empty(B, self.A, **f), values=torch.empty(T, N_, **f), next_values=torch.empty(T, N_, **f),
+                 old_logp=torch.empty(T, N_, **f), adv=torch.empty(T, N_, **f), ret=torch.empty(T, N_, **f),
+                 stats=torch.zeros(2, dtype=torch.float64, device=dev), losses=torch.zeros(E * MB, 4, **f),
+                 idx=torch.empty(E, B_global if not self.dist.enabled else B, dtype=torch.int32, device=dev),
+                 h_idx=[torch.empty(B_global if not self.dist.enabled else B, dtype=torch.int32).pin_memory() for _ in range(E)])
+        m_max = B_global // MB if not self.dist.enabled else B      # a rank may own a whole global minibatch in the worst case
+        if self.dist.enabled:
+            m_max = min(B, B_global // MB)
+        b["train_ws"] = torch.empty(self.ctx.mlp_workspace_bytes(self.fm.desc, m_max, True) // 4 + 256, **f)
+        b["m_max"] = m_max
+        self._bufs[key] = b
+        return b
+
+    def prepass(self, buf: RolloutBuffer, b):
+        """ppo.py:235-238: old log-probs, values, next_values with the pre-update parameters."""
+        B = buf.T * buf.N
+        ctx, desc = self.ctx, self.fm.desc
+        ctx.mlp_forward(desc, self.P, buf.obs, B, 3, b["head"], b["values"], self.fwd_ws)
+        if self.continuous:
+            lay = self.fm.layout
+            ctx.logprob_gaussian(b["head"], self.P[lay.log_std:lay.log_std + self.A], buf.actions.view(B, self.A), b["old_logp"].view(B))
+        else:
+            ctx.logprob_categorical(b["head"], buf.actions.view(B), b["old_logp"].view(B))
+        ctx.mlp_forward(desc, self.P, buf.next_obs, B, 2, None, b["next_values"], self.fwd_ws)
+
+    def learn(self, buf: RolloutBuffer, events=None):
+        cfg, ctx, dist = self.cfg, self.ctx, self.dist
+        T, N_ = buf.T, buf.N
+        E, MB = cfg.num_epochs, cfg.num_minibatches
+        B = T * N_
+        B_global = B * dist.world
+        if B_global % MB != 0:              # the reference's reshape raises here (ppo.py:255)
+            raise ValueError(f"cannot reshape array of size {E * B_global} into shape ({E},{MB},{B_global // MB})")
+        M_global = B_global // MB
+        self._resync_optimizer()
+        b = self._alloc(T, N_, E, MB)
+        shard = (N_ * dist.world, dist.rank * N_, N_) if dist.enabled else None
+        worker = _PermWorker(B_global, E, MB, [h.numpy() for h in b["h_idx"]], shard)
+        worker.start()                      # host permutation overlaps the pre-update pass on the GPU
+
+        def mark(name):
+            if events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                events[name] = ev
+        mark("start")
+        self.prepass(buf, b)
+        mark("prepass_end")
+        b["stats"].zero_()
+        ctx.gae(buf.rewards, buf.terminations, buf.truncations, b["values"], b["next_values"], cfg.gamma, cfg.gae_lambda,
+                advantages=b["adv"], returns=b["ret"], stats=b["stats"])
+        dist.all_reduce_sum(b["stats"])     # global mean/std of the advantages (ppo.py:243)
+        mark("gae_end")
+
+        hyper = self._hyper(cfg, M_global, B_global)
+        desc = self.fm.desc
+        obs_flat = buf.obs.view(B, self.D)
+        actions = buf.actions.view(B, self.A) if self.continuous else buf.actions.view(B)
+        old_logp, adv, ret = b["old_logp"].view(B), b["adv"].view(B), b["ret"].view(B)
+        losses = b["losses"]
+        for e in range(E):
+            worker.wait(e)
+            b["idx"][e].copy_(b["h_idx"][e], non_blocking=True)
+            for k in range(MB):
+                if dist.enabled:
+                    off, m = worker.counts[e][k]
+                else:
+                    off, m = k * M_global, M_global
+                self.adam_step += 1
+                hyper.step = self.adam_step
+                if m > 0:
+                    ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"],
+                                           b["idx"][e][off:off + m], m, hyper, losses[e * MB + k], b["train_ws"])
+                else:
+                    self.G.zero_()
+                    losses[e * MB + k].zero_()
+                if dist.enabled:
+                    dist.all_reduce_sum(self.G)              # env-sharded DP: sum of per-shard gradients
+                    dist.all_reduce_sum(losses[e * MB + k])
+                ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+        mark("update_end")
+        worker.finish()
+        self._publish_steps()
+        self.last_losses = losses
+
+
+class AutogradEngine(_EngineBase):
+    """learn() for a user network_cls: module under torch autograd, everything else on libdppo kernels."""
+
+    def __init__(self, ctx, network, cfg, continuous, device, dist: _Dist):
+        self.ctx, self.cfg, self.device, self.dist, self.continuous = ctx, cfg, device, dist, continuous
+        self.network = network
+        offsets, o = {}, 0
+        for name, p in network.named_parameters():
+            offsets[name] = (o, tuple(p.shape))
+            o += (p.numel() + 3) // 4 * 4
+        self._adopt(network, offsets, max(o, 4))
+        self.last_losses = None
+
+    def learn(self, buf: RolloutBuffer, events=None):
+        cfg, ctx, dist, net = self.cfg, self.ctx, self.dist, self.network
+        if dist.enabled:
+            raise NotImplementedError("data parallelism is implemented for the default networks only")
+        T, N_ = buf.T, buf.N
+        E, MB = cfg.num_epochs, cfg.num_minibatches
+        B = T * N_
+        if B % MB != 0:
+            raise ValueError(f"cannot reshape array of size {E * B} into shape ({E},{MB},{B // MB})")
+        M = B // MB
+        self._resync_optimizer()
+        dev = self.device
+        h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
+        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
+        worker.start()
+        obs, nobs = buf.obs, buf.next_obs
+        A = buf.A
+        old_logp = torch.empty(B, device=dev)
+        with torch.inference_mode():
+            if self.continuous:
+                means, log_stds, values = net.get_means_log_stds_and_values(obs)
+                ls = log_stds.reshape(B, A)
+                if bool((ls == ls[:1]).all()):                         # state-independent std: shared [A] vector
+                    ctx.logprob_gaussian(means.reshape(B, A).contiguous(), ls[0].contiguous(), buf.actions.view(B, A), old_logp)
+                else:
+                    old_logp.copy_(torch.distributions.Normal(means, log_stds.exp()).log_prob(buf.actions).sum(-1).reshape(B))
+            else:
+                logits, values = net.get_logits_and_values(obs)
+                ctx.logprob_categorical(logits.reshape(B, -1).contiguous(), buf.actions.view(B), old_logp)
+            next_values = net.get_values(nobs)
+        values = values.reshape(T, N_).contiguous().clone()
+        next_values = next_values.reshape(T, N_).contiguous().clone()
+        stats = torch.zeros(2, dtype=torch.float64, device=dev)
+        adv = torch.empty(T, N_, device=dev)
+        ret = torch.empty(T, N_, device=dev)
+        ctx.gae(buf.rewards, buf.terminations, buf.truncations, values, next_values, cfg.gamma, cfg.gae_lambda,
+                advantages=adv, returns=ret, stats=stats)
+        if cfg.advantage_norm:
+            adv = ctx.adv_normalize(adv, stats, B)
+        hyper = self._hyper(cfg, M, B)
+        hyper.advantage_norm = 0                       # already normalised above
+        obs_flat, adv_f, ret_f = obs.view(B, -1), adv.view(B), ret.view(B)
+        act_bits = buf.actions.view(B, A) if self.continuous else buf.actions.view(B).view(torch.float32)
+        losses = torch.zeros(E * MB, 4, device=dev)
+        loss_ws = torch.empty(ctx.ppo_loss_workspace_bytes(M, max(A, 32)) // 4 + 64, device=dev)
+        idx = torch.empty(E, B, dtype=torch.int32, device=dev)
+        for e in range(E):
+            worker.wait(e)
+            idx[e].copy_(h_idx[e], non_blocking=True)
+            for k in range(MB):
+                mb = idx[e][k * M:(k + 1) * M]
+                x = ctx.gather_rows(obs_flat, mb)
+                a_mb = ctx.gather_rows(act_bits, mb)
+                lp_mb, adv_mb, ret_mb = ctx.gather_rows(old_logp, mb), ctx.gather_rows(adv_f, mb), ctx.gather_rows(ret_f, mb)
+                self.adam_step += 1
+                hyper.step = self.adam_step
+                self.G.zero_()
+                dval = torch.empty(M, device=dev)
+                if self.continuous:
+                    mean, log_std, val = net.get_means_log_stds_and_values(x)
+                    mean_c, ls_c, val_c = mean.contiguous(), log_std.contiguous(), val.contiguous()
+                    dmean, dls = torch.empty_like(mean_c), torch.empty_like(ls_c)
+                    ctx.ppo_loss_gaussian(mean_c.detach(), ls_c.detach(), val_c.detach(), a_mb, lp_mb, adv_mb, ret_mb, hyper,
+                                          losses[e * MB + k], dmean, dls, dval, loss_ws, log_std_row_stride=ls_c.shape[-1])
+                    torch.autograd.backward([mean_c, ls_c, val_c], [dmean, dls, dval])
+                else:
+                    logits, val = net.get_logits_and_values(x)
+                    logits_c, val_c = logits.contiguous(), val.contiguous()
+                    dlogits = torch.empty_like(logits_c)
+                    ctx.ppo_loss_discrete(logits_c.detach(), val_c.detach(), a_mb.view(torch.int32), lp_mb, adv_mb, ret_mb, hyper,
+                                          losses[e * MB + k], dlogits, dval, loss_ws)
+                    torch.autograd.backward([logits_c, val_c], [dlogits, dval])
+                ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+        worker.finish()
+        self._publish_steps()
+        self.last_losses = losses
+
+
+# ------------------------------------------------------------------------------------------------
+# Agents
+# ------------------------------------------------------------------------------------------------
+class _PPOBase:
+    _continuous = False
+    _default_network: Any = None
+
+    def _setup(self, env_fn, cfg, network_cls, process_group=None, dp=False):
+        self.device = _require_cuda()
+        self.ctx = N.get_context(self.device.index)
+        if cfg.seed is not None:
+            np.random.seed(cfg.seed)                                   # ppo.py:120-122
+            torch.manual_seed(cfg.seed)
+        self._dist = _Dist(process_group, dp)
+
+        if getattr(env_fn, "vectorized", False):                       # additive: env_fn(num_envs) -> batched vector env
+            self.envs = env_fn(cfg.num_envs)
+        else:
+            self.envs = gym.vector.SyncVectorEnv([env_fn for _ in range(cfg.num_envs)], copy=True, autoreset_mode="Disabled")
+        obs_space, act_space = self.envs.single_observation_space, self.envs.single_action_space
+        self.network = network_cls(obs_space, act_space, cfg=cfg).to(self.device)
+        network_parameter_init_(self.network, gain=sqrt(2.0), small_actor_out=not self._continuous)
+        if self._dist.enabled:                                          # replicas start from rank 0's parameters
+            for p in self.network.parameters():
+                self._dist.dist.broadcast(p.data, src=0, group=self._dist.group)
+
+        self.obs_dim = int(np.prod(obs_space.shape))
+        self.act_dim = int(np.prod(act_space.shape)) if self._continuous else int(act_space.n)
+        if type(self.network) is self._default_network:
+            self.engine = FusedMlpEngine(self.ctx, self.network, cfg, self.obs_dim, self.act_dim, self._continuous,
+                                         self.device, self._dist)
+            self.network.engine = self.engine
+        else:
+            self.engine = AutogradEngine(self.ctx, self.network, cfg, self._continuous, self.device, self._dist)
+
+        self.optimizer = torch.optim.Adam(self.network.parameters(), lr=cfg.lr, eps=cfg.adam_eps)       # ppo.py:135
+        self.engine.bind_optimizer(self.optimizer)
+        self.lr_scheduler = torch.optim.lr_scheduler.LinearLR(                                          # ppo.py:137-142
+            self.optimizer, start_factor=1.0, end_factor=0.05 if cfg.decay_lr else 1.0,
+            total_iters=cfg.total_steps // (cfg.num_envs * cfg.rollout_steps))
+        self.logger = Logger()
+        self.timer = Timer()
+        self.checkpointer = Checkpointer(folder="models", run_name="default")
+        self.ticker = Ticker(cfg.total_steps, cfg.num_envs, cfg.rollout_steps, verbose=cfg.verbose)
+        self.cfg = cfg
+        self._buffer = None
+
+    # ---- rollout (ppo.py:153-186) -------------------------------------------------------------------
+    def rollout(self) -> RolloutBuffer:
+        """Collect one rollout; returns the device-resident buffer (list-like for user code)."""
+        cfg = self.cfg
+        if self._buffer is None:
+            self._buffer = RolloutBuffer(self.ctx, cfg.rollout_steps, cfg.num_envs, self.obs_dim,
+                                         self.act_dim if self._continuous else 1, self._continuous, self.device)
+        buf = self._buffer
+        buf.filled = 0
+        observations = self.current_observations
+        for step_idx in range(cfg.rollout_steps):
+            actions = self.network.get_actions(observations, device=self.device)
+            next_observations, rewards, terminations, truncations, infos = self.envs.step(actions)
+            buf.store(step_idx, observations, next_observations, actions, rewards, terminations, truncations)
+            dones = np.logical_or(terminations, truncations)
+            if np.any(dones):                                          # autoreset disabled: masked reset (ppo.py:174-179)
+                observations, infos = self.envs.reset(options={"reset_mask": dones})
+            else:
+                observations = next_observations
+            if self.ticker is not None:
+                self.ticker.tick(rewards, dones)
+        self.current_observations = observations
+        return buf
+
+    # ---- GAE (ppo.py:188-222) -----------------------------------------------------------------------
+    def calculate_advantage(self, rewards, terminations, truncations, values, next_values) -> torch.Tensor:
+        """Generalised Advantage Estimation on the GPU (dppo_gae_f32); [T, N] float32 tensors in, [T, N] out."""
+        args = [torch.as_tensor(x).to(self.device, torch.float32).contiguous() for x in
+                (rewards, terminations, truncations, values, next_values)]
+        return self.ctx.gae(*args, self.cfg.gamma, self.cfg.gae_lambda)
+
+    # ---- learn (ppo.py:224-287) ----------------------------------------------------------------------
+    def learn(self, experience, events=None) -> None:
+        """Update policy and value networks from a rollout: either the RolloutBuffer `rollout()`
+        returned, or a reference-style list of per-step NumPy arrays."""
+        buf = experience if isinstance(experience, RolloutBuffer) else \
+            RolloutBuffer.from_lists(self.ctx, experience, self._continuous, self.device)
+        self.engine.learn(buf, events)
+        self.optimizer._opt_called = True                              # the kernels performed the optimiser steps
+        self.lr_scheduler.step()                                       # ppo.py:287
+
+    @property
+    def last_losses(self):
+        """[E*MB, 4] device tensor: policy, value, entropy, total loss of every minibatch of the last learn()."""
+        return self.engine.last_losses
+
+    # ---- train (ppo.py:289-312) ----------------------------------------------------------------------
+    def train(self) -> None:
+        cfg = self.cfg
+        self.current_observations, _ = self.envs.reset(seed=cfg.seed)
+        last_checkpoint_time = time.time()
+        total_rollouts = cfg.total_steps // (cfg.rollout_steps * cfg.num_envs)
+        env_steps = 0
+        for rollout_idx in range(total_rollouts):
+            experience = self.rollout()
+            self.learn(experience)
+            env_steps = (rollout_idx + 1) * cfg.rollout_steps * cfg.num_envs
+            if cfg.checkpoint and time.time() - last_checkpoint_time >= cfg.save_interval:
+                self.checkpointer.save(env_steps, self.network, self.optimizer)
+                last_checkpoint_time = time.time()
+        if cfg.checkpoint and total_rollouts > 0:
+            self.checkpointer.save(env_steps, self.network, self.optimizer)
+        self.envs.close()
+
+
+class PPO(_PPOBase):
+    """Discrete-action PPO (reference: diamond/ppo.py:111-312)."""
+    _continuous = False
+    _default_network = ActorCriticNetwork
+
+    def __init__(self, env_fn: Callable[[], Any], cfg: PPOConfig = PPOConfig(), network_cls: Any = ActorCriticNetwork,
+                 *, process_group=None, dp: bool = False) -> None:
+        self._setup(env_fn, cfg, network_cls, process_group, dp)
+        self.current_step = 0
+
+
+class ContinuousPPO(_PPOBase):
+    """Gaussian-policy PPO (reference: diamond/continuous_ppo.py:124-324)."""
+    _continuous = True
+    _default_network = ContinuousActorCriticNetwork
+
+    def __init__(self, env_fn: Callable[[], Any], cfg: ContinuousPPOConfig = ContinuousPPOConfig(),
+                 network_cls: Any = ContinuousActorCriticNetwork, *, process_group=None, dp: bool = False) -> None:
+        self._setup(env_fn, cfg, network_cls, process_group, dp)

@@ -1,0 +1,177 @@
+/* dppo.h — C ABI of libdppo.so, the sm_100a implementation of Diamond PPO's hot path.
+ *
+ * The reference (Auxeno/diamond-ppo) is pure Python/PyTorch and has no FFI layer; its "plugin
+ * boundary" for this path is the Python API (PPO / ContinuousPPO / RecurrentPPO, the PPOConfig
+ * family and the custom-network interface).  This header is the native boundary a maintainer
+ * would bind from that Python code (ctypes); every entry point names the
+ * reference lines whose arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; dppo_last_error(ctx) has the text
+ *   - all device pointers are caller-owned (PyTorch tensors); the library allocates nothing on
+ *     the device.  Scratch memory is passed in as `ws` (size from the *_workspace_bytes calls)
+ *   - every launch is asynchronous on the cudaStream_t passed as `stream` (void*); no entry
+ *     point synchronises the device
+ *   - only sm_100a SASS is embedded: creating a context on any other GPU is an error.  There
+ *     is no CPU fallback
+ *   - layouts: rollout tensors are time-major [T, N, ...] with the env index contiguous
+ *     (flat sample index i = t*N + env, diamond/ppo.py:246-249); weights are row-major
+ *     [out, in] like torch.nn.Linear
+ */
+#ifndef DPPO_H
+#define DPPO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPPO_VERSION 100
+#define DPPO_MAX_ACT 32          /* action count / action dims handled by the fused head kernels */
+
+typedef struct dppo_ctx dppo_ctx;
+
+/* Default actor-critic MLP (diamond/ppo.py:40-71, diamond/continuous_ppo.py:50-82). */
+typedef struct dppo_mlp_desc {
+    int32_t obs_dim;      /* D */
+    int32_t hidden;       /* H = cfg.network_hidden_dim */
+    int32_t act_dim;      /* A: Discrete.n, or prod(Box.shape) when continuous */
+    int32_t continuous;   /* 0: categorical logits head; 1: gaussian mean head + actor_log_std */
+} dppo_mlp_desc;
+
+/* Offsets (in floats) of each tensor inside the flat parameter / gradient / Adam buffers.
+ * w3/b3 hold actor_head.0 (rows 0..H-1) and critic_head.0 (rows H..2H-1) back to back so both
+ * first head layers run as one [2H, H] product.  Every offset is a multiple of 4 floats. */
+typedef struct dppo_mlp_layout {
+    int64_t w1, b1;       /* base.0  [H, D], [H] */
+    int64_t w2, b2;       /* base.2  [H, H], [H] */
+    int64_t w3, b3;       /* actor_head.0 | critic_head.0  [2H, H], [2H] */
+    int64_t wa, ba;       /* actor_head.2 (actor_mean_head.2)  [A, H], [A] */
+    int64_t wc, bc;       /* critic_head.2  [1, H], [1] */
+    int64_t log_std;      /* actor_log_std [A] (continuous only, else -1) */
+    int64_t total;        /* floats in the flat buffer (padded) */
+} dppo_mlp_layout;
+
+/* Hyper-parameters of one optimiser step (PPOConfig fields, diamond/ppo.py:17-37). */
+typedef struct dppo_hyper {
+    float ppo_clip;           /* cfg.ppo_clip */
+    float value_loss_weight;  /* cfg.value_loss_weight */
+    float entropy_beta;       /* cfg.entropy_beta */
+    float grad_norm_clip;     /* cfg.grad_norm_clip */
+    float adam_eps;           /* cfg.adam_eps */
+    float pad0;
+    double lr;                /* current learning rate (after LinearLR, ppo.py:137-142) */
+    double beta1, beta2;      /* 0.9, 0.999 (torch.optim.Adam defaults, ppo.py:135) */
+    int64_t step;             /* 1-based Adam step count of THIS update */
+    int32_t advantage_norm;   /* cfg.advantage_norm: normalise with adv_stats while gathering */
+    int32_t pad1;
+    int64_t adv_count;        /* number of samples behind adv_stats (global batch T*N) */
+    int64_t loss_denominator; /* rows the loss means divide by (global minibatch size) */
+} dppo_hyper;
+
+/* ---- context -------------------------------------------------------------------------- */
+int dppo_create(dppo_ctx** out, int device);
+int dppo_destroy(dppo_ctx* ctx);
+const char* dppo_last_error(dppo_ctx* ctx);          /* ctx may be NULL: last create() error */
+int dppo_version(void);
+int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- rollout buffer + batched action sampling (diamond/ppo.py:153-186, 73-82) ---------- */
+/* Unpack one vectorised env step, staged as ONE packed record
+ *   [obs f32 N*D | next_obs f32 N*D | rewards f64 N | actions (i64 N | f32 N*A) | term u8 N | trunc u8 N]
+ * (the six arrays diamond/ppo.py:165-172 appends), into row t of the time-major device buffers
+ * with the casts of ppo.py:229-232 (rewards/terminations/truncations -> f32; actions i64 -> i32). */
+int dppo_buffer_store_step(dppo_ctx* ctx, const void* record, int t, int N, int D, int act_dim, int continuous,
+                           float* obs, float* next_obs, void* actions, float* rewards,
+                           float* terminations, float* truncations, void* stream);
+int64_t dppo_step_record_bytes(int N, int D, int act_dim, int continuous);
+
+/* Categorical(logits).sample() (ppo.py:81) with a counter-based generator keyed by
+ * (seed, global env id, draw counter): results do not depend on the launch shape or GPU count.
+ * Also emits log_prob(action) (recurrent_ppo.py:219-221).  actions: int64 [N]. */
+int dppo_sample_categorical(dppo_ctx* ctx, const float* logits, int N, int A, uint64_t seed, uint64_t counter,
+                            int64_t env_offset, int64_t* actions, float* log_probs, void* stream);
+/* JointNormal(mean, exp(log_std)).sample() (continuous_ppo.py:92). actions: f32 [N, A]. */
+int dppo_sample_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, int N, int A, uint64_t seed,
+                         uint64_t counter, int64_t env_offset, float* actions, float* log_probs, void* stream);
+
+/* ---- GAE (diamond/ppo.py:188-222) + returns/normalisation (ppo.py:241-243) -------------- */
+/* advantages[t,e], returns[t,e] = values + advantages (returns may be NULL).  If stats != NULL,
+ * adds sum(A) and sum(A^2) (fp64) to stats[0..1] (caller zeroes them; under env-sharded data
+ * parallelism the caller all-reduces the two doubles before normalising). */
+int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* terminations, const float* truncations,
+                 const float* values, const float* next_values, float* advantages, float* returns,
+                 double* stats, int T, int N, double gamma, double gae_lambda, void* stream);
+/* out = (adv - mean) / (std + 1e-6), unbiased std over `count` samples described by stats. */
+int dppo_adv_normalize_f32(dppo_ctx* ctx, const float* adv, float* out, const double* stats, int64_t count,
+                           int64_t n, void* stream);
+
+/* ---- minibatch permutation + gather (diamond/ppo.py:252-255, 261-272) ------------------ */
+/* HOST function (no device work): np.random.permutation(n) of the legacy global RandomState,
+ * bit-exact: MT19937 state (key[624], *pos) is taken from / returned to np.random.get_state().
+ * out: int32 [n].  Meant to run on a worker thread while the GPU processes the previous epoch. */
+int dppo_permutation_mt19937(uint32_t* key, int32_t* pos, int64_t n, int32_t* out);
+int dppo_mt19937_seed(uint32_t* key, int32_t* pos, uint32_t seed);      /* np.random.seed(int) */
+/* dst[i, :] = src[idx[i], :]  (row_floats floats per row); the fused update gathers on the fly,
+ * this standalone form serves the custom-network path. */
+int dppo_gather_rows_f32(dppo_ctx* ctx, const float* src, const int32_t* idx, float* dst, int64_t rows,
+                         int row_floats, void* stream);
+
+/* ---- actor-critic MLP: forward, fused update (diamond/ppo.py:91-96, 235-238, 258-285) --- */
+int dppo_mlp_layout_compute(const dppo_mlp_desc* desc, dppo_mlp_layout* out);
+int64_t dppo_mlp_workspace_bytes(const dppo_mlp_desc* desc, int64_t rows, int training);
+
+/* Forward only (pre-update pass ppo.py:235-238 and get_actions ppo.py:75-79).
+ * heads bit0: actor output head_out [rows, A] (logits / means); bit1: values [rows].
+ * idx (optional int32 [rows]) gathers input rows from obs. */
+int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* desc, const float* params, const float* obs,
+                     const int32_t* idx, int64_t rows, int heads, float* head_out, float* values,
+                     void* ws, int64_t ws_bytes, void* stream);
+int dppo_logprob_categorical(dppo_ctx* ctx, const float* logits, const int32_t* actions, float* log_probs,
+                             int64_t rows, int A, void* stream);
+int dppo_logprob_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, const float* actions,
+                          float* log_probs, int64_t rows, int A, void* stream);
+
+/* One minibatch of ppo.py:258-283: gather rows idx[0..M) of the flat rollout tensors, forward,
+ * clipped-surrogate + value + entropy loss, full backward.  Writes the flat gradient (layout of
+ * dppo_mlp_layout) to grads and (policy, value, entropy, total) to losses[0..3].
+ * actions: int32 [B] (discrete) or f32 [B, A] (continuous).  adv is the UN-normalised advantage
+ * when hyper->advantage_norm is set (normalised on the fly from adv_stats), else used as is. */
+int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* desc, const float* params, float* grads,
+                            const float* obs, const void* actions, const float* old_log_probs, const float* adv,
+                            const float* returns, const double* adv_stats, const int32_t* idx, int64_t M,
+                            const dppo_hyper* hyper, float* losses, void* ws, int64_t ws_bytes, void* stream);
+
+/* clip_grad_norm_ (ppo.py:284) + Adam (ppo.py:285) over flat buffers of n floats.
+ * grad_norm_out (optional, device float) receives the pre-clip global norm. */
+int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const dppo_hyper* hyper, float* grad_norm_out, void* ws, int64_t ws_bytes, void* stream);
+int64_t dppo_clip_adam_workspace_bytes(int64_t n);
+
+/* Standalone loss forward+backward for custom network_cls modules (readme.md:89-111): the user
+ * module runs under PyTorch autograd, this provides loss values and d(loss)/d(outputs).
+ * Rows are already gathered (M rows).  losses[0..3] = policy, value, entropy, total. */
+int dppo_ppo_loss_discrete(dppo_ctx* ctx, const float* logits, const float* values, const int32_t* actions,
+                           const float* old_log_probs, const float* adv, const float* returns, int64_t M, int A,
+                           const dppo_hyper* hyper, float* losses, float* dlogits, float* dvalues,
+                           void* ws, int64_t ws_bytes, void* stream);
+/* log_std_row_stride == 0: log_std is one shared [A] vector (actor_log_std, continuous_ppo.py:76) and
+ * dlog_std receives its summed gradient [A]; otherwise log_std is per-row ([M, stride]) and dlog_std
+ * receives per-row gradients [M, A] (state-dependent std of a custom network). */
+int dppo_ppo_loss_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, int64_t log_std_row_stride, const float* values,
+                           const float* actions, const float* old_log_probs, const float* adv, const float* returns,
+                           int64_t M, int A, const dppo_hyper* hyper, float* losses, float* dmean, float* dlog_std,
+                           float* dvalues, void* ws, int64_t ws_bytes, void* stream);
+int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
+
+/* ---- measurement helper ---------------------------------------------------------------- */
+/* Runs a register-resident FFMA loop on every SM (iters FMAs per thread, 16 independent chains;
+ * sink: >= 65 floats of finite values);
+ * bench.py times it with CUDA events to obtain the FP32 FMA-pipe peak of this very GPU. */
+int dppo_fma_peak_kernel(dppo_ctx* ctx, float* sink, int64_t iters, int* blocks_out, int* threads_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPPO_H */

@@ -1,0 +1,246 @@
+"""GPU: the drop-in agents against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py): same initial parameters, same synthetic experience, same
+np.random seed -> losses and updated parameters within BASELINE.json's tolerances (1e-4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_env_fn(D, A, cont):
+    from diamond import envs
+    return lambda: envs.SyntheticEnv(D, A, continuous=cont)
+
+
+def build_agent(g, epochs, network_cls=None, **extra):
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig
+    D, act, H, N_, T, E, MB, cont = (int(x) for x in g["meta"])
+    Agent, Cfg = (ContinuousPPO, ContinuousPPOConfig) if cont else (PPO, PPOConfig)
+    cfg = Cfg(num_envs=N_, rollout_steps=T, network_hidden_dim=H, num_epochs=epochs, num_minibatches=MB, verbose=False,
+              seed=42, **extra)
+    kw = {} if network_cls is None else dict(network_cls=network_cls)
+    agent = Agent(make_env_fn(D, act, bool(cont)), cfg, **kw)
+    sd = {k[len("init."):]: torch.as_tensor(g[k]) for k in g.files if k.startswith("init.")}
+    agent.network.load_state_dict(sd)
+    return agent
+
+
+def experience_from(g):
+    T = g["rewards"].shape[0]
+    return [[g["obs"][t], g["next_obs"][t], g["actions"][t], g["rewards"][t], g["terminations"][t], g["truncations"][t]]
+            for t in range(T)]
+
+
+def check(agent, g, tag, ptol=1e-4, ltol=1e-4):
+    losses = agent.last_losses.cpu().numpy()
+    np.testing.assert_allclose(losses, g[f"{tag}.losses"], rtol=ltol, atol=5e-6)
+    sd = agent.network.state_dict()
+    for k in g.files:
+        if k.startswith(f"{tag}.params."):
+            name = k[len(f"{tag}.params."):]
+            ref = g[k]
+            err = np.abs(sd[name].cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+            assert err <= ptol, (name, err)
+
+
+@pytest.mark.parametrize("name", ["C", "L", "Ssmall", "Pn", "Pn3"])
+def test_learn_one_epoch_matches_reference(name):
+    g = np.load(os.path.join(GOLDEN, f"learn_{name}.npz"))
+    agent = build_agent(g, 1)
+    np.random.seed(123)
+    agent.learn(experience_from(g))
+    check(agent, g, "e1")
+    # the numpy global stream advanced exactly as the reference's np.random.permutation call would have
+    B = g["rewards"].size
+    after = np.random.randint(0, 2 ** 31, 3)
+    np.random.seed(123); np.random.permutation(B)
+    np.testing.assert_array_equal(after, np.random.randint(0, 2 ** 31, 3))
+
+
+@pytest.mark.parametrize("name", ["C", "L", "Ssmall", "Pn", "Pn3"])
+def test_learn_default_epochs_matches_reference(name):
+    g = np.load(os.path.join(GOLDEN, f"learn_{name}.npz"))
+    E = int(g["meta"][5])
+    agent = build_agent(g, E)
+    np.random.seed(123)
+    agent.learn(experience_from(g))
+    check(agent, g, f"e{E}", ptol=2e-4, ltol=2e-4)
+
+
+def test_learn_nondefault_hyperparameters_and_lr_decay():
+    g = np.load(os.path.join(GOLDEN, "learn_Cdecay.npz"))
+    extra = dict(decay_lr=True, total_steps=8 * 32 * 10, advantage_norm=False, ppo_clip=0.1, value_loss_weight=0.5,
+                 entropy_beta=0.02, grad_norm_clip=0.3, gamma=0.97, gae_lambda=0.9)
+    agent = build_agent(g, 1, **extra)
+    np.random.seed(123)
+    agent.learn(experience_from(g))
+    check(agent, g, "e1")
+    assert abs(agent.optimizer.param_groups[0]["lr"] - float(g["e1.lr_after"])) < 1e-12
+
+
+def test_adam_state_visible_through_optimizer_state_dict():
+    g = np.load(os.path.join(GOLDEN, "learn_C.npz"))
+    agent = build_agent(g, 1)
+    np.random.seed(123)
+    agent.learn(experience_from(g))
+    names = [n for n, _ in agent.network.named_parameters()]
+    st = agent.optimizer.state_dict()["state"]
+    for i, n in enumerate(names):
+        np.testing.assert_allclose(st[i]["exp_avg"].cpu().numpy(), g[f"e1.exp_avg.{n}"], rtol=1e-3, atol=1e-7)
+        np.testing.assert_allclose(st[i]["exp_avg_sq"].cpu().numpy(), g[f"e1.exp_avg_sq.{n}"], rtol=1e-3, atol=1e-10)
+        assert float(st[i]["step"]) == float(g[f"e1.step.{n}"])
+
+
+def test_calculate_advantage_api_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "learn_C.npz"))
+    agent = build_agent(g, 1)
+    f = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32))
+    adv = agent.calculate_advantage(f(g["rewards"]), f(g["terminations"]), f(g["truncations"]), f(g["gae.values"]),
+                                    f(g["gae.next_values"]))
+    assert adv.shape == (128, 8) and adv.is_cuda
+    ref = g["gae.advantages"]
+    assert np.abs(adv.cpu().numpy() - ref).max() / np.abs(ref).max() <= 1e-5
+
+
+class CustomDiscreteNet(torch.nn.Module):
+    """A user network in the style of readme.md:93-109 (different activation, separate trunks)."""
+
+    def __init__(self, observation_space, action_space, cfg):
+        super().__init__()
+        d, h = int(np.prod(observation_space.shape)), cfg.network_hidden_dim
+        self.actor = torch.nn.Sequential(torch.nn.Linear(d, h), torch.nn.ReLU(), torch.nn.Linear(h, action_space.n))
+        self.critic = torch.nn.Sequential(torch.nn.Linear(d, h), torch.nn.ReLU(), torch.nn.Linear(h, 1))
+        self.actor_out_layer = self.actor[-1]
+
+    def get_actions(self, observations, device):
+        with torch.inference_mode():
+            logits = self.actor(torch.as_tensor(observations, dtype=torch.float32, device=device))
+        return torch.distributions.Categorical(logits=logits).sample().cpu().numpy()
+
+    def get_values(self, observations):
+        with torch.inference_mode():
+            return self.critic(observations).squeeze(-1)
+
+    def get_logits_and_values(self, x):
+        return self.actor(x), self.critic(x).squeeze(-1)
+
+
+def test_custom_network_path_matches_torch_reference_math():
+    """Custom network_cls: kernels for buffer/GAE/gather/loss/clip+Adam around torch autograd.  Checked
+    against the same update written with torch ops (the reference's learn() loop, ppo.py:258-285)."""
+    from diamond import PPO, PPOConfig, envs
+    from oracle import ppo_oracle as O
+    D, A, N_, T, MB = 6, 3, 8, 32, 4
+    cfg = PPOConfig(num_envs=N_, rollout_steps=T, num_epochs=2, num_minibatches=MB, verbose=False, network_hidden_dim=32)
+    agent = PPO(lambda: envs.SyntheticEnv(D, A), cfg, network_cls=CustomDiscreteNet)
+    ref_net = CustomDiscreteNet(envs.Box(shape=(D,)), envs.Discrete(A), cfg)
+    ref_net.load_state_dict({k: v.detach().cpu().clone() for k, v in agent.network.state_dict().items()})
+    rng = np.random.default_rng(0)
+    exp = [[rng.standard_normal((N_, D)).astype(np.float32), rng.standard_normal((N_, D)).astype(np.float32),
+            rng.integers(0, A, N_), rng.standard_normal(N_), rng.random(N_) < 0.05, rng.random(N_) < 0.05] for _ in range(T)]
+    np.random.seed(7)
+    agent.learn(exp)
+    # torch reference
+    obs, nobs, act, rew, term, trunc = (np.asarray(x) for x in zip(*exp))
+    t = torch.as_tensor
+    obs_t, nobs_t = t(obs), t(nobs)
+    with torch.no_grad():
+        logits, values = ref_net.get_logits_and_values(obs_t)
+        old_lp = torch.distributions.Categorical(logits=logits).log_prob(t(act))
+        nv = ref_net.get_values(nobs_t)
+    adv = O.gae(rew.astype(np.float32), term.astype(np.float32), trunc.astype(np.float32), values.numpy(), nv.numpy())
+    ret, adv_n = O.returns_and_normalise(values.numpy(), adv, True)
+    B = T * N_
+    opt = torch.optim.Adam(ref_net.parameters(), lr=cfg.lr, eps=cfg.adam_eps)
+    np.random.seed(7)
+    perms = np.stack([np.random.permutation(B) for _ in range(2)]).reshape(2, MB, B // MB)
+    fo, fa, fl, fadv, fret = obs_t.reshape(B, D), t(act).reshape(B), old_lp.reshape(B), t(adv_n).reshape(B), t(ret).reshape(B)
+    ref_losses = []
+    for pe in perms:
+        for mb in pe:
+            lg, v = ref_net.get_logits_and_values(fo[mb])
+            dist = torch.distributions.Categorical(logits=lg)
+            ratio = (dist.log_prob(fa[mb]) - fl[mb]).exp()
+            lp = torch.max(-fadv[mb] * ratio, -fadv[mb] * torch.clamp(ratio, 0.8, 1.2)).mean()
+            lv = 0.5 * torch.nn.functional.mse_loss(v, fret[mb])
+            loss = lp + lv - 0.01 * dist.entropy().mean()
+            opt.zero_grad(); loss.backward()
+            torch.nn.utils.clip_grad_norm_(ref_net.parameters(), cfg.grad_norm_clip)
+            opt.step()
+            ref_losses.append(float(loss))
+    np.testing.assert_allclose(agent.last_losses[:, 3].cpu().numpy(), ref_losses, rtol=1e-4, atol=1e-6)
+    for (n, p), (_, q) in zip(agent.network.named_parameters(), ref_net.named_parameters()):
+        err = (p.detach().cpu() - q.detach()).abs().max() / q.detach().abs().max()
+        assert float(err) <= 1e-4, (n, float(err))
+
+
+@pytest.mark.parametrize("env_id,agent_kind", [("CartPole-v1", "ppo"), ("LunarLander-v3", "ppo"), ("Pendulum-v1", "cont")])
+def test_train_end_to_end_small(env_id, agent_kind):
+    """BASELINE.json configs 1-3 plumbing: agent.train() with rollout -> device buffer -> learn."""
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig, envs
+    if agent_kind == "ppo":
+        cfg = PPOConfig(num_envs=8, rollout_steps=128, total_steps=8 * 128 * 3, verbose=False)
+        agent = PPO(lambda: envs.make(env_id), cfg)
+    else:
+        cfg = ContinuousPPOConfig(num_envs=16, rollout_steps=64, total_steps=16 * 64 * 3, verbose=False)
+        agent = ContinuousPPO(lambda: envs.make(env_id), cfg)
+    before = {k: v.detach().clone() for k, v in agent.network.state_dict().items()}
+    agent.train()
+    after = agent.network.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before)
+    assert all(torch.isfinite(v).all() for v in after.values())
+    assert torch.isfinite(agent.last_losses).all()
+    assert agent.ticker.logs["total_steps"] == cfg.total_steps
+    assert agent.engine.adam_step == 3 * cfg.num_epochs * cfg.num_minibatches
+
+
+def test_cartpole_learns():
+    """PPO on CartPole-v1 through the kernels actually improves the policy (mean return > random's ~22)."""
+    from diamond import PPO, PPOConfig, envs
+    cfg = PPOConfig(num_envs=8, rollout_steps=128, total_steps=8 * 128 * 40, verbose=False)
+    agent = PPO(lambda: envs.make("CartPole-v1"), cfg)
+    agent.train()
+    assert np.mean(agent.ticker.logs["episode_returns"][-20:]) > 60.0
+
+
+def test_rollout_buffer_matches_reference_list_semantics():
+    from diamond import PPO, PPOConfig, envs
+    cfg = PPOConfig(num_envs=4, rollout_steps=16, total_steps=64, verbose=False)
+    agent = PPO(lambda: envs.make("CartPole-v1"), cfg)
+    agent.current_observations, _ = agent.envs.reset(seed=0)
+    exp = agent.rollout()
+    assert len(exp) == 16
+    step = exp[3]
+    assert [a.dtype for a in step] == [np.float32, np.float32, np.int64, np.float64, np.bool_, np.bool_]
+    assert step[0].shape == (4, 4) and step[2].shape == (4,)
+    # obs[t+1] equals next_obs[t] wherever the env was not reset (autoreset disabled semantics)
+    for t in range(15):
+        done = exp[t][4] | exp[t][5]
+        np.testing.assert_array_equal(exp[t + 1][0][~done], exp[t][1][~done])
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from diamond import PPO, PPOConfig, envs
+    from diamond.utils import Checkpointer
+    g = np.load(os.path.join(GOLDEN, "learn_C.npz"))
+    agent = build_agent(g, 1)
+    np.random.seed(123)
+    agent.learn(experience_from(g))
+    ck = Checkpointer(folder=tmp_path, run_name="t")
+    path = ck.save(1024, agent.network, agent.optimizer)
+    payload = torch.load(path, map_location="cpu")
+    assert set(payload) == {"step", "model_state", "opt_state"}
+    agent2 = build_agent(g, 1)
+    ck.load(path, agent2.network, agent2.optimizer)
+    for k, v in agent.network.state_dict().items():
+        assert torch.equal(v, agent2.network.state_dict()[k])
+    # resumed agent continues identically (Adam moments restored into the flat buffers)
+    np.random.seed(5); agent.learn(experience_from(g))
+    np.random.seed(5); agent2.learn(experience_from(g))
+    for k, v in agent.network.state_dict().items():
+        assert torch.allclose(v, agent2.network.state_dict()[k], rtol=0, atol=0), k

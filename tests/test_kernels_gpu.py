@@ -1,0 +1,342 @@
+"""GPU: each CUDA kernel, called through the C ABI, against the CPU oracle on identical inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ppo_oracle as O
+from oracle import c_oracle as CO
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+GAE_CASES = ["kat1", "kat2", "rand_small", "rand_ragged", "rand_mid", "t1", "both_masks"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from diamond import _native as N
+    return N.get_context(0)
+
+
+def dev(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device="cuda", dtype=dtype).contiguous()
+
+
+def nerr(a, ref):
+    a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+# ---------------------------------------------------------------- GAE -------------------------
+@pytest.mark.parametrize("case", GAE_CASES)
+@pytest.mark.parametrize("tag,gam,lam", [("", 0.99, 0.95), (".g9l8", 0.9, 0.8)])
+def test_gae_golden(ctx, case, tag, gam, lam):
+    g = np.load(os.path.join(GOLDEN, "gae.npz"))
+    args = [dev(g[f"{case}.{k}"]) for k in ("rewards", "terminations", "truncations", "values", "next_values")]
+    ret = torch.empty_like(args[0])
+    stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+    adv = ctx.gae(*args, gam, lam, returns=ret, stats=stats)
+    ref = g[f"{case}{tag}.advantages"]
+    # tolerance of BASELINE.json north_star: 1e-5 relative, normalised
+    assert nerr(adv.cpu().numpy(), ref) <= 1e-5
+    np.testing.assert_allclose(adv.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ret.cpu().numpy(), g[f"{case}.values"] + ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(stats.cpu().numpy(), [ref.astype(np.float64).sum(), (ref.astype(np.float64) ** 2).sum()],
+                               rtol=1e-5, atol=1e-5)
+    if tag == "" and f"{case}.adv_norm" in g:
+        an = ctx.adv_normalize(adv, stats, adv.numel())
+        refn = g[f"{case}.adv_norm"]
+        assert np.abs(an.cpu().numpy() - refn).max() <= 2e-5 * max(1.0, np.abs(refn).max())
+
+
+@pytest.mark.parametrize("T,N", [(128, 4096), (128, 1000), (300, 77), (5, 33), (128, 8)])
+def test_gae_random_vs_c_oracle(ctx, T, N):
+    rng = np.random.default_rng(T * 1000 + N)
+    r = rng.standard_normal((T, N)).astype(np.float32)
+    te = (rng.random((T, N)) < 0.01).astype(np.float32)
+    tr = ((rng.random((T, N)) < 0.01) & (te == 0)).astype(np.float32)
+    v = rng.standard_normal((T, N)).astype(np.float32)
+    nv = rng.standard_normal((T, N)).astype(np.float32)
+    ref_a, ref_r = CO.gae(r, te, tr, v, nv)
+    ret = torch.empty(T, N, device="cuda")
+    adv = ctx.gae(dev(r), dev(te), dev(tr), dev(v), dev(nv), 0.99, 0.95, returns=ret)
+    assert nerr(adv.cpu().numpy(), ref_a) <= 1e-5
+    assert nerr(ret.cpu().numpy(), ref_r) <= 1e-5
+    # masks cut the trace exactly: an advantage at a terminated step equals r - v
+    a = adv.cpu().numpy()
+    np.testing.assert_allclose(a[te == 1], (r - v)[te == 1], rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------- MLP -------------------------
+def rand_params(rng, names, D, H, A, cont, scale=0.3):
+    head = "actor_mean_head" if cont else "actor_head"
+    shapes = {"base.0.weight": (H, D), "base.0.bias": (H,), "base.2.weight": (H, H), "base.2.bias": (H,),
+              f"{head}.0.weight": (H, H), f"{head}.0.bias": (H,), f"{head}.2.weight": (A, H), f"{head}.2.bias": (A,),
+              "critic_head.0.weight": (H, H), "critic_head.0.bias": (H,), "critic_head.2.weight": (1, H),
+              "critic_head.2.bias": (1,), "actor_log_std": (1, A)}
+    p = {}
+    for n in names:
+        fan_in = shapes[n][-1] if len(shapes[n]) > 1 else 1
+        s = scale if len(shapes[n]) == 1 else 1.0 / np.sqrt(fan_in)
+        p[n] = torch.as_tensor((rng.standard_normal(shapes[n]) * s).astype(np.float32))
+    return p
+
+
+CONFIGS = [
+    # D, H, A, cont, B, M
+    (4, 64, 2, False, 1024, 128),
+    (8, 64, 4, False, 1024, 128),
+    (3, 64, 1, True, 4096, 512),
+    (5, 64, 3, True, 512, 128),
+    (64, 128, 4, False, 1024, 128),
+    (64, 256, 4, False, 8192, 2048),
+    (17, 96, 7, False, 700, 333),
+    (64, 256, 6, True, 4096, 1500),
+]
+
+
+@pytest.mark.parametrize("D,H,A,cont,B,M", CONFIGS)
+def test_mlp_forward_and_logprob(ctx, D, H, A, cont, B, M):
+    from diamond.flat import FlatMlp
+    rng = np.random.default_rng(D * 7 + H)
+    names = O.CONTINUOUS_PARAM_NAMES if cont else O.DISCRETE_PARAM_NAMES
+    p = rand_params(rng, names, D, H, A, cont)
+    fm = FlatMlp(D, H, A, cont)
+    flat = fm.pack(p, device="cuda")
+    obs = rng.standard_normal((B, D)).astype(np.float32)
+    ref_out, ref_v = O.mlp_forward(p, torch.as_tensor(obs), cont)
+    ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, 300, False) // 4, device="cuda")      # forces row chunking
+    out = torch.empty(B, A, device="cuda"); val = torch.empty(B, device="cuda")
+    ctx.mlp_forward(fm.desc, flat, dev(obs), B, 3, out, val, ws)
+    assert nerr(out.cpu().numpy(), ref_out.numpy()) <= 1e-5
+    assert nerr(val.cpu().numpy(), ref_v.numpy()) <= 1e-5
+    # critic-only and gathered rows
+    idx = rng.permutation(B)[:M].astype(np.int32)
+    val2 = torch.empty(M, device="cuda")
+    ctx.mlp_forward(fm.desc, flat, dev(obs), M, 2, None, val2, ws, idx=dev(idx, torch.int32))
+    assert nerr(val2.cpu().numpy(), ref_v.numpy()[idx]) <= 1e-5
+    lp = torch.empty(B, device="cuda")
+    if cont:
+        act = rng.standard_normal((B, A)).astype(np.float32)
+        ctx.logprob_gaussian(out, flat[fm.layout.log_std:fm.layout.log_std + A], dev(act), lp)
+        ref_lp = O.normal_log_prob(ref_out, p["actor_log_std"].expand_as(ref_out), torch.as_tensor(act))
+    else:
+        act = rng.integers(0, A, B)
+        ctx.logprob_categorical(out, dev(act, torch.int32), lp)
+        ref_lp, _ = O.categorical_log_prob(ref_out, torch.as_tensor(act))
+    np.testing.assert_allclose(lp.cpu().numpy(), ref_lp.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def make_hyper(N, M, step=1, adv_norm=False, adv_count=0, **kw):
+    cfg = O.default_cfg(**kw)
+    h = N.Hyper()
+    h.ppo_clip, h.value_loss_weight, h.entropy_beta = cfg["ppo_clip"], cfg["value_loss_weight"], cfg["entropy_beta"]
+    h.grad_norm_clip, h.adam_eps, h.lr = cfg["grad_norm_clip"], cfg["adam_eps"], cfg["lr"]
+    h.beta1, h.beta2, h.step = 0.9, 0.999, step
+    h.advantage_norm, h.adv_count, h.loss_denominator = int(adv_norm), adv_count, M
+    return h, cfg
+
+
+@pytest.mark.parametrize("D,H,A,cont,B,M", CONFIGS)
+def test_mlp_grad_minibatch_vs_oracle(ctx, D, H, A, cont, B, M):
+    from diamond import _native as N
+    from diamond.flat import FlatMlp
+    rng = np.random.default_rng(D * 13 + H + A)
+    names = O.CONTINUOUS_PARAM_NAMES if cont else O.DISCRETE_PARAM_NAMES
+    p = rand_params(rng, names, D, H, A, cont)
+    fm = FlatMlp(D, H, A, cont)
+    flat = fm.pack(p, device="cuda")
+    obs = rng.standard_normal((B, D)).astype(np.float32)
+    act = rng.standard_normal((B, A)).astype(np.float32) if cont else rng.integers(0, A, B)
+    old_lp = (rng.standard_normal(B) * 0.3 - (1.0 if not cont else 1.5 * A)).astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
+    ret = rng.standard_normal(B).astype(np.float32)
+    idx = rng.permutation(B)[:M].astype(np.int32)
+    hyper, cfg = make_hyper(N, M)
+    t = torch.as_tensor
+    sel = torch.as_tensor(idx.astype(np.int64))
+    losses_ref, g_ref = O.loss_and_grads(p, t(obs)[sel], t(act)[sel], t(old_lp)[sel], t(adv)[sel], t(ret)[sel], cfg, cont)
+
+    grads = torch.full((fm.total,), 7.0, device="cuda")
+    losses = torch.zeros(4, device="cuda")
+    ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, M, True) // 4 + 64, device="cuda")
+    ctx.mlp_grad_minibatch(fm.desc, flat, grads, dev(obs), dev(act, torch.float32 if cont else torch.int32), dev(old_lp),
+                           dev(adv), dev(ret), None, dev(idx, torch.int32), M, hyper, losses, ws)
+    torch.cuda.synchronize()
+    got = losses.cpu().numpy()
+    ref = np.array([losses_ref[k] for k in ("policy", "value", "entropy", "total")])
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-6)
+    gv = fm.views(grads)
+    for n in names:
+        e = nerr(gv[n].cpu().numpy(), g_ref[n].numpy())
+        assert e <= 2e-5, (n, e)
+    # padding between tensors is zeroed
+    used = torch.zeros(fm.total, dtype=torch.bool)
+    for n, (off, shape) in fm.slices.items():
+        used[off:off + int(np.prod(shape))] = True
+    assert float(grads.cpu()[~used].abs().sum()) == 0.0
+
+
+def test_mlp_grad_advantage_norm_on_the_fly(ctx):
+    from diamond import _native as N
+    from diamond.flat import FlatMlp
+    D, H, A, B, M = 8, 64, 4, 2048, 256
+    rng = np.random.default_rng(3)
+    p = rand_params(rng, O.DISCRETE_PARAM_NAMES, D, H, A, False)
+    fm = FlatMlp(D, H, A, False)
+    flat = fm.pack(p, device="cuda")
+    obs = rng.standard_normal((B, D)).astype(np.float32)
+    act = rng.integers(0, A, B)
+    old_lp = (rng.standard_normal(B) * 0.3 - 1.0).astype(np.float32)
+    adv = (rng.standard_normal(B) * 3 + 1.5).astype(np.float32)
+    ret = rng.standard_normal(B).astype(np.float32)
+    idx = rng.permutation(B)[:M].astype(np.int32)
+    _, adv_n = O.returns_and_normalise(np.zeros(B, np.float32), adv, True)
+    hyper, cfg = make_hyper(N, M, adv_norm=True, adv_count=B)
+    t = torch.as_tensor
+    sel = t(idx.astype(np.int64))
+    losses_ref, g_ref = O.loss_and_grads(p, t(obs)[sel], t(act)[sel], t(old_lp)[sel], t(adv_n)[sel], t(ret)[sel], cfg, False)
+    stats = torch.tensor([adv.astype(np.float64).sum(), (adv.astype(np.float64) ** 2).sum()], dtype=torch.float64, device="cuda")
+    grads = torch.empty(fm.total, device="cuda"); losses = torch.zeros(4, device="cuda")
+    ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, M, True) // 4 + 64, device="cuda")
+    ctx.mlp_grad_minibatch(fm.desc, flat, grads, dev(obs), dev(act, torch.int32), dev(old_lp), dev(adv), dev(ret), stats,
+                           dev(idx, torch.int32), M, hyper, losses, ws)
+    np.testing.assert_allclose(losses.cpu().numpy(), [losses_ref[k] for k in ("policy", "value", "entropy", "total")], rtol=1e-4, atol=1e-6)
+    gv = fm.views(grads)
+    for n in O.DISCRETE_PARAM_NAMES:
+        assert nerr(gv[n].cpu().numpy(), g_ref[n].numpy()) <= 5e-5, n
+
+
+@pytest.mark.parametrize("n", [13, 12995, 215301])
+def test_clip_adam_vs_oracle(ctx, n):
+    from diamond import _native as N
+    rng = np.random.default_rng(n)
+    p0 = rng.standard_normal(n).astype(np.float32)
+    names = ["x"]
+    p = {"x": torch.as_tensor(p0.copy())}
+    state = O.new_adam_state(p, names)
+    dp, dm, dv = dev(p0), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ws = torch.empty(ctx.clip_adam_workspace_bytes(n) // 8 + 1, dtype=torch.float64, device="cuda")
+    gn = torch.zeros(1, device="cuda")
+    for step in range(1, 6):
+        g = (rng.standard_normal(n) * (0.01 if step % 2 else 3.0)).astype(np.float32)
+        grads = {"x": torch.as_tensor(g.copy())}
+        ref_norm = O.clip_grad_norm_(grads, names, 0.5)
+        O.adam_step_(p, grads, state, names, 3e-4, 1e-5)
+        hyper, _ = make_hyper(N, 1, step=step)
+        dg = dev(g)
+        ctx.clip_adam_step(dp, dg, dm, dv, hyper, ws, gn)
+        assert abs(float(gn) - ref_norm) <= 1e-5 * ref_norm
+        assert nerr(dg.cpu().numpy(), grads["x"].numpy()) <= 1e-5   # torch sums the norm in fp32, the kernel in fp64
+    assert nerr(dp.cpu().numpy(), p["x"].numpy()) <= 1e-5
+    assert nerr(dm.cpu().numpy(), state["exp_avg"]["x"].numpy()) <= 1e-5
+    assert nerr(dv.cpu().numpy(), state["exp_avg_sq"]["x"].numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("cont", [False, True])
+def test_standalone_loss_vs_oracle(ctx, cont):
+    from diamond import _native as N
+    M, A = 1000, 5
+    rng = np.random.default_rng(5)
+    head = torch.as_tensor(rng.standard_normal((M, A)).astype(np.float32), ).requires_grad_(True)
+    values = torch.as_tensor(rng.standard_normal(M).astype(np.float32)).requires_grad_(True)
+    log_std = torch.as_tensor((rng.standard_normal((1, A)) * 0.2).astype(np.float32)).requires_grad_(True)
+    act = rng.standard_normal((M, A)).astype(np.float32) if cont else rng.integers(0, A, M)
+    old_lp = (rng.standard_normal(M) * 0.3 - 2).astype(np.float32)
+    adv = rng.standard_normal(M).astype(np.float32); ret = rng.standard_normal(M).astype(np.float32)
+    # torch-autograd reference of the same loss (what the reference computes for a custom network)
+    if cont:
+        dist = torch.distributions.Normal(head, log_std.expand_as(head).exp())
+        new_lp = dist.log_prob(torch.as_tensor(act)).sum(-1); ent = dist.entropy().sum(-1).mean()
+    else:
+        dist = torch.distributions.Categorical(logits=head)
+        new_lp = dist.log_prob(torch.as_tensor(act)); ent = dist.entropy().mean()
+    ratio = (new_lp - torch.as_tensor(old_lp)).exp()
+    a = torch.as_tensor(adv)
+    lp = torch.max(-a * ratio, -a * torch.clamp(ratio, 0.8, 1.2)).mean()
+    lv = 0.5 * torch.nn.functional.mse_loss(values, torch.as_tensor(ret))
+    total = lp + 1.0 * lv + -0.01 * ent
+    total.backward()
+    hyper, _ = make_hyper(N, M)
+    ws = torch.empty(ctx.ppo_loss_workspace_bytes(M, A) // 4 + 16, device="cuda")
+    losses = torch.zeros(4, device="cuda"); dhead = torch.empty(M, A, device="cuda"); dval = torch.empty(M, device="cuda")
+    if cont:
+        dls = torch.empty(A, device="cuda")
+        ctx.ppo_loss_gaussian(dev(head.detach().numpy()), dev(log_std.detach().numpy().reshape(-1)), dev(values.detach().numpy()),
+                              dev(act), dev(old_lp), dev(adv), dev(ret), hyper, losses, dhead, dls, dval, ws)
+        assert nerr(dls.cpu().numpy(), log_std.grad.numpy().reshape(-1)) <= 1e-4
+    else:
+        ctx.ppo_loss_discrete(dev(head.detach().numpy()), dev(values.detach().numpy()), dev(act, torch.int32), dev(old_lp),
+                              dev(adv), dev(ret), hyper, losses, dhead, dval, ws)
+    np.testing.assert_allclose(losses.cpu().numpy(), [float(lp), float(lv), float(ent), float(total)], rtol=1e-4, atol=1e-6)
+    assert nerr(dhead.cpu().numpy(), head.grad.numpy()) <= 1e-4
+    assert nerr(dval.cpu().numpy(), values.grad.numpy()) <= 1e-5
+
+
+# ---------------------------------------------------------------- rollout pieces --------------
+def test_gather_rows(ctx):
+    rng = np.random.default_rng(0)
+    src = rng.standard_normal((1000, 7)).astype(np.float32)
+    idx = rng.permutation(1000)[:300].astype(np.int32)
+    out = ctx.gather_rows(dev(src), dev(idx, torch.int32))
+    np.testing.assert_array_equal(out.cpu().numpy(), src[idx])          # bit-exact
+
+
+def test_store_step_casts_and_layout(ctx):
+    for cont in (False, True):
+        N_, D, A, T = 37, 5, 3, 4
+        rng = np.random.default_rng(1)
+        obs = torch.zeros(T, N_, D, device="cuda"); nobs = torch.zeros(T, N_, D, device="cuda")
+        actions = torch.zeros((T, N_, A) if cont else (T, N_), dtype=torch.float32 if cont else torch.int32, device="cuda")
+        rew = torch.zeros(T, N_, device="cuda"); te = torch.zeros(T, N_, device="cuda"); tr = torch.zeros(T, N_, device="cuda")
+        nbytes = ctx.step_record_bytes(N_, D, A, cont)
+        for t in range(T):
+            o = rng.standard_normal((N_, D)).astype(np.float32); no = rng.standard_normal((N_, D)).astype(np.float32)
+            r = rng.standard_normal(N_); term = rng.random(N_) < 0.3; trunc = rng.random(N_) < 0.3
+            a = rng.standard_normal((N_, A)).astype(np.float32) if cont else rng.integers(0, A, N_).astype(np.int64)
+            pad = b"\0" * (4 * ((N_ * D) & 1))
+            rec = o.tobytes() + no.tobytes() + pad + r.astype(np.float64).tobytes() + a.tobytes() + term.astype(np.uint8).tobytes() + trunc.astype(np.uint8).tobytes()
+            assert len(rec) == nbytes
+            drec = torch.frombuffer(bytearray(rec + b"\0" * (-len(rec) % 8)), dtype=torch.uint8).cuda()
+            ctx.buffer_store_step(drec, t, N_, D, A, cont, obs, nobs, actions, rew, te, tr)
+            np.testing.assert_array_equal(obs[t].cpu().numpy(), o)
+            np.testing.assert_array_equal(nobs[t].cpu().numpy(), no)
+            np.testing.assert_array_equal(rew[t].cpu().numpy(), r.astype(np.float32))
+            np.testing.assert_array_equal(te[t].cpu().numpy(), term.astype(np.float32))      # masks bit-exact
+            np.testing.assert_array_equal(tr[t].cpu().numpy(), trunc.astype(np.float32))
+            np.testing.assert_array_equal(actions[t].cpu().numpy(), a.astype(np.float32 if cont else np.int32))
+
+
+def test_sample_categorical_distribution_and_determinism(ctx):
+    N_, A = 200000, 4
+    logits = torch.tensor([[0.1, -1.0, 2.0, 0.5]], device="cuda").repeat(N_, 1).contiguous()
+    lp = torch.empty(N_, device="cuda")
+    a1 = ctx.sample_categorical(logits, seed=42, counter=7, log_probs=lp)
+    a2 = ctx.sample_categorical(logits, seed=42, counter=7)
+    assert torch.equal(a1, a2)                                           # deterministic under its own seed
+    a3 = ctx.sample_categorical(logits[1000:3000].contiguous(), seed=42, counter=7, env_offset=1000)
+    assert torch.equal(a1[1000:3000], a3)                                # keyed by global env id, not launch shape
+    a4 = ctx.sample_categorical(logits, seed=42, counter=8)
+    assert not torch.equal(a1, a4)
+    p = torch.softmax(logits[0], -1).cpu().numpy()
+    counts = np.bincount(a1.cpu().numpy(), minlength=A)
+    chi2 = ((counts - N_ * p) ** 2 / (N_ * p)).sum()
+    assert chi2 < 25.0, (chi2, counts)                                   # 3 dof, p ~ 1e-5
+    ref_lp = torch.log_softmax(logits[0], -1)[a1]
+    np.testing.assert_allclose(lp.cpu().numpy(), ref_lp.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_sample_gaussian_distribution(ctx):
+    N_, A = 200000, 3
+    mean = torch.tensor([[0.5, -2.0, 1.0]], device="cuda").repeat(N_, 1).contiguous()
+    log_std = torch.tensor([0.0, -1.0, 0.7], device="cuda")
+    lp = torch.empty(N_, device="cuda")
+    a = ctx.sample_gaussian(mean, log_std, seed=1, counter=3, log_probs=lp)
+    x = a.cpu().numpy()
+    np.testing.assert_allclose(x.mean(0), [0.5, -2.0, 1.0], atol=0.02)
+    np.testing.assert_allclose(x.std(0), np.exp([0.0, -1.0, 0.7]), rtol=0.02)
+    assert abs(np.corrcoef(x[:, 0], x[:, 1])[0, 1]) < 0.01
+    ref = torch.distributions.Normal(mean, log_std.exp()).log_prob(a).sum(-1)
+    np.testing.assert_allclose(lp.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-4)
