@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the Diamond PPO hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[4], "synthetic scale"): 4096 envs x 128 steps per GPU, obs_dim 64,
+default actor-critic MLP at hidden 256, 4 actions, 4 epochs x 8 minibatches.  A "step" is one
+PPO.learn() over that buffer: pre-update pass, GAE, advantage statistics, 32 optimiser steps.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "diamond-ppo_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+T, N_ENVS, D, H, A, E, MB = 128, 4096, 64, 256, 4, 4, 8
+FLOP_PER_SAMPLE_UPDATE = 1_252_864          # 2*(3F - D*H), F = D*H + 3H^2 + H*A + H
+FLOP_PER_SAMPLE_PREPASS = 723_968           # 2*(F + Fc)
+GAE_BYTES_PER_ELEM = 28                     # 5 fp32 reads + 2 fp32 writes
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons while the timed region runs (NVML; nvidia-smi semantics)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, threading.Event(), [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) and "None" not in name and "All" not in name:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(r for r in self.reasons if r not in ("GpuIdle", "ApplicationsClocksSetting"))}
+
+
+def synth_host_rollout(seed):
+    """Synthetic rollout of config S in the buffer's dtypes, in pinned host memory."""
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(T, N_ENVS, D, generator=g)
+    next_obs = torch.randn(T, N_ENVS, D, generator=g)
+    actions = torch.randint(0, A, (T, N_ENVS), generator=g, dtype=torch.int32)
+    rewards = torch.randn(T, N_ENVS, generator=g)
+    term = (torch.rand(T, N_ENVS, generator=g) < 0.01).float()
+    trunc = ((torch.rand(T, N_ENVS, generator=g) < 0.01) & (term == 0)).float()
+    return [x.pin_memory() for x in (obs, next_obs, actions, rewards, term, trunc)]
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's learn() on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, minibatches_per_step=2):
+    from oracle import ppo_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    host = synth_host_rollout(1)
+    obs, nobs, act, rew, term, trunc = (x.numpy() for x in host)
+    from diamond.networks import ActorCriticNetwork, network_parameter_init_
+    from diamond.config import PPOConfig
+    from diamond import envs
+    torch.manual_seed(42)
+    cfg = PPOConfig(network_hidden_dim=H)
+    net = ActorCriticNetwork(envs.Box(shape=(D,)), envs.Discrete(A), cfg)
+    network_parameter_init_(net, gain=2 ** 0.5)
+    p = {n: q.detach().clone() for n, q in net.named_parameters()}
+    names = O.DISCRETE_PARAM_NAMES
+    state = O.new_adam_state(p, names)
+    ocfg = O.default_cfg()
+    B = T * N_ENVS
+    M = B // MB
+    t0 = time.perf_counter()
+    flat_obs = torch.as_tensor(obs).reshape(B, D)
+    logp, values, next_values = O.prepass(p, flat_obs, torch.as_tensor(nobs).reshape(B, D), torch.as_tensor(act).reshape(B).long())
+    t_prepass = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    adv = O.gae(rew, term, trunc, values.reshape(T, N_ENVS).numpy(), next_values.reshape(T, N_ENVS).numpy())
+    t_gae = time.perf_counter() - t0
+    ret, adv_n = O.returns_and_normalise(values.reshape(T, N_ENVS).numpy(), adv, True)
+    adv_f, ret_f, act_f = torch.as_tensor(adv_n).reshape(B), torch.as_tensor(ret).reshape(B), torch.as_tensor(act).reshape(B).long()
+    np.random.seed(123)
+    perm = np.random.permutation(B)
+
+    def step(i):
+        for k in range(minibatches_per_step):
+            kk = (i * minibatches_per_step + k) % MB
+            idx = torch.as_tensor(perm[kk * M:(kk + 1) * M].astype(np.int64))
+            _, grads = O.loss_and_grads(p, flat_obs[idx], act_f[idx], logp[idx], adv_f[idx], ret_f[idx], ocfg, False)
+            O.clip_grad_norm_(grads, names, ocfg["grad_norm_clip"])
+            O.adam_step_(p, grads, state, names, ocfg["lr"], ocfg["adam_eps"])
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    dt = time.perf_counter() - t0
+    samples = steps * minibatches_per_step * M
+    return dict(value=samples / dt, ms_per_step=dt / steps * 1e3, cores=cores, t_prepass_s=t_prepass, t_gae_s=t_gae,
+                gae_gbps=B * GAE_BYTES_PER_ELEM / t_gae / 1e9,
+                sample=f"{minibatches_per_step} optimiser steps of {M}-row minibatches per step on the {N_ENVS}x{T} buffer "
+                       f"(pre-update pass {t_prepass:.2f}s and GAE {t_gae * 1e3:.1f}ms timed once, outside)")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    r = cpu_reference(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "ppo_update_samples_per_s", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1),
+            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                             "gae_gbps": r["gae_gbps"]},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": f"synthetic scale (BASELINE.json configs[4]): {N_ENVS} envs x {T} steps per GPU, obs_dim {D}, "
+                        f"2x{H} trunk + {H}-wide heads, {A} actions, {E} epochs x {MB} minibatches",
+            "envs_per_gpu": N_ENVS, "rollout_steps": T, "global_batch": T * N_ENVS * world, "minibatch": T * N_ENVS * world // MB,
+            "parallelism": f"env-sharded dp{world}" if world > 1 else "single GPU",
+            "permutation": "bit-exact numpy MT19937 stream (host thread, overlapped)",
+            "l2": "inputs (2 x 134 MB observations) exceed the 126 MB L2; GAE sub-benchmark cycles 20 buffer sets (294 MB)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def bench_gae(ctx, hbm_peak, sets=20, launches=200):
+    f = dict(device="cuda", dtype=torch.float32)
+    bufs = []
+    for s in range(sets):
+        r, v, nv = (torch.randn(T, N_ENVS, **f) for _ in range(3))
+        te = (torch.rand(T, N_ENVS, device="cuda") < 0.01).float()
+        tr = ((torch.rand(T, N_ENVS, device="cuda") < 0.01) & (te == 0)).float()
+        bufs.append((r, te, tr, v, nv, torch.empty(T, N_ENVS, **f), torch.empty(T, N_ENVS, **f)))
+    for i in range(2 * sets):
+        b = bufs[i % sets]
+        ctx.gae(*b[:5], 0.99, 0.95, advantages=b[5], returns=b[6])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(launches):
+        b = bufs[i % sets]
+        ctx.gae(*b[:5], 0.99, 0.95, advantages=b[5], returns=b[6])
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / launches
+    bytes_ = T * N_ENVS * GAE_BYTES_PER_ELEM
+    gbps = bytes_ / (us * 1e-6) / 1e9
+    return {"us_per_launch": us, "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak, "bound": "hbm",
+            "bytes_per_launch": bytes_, "launches": launches, "buffer_sets": sets}
+
+
+def bench_fma_peak(ctx):
+    sink = torch.ones(128, device="cuda")
+    iters = 1 << 16
+    ctx.fma_peak(sink, iters)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        blocks, threads = ctx.fma_peak(sink, iters)
+    e1.record()
+    torch.cuda.synchronize()
+    flops = 5 * 2.0 * iters * blocks * threads
+    return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from diamond import PPO, PPOConfig, envs, _native
+    from diamond.agents import RolloutBuffer
+    torch.cuda.set_device(local_rank)
+    ctx = _native.get_context(local_rank)
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
+
+    def env_fn(n):
+        return envs.BatchedSyntheticVectorEnv(n, D, A)
+    env_fn.vectorized = True
+    cfg = PPOConfig(num_envs=N_ENVS, rollout_steps=T, network_hidden_dim=H, num_epochs=E, num_minibatches=MB, verbose=False,
+                    total_steps=T * N_ENVS * 1000)
+    agent = PPO(env_fn, cfg, dp=world > 1)
+    host = synth_host_rollout(1 + rank)
+    buf = RolloutBuffer(ctx, T, N_ENVS, D, 1, False, agent.device)
+    buf.load_host(*host)
+    torch.cuda.synchronize()
+    np.random.seed(123)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: `value` ----
+    for _ in range(args.warmup):
+        agent.learn(buf)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    ev_all = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ev = {}
+        agent.learn(buf, events=ev)
+        ev_all.append(ev)
+    e1.record()
+    barrier()
+    launches = ctx.launches - launches0
+    clocks = sampler.result()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_total) / args.steps
+    t_pre = np.mean([ev["start"].elapsed_time(ev["prepass_end"]) for ev in ev_all])
+    t_gae = np.mean([ev["prepass_end"].elapsed_time(ev["gae_end"]) for ev in ev_all])
+    t_upd = np.mean([ev["gae_end"].elapsed_time(ev["update_end"]) for ev in ev_all])
+    sample_updates = E * T * N_ENVS * world
+    value = sample_updates / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers: `e2e` ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h_losses = torch.empty(E * MB, 4).pin_memory()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    h2d = 0
+    for _ in range(args.steps):
+        h2d = buf.load_host(*host)                    # this step's inputs: pinned host -> device
+        agent.learn(buf)
+        h_losses.copy_(agent.last_losses, non_blocking=True)     # result read back
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = sample_updates / (float(ms_e2e) / args.steps * 1e-3)
+    assert torch.isfinite(h_losses).all()
+
+    if rank != 0:
+        return
+    # ---- roofline evidence (rank 0) ----
+    fma_peak = bench_fma_peak(ctx)
+    gae = bench_gae(ctx, hbm_peak)
+    upd_tflops = E * T * N_ENVS * FLOP_PER_SAMPLE_UPDATE / (t_upd * 1e-3) / 1e12
+    line = {
+        "metric": "ppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "phases_ms": {"prepass": t_pre, "gae_and_stats": t_gae, "update_loop": t_upd},
+        "update_loop_samples_per_s": E * T * N_ENVS * world / (t_upd * 1e-3),
+        "roofline": {"bound": "fma", "kernel": "gemm_kernel/wgrad_kernel (FP32 FFMA GEMMs of the update loop)",
+                     "achieved": upd_tflops, "peak": fma_peak, "unit": "TFLOP/s", "frac": upd_tflops / fma_peak,
+                     "peak_source": "FP32 FMA-pipe peak measured in this run by dppo_fma_peak_kernel "
+                                    "(MEASURED_PEAKS.json has no fp32 figure; bf16 tensor peak there: %.1f TF/s, %s)" % (bf16_peak, peak_src),
+                     "flop_per_sample_update": FLOP_PER_SAMPLE_UPDATE, "traffic": None},
+        "roofline_gae": dict(gae, kernel="gae_kernel<8>", peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=None),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_losses.numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(4, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                "gae_gbps": r["gae_gbps"]}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

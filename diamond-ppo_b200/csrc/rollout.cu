@@ -83,7 +83,7 @@ __global__ void store_step_kernel(const unsigned char* __restrict__ rec, int t, 
     const int64_t nd = (int64_t)N * D;
     const float* r_obs = reinterpret_cast<const float*>(rec);
     const float* r_nobs = r_obs + nd;
-    const double* r_rew = reinterpret_cast<const double*>(r_nobs + nd + (nd & 1));       // 8-byte aligned
+    const double* r_rew = reinterpret_cast<const double*>(r_nobs + nd);                  // 8*nd bytes in: 8-byte aligned
     const unsigned char* r_act = reinterpret_cast<const unsigned char*>(r_rew + N);
     const int64_t act_bytes = continuous ? (int64_t)N * A * 4 : (int64_t)N * 8;
     const unsigned char* r_term = r_act + act_bytes;
@@ -115,7 +115,7 @@ __global__ void store_step_kernel(const unsigned char* __restrict__ rec, int t, 
 extern "C" int64_t dppo_step_record_bytes(int N, int D, int act_dim, int continuous)
 {
     const int64_t nd = (int64_t)N * D;
-    int64_t b = (2 * nd + (nd & 1)) * 4;           // obs, next_obs (+pad to 8 bytes)
+    int64_t b = 2 * nd * 4;                        // obs, next_obs
     b += (int64_t)N * 8;                           // rewards f64
     b += continuous ? (int64_t)N * act_dim * 4 : (int64_t)N * 8;
     b += 2 * (int64_t)N;                           // terminations, truncations (u8)

@@ -73,7 +73,7 @@ class RolloutBuffer:
         nd = self.N * self.D
         o = 0
         obs = raw[o:o + nd * 4].view(np.float32).reshape(self.N, self.D); o += nd * 4
-        nobs = raw[o:o + nd * 4].view(np.float32).reshape(self.N, self.D); o += nd * 4 + 4 * (nd & 1)
+        nobs = raw[o:o + nd * 4].view(np.float32).reshape(self.N, self.D); o += nd * 4
         rew = raw[o:o + self.N * 8].view(np.float64); o += self.N * 8
         if self.continuous:
             act = raw[o:o + self.N * self.A * 4].view(np.float32).reshape(self.N, self.A); o += self.N * self.A * 4
@@ -130,6 +130,18 @@ class RolloutBuffer:
                                                                     buf.terminations, buf.truncations))
         buf.filled = T
         return buf
+
+    def load_host(self, obs, next_obs, actions, rewards, terminations, truncations) -> int:
+        """Fill the whole buffer from host tensors already in this buffer's dtypes/shapes (pinned
+        memory makes the copies asynchronous).  Returns the bytes copied host->device."""
+        n = 0
+        for dst, src in ((self.obs, obs), (self.next_obs, next_obs), (self.actions, actions), (self.rewards, rewards),
+                         (self.terminations, terminations), (self.truncations, truncations)):
+            dst.copy_(src.view(dst.shape), non_blocking=True)
+            n += dst.numel() * dst.element_size()
+        self.filled = self.T
+        self.h2d_bytes += n
+        return n
 
     # ---- list-like view for user code ---------------------------------------------------------
     def __len__(self) -> int:

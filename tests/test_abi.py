@@ -93,4 +93,4 @@ def test_step_record_bytes():
     from diamond import _native as N
     lib = N.load_library()
     assert lib.dppo_step_record_bytes(8, 4, 2, 0) == 2 * 8 * 4 * 4 + 8 * 8 + 8 * 8 + 2 * 8
-    assert lib.dppo_step_record_bytes(3, 3, 2, 1) == (2 * 9 + 1) * 4 + 3 * 8 + 3 * 2 * 4 + 2 * 3
+    assert lib.dppo_step_record_bytes(3, 3, 2, 1) == 2 * 9 * 4 + 3 * 8 + 3 * 2 * 4 + 2 * 3

@@ -296,8 +296,7 @@ def test_store_step_casts_and_layout(ctx):
             o = rng.standard_normal((N_, D)).astype(np.float32); no = rng.standard_normal((N_, D)).astype(np.float32)
             r = rng.standard_normal(N_); term = rng.random(N_) < 0.3; trunc = rng.random(N_) < 0.3
             a = rng.standard_normal((N_, A)).astype(np.float32) if cont else rng.integers(0, A, N_).astype(np.int64)
-            pad = b"\0" * (4 * ((N_ * D) & 1))
-            rec = o.tobytes() + no.tobytes() + pad + r.astype(np.float64).tobytes() + a.tobytes() + term.astype(np.uint8).tobytes() + trunc.astype(np.uint8).tobytes()
+            rec = o.tobytes() + no.tobytes() + r.astype(np.float64).tobytes() + a.tobytes() + term.astype(np.uint8).tobytes() + trunc.astype(np.uint8).tobytes()
             assert len(rec) == nbytes
             drec = torch.frombuffer(bytearray(rec + b"\0" * (-len(rec) % 8)), dtype=torch.uint8).cuda()
             ctx.buffer_store_step(drec, t, N_, D, A, cont, obs, nobs, actions, rew, te, tr)
