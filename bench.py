@@ -182,11 +182,20 @@ def bench_gae(ctx, hbm_peak, sets=20, launches=200):
         b = bufs[i % sets]
         ctx.gae(*b[:5], 0.99, 0.95, advantages=b[5], returns=b[6])
     torch.cuda.synchronize()
+    # `launches` back-to-back launches cycling through the buffer sets, replayed as one CUDA graph so that the
+    # host-side launch cost of the Python binding does not enter the per-launch device time
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(launches):
+                b = bufs[i % sets]
+                ctx.gae(*b[:5], 0.99, 0.95, advantages=b[5], returns=b[6])
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(launches):
-        b = bufs[i % sets]
-        ctx.gae(*b[:5], 0.99, 0.95, advantages=b[5], returns=b[6])
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / launches
