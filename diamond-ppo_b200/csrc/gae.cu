@@ -25,6 +25,10 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ terms, c
     __shared__ float s_carry[32];
     __shared__ double s_red[2][GAE_WARPS];
 
+    // Programmatic dependent launch: let the next kernel in the stream get its CTAs resident now
+    // (it still waits at its own griddepcontrol.wait), and wait for everything this launch depends
+    // on before the first global access.  Without the launch attribute both are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * 32 + lane;
@@ -34,6 +38,7 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ terms, c
 
     if (warp == 0) s_carry[lane] = 0.0f;
     float sum = 0.0f, sumsq = 0.0f;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     for (int pass = passes - 1; pass >= 0; --pass) {
         const int t0 = pass * SPAN + warp * L;
@@ -127,8 +132,17 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
     const int blocks = (N + 31) / 32;
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     const int per_warp = (T + GAE_WARPS - 1) / GAE_WARPS;
-#define GAE_LAUNCH(L) gae_kernel<L><<<blocks, GAE_WARPS * 32, 0, st>>>(rewards, terminations, truncations, values, \
-                                        next_values, advantages, returns, stats, T, N, g, gl)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(GAE_WARPS * 32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define GAE_LAUNCH(L) cudaLaunchKernelEx(&cfg, gae_kernel<L>, rewards, terminations, truncations, values, \
+                                         next_values, advantages, returns, stats, T, N, g, gl)
     if (per_warp <= 1) GAE_LAUNCH(1);
     else if (per_warp <= 2) GAE_LAUNCH(2);
     else if (per_warp <= 4) GAE_LAUNCH(4);
