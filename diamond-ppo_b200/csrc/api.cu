@@ -43,12 +43,15 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->err[0] = 0;
+    c->tm_cache = nullptr;
+    c->tm_cache_free = nullptr;
     *out = c;
     return 0;
 }
 
 extern "C" int dppo_destroy(dppo_ctx* ctx)
 {
+    if (ctx && ctx->tm_cache && ctx->tm_cache_free) ctx->tm_cache_free(ctx->tm_cache);
     delete ctx;
     return 0;
 }
@@ -90,7 +93,7 @@ struct TrainWs {
 // Carves the training workspace for M rows.  sm_count fixes the split-K / head grid sizes.
 TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
 {
-    dppo_ctx fake; fake.sm_count = sm_count;
+    dppo_ctx fake = {}; fake.sm_count = sm_count;
     const int64_t D = d->obs_dim, H = d->hidden, A = d->act_dim;
     TrainWs w;
     int64_t o = 0;

@@ -12,6 +12,8 @@ struct dppo_ctx {
     int sm_count;
     int cc_major, cc_minor;
     char err[512];
+    void* tm_cache;                       // tensor-map cache owned by gae.cu
+    void (*tm_cache_free)(void*);
 };
 
 extern char g_dppo_create_error[512];

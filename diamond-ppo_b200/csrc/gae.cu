@@ -8,11 +8,219 @@
 // memory, and after one barrier each thread folds the maps of the later chunks into its carry.
 // All 5*L loads of a thread are independent and issued before the first use, so the whole CTA
 // tile (5 * T * 128 B) is in flight at once -- the kernel is a pure HBM stream.
+//
+// Two variants share the scan: `gae_tma_kernel` stages the five [T x envs] input tiles through shared
+// memory with one 2-D TMA bulk-tensor load each (cp.async.bulk.tensor, completion on an mbarrier), so the
+// whole tile is in flight without occupying L1 miss slots -- the register variant `gae_kernel` keeps
+// 5*L loads per thread in flight and was measured L1-miss-slot bound (3.2 TB/s at 4096 x 128).  The
+// TMA variant also sizes the env block so that the grid covers all SMs (28 envs x 147 CTAs at N=4096).
+// The register variant remains for shapes TMA cannot describe (N not a multiple of 4, unaligned bases).
+#include <cuda.h>
+
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int GAE_WARPS = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "GAE_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GAE_DONE_%=;\n\t"
+        "bra GAE_WAIT_%=;\n\t"
+        "GAE_DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// One affine-map scan shared by both kernels (see the header comment).
+template <int L>
+struct GaeScan {
+    float a[L], p[L];
+    __device__ __forceinline__ void local(const float (&r)[L], const float (&te)[L], const float (&tr)[L], const float (&v)[L],
+                                          const float (&nv)[L], float gamma, float gamma_lambda)
+    {
+        float acc = 0.0f, prod = 1.0f;
+#pragma unroll
+        for (int j = L - 1; j >= 0; --j) {
+            const float nt = 1.0f - te[j];
+            const float ntr = 1.0f - tr[j];
+            const float delta = r[j] + gamma * nv[j] * nt - v[j];      // ppo.py:206-210
+            const float c = gamma_lambda * nt * ntr;                    // ppo.py:215-218
+            acc = delta + c * acc;
+            prod = c * prod;
+            a[j] = acc;
+            p[j] = prod;
+        }
+    }
+};
+
+template <int L>
+__global__ void __launch_bounds__(GAE_WARPS * 32)
+gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_te,
+               const __grid_constant__ CUtensorMap tm_tr, const __grid_constant__ CUtensorMap tm_v,
+               const __grid_constant__ CUtensorMap tm_nv, float* __restrict__ adv_out, float* __restrict__ ret_out,
+               double* __restrict__ stats, int T, int N, int epc, int box_rows, int region_bytes, float gamma, float gamma_lambda)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ float s_a0[GAE_WARPS][32];
+    __shared__ float s_p0[GAE_WARPS][32];
+    __shared__ float s_carry[32];
+    __shared__ double s_red[2][GAE_WARPS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int env0 = blockIdx.x * epc;
+    const int env = env0 + lane;
+    const bool env_ok = lane < epc && env < N;
+    constexpr int SPAN = GAE_WARPS * L;
+    const int passes = (T + SPAN - 1) / SPAN;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    if (warp == 0) s_carry[lane] = 0.0f;
+    __syncthreads();
+
+    const float* s_r = reinterpret_cast<const float*>(dyn);
+    const float* s_te = reinterpret_cast<const float*>(dyn + region_bytes);
+    const float* s_tr = reinterpret_cast<const float*>(dyn + 2 * region_bytes);
+    const float* s_v = reinterpret_cast<const float*>(dyn + 3 * region_bytes);
+    const float* s_nv = reinterpret_cast<const float*>(dyn + 4 * region_bytes);
+    float sum = 0.0f, sumsq = 0.0f;
+    uint32_t parity = 0;
+
+    for (int pass = passes - 1; pass >= 0; --pass) {
+        const int tbase = pass * SPAN;
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&mbar, 5u * (uint32_t)(box_rows * epc * 4));
+            tma_load_2d(dyn, &tm_r, env0, tbase, &mbar);
+            tma_load_2d(dyn + region_bytes, &tm_te, env0, tbase, &mbar);
+            tma_load_2d(dyn + 2 * region_bytes, &tm_tr, env0, tbase, &mbar);
+            tma_load_2d(dyn + 3 * region_bytes, &tm_v, env0, tbase, &mbar);
+            tma_load_2d(dyn + 4 * region_bytes, &tm_nv, env0, tbase, &mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        float r[L], te[L], tr[L], v[L], nv[L];
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            const int row = warp * L + j;
+            const bool ok = row < box_rows && lane < epc;      // rows past T inside the box are zero-filled by TMA
+            const int i = row * epc + lane;
+            r[j] = ok ? s_r[i] : 0.0f;
+            te[j] = ok ? s_te[i] : 0.0f;
+            tr[j] = ok ? s_tr[i] : 0.0f;
+            v[j] = ok ? s_v[i] : 0.0f;
+            nv[j] = ok ? s_nv[i] : 0.0f;
+        }
+        GaeScan<L> sc;
+        sc.local(r, te, tr, v, nv, gamma, gamma_lambda);
+        s_a0[warp][lane] = sc.a[0];
+        s_p0[warp][lane] = sc.p[0];
+        __syncthreads();
+        float carry = s_carry[lane];
+#pragma unroll
+        for (int w = GAE_WARPS - 1; w >= 1; --w)
+            if (w > warp) carry = s_a0[w][lane] + s_p0[w][lane] * carry;
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            const int t = tbase + warp * L + j;
+            if (env_ok && t < T) {
+                const int64_t i = (int64_t)t * N + env;
+                const float A = sc.a[j] + sc.p[j] * carry;
+                adv_out[i] = A;
+                if (ret_out) ret_out[i] = v[j] + A;                     // ppo.py:241
+                sum += A;
+                sumsq += A * A;
+            }
+        }
+        if (passes > 1) {
+            __syncthreads();
+            if (warp == 0) s_carry[lane] = sc.a[0] + sc.p[0] * carry;
+            __syncthreads();
+        }
+    }
+
+    if (stats) {
+        double ds = warp_sum_d((double)sum), dq = warp_sum_d((double)sumsq);
+        if (lane == 0) { s_red[0][warp] = ds; s_red[1][warp] = dq; }
+        __syncthreads();
+        if (warp == 0) {
+            ds = lane < GAE_WARPS ? s_red[0][lane] : 0.0;
+            dq = lane < GAE_WARPS ? s_red[1][lane] : 0.0;
+            ds = warp_sum_d(ds); dq = warp_sum_d(dq);
+            if (lane == 0) { atomicAdd(stats, ds); atomicAdd(stats + 1, dq); }
+        }
+    }
+}
+
+// ---- host: tensor maps ----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+struct TmEntry { const void* ptr; int T, N, epc, rows; CUtensorMap map; };
+struct TmCache { std::vector<TmEntry> e; size_t next = 0; };
+void tm_cache_free(void* p) { delete static_cast<TmCache*>(p); }
+
+bool get_tensor_map(dppo_ctx* ctx, const float* ptr, int T, int N, int epc, int rows, CUtensorMap* out)
+{
+    if (!ctx->tm_cache) { ctx->tm_cache = new TmCache(); ctx->tm_cache_free = tm_cache_free; }
+    TmCache* c = static_cast<TmCache*>(ctx->tm_cache);
+    for (const TmEntry& t : c->e)
+        if (t.ptr == ptr && t.T == T && t.N == N && t.epc == epc && t.rows == rows) { *out = t.map; return true; }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    TmEntry t;
+    t.ptr = ptr; t.T = T; t.N = N; t.epc = epc; t.rows = rows;
+    const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)T};
+    const cuuint64_t gstride[1] = {(cuuint64_t)N * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)epc, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&t.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (c->e.size() < 256) c->e.push_back(t);
+    else { c->e[c->next] = t; c->next = (c->next + 1) % 256; }
+    *out = t.map;
+    return true;
+}
 
 template <int L>
 __global__ void __launch_bounds__(GAE_WARPS * 32)
@@ -25,10 +233,6 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ terms, c
     __shared__ float s_carry[32];
     __shared__ double s_red[2][GAE_WARPS];
 
-    // Programmatic dependent launch: let the next kernel in the stream get its CTAs resident now
-    // (it still waits at its own griddepcontrol.wait), and wait for everything this launch depends
-    // on before the first global access.  Without the launch attribute both are no-ops.
-    asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * 32 + lane;
@@ -38,7 +242,6 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ terms, c
 
     if (warp == 0) s_carry[lane] = 0.0f;
     float sum = 0.0f, sumsq = 0.0f;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     for (int pass = passes - 1; pass >= 0; --pass) {
         const int t0 = pass * SPAN + warp * L;
@@ -132,17 +335,38 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
     const int blocks = (N + 31) / 32;
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     const int per_warp = (T + GAE_WARPS - 1) / GAE_WARPS;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(GAE_WARPS * 32);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-#define GAE_LAUNCH(L) cudaLaunchKernelEx(&cfg, gae_kernel<L>, rewards, terminations, truncations, values, \
-                                         next_values, advantages, returns, stats, T, N, g, gl)
+
+    // TMA variant: needs 16-byte row pitch and base alignment (tensor-map requirements)
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (N % 4 == 0 && al16(rewards) && al16(terminations) && al16(truncations) && al16(values) && al16(next_values)) {
+        int epc = (N + ctx->sm_count - 1) / ctx->sm_count;
+        epc = (epc + 3) / 4 * 4;
+        if (epc > 32) epc = 32;
+        const int L = per_warp <= 1 ? 1 : per_warp <= 2 ? 2 : per_warp <= 4 ? 4 : 8;
+        const int span = GAE_WARPS * L;
+        const int rows = T < span ? T : span;
+        const int region = (rows * epc * 4 + 127) / 128 * 128;
+        CUtensorMap m[5];
+        const float* ptrs[5] = {rewards, terminations, truncations, values, next_values};
+        bool ok = true;
+        for (int i = 0; i < 5 && ok; ++i) ok = get_tensor_map(ctx, ptrs[i], T, N, epc, rows, &m[i]);
+        if (ok) {
+            const int grid = (N + epc - 1) / epc;
+            const size_t smem = (size_t)5 * region;
+#define GAE_TMA_LAUNCH(LL)                                                                                              \
+            do {                                                                                                        \
+                cudaFuncSetAttribute(gae_tma_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+                gae_tma_kernel<LL><<<grid, GAE_WARPS * 32, smem, st>>>(m[0], m[1], m[2], m[3], m[4], advantages, returns, stats, \
+                                                                       T, N, epc, rows, region, g, gl);                 \
+            } while (0)
+            if (L == 1) GAE_TMA_LAUNCH(1); else if (L == 2) GAE_TMA_LAUNCH(2); else if (L == 4) GAE_TMA_LAUNCH(4); else GAE_TMA_LAUNCH(8);
+#undef GAE_TMA_LAUNCH
+            DPPO_CHECK_LAUNCH(ctx, "gae_tma_kernel");
+            return 0;
+        }
+    }
+#define GAE_LAUNCH(L) gae_kernel<L><<<blocks, GAE_WARPS * 32, 0, st>>>(rewards, terminations, truncations, values, \
+                                        next_values, advantages, returns, stats, T, N, g, gl)
     if (per_warp <= 1) GAE_LAUNCH(1);
     else if (per_warp <= 2) GAE_LAUNCH(2);
     else if (per_warp <= 4) GAE_LAUNCH(4);
