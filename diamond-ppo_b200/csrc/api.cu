@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "heads.cuh"
 #include "optim.cuh"
+#include "gemm_tc.cuh"
 
 char g_dppo_create_error[512] = "";
 
@@ -43,6 +44,8 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->err[0] = 0;
+    c->use_tensor_cores = 1;
+    c->gae_variant = 0;
     c->tm_cache = nullptr;
     c->tm_cache_free = nullptr;
     *out = c;
@@ -54,6 +57,14 @@ extern "C" int dppo_destroy(dppo_ctx* ctx)
     if (ctx && ctx->tm_cache && ctx->tm_cache_free) ctx->tm_cache_free(ctx->tm_cache);
     delete ctx;
     return 0;
+}
+
+extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return 1;
+    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value != 0; return 0; }
+    if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
+    DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
 
 extern "C" int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
@@ -83,10 +94,32 @@ extern "C" int dppo_mlp_layout_compute(const dppo_mlp_desc* d, dppo_mlp_layout* 
 
 namespace {
 
+struct WImages {
+    unsigned char *w1f, *w2f, *w3f, *w3b, *w2b;
+    int64_t bytes;
+};
+
+// hi/lo pre-swizzled weight images for the tensor-core GEMMs (forward: W1, W2, W3; dgrad: W3^T, W2^T)
+WImages carve_images(const dppo_mlp_desc* d, char* base)
+{
+    const int64_t D = d->obs_dim, H = d->hidden;
+    WImages w;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { unsigned char* p = reinterpret_cast<unsigned char*>(base + o); o += align_up(bytes, 1024); return p; };
+    w.w1f = take(dppo_tc_image_bytes((int)H, (int)D));
+    w.w2f = take(dppo_tc_image_bytes((int)H, (int)H));
+    w.w3f = take(dppo_tc_image_bytes((int)(2 * H), (int)H));
+    w.w3b = take(dppo_tc_image_bytes((int)H, (int)(2 * H)));
+    w.w2b = take(dppo_tc_image_bytes((int)H, (int)H));
+    w.bytes = o;
+    return w;
+}
+
 struct TrainWs {
     float *h1, *h2, *h3, *d3, *d2, *d1;
     float *p3, *p2, *p1, *c2, *c1, *hp;
     int s3, s2, s1, tiles2, tiles1, head_blocks, head_stride;
+    int64_t img_off;
     int64_t bytes;
 };
 
@@ -113,6 +146,9 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     w.head_blocks = head_train_blocks(&fake, M);
     w.head_stride = (int)align_up(head_partial_floats((int)H, (int)A), 4);
     w.hp = take((int64_t)w.head_blocks * w.head_stride);
+    o = align_up(o, 1024);
+    w.img_off = o;
+    o += carve_images(d, nullptr).bytes;
     w.bytes = o;
     return w;
 }
@@ -130,7 +166,7 @@ extern "C" int64_t dppo_mlp_workspace_bytes(const dppo_mlp_desc* d, int64_t rows
 {
     if (!d || rows <= 0) return 0;
     const int64_t H = d->hidden;
-    if (!training) return align_up(rows * H * 4, 256) * 2 + align_up(rows * 2 * H * 4, 256);
+    if (!training) return align_up(rows * H * 4, 256) * 2 + align_up(rows * 2 * H * 4, 256) + 1024 + carve_images(d, nullptr).bytes;
     // sized for the B200's 148 SMs or the current device, whichever is larger
     int sms = current_sm_count();
     if (sms < 148) sms = 148;
@@ -150,27 +186,47 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
     if (dppo_mlp_layout_compute(d, &L)) DPPO_FAIL(ctx, "mlp_forward: bad descriptor");
     const int D = d->obs_dim, H = d->hidden, A = d->act_dim;
     cudaStream_t st = (cudaStream_t)stream;
+    // weight images (tensor-core path) sit at the front of the workspace; the rest is chunked over rows
+    const int64_t img_bytes = align_up(carve_images(d, nullptr).bytes, 1024);
+    char* base0 = (char*)ws;
+    char* aligned = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base0) + 1023) & ~(uintptr_t)1023);
+    const int64_t head_room = (aligned - base0) + img_bytes;
+    const bool tc_on = ctx->use_tensor_cores && ws_bytes > head_room + 3 * 256;
+    WImages img = carve_images(d, aligned);
+    char* base = tc_on ? aligned + img_bytes : base0;
+    const int64_t avail = tc_on ? ws_bytes - head_room : ws_bytes;
     // chunk the rows so that h1 | h2 | h3 fit the workspace
     const int64_t per_row = (int64_t)4 * H * 4;
-    int64_t chunk = (ws_bytes - 3 * 256) / per_row;
+    int64_t chunk = (avail - 3 * 256) / per_row;
     if (chunk > rows) chunk = rows;
     if (chunk < 1) DPPO_FAIL(ctx, "mlp_forward: workspace too small (%lld bytes, need >= %lld per row)", (long long)ws_bytes, (long long)per_row);
-    char* base = (char*)ws;
     float* h1 = (float*)base;
     float* h2 = (float*)(base + align_up(chunk * H * 4, 256));
     float* h3 = (float*)(base + 2 * align_up(chunk * H * 4, 256));
     const bool actor = heads & 1, critic = heads & 2;
+    const int64_t w3off = actor ? 0 : (int64_t)H * H;
+    const int b3off = actor ? 0 : H;
+    const int n3 = (actor && critic) ? 2 * H : H;
+    const int64_t first = rows < chunk ? rows : chunk;
+    const bool tc1 = tc_on && dppo_tc_supported(first, H, D), tc2 = tc_on && dppo_tc_supported(first, H, H),
+               tc3 = tc_on && dppo_tc_supported(first, n3, H);
+    if (tc1 && dppo_tc_prep_weights(ctx, params + L.w1, H, D, 0, img.w1f, st)) return 1;
+    if (tc2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 0, img.w2f, st)) return 1;
+    if (tc3 && dppo_tc_prep_weights(ctx, params + L.w3 + w3off, n3, H, 0, img.w3f, st)) return 1;
     for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
         const int64_t n = rows - r0 < chunk ? rows - r0 : chunk;
         const float* x = idx ? obs : obs + r0 * D;
         const int32_t* rowsel = idx ? idx + r0 : nullptr;
-        if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
-        if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
+        if (tc1 && dppo_tc_supported(n, H, D)) {
+            if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
+        } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
+        if (tc2 && dppo_tc_supported(n, H, H)) {
+            if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
+        } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
         // first head layers: both (one [2H,H] product) or only the requested half
-        const int64_t w3off = actor ? 0 : (int64_t)H * H;
-        const int b3off = actor ? 0 : H;
-        const int n3 = (actor && critic) ? 2 * H : H;
-        if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
+        if (tc3 && dppo_tc_supported(n, n3, H)) {
+            if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
+        } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
         const float* ha = actor ? h3 : nullptr;
         const float* hc = critic ? (actor ? h3 + H : h3) : nullptr;
         if (launch_head_eval(ctx, ha, hc, n3, params + L.wa, params + L.ba, params + L.wc, params + L.bc,
@@ -197,10 +253,29 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     cudaStream_t st = (cudaStream_t)stream;
     const float inv_m = 1.0f / (float)(hy->loss_denominator > 0 ? hy->loss_denominator : M);
 
+    // tensor-core path: split/swizzle the current weights once per optimiser step
+    char* img_base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>((char*)ws + w.img_off) + 1023) & ~(uintptr_t)1023);
+    const bool img_fits = (img_base - (char*)ws) + carve_images(d, nullptr).bytes <= ws_bytes;
+    const bool tc_on = ctx->use_tensor_cores && img_fits;
+    WImages img = carve_images(d, img_base);
+    const bool tc1 = tc_on && dppo_tc_supported(M, H, D), tc2 = tc_on && dppo_tc_supported(M, H, H),
+               tc3 = tc_on && dppo_tc_supported(M, 2 * H, H), tcb3 = tc_on && dppo_tc_supported(M, H, 2 * H), tcb2 = tc2;
+    if (tc1 && dppo_tc_prep_weights(ctx, params + L.w1, H, D, 0, img.w1f, st)) return 1;
+    if (tc2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 0, img.w2f, st)) return 1;
+    if (tc3 && dppo_tc_prep_weights(ctx, params + L.w3, 2 * H, H, 0, img.w3f, st)) return 1;
+    if (tcb3 && dppo_tc_prep_weights(ctx, params + L.w3, 2 * H, H, 1, img.w3b, st)) return 1;
+    if (tcb2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 1, img.w2b, st)) return 1;
+
     // forward (ppo.py:261), activations kept for the backward pass
-    if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, obs, D, idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
-    if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
-    if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
+    if (tc1) {
+        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, obs, D, idx, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
+    } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, obs, D, idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
+    if (tc2) {
+        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
+    } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
+    if (tc3) {
+        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
+    } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
 
     // heads + loss (ppo.py:264-280) + backward into the first head layers
     HeadTrainArgs ha;
@@ -218,8 +293,15 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     if (launch_head_train_kernel(ctx, ha, d->continuous, w.head_blocks, st)) return 1;
 
     // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused
-    if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
-    if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+    int tiles2 = w.tiles2, tiles1 = w.tiles1;
+    if (tcb3) {
+        tiles2 = (int)((M + 127) / 128);
+        if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, nullptr, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+    } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+    if (tcb2) {
+        tiles1 = (int)((M + 127) / 128);
+        if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, nullptr, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+    } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     // weight gradients: deterministic split-K partials
     if (dppo_wgrad(ctx, w.d3, 2 * H, w.h2, H, nullptr, w.p3, w.s3, M, 2 * H, H, st)) return 1;
     if (dppo_wgrad(ctx, w.d2, H, w.h1, H, nullptr, w.p2, w.s2, M, H, H, st)) return 1;
@@ -233,9 +315,9 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
         tab.seg[n].nparts = nparts; tab.seg[n].pad = 0; ++n;
     };
     seg(L.w1, (int64_t)H * D, w.p1, (int64_t)H * D, w.s1);
-    seg(L.b1, H, w.c1, H, w.tiles1);
+    seg(L.b1, H, w.c1, H, tiles1);
     seg(L.w2, (int64_t)H * H, w.p2, (int64_t)H * H, w.s2);
-    seg(L.b2, H, w.c2, H, w.tiles2);
+    seg(L.b2, H, w.c2, H, tiles2);
     seg(L.w3, (int64_t)2 * H * H, w.p3, (int64_t)2 * H * H, w.s3);
     const int off_dba = A * H, off_dwc = A * H + A, off_dbc = off_dwc + H, off_dls = off_dbc + 1, off_b3 = off_dls + A,
               off_loss = off_b3 + 2 * H;

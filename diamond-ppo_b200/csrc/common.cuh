@@ -12,6 +12,8 @@ struct dppo_ctx {
     int sm_count;
     int cc_major, cc_minor;
     char err[512];
+    int use_tensor_cores;                 // 1: 3xTF32 tcgen05 GEMMs where the shape allows (default); 0: FP32 FFMA GEMMs only
+    int gae_variant;                      // 0: auto, 1: register-staged kernel, 2: TMA-staged kernel
     void* tm_cache;                       // tensor-map cache owned by gae.cu
     void (*tm_cache_free)(void*);
 };

@@ -338,7 +338,7 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
 
     // TMA variant: needs 16-byte row pitch and base alignment (tensor-map requirements)
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (N % 4 == 0 && al16(rewards) && al16(terminations) && al16(truncations) && al16(values) && al16(next_values)) {
+    if (ctx->gae_variant != 1 && N % 4 == 0 && al16(rewards) && al16(terminations) && al16(truncations) && al16(values) && al16(next_values)) {
         int epc = (N + ctx->sm_count - 1) / ctx->sm_count;
         epc = (epc + 3) / 4 * 4;
         if (epc > 32) epc = 32;

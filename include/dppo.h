@@ -76,6 +76,11 @@ int dppo_destroy(dppo_ctx* ctx);
 const char* dppo_last_error(dppo_ctx* ctx);          /* ctx may be NULL: last create() error */
 int dppo_version(void);
 int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+/* Kernel-variant switches used by tests and bench.py for A/B measurements:
+ *   "tensor_cores" 1 (default): 3xTF32 tcgen05 GEMMs where the shape allows (rows >= 1024, K % 16 == 0,
+ *                  N % 256 == 0 or N == 128), 0: FP32 FFMA GEMMs everywhere
+ *   "gae_variant"  0 (default): TMA-staged GAE kernel when the layout allows, 1: register-staged, 2: TMA */
+int dppo_set_option(dppo_ctx* ctx, const char* name, int value);
 
 /* ---- rollout buffer + batched action sampling (diamond/ppo.py:153-186, 73-82) ---------- */
 /* Unpack one vectorised env step, staged as ONE packed record

@@ -339,3 +339,57 @@ def test_sample_gaussian_distribution(ctx):
     assert abs(np.corrcoef(x[:, 0], x[:, 1])[0, 1]) < 0.01
     ref = torch.distributions.Normal(mean, log_std.exp()).log_prob(a).sum(-1)
     np.testing.assert_allclose(lp.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------- tensor-core (3xTF32 tcgen05) path ----
+@pytest.mark.parametrize("D,H,A,rows", [(64, 256, 4, 4096), (64, 256, 4, 5000), (32, 128, 3, 2048), (16, 512, 5, 1024)])
+def test_tensor_core_forward_matches_fp32_path_and_oracle(ctx, D, H, A, rows):
+    from diamond.flat import FlatMlp
+    rng = np.random.default_rng(H + rows)
+    p = rand_params(rng, O.DISCRETE_PARAM_NAMES, D, H, A, False)
+    fm = FlatMlp(D, H, A, False)
+    flat = fm.pack(p, device="cuda")
+    obs = rng.standard_normal((rows, D)).astype(np.float32)
+    ref_out, ref_v = O.mlp_forward(p, torch.as_tensor(obs), False)
+    ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, rows, False) // 4 + 512, device="cuda")
+    res = {}
+    for tc in (1, 0):
+        ctx.set_option("tensor_cores", tc)
+        out = torch.empty(rows, A, device="cuda"); val = torch.empty(rows, device="cuda")
+        ctx.mlp_forward(fm.desc, flat, dev(obs), rows, 3, out, val, ws)
+        torch.cuda.synchronize()
+        res[tc] = (out.cpu().numpy(), val.cpu().numpy())
+    ctx.set_option("tensor_cores", 1)
+    for tc in (1, 0):
+        assert nerr(res[tc][0], ref_out.numpy()) <= 1e-5, tc
+        assert nerr(res[tc][1], ref_v.numpy()) <= 1e-5, tc
+    assert nerr(res[1][0], res[0][0]) <= 1e-5
+    assert nerr(res[1][1], res[0][1]) <= 1e-5
+
+
+def test_tensor_core_training_step_matches_fp32_path(ctx):
+    from diamond import _native as N
+    from diamond.flat import FlatMlp
+    D, H, A, B, M = 64, 256, 4, 8192, 4096
+    rng = np.random.default_rng(11)
+    p = rand_params(rng, O.DISCRETE_PARAM_NAMES, D, H, A, False)
+    fm = FlatMlp(D, H, A, False)
+    flat = fm.pack(p, device="cuda")
+    obs = dev(rng.standard_normal((B, D)).astype(np.float32)); act = dev(rng.integers(0, A, B), torch.int32)
+    old_lp = dev((rng.standard_normal(B) * 0.3 - 1.0).astype(np.float32))
+    adv = dev(rng.standard_normal(B).astype(np.float32)); ret = dev(rng.standard_normal(B).astype(np.float32))
+    idx = dev(rng.permutation(B)[:M].astype(np.int32), torch.int32)
+    hyper, cfg = make_hyper(N, M)
+    ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, M, True) // 4 + 512, device="cuda")
+    out = {}
+    for tc in (1, 0):
+        ctx.set_option("tensor_cores", tc)
+        grads = torch.zeros(fm.total, device="cuda"); losses = torch.zeros(4, device="cuda")
+        ctx.mlp_grad_minibatch(fm.desc, flat, grads, obs, act, old_lp, adv, ret, None, idx, M, hyper, losses, ws)
+        torch.cuda.synchronize()
+        out[tc] = (grads.cpu().numpy(), losses.cpu().numpy())
+    ctx.set_option("tensor_cores", 1)
+    np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-5, atol=1e-7)
+    gv1, gv0 = fm.views(torch.as_tensor(out[1][0])), fm.views(torch.as_tensor(out[0][0]))
+    for n in O.DISCRETE_PARAM_NAMES:
+        assert nerr(gv1[n].numpy(), gv0[n].numpy()) <= 2e-5, n
