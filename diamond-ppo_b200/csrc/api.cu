@@ -44,7 +44,7 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->err[0] = 0;
-    c->use_tensor_cores = 1;
+    c->use_tensor_cores = 2;
     c->gae_variant = 0;
     c->tm_cache = nullptr;
     c->tm_cache_free = nullptr;
@@ -62,7 +62,7 @@ extern "C" int dppo_destroy(dppo_ctx* ctx)
 extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
 {
     if (!ctx || !name) return 1;
-    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value != 0; return 0; }
+    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value < 0 ? 0 : value > 2 ? 2 : value; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
     DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
@@ -116,9 +116,10 @@ WImages carve_images(const dppo_mlp_desc* d, char* base)
 }
 
 struct TrainWs {
-    float *h1, *h2, *h3, *d3, *d2, *d1;
+    float *h1, *h2, *h3, *d3, *d2, *d1, *xg;
     float *p3, *p2, *p1, *c2, *c1, *hp;
     int s3, s2, s1, tiles2, tiles1, head_blocks, head_stride;
+    int t3, t2, t1;          // split counts of the tcgen05 weight-gradient kernels (0: shape unsupported)
     int64_t img_off;
     int64_t bytes;
 };
@@ -133,16 +134,22 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     auto take = [&](int64_t floats) { float* p = reinterpret_cast<float*>(base + o); o += align_up(floats * 4, 256); return p; };
     w.h1 = take(M * H); w.h2 = take(M * H); w.h3 = take(M * 2 * H);
     w.d3 = take(M * 2 * H); w.d2 = take(M * H); w.d1 = take(M * H);
+    w.xg = take(M * D);
     w.s3 = dppo_wgrad_splits(&fake, M, (int)(2 * H), (int)H);
     w.s2 = dppo_wgrad_splits(&fake, M, (int)H, (int)H);
     w.s1 = dppo_wgrad_splits(&fake, M, (int)H, (int)D);
-    w.p3 = take((int64_t)w.s3 * 2 * H * H);
-    w.p2 = take((int64_t)w.s2 * H * H);
-    w.p1 = take((int64_t)w.s1 * H * D);
+    w.t3 = dppo_tc2_wgrad_supported(M, (int)(2 * H), (int)H) ? dppo_tc2_wgrad_splits(&fake, M, (int)(2 * H), (int)H) : 0;
+    w.t2 = dppo_tc2_wgrad_supported(M, (int)H, (int)H) ? dppo_tc2_wgrad_splits(&fake, M, (int)H, (int)H) : 0;
+    w.t1 = dppo_tc2_wgrad_supported(M, (int)H, (int)D) ? dppo_tc2_wgrad_splits(&fake, M, (int)H, (int)D) : 0;
+    auto mx = [](int a, int b) { return a > b ? a : b; };
+    w.p3 = take((int64_t)mx(w.s3, w.t3) * 2 * H * H);
+    w.p2 = take((int64_t)mx(w.s2, w.t2) * H * H);
+    w.p1 = take((int64_t)mx(w.s1, w.t1) * H * D);
     w.tiles2 = dppo_gemm_row_tiles(M, (int)H);
     w.tiles1 = dppo_gemm_row_tiles(M, (int)H);
-    w.c2 = take((int64_t)w.tiles2 * H);
-    w.c1 = take((int64_t)w.tiles1 * H);
+    const int cparts = mx(dppo_tc2_colsum_parts(M), w.tiles2);
+    w.c2 = take((int64_t)cparts * H);
+    w.c1 = take((int64_t)cparts * H);
     w.head_blocks = head_train_blocks(&fake, M);
     w.head_stride = (int)align_up(head_partial_floats((int)H, (int)A), 4);
     w.hp = take((int64_t)w.head_blocks * w.head_stride);
@@ -210,6 +217,7 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
     const int64_t first = rows < chunk ? rows : chunk;
     const bool tc1 = tc_on && dppo_tc_supported(first, H, D), tc2 = tc_on && dppo_tc_supported(first, H, H),
                tc3 = tc_on && dppo_tc_supported(first, n3, H);
+    const bool v2 = ctx->use_tensor_cores >= 2;
     if (tc1 && dppo_tc_prep_weights(ctx, params + L.w1, H, D, 0, img.w1f, st)) return 1;
     if (tc2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 0, img.w2f, st)) return 1;
     if (tc3 && dppo_tc_prep_weights(ctx, params + L.w3 + w3off, n3, H, 0, img.w3f, st)) return 1;
@@ -217,14 +225,20 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
         const int64_t n = rows - r0 < chunk ? rows - r0 : chunk;
         const float* x = idx ? obs : obs + r0 * D;
         const int32_t* rowsel = idx ? idx + r0 : nullptr;
-        if (tc1 && dppo_tc_supported(n, H, D)) {
+        if (tc1 && v2 && !rowsel && dppo_tc2_gemm_supported(n, H, D)) {
+            if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
+        } else if (tc1 && dppo_tc_supported(n, H, D)) {
             if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
-        if (tc2 && dppo_tc_supported(n, H, H)) {
+        if (tc2 && v2 && dppo_tc2_gemm_supported(n, H, H)) {
+            if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
+        } else if (tc2 && dppo_tc_supported(n, H, H)) {
             if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
         // first head layers: both (one [2H,H] product) or only the requested half
-        if (tc3 && dppo_tc_supported(n, n3, H)) {
+        if (tc3 && v2 && dppo_tc2_gemm_supported(n, n3, H)) {
+            if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
+        } else if (tc3 && dppo_tc_supported(n, n3, H)) {
             if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
         const float* ha = actor ? h3 : nullptr;
@@ -266,14 +280,32 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     if (tcb3 && dppo_tc_prep_weights(ctx, params + L.w3, 2 * H, H, 1, img.w3b, st)) return 1;
     if (tcb2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 1, img.w2b, st)) return 1;
 
+    const bool v2 = ctx->use_tensor_cores >= 2;
+    const bool g1 = tc1 && v2 && dppo_tc2_gemm_supported(M, H, D), g2 = tc2 && v2 && dppo_tc2_gemm_supported(M, H, H),
+               g3 = tc3 && v2 && dppo_tc2_gemm_supported(M, 2 * H, H), gb3 = tcb3 && v2 && dppo_tc2_gemm_supported(M, H, 2 * H), gb2 = g2;
+    const bool wg3 = tc_on && v2 && w.t3 > 0, wg2 = tc_on && v2 && w.t2 > 0, wg1 = tc_on && v2 && w.t1 > 0;
+    // the TMA-fed kernels read contiguous rows: gather the minibatch observations once (ppo.py:261 observations[mb])
+    const float* x1 = obs;
+    const int32_t* x1_idx = idx;
+    if (idx && (g1 || wg1)) {
+        if (dppo_gather_rows_f32(ctx, obs, idx, w.xg, M, D, stream)) return 1;
+        x1 = w.xg; x1_idx = nullptr;
+    }
+
     // forward (ppo.py:261), activations kept for the backward pass
-    if (tc1) {
-        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, obs, D, idx, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
-    } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, obs, D, idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
-    if (tc2) {
+    if (g1) {
+        if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
+    } else if (tc1) {
+        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
+    } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
+    if (g2) {
+        if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
+    } else if (tc2) {
         if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
-    if (tc3) {
+    if (g3) {
+        if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
+    } else if (tc3) {
         if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
 
@@ -294,18 +326,31 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
 
     // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused
     int tiles2 = w.tiles2, tiles1 = w.tiles1;
-    if (tcb3) {
+    if (gb3) {
+        tiles2 = dppo_tc2_colsum_parts(M);
+        if (dppo_tc2_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+    } else if (tcb3) {
         tiles2 = (int)((M + 127) / 128);
         if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, nullptr, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
-    if (tcb2) {
+    if (gb2) {
+        tiles1 = dppo_tc2_colsum_parts(M);
+        if (dppo_tc2_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+    } else if (tcb2) {
         tiles1 = (int)((M + 127) / 128);
         if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, nullptr, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     // weight gradients: deterministic split-K partials
-    if (dppo_wgrad(ctx, w.d3, 2 * H, w.h2, H, nullptr, w.p3, w.s3, M, 2 * H, H, st)) return 1;
-    if (dppo_wgrad(ctx, w.d2, H, w.h1, H, nullptr, w.p2, w.s2, M, H, H, st)) return 1;
-    if (dppo_wgrad(ctx, w.d1, H, obs, D, idx, w.p1, w.s1, M, H, D, st)) return 1;
+    const int n3p = wg3 ? w.t3 : w.s3, n2p = wg2 ? w.t2 : w.s2, n1p = wg1 ? w.t1 : w.s1;
+    if (wg3) {
+        if (dppo_tc2_wgrad(ctx, w.d3, 2 * H, w.h2, H, w.p3, w.t3, M, 2 * H, H, st)) return 1;
+    } else if (dppo_wgrad(ctx, w.d3, 2 * H, w.h2, H, nullptr, w.p3, w.s3, M, 2 * H, H, st)) return 1;
+    if (wg2) {
+        if (dppo_tc2_wgrad(ctx, w.d2, H, w.h1, H, w.p2, w.t2, M, H, H, st)) return 1;
+    } else if (dppo_wgrad(ctx, w.d2, H, w.h1, H, nullptr, w.p2, w.s2, M, H, H, st)) return 1;
+    if (wg1) {
+        if (dppo_tc2_wgrad(ctx, w.d1, H, x1, D, w.p1, w.t1, M, H, D, st)) return 1;
+    } else if (dppo_wgrad(ctx, w.d1, H, x1, D, x1_idx, w.p1, w.s1, M, H, D, st)) return 1;
 
     // assemble the flat gradient
     GradSegTable tab;
@@ -314,11 +359,11 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
         tab.seg[n].dst = dst; tab.seg[n].count = count; tab.seg[n].src = src; tab.seg[n].stride = stride;
         tab.seg[n].nparts = nparts; tab.seg[n].pad = 0; ++n;
     };
-    seg(L.w1, (int64_t)H * D, w.p1, (int64_t)H * D, w.s1);
+    seg(L.w1, (int64_t)H * D, w.p1, (int64_t)H * D, n1p);
     seg(L.b1, H, w.c1, H, tiles1);
-    seg(L.w2, (int64_t)H * H, w.p2, (int64_t)H * H, w.s2);
+    seg(L.w2, (int64_t)H * H, w.p2, (int64_t)H * H, n2p);
     seg(L.b2, H, w.c2, H, tiles2);
-    seg(L.w3, (int64_t)2 * H * H, w.p3, (int64_t)2 * H * H, w.s3);
+    seg(L.w3, (int64_t)2 * H * H, w.p3, (int64_t)2 * H * H, n3p);
     const int off_dba = A * H, off_dwc = A * H + A, off_dbc = off_dwc + H, off_dls = off_dbc + 1, off_b3 = off_dls + A,
               off_loss = off_b3 + 2 * H;
     seg(L.b3, 2 * H, w.hp + off_b3, w.head_stride, w.head_blocks);
@@ -330,4 +375,52 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     tab.nseg = n;
     return launch_grad_reduce(ctx, tab, grads, L.total, w.hp + off_loss, w.head_blocks, w.head_stride, hy->value_loss_weight,
                               hy->entropy_beta, inv_m, losses, st);
+}
+
+// ---- tensor-core building blocks exposed for unit tests and A/B measurements ----------------------
+extern "C" int64_t dppo_tc_linear_workspace_bytes(int N, int K) { return dppo_tc_image_bytes(N, K) + 1024; }
+
+extern "C" int dppo_tc_colsum_parts(int64_t M, int variant) { return variant >= 2 ? dppo_tc2_colsum_parts(M) : (int)((M + 127) / 128); }
+
+extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
+                                  const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
+                                  int variant, void* stream)
+{
+    if (!ctx) return 1;
+    if (!A || !W || !C || !ws) DPPO_FAIL(ctx, "tc_linear: null argument");
+    if (epi == DPPO_EPI_BIAS_TANH && !bias) DPPO_FAIL(ctx, "tc_linear: bias is null");
+    if (epi == DPPO_EPI_TANH_BWD && !Hact) DPPO_FAIL(ctx, "tc_linear: Hact is null");
+    unsigned char* img = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+    if ((img - (unsigned char*)ws) + dppo_tc_image_bytes(N, K) > ws_bytes) DPPO_FAIL(ctx, "tc_linear: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows_w = transpose ? K : N, cols_w = transpose ? N : K;
+    if (variant >= 2 ? !dppo_tc2_gemm_supported(M, N, K) : !dppo_tc_supported(M, N, K))
+        DPPO_FAIL(ctx, "tc_linear: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+    if (dppo_tc_prep_weights(ctx, W, rows_w, cols_w, transpose, img, st)) return 1;
+    if (variant >= 2) return dppo_tc2_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
+    return dppo_tc_gemm(ctx, epi, A, K, nullptr, img, bias, Hact, N, C, N, colsum, M, N, K, st);
+}
+
+extern "C" int64_t dppo_tc_wgrad_workspace_bytes(dppo_ctx* ctx, int64_t M, int N1, int N2)
+{
+    if (!ctx || !dppo_tc2_wgrad_supported(M, N1, N2)) return 0;
+    return (int64_t)dppo_tc2_wgrad_splits(ctx, M, N1, N2) * N1 * N2 * 4 + 256;
+}
+
+extern "C" int dppo_tc_wgrad_f32(dppo_ctx* ctx, const float* Dm, const float* Hm, int64_t M, int N1, int N2, float* dW, void* ws,
+                                 int64_t ws_bytes, void* stream)
+{
+    if (!ctx) return 1;
+    if (!Dm || !Hm || !dW || !ws) DPPO_FAIL(ctx, "tc_wgrad: null argument");
+    if (!dppo_tc2_wgrad_supported(M, N1, N2)) DPPO_FAIL(ctx, "tc_wgrad: unsupported shape M=%lld N1=%d N2=%d", (long long)M, N1, N2);
+    float* parts = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    const int splits = dppo_tc2_wgrad_splits(ctx, M, N1, N2);
+    if (((char*)parts - (char*)ws) + (int64_t)splits * N1 * N2 * 4 > ws_bytes) DPPO_FAIL(ctx, "tc_wgrad: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dppo_tc2_wgrad(ctx, Dm, N1, Hm, N2, parts, splits, M, N1, N2, st)) return 1;
+    GradSegTable tab;
+    tab.seg[0].dst = 0; tab.seg[0].count = (int64_t)N1 * N2; tab.seg[0].src = parts; tab.seg[0].stride = (int64_t)N1 * N2;
+    tab.seg[0].nparts = splits; tab.seg[0].pad = 0;
+    tab.nseg = 1;
+    return launch_grad_reduce(ctx, tab, dW, (int64_t)N1 * N2, nullptr, 0, 0, 0.f, 0.f, 0.f, nullptr, st);
 }

@@ -8,3 +8,14 @@ int64_t dppo_tc_image_bytes(int N, int K);        // bytes of the hi/lo weight i
 int dppo_tc_prep_weights(dppo_ctx* ctx, const float* W, int rows_w, int cols_w, int transpose, unsigned char* img, cudaStream_t st);
 int dppo_tc_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const int32_t* a_rows, const unsigned char* Wimg, const float* bias,
                  const float* Hact, int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);
+
+// Warp-specialised persistent variants (gemm_tc2.cu): TMA-fed operand ring, dedicated split / MMA / epilogue warps.
+bool dppo_tc2_gemm_supported(int64_t M, int N, int K);
+int dppo_tc2_colsum_parts(int64_t M);            // colsum partial rows written by the TANH_BWD epilogue (4 per 128-row tile)
+int dppo_tc2_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact,
+                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);
+// dW[N1,N2] = sum_m D[m,N1] * H[m,N2] as `splits` deterministic row-range partials [splits][N1][N2]
+bool dppo_tc2_wgrad_supported(int64_t M, int N1, int N2);
+int dppo_tc2_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2);
+int dppo_tc2_wgrad(dppo_ctx* ctx, const float* Dm, int ldd, const float* Hm, int ldh, float* partials, int splits, int64_t M, int N1,
+                   int N2, cudaStream_t st);

@@ -77,8 +77,9 @@ const char* dppo_last_error(dppo_ctx* ctx);          /* ctx may be NULL: last cr
 int dppo_version(void);
 int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
 /* Kernel-variant switches used by tests and bench.py for A/B measurements:
- *   "tensor_cores" 1 (default): 3xTF32 tcgen05 GEMMs where the shape allows (rows >= 1024, K % 16 == 0,
- *                  N % 256 == 0 or N == 128), 0: FP32 FFMA GEMMs everywhere
+ *   "tensor_cores" 2 (default): warp-specialised persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where the
+ *                  shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 1: first-generation tcgen05
+ *                  GEMMs (forward/dgrad only), 0: FP32 FFMA GEMMs everywhere
  *   "gae_variant"  0 (default): TMA-staged GAE kernel when the layout allows, 1: register-staged, 2: TMA */
 int dppo_set_option(dppo_ctx* ctx, const char* name, int value);
 
@@ -169,6 +170,24 @@ int dppo_ppo_loss_gaussian(dppo_ctx* ctx, const float* mean, const float* log_st
                            int64_t M, int A, const dppo_hyper* hyper, float* losses, float* dmean, float* dlog_std,
                            float* dvalues, void* ws, int64_t ws_bytes, void* stream);
 int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
+
+/* ---- tensor-core building blocks of the fused update (unit tests, A/B measurements) ---------- */
+/* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate).
+ * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).
+ * epi 1: C = tanh(A W^T + bias); epi 2: C = (A W) * (1 - Hact^2) with Hact [M,N], and, if colsum != NULL,
+ * per-row-block column sums of C in colsum [dppo_tc_colsum_parts(M, variant), N] (bias-gradient partials).
+ * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed).
+ * ws (dppo_tc_linear_workspace_bytes) holds the split weight images. */
+int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
+                       const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
+                       int variant, void* stream);
+int64_t dppo_tc_linear_workspace_bytes(int N, int K);
+int dppo_tc_colsum_parts(int64_t M, int variant);
+/* dW[N1,N2] = sum_m D[m,N1] * H[m,N2]  (weight gradient of a Linear layer, ppo.py:283): split over row
+ * ranges on tcgen05, partials summed in a fixed order (bit-reproducible). */
+int dppo_tc_wgrad_f32(dppo_ctx* ctx, const float* D, const float* H, int64_t M, int N1, int N2, float* dW, void* ws,
+                      int64_t ws_bytes, void* stream);
+int64_t dppo_tc_wgrad_workspace_bytes(dppo_ctx* ctx, int64_t M, int N1, int N2);
 
 /* ---- measurement helper ---------------------------------------------------------------- */
 /* Runs a register-resident FFMA loop on every SM (iters FMAs per thread, 16 independent chains;

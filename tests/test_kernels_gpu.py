@@ -353,18 +353,19 @@ def test_tensor_core_forward_matches_fp32_path_and_oracle(ctx, D, H, A, rows):
     ref_out, ref_v = O.mlp_forward(p, torch.as_tensor(obs), False)
     ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, rows, False) // 4 + 512, device="cuda")
     res = {}
-    for tc in (1, 0):
+    for tc in (2, 1, 0):
         ctx.set_option("tensor_cores", tc)
         out = torch.empty(rows, A, device="cuda"); val = torch.empty(rows, device="cuda")
         ctx.mlp_forward(fm.desc, flat, dev(obs), rows, 3, out, val, ws)
         torch.cuda.synchronize()
         res[tc] = (out.cpu().numpy(), val.cpu().numpy())
-    ctx.set_option("tensor_cores", 1)
-    for tc in (1, 0):
+    ctx.set_option("tensor_cores", 2)
+    for tc in (2, 1, 0):
         assert nerr(res[tc][0], ref_out.numpy()) <= 1e-5, tc
         assert nerr(res[tc][1], ref_v.numpy()) <= 1e-5, tc
-    assert nerr(res[1][0], res[0][0]) <= 1e-5
-    assert nerr(res[1][1], res[0][1]) <= 1e-5
+    for tc in (2, 1):
+        assert nerr(res[tc][0], res[0][0]) <= 1e-5
+        assert nerr(res[tc][1], res[0][1]) <= 1e-5
 
 
 def test_tensor_core_training_step_matches_fp32_path(ctx):
@@ -382,14 +383,60 @@ def test_tensor_core_training_step_matches_fp32_path(ctx):
     hyper, cfg = make_hyper(N, M)
     ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, M, True) // 4 + 512, device="cuda")
     out = {}
-    for tc in (1, 0):
+    for tc in (2, 1, 0):
         ctx.set_option("tensor_cores", tc)
         grads = torch.zeros(fm.total, device="cuda"); losses = torch.zeros(4, device="cuda")
         ctx.mlp_grad_minibatch(fm.desc, flat, grads, obs, act, old_lp, adv, ret, None, idx, M, hyper, losses, ws)
         torch.cuda.synchronize()
         out[tc] = (grads.cpu().numpy(), losses.cpu().numpy())
-    ctx.set_option("tensor_cores", 1)
-    np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-5, atol=1e-7)
-    gv1, gv0 = fm.views(torch.as_tensor(out[1][0])), fm.views(torch.as_tensor(out[0][0]))
-    for n in O.DISCRETE_PARAM_NAMES:
-        assert nerr(gv1[n].numpy(), gv0[n].numpy()) <= 2e-5, n
+    ctx.set_option("tensor_cores", 2)
+    gv0 = fm.views(torch.as_tensor(out[0][0]))
+    for tc in (2, 1):
+        np.testing.assert_allclose(out[tc][1], out[0][1], rtol=1e-5, atol=1e-7)
+        gv = fm.views(torch.as_tensor(out[tc][0]))
+        for n in O.DISCRETE_PARAM_NAMES:
+            assert nerr(gv[n].numpy(), gv0[n].numpy()) <= 2e-5, (tc, n)
+
+
+# fp32 parity needs ~1e-6; single-pass TF32 would sit near 5e-4 on these products
+TC_TOL = 3e-5
+
+
+@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 64), (4096, 256, 256), (4096, 512, 256), (5000, 256, 512), (1024, 128, 64),
+                                   (65536, 256, 256)])
+def test_tc_linear_forward_vs_fp64(ctx, variant, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    C, _ = ctx.tc_linear(1, A, W, False, bias=b, variant=variant)
+    ref = torch.tanh(A.double() @ W.double().T + b.double())
+    assert (C.double() - ref).abs().max().item() <= TC_TOL
+
+
+@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 512), (4096, 256, 256), (5000, 256, 256), (65536, 256, 512)])
+def test_tc_linear_dgrad_vs_fp64(ctx, variant, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(K, N, device="cuda", generator=g) / K ** 0.5
+    Hact = torch.tanh(torch.randn(M, N, device="cuda", generator=g))
+    C, cs = ctx.tc_linear(2, A, W, True, Hact=Hact, colsum=True, variant=variant)
+    ref = (A.double() @ W.double()) * (1.0 - Hact.double() ** 2)
+    assert (C.double() - ref).abs().max().item() <= TC_TOL * max(1.0, ref.abs().max().item())
+    col = ref.sum(0)
+    assert (cs.double().sum(0) - col).abs().max().item() <= 3e-5 * max(1.0, col.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N1,N2", [(4096, 256, 256), (4096, 512, 256), (4096, 256, 64), (5000, 256, 256), (65536, 512, 256),
+                                     (65536, 256, 64), (4100, 128, 128)])
+def test_tc_wgrad_vs_fp64(ctx, M, N1, N2):
+    g = torch.Generator(device="cuda").manual_seed(M + N1 + N2)
+    Dm = torch.randn(M, N1, device="cuda", generator=g)
+    Hm = torch.randn(M, N2, device="cuda", generator=g)
+    dW = ctx.tc_wgrad(Dm, Hm)
+    ref = Dm.double().T @ Hm.double()
+    assert ((dW.double() - ref).abs().max() / ref.abs().max()).item() <= TC_TOL
+    # bit-reproducible (fixed summation order)
+    assert torch.equal(dW, ctx.tc_wgrad(Dm, Hm))
