@@ -44,8 +44,9 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->err[0] = 0;
-    c->use_tensor_cores = 2;
+    c->use_tensor_cores = 3;
     c->gae_variant = 0;
+    c->tc_debug = 0;
     c->tm_cache = nullptr;
     c->tm_cache_free = nullptr;
     *out = c;
@@ -62,8 +63,9 @@ extern "C" int dppo_destroy(dppo_ctx* ctx)
 extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
 {
     if (!ctx || !name) return 1;
-    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value < 0 ? 0 : value > 2 ? 2 : value; return 0; }
+    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value < 0 ? 0 : value > 3 ? 3 : value; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
+    if (!strcmp(name, "tc_debug")) { ctx->tc_debug = value; return 0; }
     DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
 
@@ -93,6 +95,15 @@ extern "C" int dppo_mlp_layout_compute(const dppo_mlp_desc* d, dppo_mlp_layout* 
 }
 
 namespace {
+
+// persistent tcgen05 GEMM: CTA pairs (level 3) or single CTAs (level 2)
+int tc_gemm_v23(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact, int ldh,
+                float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st)
+{
+    if (ctx->use_tensor_cores >= 3 && dppo_tc3_gemm_supported(M, N, K))
+        return dppo_tc3_gemm(ctx, epi, A, lda, Wimg, bias, Hact, ldh, C, ldc, colsum, M, N, K, st);
+    return dppo_tc2_gemm(ctx, epi, A, lda, Wimg, bias, Hact, ldh, C, ldc, colsum, M, N, K, st);
+}
 
 struct WImages {
     unsigned char *w1f, *w2f, *w3f, *w3b, *w2b;
@@ -226,18 +237,18 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
         const float* x = idx ? obs : obs + r0 * D;
         const int32_t* rowsel = idx ? idx + r0 : nullptr;
         if (tc1 && v2 && !rowsel && dppo_tc2_gemm_supported(n, H, D)) {
-            if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
+            if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
         } else if (tc1 && dppo_tc_supported(n, H, D)) {
             if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
         if (tc2 && v2 && dppo_tc2_gemm_supported(n, H, H)) {
-            if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
+            if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
         } else if (tc2 && dppo_tc_supported(n, H, H)) {
             if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
         // first head layers: both (one [2H,H] product) or only the requested half
         if (tc3 && v2 && dppo_tc2_gemm_supported(n, n3, H)) {
-            if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
+            if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
         } else if (tc3 && dppo_tc_supported(n, n3, H)) {
             if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
@@ -294,17 +305,17 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
 
     // forward (ppo.py:261), activations kept for the backward pass
     if (g1) {
-        if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
+        if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
     } else if (tc1) {
         if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
     if (g2) {
-        if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
+        if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
     } else if (tc2) {
         if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
     if (g3) {
-        if (dppo_tc2_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
+        if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
     } else if (tc3) {
         if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
@@ -328,14 +339,14 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     int tiles2 = w.tiles2, tiles1 = w.tiles1;
     if (gb3) {
         tiles2 = dppo_tc2_colsum_parts(M);
-        if (dppo_tc2_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+        if (tc_gemm_v23(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     } else if (tcb3) {
         tiles2 = (int)((M + 127) / 128);
         if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, nullptr, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     if (gb2) {
         tiles1 = dppo_tc2_colsum_parts(M);
-        if (dppo_tc2_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+        if (tc_gemm_v23(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     } else if (tcb2) {
         tiles1 = (int)((M + 127) / 128);
         if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, nullptr, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
@@ -397,6 +408,7 @@ extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_
     if (variant >= 2 ? !dppo_tc2_gemm_supported(M, N, K) : !dppo_tc_supported(M, N, K))
         DPPO_FAIL(ctx, "tc_linear: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
     if (dppo_tc_prep_weights(ctx, W, rows_w, cols_w, transpose, img, st)) return 1;
+    if (variant >= 3) return dppo_tc3_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
     if (variant >= 2) return dppo_tc2_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
     return dppo_tc_gemm(ctx, epi, A, K, nullptr, img, bias, Hact, N, C, N, colsum, M, N, K, st);
 }

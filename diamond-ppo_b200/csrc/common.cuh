@@ -14,6 +14,7 @@ struct dppo_ctx {
     char err[512];
     int use_tensor_cores;                 // 1: 3xTF32 tcgen05 GEMMs where the shape allows (default); 0: FP32 FFMA GEMMs only
     int gae_variant;                      // 0: auto, 1: register-staged kernel, 2: TMA-staged kernel
+    int tc_debug;                         // bit mask of experiment switches of the tc2 kernels (wrong results; timing only)
     void* tm_cache;                       // tensor-map cache owned by gae.cu
     void (*tm_cache_free)(void*);
 };

@@ -19,3 +19,8 @@ bool dppo_tc2_wgrad_supported(int64_t M, int N1, int N2);
 int dppo_tc2_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2);
 int dppo_tc2_wgrad(dppo_ctx* ctx, const float* Dm, int ldd, const float* Hm, int ldh, float* partials, int splits, int64_t M, int N1,
                    int N2, cudaStream_t st);
+
+// CTA-pair (cta_group::2) variant of the forward / dgrad GEMM (gemm_tc3.cu); same contract as dppo_tc2_gemm
+bool dppo_tc3_gemm_supported(int64_t M, int N, int K);
+int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact,
+                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);

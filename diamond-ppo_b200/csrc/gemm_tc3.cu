@@ -1,0 +1,293 @@
+// CTA-pair (tcgen05 cta_group::2) 3xTF32 GEMM of the wide actor-critic MLP (diamond/ppo.py:261 forward, :283 dgrad):
+//   C[M,N] = epi(A[M,K] * B^T)     A: fp32 activations, B: pre-split weight images (prep_weights_kernel, gemm_tc.cu)
+//
+// Why pairs: measured on B200, a shared-memory-operand tcgen05.mma of one CTA (M=128, N=256, K=8 tf32) is paced by the
+// tensor core's 64 B/clk operand port -- it fetches 4 KB of A and 8 KB of B per instruction, 192 clk instead of the 128 clk
+// the math needs -- and 148 CTAs each streaming full weight chunks ask the L2 for more than it delivers.  With
+// cta_group::2 the two SMs of a TPC compute one 256 x 256 tile together: each SM feeds its own 128 rows of A and HALF of the
+// weight rows (8 KB per instruction per SM = the port rate), keeps 128 x 256 of the accumulator in its own TMEM, and loads
+// half of the weight bytes.  A ring stage shrinks to 32 KB, so six stages fit beside the epilogue staging.
+//
+// One cluster = 2 CTAs x 448 threads (same roles in both CTAs; see gemm_tc2.cu for the 1-CTA variant):
+//   warp 0      producer : TMA for this CTA's 128 activation rows + bulk copies of its half of the weight chunk
+//   warp 1      MMA      : leader CTA only -- issues tcgen05.mma.cta_group::2, commits (multicast) to both CTAs' barriers
+//   warps 2-5   split    : hi/lo split of this CTA's activation chunk, then one arrival per warp on the LEADER's barrier
+//   warps 6-13  epilogue : tcgen05.ld of this CTA's 128 x 256 accumulator half, layer epilogue, staged TMA store
+// Accumulators are double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+#include "gemm_tc.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int THREADS = 448;
+constexpr int W_PROD = 0, W_MMA = 1, W_SPLIT0 = 2, N_SPLIT = 4, W_EPI0 = 6, N_EPI = 8;
+constexpr int SPLIT_THREADS = N_SPLIT * 32;
+constexpr int KC = 16;                     // k per chunk (one SWIZZLE_64B atom width)
+constexpr int BM = 128;                    // rows per CTA (the pair computes 256)
+constexpr int A_IMG = BM * KC * 4;         // 8 KB: one image (hi or lo) of this CTA's activation chunk
+constexpr int STAGES = 6;
+constexpr int STG_BLK = 32 * 128;          // one 32-row x 32-column fp32 staging block (SWIZZLE_128B layout)
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, const unsigned char* __restrict__ Wimg,
+                const float* __restrict__ bias, const float* __restrict__ Hact, int ldh, float* __restrict__ colsum, int64_t M,
+                int N, int K, int n_tile, int pair_tiles, int dbg)
+{
+    extern __shared__ unsigned char dyn_raw[];
+    __shared__ __align__(8) uint64_t full[STAGES], ready[STAGES], empty[STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t s_tmem;
+
+    unsigned char* dyn = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int half_n = n_tile / 2;                       // weight rows held by each CTA
+    const int b_half = half_n * KC * 4;                  // bytes of one image (hi or lo) of this CTA's weight rows
+    const int b_img = n_tile * KC * 4;                   // bytes of one full image in the weight-image buffer
+    const int stage_bytes = 2 * A_IMG + 2 * b_half;      // [A_hi | A_lo | B_hi(half) | B_lo(half)]
+    const int n_tiles = N / n_tile;
+    const int total = pair_tiles * n_tiles;
+    const int chunks = K / KC;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 2 * N_SPLIT); mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * N_EPI); }
+        fence_mbar_init();
+    }
+    if (warp == W_MMA) tmem_alloc2(&s_tmem, 512);
+    fence_before();
+    cluster_sync();                                      // barriers of both CTAs initialised before any remote arrival
+    fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp == W_PROD) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = cluster_id; tile < total; tile += n_clusters) {
+                const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+                const int m0 = m_pair * 2 * BM + (int)rank * BM;
+                const unsigned char* wsrc = Wimg + (int64_t)n_blk * chunks * 2 * b_img + (int64_t)rank * b_half;
+                const int next = tile + n_clusters;
+                const int next_m = next < total ? next / n_tiles : -1;
+                for (int c = 0; c < chunks; ++c) {
+                    // pull the next tile's activations into L2 while this tile computes
+                    if (next_m >= 0 && next_m != m_pair) tma_prefetch_2d(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM);
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const bool skip_b = (dbg & 1) && (tile != cluster_id || c >= STAGES);
+                    mbar_expect_tx(&full[s], (uint32_t)(A_IMG + (skip_b ? 0 : 2 * b_half)));
+                    unsigned char* st = dyn + s * stage_bytes;
+                    tma_load_2d(st, &tmA, c * KC, m0, &full[s]);
+                    if (!skip_b) {
+                        const unsigned char* w = wsrc + (int64_t)c * 2 * b_img;
+                        bulk_copy_g2s(st + 2 * A_IMG, w, (uint32_t)b_half, &full[s]);                    // hi rows of this half
+                        bulk_copy_g2s(st + 2 * A_IMG + b_half, w + b_img, (uint32_t)b_half, &full[s]);   // lo rows of this half
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == W_MMA) {
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = idesc_tf32(2 * BM, n_tile, 0, 0);
+            int s = 0;
+            uint32_t ph = 0, it = 0;
+            for (int tile = cluster_id; tile < total; tile += n_clusters, ++it) {
+                const uint32_t set = it & 1;
+                mbar_wait(&tempty[set], ((it >> 1) & 1) ^ 1);            // both CTAs' epilogues have drained this accumulator
+                fence_after();
+                const uint32_t d = tmem + set * 256;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(&ready[s], ph);                           // both CTAs: chunk landed and split
+                    fence_after();
+                    const uint32_t a_hi = smem_u32(dyn + s * stage_bytes), a_lo = a_hi + A_IMG;
+                    const uint32_t b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + (uint32_t)b_half;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint32_t ko = ks * 32;                    // 8 tf32 = 32 bytes along K inside the swizzle atom
+                        if (!(dbg & 4)) {
+                            umma_tf32_2cta(d, desc_k_sw64(a_hi + ko), desc_k_sw64(b_lo + ko), idesc, (c | ks) != 0);
+                            umma_tf32_2cta(d, desc_k_sw64(a_lo + ko), desc_k_sw64(b_hi + ko), idesc, 1u);
+                            umma_tf32_2cta(d, desc_k_sw64(a_hi + ko), desc_k_sw64(b_hi + ko), idesc, 1u);
+                        } else {
+                            umma_tf32_2cta(d, desc_k_sw64(a_hi + ko), desc_k_sw64(b_hi + ko), idesc, (c | ks) != 0);
+                        }
+                    }
+                    umma_commit_2cta(&empty[s], 3);                     // frees the stage in both CTAs
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_2cta(&tfull[set], 3);
+            }
+        }
+        __syncwarp();
+    } else if (warp < W_EPI0) {
+        // hi/lo split of this CTA's activation chunk; one arrival per warp on the leader's ready barrier
+        const int ct = tid - W_SPLIT0 * 32;
+        constexpr int PER = A_IMG / 16 / SPLIT_THREADS;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = cluster_id; tile < total; tile += n_clusters) {
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&full[s], ph);
+                const uint32_t hi = smem_u32(dyn + s * stage_bytes) + ct * 16;
+                float4 x[PER];
+#pragma unroll
+                for (int j = 0; j < PER; ++j) x[j] = lds128(hi + j * SPLIT_THREADS * 16);
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const float4 l = split_tf32x4(x[j]);
+                    sts128(hi + j * SPLIT_THREADS * 16, x[j]);
+                    sts128(hi + A_IMG + j * SPLIT_THREADS * 16, l);
+                }
+                fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&ready[s]), 0));
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // epilogue over this CTA's 128 rows: warp -> TMEM lane quadrant (warp % 4) and column half.  Results leave through a
+        // per-warp 32x32 staging block in the SWIZZLE_128B layout and a TMA store (full 128-byte row segments reach HBM).
+        const int ew = warp - W_EPI0;
+        const int q = warp & 3, grp = ew >> 2;
+        const int ncols = n_tile / 2;
+        const int col0 = grp * ncols;
+        const int nblk = ncols / 32;
+        const uint32_t stg = smem_u32(dyn + STAGES * stage_bytes) + (uint32_t)ew * STG_BLK;
+        const uint32_t row_off = (uint32_t)lane * 128, sw = (uint32_t)(lane & 7);
+        uint32_t it = 0;
+        if (lane == 0) tma_prefetch_desc(&tmC);
+        for (int tile = cluster_id; tile < total; tile += n_clusters, ++it) {
+            const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+            const int n0 = n_blk * n_tile + col0;
+            const int m0 = m_pair * 2 * BM + (int)rank * BM + q * 32;
+            const int64_t m = (int64_t)m0 + lane;
+            const uint32_t set = it & 1;
+            mbar_wait(&tfull[set], (it >> 1) & 1);
+            fence_after();
+            for (int k = 0; k < ((dbg & 8) ? 0 : nblk); ++k) {
+                const int n = n0 + k * 32;
+                uint32_t r[32];
+                tmem_ld32_issue(tmem + set * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + k * 32), r);
+                float4 aux[8];                                          // bias (forward) or the layer's activations (dgrad)
+                if (EPI == DPPO_EPI_BIAS_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) aux[j] = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        aux[j] = m < M ? __ldg(reinterpret_cast<const float4*>(Hact + m * (int64_t)ldh + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                tmem_ld32_wait(r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (EPI == DPPO_EPI_BIAS_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (dbg & 32) {
+                            v[4 * j] += aux[j].x; v[4 * j + 1] += aux[j].y; v[4 * j + 2] += aux[j].z; v[4 * j + 3] += aux[j].w;
+                        } else {
+                            v[4 * j] = tanhf(v[4 * j] + aux[j].x); v[4 * j + 1] = tanhf(v[4 * j + 1] + aux[j].y);
+                            v[4 * j + 2] = tanhf(v[4 * j + 2] + aux[j].z); v[4 * j + 3] = tanhf(v[4 * j + 3] + aux[j].w);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[4 * j] *= (1.0f - aux[j].x * aux[j].x); v[4 * j + 1] *= (1.0f - aux[j].y * aux[j].y);
+                        v[4 * j + 2] *= (1.0f - aux[j].z * aux[j].z); v[4 * j + 3] *= (1.0f - aux[j].w * aux[j].w);
+                    }
+                }
+                if (lane == 0) bulk_wait_read<0>();                     // the previous store has read the staging block
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sts128(stg + row_off + ((((uint32_t)j) ^ sw) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !(dbg & 16)) {
+                    tma_store_2d(&tmC, n, m0, stg);                     // rows >= M are clipped by the tensor map
+                    bulk_commit();
+                }
+                if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr) {
+                    // rows >= M hold exact zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
+                    // warp transpose-reduce: afterwards lane l holds the sum over the warp's 32 rows of column l
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const bool up = lane & o;
+                            const float send = up ? v[i] : v[i + o];
+                            const float keep = up ? v[i + o] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    colsum[((int64_t)m_pair * 8 + rank * 4 + q) * N + n + lane] = v[0];
+                }
+            }
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tempty[set]), 0));
+        }
+        if (lane == 0) bulk_wait<0>();             // staging memory must outlive the last store's read
+        __syncwarp();
+    }
+
+    // no CTA may exit (or free TMEM) while its peer can still touch its shared memory, barriers or TMEM
+    fence_before();
+    cluster_sync();
+    if (warp == W_MMA) {
+        fence_after();
+        tmem_dealloc2(tmem, 512);
+    }
+}
+
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+bool dppo_tc3_gemm_supported(int64_t M, int N, int K)
+{
+    return M >= 1024 && M < (int64_t)1 << 31 && K % KC == 0 && (N % 256 == 0 || N == 128);
+}
+
+int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact,
+                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st)
+{
+    if (!dppo_tc3_gemm_supported(M, N, K)) DPPO_FAIL(ctx, "tc3_gemm: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+    if (lda % 4 != 0 || ldc % 4 != 0 || !al16(A) || !al16(C) || !al16(Wimg) || (Hact && (!al16(Hact) || ldh % 4 != 0)) || (bias && !al16(bias)))
+        DPPO_FAIL(ctx, "tc3_gemm: operands must be 16-byte aligned with row pitches multiple of 4 floats");
+    CUtensorMap tmA, tmC;
+    if (!dppo_make_tensor_map_2d(&tmA, A, M, K, lda, KC, BM, 2) || !dppo_make_tensor_map_2d(&tmC, C, M, N, ldc, 32, 32, 3))
+        DPPO_FAIL(ctx, "tc3_gemm: cuTensorMapEncodeTiled failed");
+    const int n_tile = dppo_tc_n_tile(N);
+    const int pair_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
+    const int total = pair_tiles * (N / n_tile);
+    const size_t smem = (size_t)STAGES * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK + 1024;
+    int clusters = ctx->sm_count / 2;
+    if (clusters > total) clusters = total;
+    const int grid = 2 * clusters;
+    if (epi == DPPO_EPI_BIAS_TANH) {
+        cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc3_gemm_kernel<DPPO_EPI_BIAS_TANH><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,
+                                                                          ctx->tc_debug);
+    } else if (epi == DPPO_EPI_TANH_BWD) {
+        cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc3_gemm_kernel<DPPO_EPI_TANH_BWD><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,
+                                                                         ctx->tc_debug);
+    } else {
+        DPPO_FAIL(ctx, "tc3_gemm: unknown epilogue %d", epi);
+    }
+    DPPO_CHECK_LAUNCH(ctx, "tc3_gemm_kernel");
+    return 0;
+}

@@ -4,26 +4,69 @@
 
 namespace {
 
+// One thread per float4 of the flat gradient: sums the segment's partials in a fixed order (partial 0, 1, 2, ... into
+// eight interleaved accumulators, combined pairwise), eight independent 16-byte loads in flight per thread.  Every segment
+// starts and ends on a multiple of 4 floats (dppo_mlp_layout) and partial strides are multiples of 4 floats, so a float4
+// never straddles segments; the scalar tail path covers anything else.
 __global__ void __launch_bounds__(256)
 grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, const float* __restrict__ loss_partials,
                    int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* __restrict__ losses)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
+    const int64_t total4 = total / 4;
+    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i4 * 4;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int g = 0; g < tab.nseg; ++g) {
             const GradSeg& sg = tab.seg[g];
             if (i >= sg.dst && i < sg.dst + sg.count) {
                 const float* p = sg.src + (i - sg.dst);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                int q = 0;
-                for (; q + 3 < sg.nparts; q += 4) {
-                    s0 += __ldg(p + (int64_t)q * sg.stride);
-                    s1 += __ldg(p + (int64_t)(q + 1) * sg.stride);
-                    s2 += __ldg(p + (int64_t)(q + 2) * sg.stride);
-                    s3 += __ldg(p + (int64_t)(q + 3) * sg.stride);
+                const bool vec = (i + 4 <= sg.dst + sg.count) && ((sg.stride & 3) == 0) && (((i - sg.dst) & 3) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(sg.src) & 15u) == 0);
+                if (vec) {
+                    float4 acc[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int q = 0;
+                    for (; q + 7 < sg.nparts; q += 8) {
+                        float4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)(q + u) * sg.stride));
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+                    }
+                    for (int u = 0; q < sg.nparts; ++q, ++u) {
+                        const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)q * sg.stride));
+                        acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { acc[u].x += acc[u + 4].x; acc[u].y += acc[u + 4].y; acc[u].z += acc[u + 4].z; acc[u].w += acc[u + 4].w; }
+                    out.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+                    out.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+                    out.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z);
+                    out.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+                } else {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int e = 0; e < 4; ++e) {
+                        if (i + e >= sg.dst + sg.count) break;
+                        float s0 = 0.f;
+                        for (int q = 0; q < sg.nparts; ++q) s0 += __ldg(p + e + (int64_t)q * sg.stride);
+                        o[e] = s0;
+                    }
+                    out = make_float4(o[0], o[1], o[2], o[3]);
                 }
-                for (; q < sg.nparts; ++q) s0 += __ldg(p + (int64_t)q * sg.stride);
-                s = (s0 + s1) + (s2 + s3);
+                break;
+            }
+        }
+        *reinterpret_cast<float4*>(grads + i) = out;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(total - total4 * 4)) {
+        // (flat buffers are padded to a multiple of 4 floats; kept for callers with other sizes)
+        const int64_t i = total4 * 4 + threadIdx.x;
+        float s = 0.f;
+        for (int g = 0; g < tab.nseg; ++g) {
+            const GradSeg& sg = tab.seg[g];
+            if (i >= sg.dst && i < sg.dst + sg.count) {
+                for (int q = 0; q < sg.nparts; ++q) s += __ldg(sg.src + (i - sg.dst) + (int64_t)q * sg.stride);
                 break;
             }
         }
@@ -138,8 +181,9 @@ fma_peak_kernel(float* __restrict__ sink, int64_t iters)
 int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int64_t total, const float* loss_partials,
                        int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* losses, cudaStream_t st)
 {
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
+    if ((reinterpret_cast<uintptr_t>(grads) & 15u) != 0) DPPO_FAIL(ctx, "grad_reduce: gradient buffer must be 16-byte aligned");
+    int blocks = (int)((total / 4 + 255) / 256);
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
     if (blocks < 1) blocks = 1;
     grad_reduce_kernel<<<blocks, 256, 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses);
     DPPO_CHECK_LAUNCH(ctx, "grad_reduce_kernel");

@@ -77,8 +77,9 @@ const char* dppo_last_error(dppo_ctx* ctx);          /* ctx may be NULL: last cr
 int dppo_version(void);
 int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
 /* Kernel-variant switches used by tests and bench.py for A/B measurements:
- *   "tensor_cores" 2 (default): warp-specialised persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where the
- *                  shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 1: first-generation tcgen05
+ *   "tensor_cores" 3 (default): CTA-pair (cta_group::2) persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where
+ *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 2: the same with single-CTA
+ *                  GEMMs, 1: first-generation tcgen05
  *                  GEMMs (forward/dgrad only), 0: FP32 FFMA GEMMs everywhere
  *   "gae_variant"  0 (default): TMA-staged GAE kernel when the layout allows, 1: register-staged, 2: TMA */
 int dppo_set_option(dppo_ctx* ctx, const char* name, int value);
@@ -176,7 +177,8 @@ int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
  * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).
  * epi 1: C = tanh(A W^T + bias); epi 2: C = (A W) * (1 - Hact^2) with Hact [M,N], and, if colsum != NULL,
  * per-row-block column sums of C in colsum [dppo_tc_colsum_parts(M, variant), N] (bias-gradient partials).
- * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed).
+ * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed);
+ * 3: the same roles over CTA pairs (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC).
  * ws (dppo_tc_linear_workspace_bytes) holds the split weight images. */
 int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
                        const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
@@ -194,6 +196,12 @@ int64_t dppo_tc_wgrad_workspace_bytes(dppo_ctx* ctx, int64_t M, int N1, int N2);
  * sink: >= 65 floats of finite values);
  * bench.py times it with CUDA events to obtain the FP32 FMA-pipe peak of this very GPU. */
 int dppo_fma_peak_kernel(dppo_ctx* ctx, float* sink, int64_t iters, int* blocks_out, int* threads_out, void* stream);
+
+/* Issue rate of tcgen05.mma with shared-memory operands: every CTA (pair != 0: every CTA pair, cta_group::2, M = 256;
+ * else M = 128) issues iters back-to-back MMAs of N = n, K = 32 bytes (tf32, or bf16 if bf16 != 0) and writes the SM
+ * cycles they took to out[blockIdx] (int64 [*grid_out]; only the leader of a pair writes).  bench.py derives the
+ * tensor-pipe peak the 3xTF32 GEMMs are measured against from it. */
+int dppo_tc_mma_probe(dppo_ctx* ctx, int pair, int bf16, int n, int iters, long long* out, int* grid_out, void* stream);
 
 #ifdef __cplusplus
 }
