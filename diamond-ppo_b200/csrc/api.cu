@@ -158,7 +158,7 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     w.p1 = take((int64_t)mx(w.s1, w.t1) * H * D);
     w.tiles2 = dppo_gemm_row_tiles(M, (int)H);
     w.tiles1 = dppo_gemm_row_tiles(M, (int)H);
-    const int cparts = mx(dppo_tc2_colsum_parts(M), w.tiles2);
+    const int cparts = mx(mx(dppo_tc2_colsum_parts(M), dppo_tc3_colsum_parts(&fake, M, (int)H)), w.tiles2);
     w.c2 = take((int64_t)cparts * H);
     w.c1 = take((int64_t)cparts * H);
     w.head_blocks = head_train_blocks(&fake, M);
@@ -338,14 +338,14 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused
     int tiles2 = w.tiles2, tiles1 = w.tiles1;
     if (gb3) {
-        tiles2 = dppo_tc2_colsum_parts(M);
+        tiles2 = (ctx->use_tensor_cores >= 3 && dppo_tc3_gemm_supported(M, H, 2 * H)) ? dppo_tc3_colsum_parts(ctx, M, H) : dppo_tc2_colsum_parts(M);
         if (tc_gemm_v23(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     } else if (tcb3) {
         tiles2 = (int)((M + 127) / 128);
         if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, nullptr, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     if (gb2) {
-        tiles1 = dppo_tc2_colsum_parts(M);
+        tiles1 = (ctx->use_tensor_cores >= 3 && dppo_tc3_gemm_supported(M, H, H)) ? dppo_tc3_colsum_parts(ctx, M, H) : dppo_tc2_colsum_parts(M);
         if (tc_gemm_v23(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     } else if (tcb2) {
         tiles1 = (int)((M + 127) / 128);
@@ -391,7 +391,11 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
 // ---- tensor-core building blocks exposed for unit tests and A/B measurements ----------------------
 extern "C" int64_t dppo_tc_linear_workspace_bytes(int N, int K) { return dppo_tc_image_bytes(N, K) + 1024; }
 
-extern "C" int dppo_tc_colsum_parts(int64_t M, int variant) { return variant >= 2 ? dppo_tc2_colsum_parts(M) : (int)((M + 127) / 128); }
+extern "C" int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N, int variant)
+{
+    if (variant >= 3 && ctx) return dppo_tc3_colsum_parts(ctx, M, N);
+    return variant >= 2 ? dppo_tc2_colsum_parts(M) : (int)((M + 127) / 128);
+}
 
 extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
                                   const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,

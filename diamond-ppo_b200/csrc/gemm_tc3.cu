@@ -220,7 +220,11 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     bulk_commit();
                 }
                 if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr) {
-                    // rows >= M hold exact zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
+                    // Bias-gradient partials: one row of column sums per (CTA, lane quadrant), accumulated over all tiles of
+                    // this CTA (the row is owned by this warp pair; the launcher zeroes the buffer).  Rows >= M hold exact
+                    // zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
+                    float* cp = colsum + ((int64_t)blockIdx.x * 4 + q) * N + n + lane;
+                    const float prev = *cp;
                     // warp transpose-reduce: afterwards lane l holds the sum over the warp's 32 rows of column l
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) {
@@ -232,7 +236,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                         }
                     }
-                    colsum[((int64_t)m_pair * 8 + rank * 4 + q) * N + n + lane] = v[0];
+                    *cp = prev + v[0];
                 }
             }
             fence_before();
@@ -256,6 +260,19 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
+namespace {
+int tc3_grid(dppo_ctx* ctx, int64_t M, int N)
+{
+    const int n_tile = dppo_tc_n_tile(N);
+    const int64_t total = ((M + 2 * BM - 1) / (2 * BM)) * (N / n_tile);
+    int64_t clusters = ctx->sm_count / 2;
+    if (clusters > total) clusters = total;
+    return (int)(2 * clusters);
+}
+}  // namespace
+
+int dppo_tc3_colsum_parts(dppo_ctx* ctx, int64_t M, int N) { return 4 * tc3_grid(ctx, M, N); }
+
 bool dppo_tc3_gemm_supported(int64_t M, int N, int K)
 {
     return M >= 1024 && M < (int64_t)1 << 31 && K % KC == 0 && (N % 256 == 0 || N == 128);
@@ -274,9 +291,11 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     const int pair_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
     const int total = pair_tiles * (N / n_tile);
     const size_t smem = (size_t)STAGES * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK + 1024;
-    int clusters = ctx->sm_count / 2;
-    if (clusters > total) clusters = total;
-    const int grid = 2 * clusters;
+    const int grid = tc3_grid(ctx, M, N);
+    (void)total;
+    if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr &&
+        cudaMemsetAsync(colsum, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
+        DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tc3_gemm_kernel<DPPO_EPI_BIAS_TANH><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,

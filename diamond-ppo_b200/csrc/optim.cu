@@ -4,83 +4,84 @@
 
 namespace {
 
-// One thread per float4 of the flat gradient: sums the segment's partials in a fixed order (partial 0, 1, 2, ... into
-// eight interleaved accumulators, combined pairwise), eight independent 16-byte loads in flight per thread.  Every segment
-// starts and ends on a multiple of 4 floats (dppo_mlp_layout) and partial strides are multiples of 4 floats, so a float4
-// never straddles segments; the scalar tail path covers anything else.
-__global__ void __launch_bounds__(256)
+// Block = 32 float4 outputs x 8 partial slices.  Thread (x, y) sums partials y, y+8, y+16, ... of output float4 x in a
+// fixed order (four interleaved accumulators, four independent 16-byte loads in flight), the eight slice sums are then
+// combined in a fixed order through shared memory: deterministic, and segments with many partials (per-CTA head /
+// column-sum partials) no longer serialise on a single thread.  Every segment starts on a multiple of 4 floats
+// (dppo_mlp_layout) so a float4 never straddles segments; unaligned sources take the scalar path.
+constexpr int RED_X = 32, RED_Y = 8;
+
+__global__ void __launch_bounds__(RED_X * RED_Y)
 grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, const float* __restrict__ loss_partials,
                    int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* __restrict__ losses)
 {
-    const int64_t total4 = total / 4;
-    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = i4 * 4;
-        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int g = 0; g < tab.nseg; ++g) {
-            const GradSeg& sg = tab.seg[g];
-            if (i >= sg.dst && i < sg.dst + sg.count) {
-                const float* p = sg.src + (i - sg.dst);
-                const bool vec = (i + 4 <= sg.dst + sg.count) && ((sg.stride & 3) == 0) && (((i - sg.dst) & 3) == 0) &&
-                                 ((reinterpret_cast<uintptr_t>(sg.src) & 15u) == 0);
-                if (vec) {
-                    float4 acc[8];
+    __shared__ float4 s_part[RED_Y][RED_X];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t total4 = (total + 3) / 4;
+    for (int64_t base = (int64_t)blockIdx.x * RED_X; base < total4; base += (int64_t)gridDim.x * RED_X) {
+        const int64_t i = (base + x) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total) {
+            for (int g = 0; g < tab.nseg; ++g) {
+                const GradSeg& sg = tab.seg[g];
+                if (i >= sg.dst && i < sg.dst + sg.count) {
+                    const float* p = sg.src + (i - sg.dst);
+                    const bool vec = (i + 4 <= sg.dst + sg.count) && ((sg.stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+                    if (vec) {
+                        float4 a[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int q = 0;
-                    for (; q + 7 < sg.nparts; q += 8) {
-                        float4 v[8];
+                        for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int q = y;
+                        for (; q + 3 * RED_Y < sg.nparts; q += 4 * RED_Y) {
+                            float4 v[4];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)(q + u) * sg.stride));
+                            for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)(q + u * RED_Y) * sg.stride));
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+                            for (int u = 0; u < 4; ++u) { a[u].x += v[u].x; a[u].y += v[u].y; a[u].z += v[u].z; a[u].w += v[u].w; }
+                        }
+                        for (int u = 0; q < sg.nparts; q += RED_Y, ++u) {
+                            const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)q * sg.stride));
+                            a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
+                        }
+                        acc.x = (a[0].x + a[1].x) + (a[2].x + a[3].x);
+                        acc.y = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+                        acc.z = (a[0].z + a[1].z) + (a[2].z + a[3].z);
+                        acc.w = (a[0].w + a[1].w) + (a[2].w + a[3].w);
+                    } else {
+                        float o[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int e = 0; e < 4; ++e) {
+                            if (i + e >= sg.dst + sg.count) break;
+                            float s0 = 0.f;
+                            for (int q = y; q < sg.nparts; q += RED_Y) s0 += __ldg(p + e + (int64_t)q * sg.stride);
+                            o[e] = s0;
+                        }
+                        acc = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    for (int u = 0; q < sg.nparts; ++q, ++u) {
-                        const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)q * sg.stride));
-                        acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { acc[u].x += acc[u + 4].x; acc[u].y += acc[u + 4].y; acc[u].z += acc[u + 4].z; acc[u].w += acc[u + 4].w; }
-                    out.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
-                    out.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
-                    out.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z);
-                    out.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
-                } else {
-                    float o[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int e = 0; e < 4; ++e) {
-                        if (i + e >= sg.dst + sg.count) break;
-                        float s0 = 0.f;
-                        for (int q = 0; q < sg.nparts; ++q) s0 += __ldg(p + e + (int64_t)q * sg.stride);
-                        o[e] = s0;
-                    }
-                    out = make_float4(o[0], o[1], o[2], o[3]);
+                    break;
                 }
-                break;
             }
         }
-        *reinterpret_cast<float4*>(grads + i) = out;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (int)(total - total4 * 4)) {
-        // (flat buffers are padded to a multiple of 4 floats; kept for callers with other sizes)
-        const int64_t i = total4 * 4 + threadIdx.x;
-        float s = 0.f;
-        for (int g = 0; g < tab.nseg; ++g) {
-            const GradSeg& sg = tab.seg[g];
-            if (i >= sg.dst && i < sg.dst + sg.count) {
-                for (int q = 0; q < sg.nparts; ++q) s += __ldg(sg.src + (i - sg.dst) + (int64_t)q * sg.stride);
-                break;
-            }
+        s_part[y][x] = acc;
+        __syncthreads();
+        if (y == 0 && i < total) {
+            float4 r = s_part[0][x];
+#pragma unroll
+            for (int k = 1; k < RED_Y; ++k) { const float4 v = s_part[k][x]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+            if (i + 4 <= total) *reinterpret_cast<float4*>(grads + i) = r;
+            else { const float rr[4] = {r.x, r.y, r.z, r.w}; for (int e = 0; i + e < total; ++e) grads[i + e] = rr[e]; }
         }
-        grads[i] = s;
+        __syncthreads();
     }
     if (blockIdx.x == 0 && losses != nullptr) {
         __shared__ float l[3];
-        if (threadIdx.x < 3) {
+        const int t = y * RED_X + x;
+        if (t < 3) {
             float s = 0.f;
-            for (int p = 0; p < loss_nparts; ++p) s += loss_partials[(int64_t)p * loss_stride + threadIdx.x];
-            l[threadIdx.x] = s;
+            for (int p = 0; p < loss_nparts; ++p) s += loss_partials[(int64_t)p * loss_stride + t];
+            l[t] = s;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (t == 0) {
             const float pol = l[0] * inv_m, val = 0.5f * l[1] * inv_m, ent = l[2] * inv_m;    // ppo.py:270-274
             losses[0] = pol; losses[1] = val; losses[2] = ent;
             losses[3] = pol + vw * val + -beta * ent;                                          // ppo.py:276-280
@@ -182,10 +183,10 @@ int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int
                        int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* losses, cudaStream_t st)
 {
     if ((reinterpret_cast<uintptr_t>(grads) & 15u) != 0) DPPO_FAIL(ctx, "grad_reduce: gradient buffer must be 16-byte aligned");
-    int blocks = (int)((total / 4 + 255) / 256);
-    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    int64_t want = ((total + 3) / 4 + RED_X - 1) / RED_X;
+    int blocks = (int)(want < 16 * (int64_t)ctx->sm_count ? want : 16 * (int64_t)ctx->sm_count);
     if (blocks < 1) blocks = 1;
-    grad_reduce_kernel<<<blocks, 256, 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses);
+    grad_reduce_kernel<<<blocks, dim3(RED_X, RED_Y), 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses);
     DPPO_CHECK_LAUNCH(ctx, "grad_reduce_kernel");
     return 0;
 }

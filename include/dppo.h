@@ -176,7 +176,7 @@ int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
 /* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate).
  * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).
  * epi 1: C = tanh(A W^T + bias); epi 2: C = (A W) * (1 - Hact^2) with Hact [M,N], and, if colsum != NULL,
- * per-row-block column sums of C in colsum [dppo_tc_colsum_parts(M, variant), N] (bias-gradient partials).
+ * partial column sums of C in colsum [dppo_tc_colsum_parts(ctx, M, N, variant), N] (bias-gradient partials).
  * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed);
  * 3: the same roles over CTA pairs (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC).
  * ws (dppo_tc_linear_workspace_bytes) holds the split weight images. */
@@ -184,7 +184,7 @@ int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K,
                        const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
                        int variant, void* stream);
 int64_t dppo_tc_linear_workspace_bytes(int N, int K);
-int dppo_tc_colsum_parts(int64_t M, int variant);
+int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N, int variant);
 /* dW[N1,N2] = sum_m D[m,N1] * H[m,N2]  (weight gradient of a Linear layer, ppo.py:283): split over row
  * ranges on tcgen05, partials summed in a fixed order (bit-reproducible). */
 int dppo_tc_wgrad_f32(dppo_ctx* ctx, const float* D, const float* H, int64_t M, int N1, int N2, float* dW, void* ws,
