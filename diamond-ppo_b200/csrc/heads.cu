@@ -89,8 +89,10 @@ __device__ __forceinline__ Dist<CONT> eval_dist(float z, int lane, int A, int ac
 // ---------------------------------------------------------------------------------------------
 // Training kernel: heads forward + loss + backward into the first head layers.
 // ---------------------------------------------------------------------------------------------
-template <bool CONT, int KPL>
-__global__ void __launch_bounds__(HEAD_WARPS * 32)
+// VEC == 4 (H a multiple of 128): lane owns columns 128*g + 4*lane + c and moves them as float4; VEC == 1: lane owns
+// columns lane + 32*i.  R rows are in flight per warp iteration (their loads are issued together).
+template <bool CONT, int KPL, int VEC, int R>
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 2)
 head_train_kernel(HeadTrainArgs a)
 {
     extern __shared__ float smem[];
@@ -111,6 +113,9 @@ head_train_kernel(HeadTrainArgs a)
     const float bias_c = a.bc[0];
     const float log_std = (CONT && lane < A) ? a.log_std[lane] : 0.f;
 
+    // column owned by element e of this lane
+    auto kof = [&](int e) { return VEC == 4 ? ((e >> 2) * 128 + 4 * lane + (e & 3)) : lane + 32 * e; };
+
     float acc_b3[2 * KPL];
 #pragma unroll
     for (int i = 0; i < 2 * KPL; ++i) acc_b3[i] = 0.f;
@@ -119,90 +124,161 @@ head_train_kernel(HeadTrainArgs a)
 
     const int64_t warp_global = (int64_t)blockIdx.x * HEAD_WARPS + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * HEAD_WARPS;
-    for (int64_t m = warp_global; m < a.M; m += warp_stride) {
-        const int64_t src = a.idx ? (int64_t)a.idx[m] : m;
-        const float* h3 = a.h3 + m * (int64_t)(2 * H);
-        float ha[KPL], hc[KPL];
+    for (int64_t mb = warp_global * R; mb < a.M; mb += warp_stride * R) {
+        float ha[R][KPL], hc[R][KPL], old_lp[R], advv[R], ret[R], act_f[R];
+        int act_i[R];
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) {
-            const int k = lane + 32 * i;
-            ha[i] = k < H ? __ldg(h3 + k) : 0.f;
-            hc[i] = k < H ? __ldg(h3 + H + k) : 0.f;
-        }
-        const float old_lp = __ldg(a.old_logp + src);
-        float adv = __ldg(a.adv + src);
-        adv = (adv - mean) / denom;
-        const float ret = __ldg(a.ret + src);
-        int act_i = 0;
-        float act_f = 0.f;
-        if (CONT) act_f = lane < A ? __ldg(a.actions_f + src * A + lane) : 0.f;
-        else act_i = __ldg(a.actions_i + src);
-
-        // head products
-        float z = 0.f;
-        for (int j = 0; j < A; ++j) {
-            float part = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const int64_t m = mb + r;
+            const bool ok = m < a.M;
+            const int64_t src = ok ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
+            const float* h3 = a.h3 + (ok ? m : 0) * (int64_t)(2 * H);
+            if (VEC == 4) {
 #pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int k = lane + 32 * i;
-                if (k < H) part = fmaf(ha[i], s_wa[j * H + k], part);
-            }
-            part = warp_sum(part);
-            if (lane == j) z = part;
-        }
-        z += bias_a;
-        float vpart = 0.f;
-#pragma unroll
-        for (int i = 0; i < KPL; ++i) {
-            const int k = lane + 32 * i;
-            if (k < H) vpart = fmaf(hc[i], s_wc[k], vpart);
-        }
-        const float v = warp_sum(vpart) + bias_c;
-
-        const Dist<CONT> d = eval_dist<CONT>(z, lane, A, act_i, act_f, log_std);
-        const RowTerms t = policy_terms(d.new_lp, old_lp, adv, a.clip, a.inv_m);
-        float dz = 0.f;
-        if (lane < A) {
-            if (!CONT) {
-                dz = t.dlogp * ((lane == act_i ? 1.0f : 0.0f) - d.p) + (a.beta * a.inv_m) * d.p * (d.lsm + d.entropy);
+                for (int g = 0; g < KPL / 4; ++g) {
+                    const float4 va = ok ? __ldg(reinterpret_cast<const float4*>(h3 + g * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 vc = ok ? __ldg(reinterpret_cast<const float4*>(h3 + H + g * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ha[r][4 * g] = va.x; ha[r][4 * g + 1] = va.y; ha[r][4 * g + 2] = va.z; ha[r][4 * g + 3] = va.w;
+                    hc[r][4 * g] = vc.x; hc[r][4 * g + 1] = vc.y; hc[r][4 * g + 2] = vc.z; hc[r][4 * g + 3] = vc.w;
+                }
             } else {
-                dz = t.dlogp * d.diff / d.var;
-                acc_dls += t.dlogp * (d.diff * d.diff / d.var - 1.0f) - a.beta * a.inv_m;
-            }
-        }
-        const float verr = v - ret;
-        const float dv = a.vw * verr * a.inv_m;
-        l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
-        acc_dba += dz;
-        acc_dbc += dv;
-
-        // backward into the first head layers (+ head weight gradients)
-        float ga[KPL];
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) ga[i] = 0.f;
-        for (int j = 0; j < A; ++j) {
-            const float dzj = __shfl_sync(0xffffffffu, dz, j);
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) {
-                const int k = lane + 32 * i;
-                if (k < H) {
-                    ga[i] = fmaf(dzj, s_wa[j * H + k], ga[i]);
-                    acc[j * H + k] = fmaf(dzj, ha[i], acc[j * H + k]);
+                for (int i = 0; i < KPL; ++i) {
+                    const int k = lane + 32 * i;
+                    ha[r][i] = (ok && k < H) ? __ldg(h3 + k) : 0.f;
+                    hc[r][i] = (ok && k < H) ? __ldg(h3 + H + k) : 0.f;
                 }
             }
+            old_lp[r] = __ldg(a.old_logp + src);
+            advv[r] = (__ldg(a.adv + src) - mean) / denom;
+            ret[r] = __ldg(a.ret + src);
+            act_i[r] = 0; act_f[r] = 0.f;
+            if (CONT) act_f[r] = lane < A ? __ldg(a.actions_f + src * A + lane) : 0.f;
+            else act_i[r] = __ldg(a.actions_i + src);
         }
-        float* d3 = a.d3 + m * (int64_t)(2 * H);
+
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) {
-            const int k = lane + 32 * i;
-            if (k < H) {
-                const float da = ga[i] * (1.0f - ha[i] * ha[i]);
-                const float dc = dv * s_wc[k] * (1.0f - hc[i] * hc[i]);
-                d3[k] = da;
-                d3[H + k] = dc;
-                acc_b3[i] += da;
-                acc_b3[KPL + i] += dc;
-                acc[A * H + k] = fmaf(dv, hc[i], acc[A * H + k]);
+        for (int r = 0; r < R; ++r) {
+            const int64_t m = mb + r;
+            if (m >= a.M) break;                                     // warp-uniform
+            // head products
+            float z = 0.f;
+            for (int j = 0; j < A; ++j) {
+                float part = 0.f;
+                if (VEC == 4) {
+#pragma unroll
+                    for (int g = 0; g < KPL / 4; ++g) {
+                        const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
+                        part = fmaf(ha[r][4 * g], w.x, part); part = fmaf(ha[r][4 * g + 1], w.y, part);
+                        part = fmaf(ha[r][4 * g + 2], w.z, part); part = fmaf(ha[r][4 * g + 3], w.w, part);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < KPL; ++e) {
+                        const int k = kof(e);
+                        if (k < H) part = fmaf(ha[r][e], s_wa[j * H + k], part);
+                    }
+                }
+                part = warp_sum(part);
+                if (lane == j) z = part;
+            }
+            z += bias_a;
+            float vpart = 0.f;
+            float wcv[KPL];                                          // this lane's critic-head weights
+            if (VEC == 4) {
+#pragma unroll
+                for (int g = 0; g < KPL / 4; ++g) {
+                    const float4 w = reinterpret_cast<const float4*>(s_wc + g * 128)[lane];
+                    wcv[4 * g] = w.x; wcv[4 * g + 1] = w.y; wcv[4 * g + 2] = w.z; wcv[4 * g + 3] = w.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < KPL; ++e) wcv[e] = kof(e) < H ? s_wc[kof(e)] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < KPL; ++e) vpart = fmaf(hc[r][e], wcv[e], vpart);
+            const float v = warp_sum(vpart) + bias_c;
+
+            const Dist<CONT> d = eval_dist<CONT>(z, lane, A, act_i[r], act_f[r], log_std);
+            const RowTerms t = policy_terms(d.new_lp, old_lp[r], advv[r], a.clip, a.inv_m);
+            float dz = 0.f;
+            if (lane < A) {
+                if (!CONT) {
+                    dz = t.dlogp * ((lane == act_i[r] ? 1.0f : 0.0f) - d.p) + (a.beta * a.inv_m) * d.p * (d.lsm + d.entropy);
+                } else {
+                    dz = t.dlogp * d.diff / d.var;
+                    acc_dls += t.dlogp * (d.diff * d.diff / d.var - 1.0f) - a.beta * a.inv_m;
+                }
+            }
+            const float verr = v - ret[r];
+            const float dv = a.vw * verr * a.inv_m;
+            l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
+            acc_dba += dz;
+            acc_dbc += dv;
+
+            // backward into the first head layers (+ head weight gradients)
+            float ga[KPL];
+#pragma unroll
+            for (int e = 0; e < KPL; ++e) ga[e] = 0.f;
+            for (int j = 0; j < A; ++j) {
+                const float dzj = __shfl_sync(0xffffffffu, dz, j);
+                if (VEC == 4) {
+#pragma unroll
+                    for (int g = 0; g < KPL / 4; ++g) {
+                        const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
+                        ga[4 * g] = fmaf(dzj, w.x, ga[4 * g]); ga[4 * g + 1] = fmaf(dzj, w.y, ga[4 * g + 1]);
+                        ga[4 * g + 2] = fmaf(dzj, w.z, ga[4 * g + 2]); ga[4 * g + 3] = fmaf(dzj, w.w, ga[4 * g + 3]);
+                        float4* ap = reinterpret_cast<float4*>(acc + j * H + g * 128) + lane;
+                        float4 av = *ap;
+                        av.x = fmaf(dzj, ha[r][4 * g], av.x); av.y = fmaf(dzj, ha[r][4 * g + 1], av.y);
+                        av.z = fmaf(dzj, ha[r][4 * g + 2], av.z); av.w = fmaf(dzj, ha[r][4 * g + 3], av.w);
+                        *ap = av;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < KPL; ++e) {
+                        const int k = kof(e);
+                        if (k < H) {
+                            ga[e] = fmaf(dzj, s_wa[j * H + k], ga[e]);
+                            acc[j * H + k] = fmaf(dzj, ha[r][e], acc[j * H + k]);
+                        }
+                    }
+                }
+            }
+            float* d3 = a.d3 + m * (int64_t)(2 * H);
+            float da[KPL], dc[KPL];
+#pragma unroll
+            for (int e = 0; e < KPL; ++e) {
+                const int k = kof(e);
+                da[e] = dc[e] = 0.f;
+                if (VEC == 4 || k < H) {
+                    da[e] = ga[e] * (1.0f - ha[r][e] * ha[r][e]);
+                    dc[e] = dv * wcv[e] * (1.0f - hc[r][e] * hc[r][e]);
+                    acc_b3[e] += da[e];
+                    acc_b3[KPL + e] += dc[e];
+                    if (VEC != 4) acc[A * H + k] = fmaf(dv, hc[r][e], acc[A * H + k]);
+                }
+            }
+            if (VEC == 4) {
+#pragma unroll
+                for (int g = 0; g < KPL / 4; ++g) {
+                    float4* ap = reinterpret_cast<float4*>(acc + A * H + g * 128) + lane;
+                    float4 av = *ap;
+                    av.x = fmaf(dv, hc[r][4 * g], av.x); av.y = fmaf(dv, hc[r][4 * g + 1], av.y);
+                    av.z = fmaf(dv, hc[r][4 * g + 2], av.z); av.w = fmaf(dv, hc[r][4 * g + 3], av.w);
+                    *ap = av;
+                }
+#pragma unroll
+                for (int g = 0; g < KPL / 4; ++g) {
+                    reinterpret_cast<float4*>(d3 + g * 128)[lane] = make_float4(da[4 * g], da[4 * g + 1], da[4 * g + 2], da[4 * g + 3]);
+                    reinterpret_cast<float4*>(d3 + H + g * 128)[lane] = make_float4(dc[4 * g], dc[4 * g + 1], dc[4 * g + 2], dc[4 * g + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < KPL; ++e) {
+                    const int k = lane + 32 * e;
+                    if (k < H) { d3[k] = da[e]; d3[H + k] = dc[e]; }
+                }
             }
         }
     }
@@ -223,7 +299,7 @@ head_train_kernel(HeadTrainArgs a)
     float* mine = scratch + warp * sw;
 #pragma unroll
     for (int i = 0; i < KPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = kof(i);
         if (k < H) { mine[k] = acc_b3[i]; mine[H + k] = acc_b3[KPL + i]; }
     }
     mine[2 * H + lane] = acc_dba;
@@ -384,15 +460,15 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partials, int npa
     }
 }
 
-template <int KPL>
+template <int KPL, int VEC, int R>
 int launch_head_train(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int blocks, size_t smem, cudaStream_t st)
 {
     if (continuous) {
-        cudaFuncSetAttribute(head_train_kernel<true, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_train_kernel<true, KPL><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
+        cudaFuncSetAttribute(head_train_kernel<true, KPL, VEC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        head_train_kernel<true, KPL, VEC, R><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
     } else {
-        cudaFuncSetAttribute(head_train_kernel<false, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_train_kernel<false, KPL><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
+        cudaFuncSetAttribute(head_train_kernel<false, KPL, VEC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        head_train_kernel<false, KPL, VEC, R><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
     }
     DPPO_CHECK_LAUNCH(ctx, "head_train_kernel");
     return 0;
@@ -419,10 +495,11 @@ int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuo
     if (accf < scratchf) accf = scratchf;
     const size_t smem = ((size_t)(A + 1) * H + accf) * sizeof(float);
     if (smem > 200 * 1024) DPPO_FAIL(ctx, "head kernel: (A+1)*H = %d too large for shared memory", (A + 1) * H);
-    if (H <= 64) return launch_head_train<2>(ctx, a, continuous, blocks, smem, st);
-    if (H <= 128) return launch_head_train<4>(ctx, a, continuous, blocks, smem, st);
-    if (H <= 256) return launch_head_train<8>(ctx, a, continuous, blocks, smem, st);
-    return launch_head_train<16>(ctx, a, continuous, blocks, smem, st);
+    const bool vec = (H % 128 == 0) && ((reinterpret_cast<uintptr_t>(a.h3) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.d3) & 15u) == 0);
+    if (H <= 64) return launch_head_train<2, 1, 2>(ctx, a, continuous, blocks, smem, st);
+    if (H <= 128) return vec ? launch_head_train<4, 4, 2>(ctx, a, continuous, blocks, smem, st) : launch_head_train<4, 1, 2>(ctx, a, continuous, blocks, smem, st);
+    if (H <= 256) return vec ? launch_head_train<8, 4, 2>(ctx, a, continuous, blocks, smem, st) : launch_head_train<8, 1, 2>(ctx, a, continuous, blocks, smem, st);
+    return vec ? launch_head_train<16, 4, 1>(ctx, a, continuous, blocks, smem, st) : launch_head_train<16, 1, 1>(ctx, a, continuous, blocks, smem, st);
 }
 
 int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, const float* wa, const float* ba, const float* wc,
