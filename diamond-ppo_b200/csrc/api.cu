@@ -229,9 +229,18 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
     const bool tc1 = tc_on && dppo_tc_supported(first, H, D), tc2 = tc_on && dppo_tc_supported(first, H, H),
                tc3 = tc_on && dppo_tc_supported(first, n3, H);
     const bool v2 = ctx->use_tensor_cores >= 2;
-    if (tc1 && dppo_tc_prep_weights(ctx, params + L.w1, H, D, 0, img.w1f, st)) return 1;
-    if (tc2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 0, img.w2f, st)) return 1;
-    if (tc3 && dppo_tc_prep_weights(ctx, params + L.w3 + w3off, n3, H, 0, img.w3f, st)) return 1;
+    {
+        PrepJobs jobs;
+        jobs.n = 0;
+        auto job = [&](bool on, const float* W, int rows_w, int cols_w, unsigned char* im) {
+            if (on) { jobs.job[jobs.n].W = W; jobs.job[jobs.n].rows_w = rows_w; jobs.job[jobs.n].cols_w = cols_w;
+                      jobs.job[jobs.n].transpose = 0; jobs.job[jobs.n].n_tile = 0; jobs.job[jobs.n].img = im; ++jobs.n; }
+        };
+        job(tc1, params + L.w1, H, D, img.w1f);
+        job(tc2, params + L.w2, H, H, img.w2f);
+        job(tc3, params + L.w3 + w3off, n3, H, img.w3f);
+        if (dppo_tc_prep_weights_multi(ctx, jobs, st)) return 1;
+    }
     for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
         const int64_t n = rows - r0 < chunk ? rows - r0 : chunk;
         const float* x = idx ? obs : obs + r0 * D;
@@ -285,11 +294,20 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     WImages img = carve_images(d, img_base);
     const bool tc1 = tc_on && dppo_tc_supported(M, H, D), tc2 = tc_on && dppo_tc_supported(M, H, H),
                tc3 = tc_on && dppo_tc_supported(M, 2 * H, H), tcb3 = tc_on && dppo_tc_supported(M, H, 2 * H), tcb2 = tc2;
-    if (tc1 && dppo_tc_prep_weights(ctx, params + L.w1, H, D, 0, img.w1f, st)) return 1;
-    if (tc2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 0, img.w2f, st)) return 1;
-    if (tc3 && dppo_tc_prep_weights(ctx, params + L.w3, 2 * H, H, 0, img.w3f, st)) return 1;
-    if (tcb3 && dppo_tc_prep_weights(ctx, params + L.w3, 2 * H, H, 1, img.w3b, st)) return 1;
-    if (tcb2 && dppo_tc_prep_weights(ctx, params + L.w2, H, H, 1, img.w2b, st)) return 1;
+    {
+        PrepJobs jobs;
+        jobs.n = 0;
+        auto job = [&](bool on, const float* W, int rows_w, int cols_w, int transpose, unsigned char* im) {
+            if (on) { jobs.job[jobs.n].W = W; jobs.job[jobs.n].rows_w = rows_w; jobs.job[jobs.n].cols_w = cols_w;
+                      jobs.job[jobs.n].transpose = transpose; jobs.job[jobs.n].n_tile = 0; jobs.job[jobs.n].img = im; ++jobs.n; }
+        };
+        job(tc1, params + L.w1, H, D, 0, img.w1f);
+        job(tc2, params + L.w2, H, H, 0, img.w2f);
+        job(tc3, params + L.w3, 2 * H, H, 0, img.w3f);
+        job(tcb3, params + L.w3, 2 * H, H, 1, img.w3b);
+        job(tcb2, params + L.w2, H, H, 1, img.w2b);
+        if (dppo_tc_prep_weights_multi(ctx, jobs, st)) return 1;
+    }
 
     const bool v2 = ctx->use_tensor_cores >= 2;
     const bool g1 = tc1 && v2 && dppo_tc2_gemm_supported(M, H, D), g2 = tc2 && v2 && dppo_tc2_gemm_supported(M, H, H),

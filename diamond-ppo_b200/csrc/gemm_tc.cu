@@ -142,6 +142,30 @@ __global__ void prep_weights_kernel(const float* __restrict__ W, int rows_w, int
     }
 }
 
+// All weight images of one optimiser step in a single launch: blockIdx.y selects the job.
+__global__ void prep_weights_multi_kernel(PrepJobs jobs)
+{
+    const PrepJob& j = jobs.job[blockIdx.y];
+    const int N = j.transpose ? j.cols_w : j.rows_w;
+    const int K = j.transpose ? j.rows_w : j.cols_w;
+    const int64_t total = (int64_t)N * K;
+    const int chunks = K / KC;
+    const int img_bytes = j.n_tile * KC * 4;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int n, k;
+        if (j.transpose) { k = (int)(e / j.cols_w); n = (int)(e % j.cols_w); }
+        else { n = (int)(e / j.cols_w); k = (int)(e % j.cols_w); }
+        const float x = j.W[e];
+        float hi, lo;
+        split_tf32(x, hi, lo);
+        const int tile = n / j.n_tile, row = n % j.n_tile, chunk = k / KC, kk = k % KC;
+        unsigned char* base = j.img + ((int64_t)(tile * chunks + chunk) * 2) * img_bytes;
+        const int off = sw64_offset(row, kk);
+        *reinterpret_cast<float*>(base + off) = hi;
+        *reinterpret_cast<float*>(base + img_bytes + off) = lo;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The GEMM.  EPI: DPPO_EPI_BIAS_TANH (forward) or DPPO_EPI_TANH_BWD (dgrad, + column sums).
 // grid = (m_tiles, n_tiles).  Dynamic smem: STAGES * (2*A_IMG + 2*n_tile*64) + 1024 alignment slack.
@@ -335,6 +359,22 @@ int dppo_tc_prep_weights(dppo_ctx* ctx, const float* W, int rows_w, int cols_w, 
     if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
     prep_weights_kernel<<<blocks, 256, 0, st>>>(W, rows_w, cols_w, transpose, dppo_tc_n_tile(N), img);
     DPPO_CHECK_LAUNCH(ctx, "prep_weights_kernel");
+    return 0;
+}
+
+int dppo_tc_prep_weights_multi(dppo_ctx* ctx, PrepJobs jobs, cudaStream_t st)
+{
+    if (jobs.n < 1) return 0;
+    int64_t most = 0;
+    for (int i = 0; i < jobs.n; ++i) {
+        const int64_t t = (int64_t)jobs.job[i].rows_w * jobs.job[i].cols_w;
+        jobs.job[i].n_tile = dppo_tc_n_tile(jobs.job[i].transpose ? jobs.job[i].cols_w : jobs.job[i].rows_w);
+        if (t > most) most = t;
+    }
+    int blocks = (int)((most + 255) / 256);
+    if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
+    prep_weights_multi_kernel<<<dim3(blocks, jobs.n), 256, 0, st>>>(jobs);
+    DPPO_CHECK_LAUNCH(ctx, "prep_weights_multi_kernel");
     return 0;
 }
 

@@ -277,7 +277,7 @@ constexpr int GRP = WKC * 128;             // bytes of one 32-column group of a 
 // 32-column groups of WKC rows x 128 B, exactly what a SWIZZLE_128B_ATOM_32B TMA box of 32 x WKC floats delivers.
 template <int NACC>
 __global__ void __launch_bounds__(THREADS, 1)
-tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmH, float* __restrict__ partials,
+tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmP,
                  int64_t M, int N1, int N2, int n1_blocks, int rows_per_split, int stages)
 {
     extern __shared__ unsigned char dyn_raw[];
@@ -394,16 +394,23 @@ tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant_
             if (++s == stages) { s = 0; ph ^= 1; }
         }
     } else {
-        const int q = warp & 3, half = (warp - W_EPI0) >> 2;
+        // partials leave through double-buffered 32x32 staging blocks (the operand ring is free once the MMAs are done)
+        // and TMA stores into the [splits * N1, N2] partial matrix
+        const int ew = warp - W_EPI0;
+        const int q = warp & 3, half = ew >> 2;
         const int cols_per_half = N2 / 2;
         if (chunks > 0) {
             mbar_wait(&tfull, 0);
             fence_after();
         }
+        const uint32_t stg = smem_u32(dyn) + (uint32_t)ew * 2 * 4096;
+        const uint32_t row_off = (uint32_t)lane * 128, sw = (uint32_t)(lane & 7);
+        uint32_t blk = 0;
+        if (lane == 0) tma_prefetch_desc(&tmP);
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
-            float* dst = partials + ((int64_t)split * N1 + n1_0 + a * 128 + q * 32 + lane) * N2;
-            for (int cb = 0; cb < cols_per_half; cb += 32) {
+            const int prow = split * N1 + n1_0 + a * 128 + q * 32;
+            for (int cb = 0; cb < cols_per_half; cb += 32, ++blk) {
                 const int col = half * cols_per_half + cb;
                 float v[32];
                 if (chunks > 0) {
@@ -412,11 +419,22 @@ tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
+                const uint32_t buf = stg + (blk & 1) * 4096;
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + col + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 8; ++j)
+                    sts128(buf + row_off + ((((uint32_t)j) ^ sw) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmP, col, prow, buf);
+                    bulk_commit();
+                }
             }
         }
+        if (lane == 0) bulk_wait<0>();
+        __syncwarp();
     }
 
     fence_before();
@@ -515,6 +533,8 @@ struct WgradPlan { int nacc, n1_blocks, rows_per_split, splits, stages; size_t s
 WgradPlan wgrad_plan(int sm_count, int64_t M, int N1, int N2)
 {
     WgradPlan p;
+    // two accumulators share every H chunk: one accumulator per CTA (N1 spread over CTAs) was measured slower -- the
+    // H tile is then streamed by twice as many CTAs and the kernel becomes L2-bound
     p.nacc = (N1 % 256 == 0) ? 2 : 1;
     p.n1_blocks = N1 / (128 * p.nacc);
     int splits = sm_count / p.n1_blocks;
@@ -540,16 +560,17 @@ int dppo_tc2_wgrad(dppo_ctx* ctx, const float* Dm, int ldd, const float* Hm, int
     if (ldd % 4 != 0 || ldh % 4 != 0 || !al16(Dm) || !al16(Hm) || !al16(partials)) DPPO_FAIL(ctx, "tc2_wgrad: operands must be 16-byte aligned");
     const WgradPlan p = wgrad_plan(ctx->sm_count, M, N1, N2);
     if (p.splits != splits) DPPO_FAIL(ctx, "tc2_wgrad: caller sized the partials for %d splits, plan has %d", splits, p.splits);
-    CUtensorMap tmD, tmH;
-    if (!dppo_make_tensor_map_2d(&tmD, Dm, M, N1, ldd, 32, WKC, 4) || !dppo_make_tensor_map_2d(&tmH, Hm, M, N2, ldh, 32, WKC, 4))
+    CUtensorMap tmD, tmH, tmP;
+    if (!dppo_make_tensor_map_2d(&tmD, Dm, M, N1, ldd, 32, WKC, 4) || !dppo_make_tensor_map_2d(&tmH, Hm, M, N2, ldh, 32, WKC, 4) ||
+        !dppo_make_tensor_map_2d(&tmP, partials, (int64_t)p.splits * N1, N2, N2, 32, 32, 3))
         DPPO_FAIL(ctx, "tc2_wgrad: cuTensorMapEncodeTiled failed");
     const int grid = p.n1_blocks * p.splits;
     if (p.nacc == 2) {
         cudaFuncSetAttribute(tc2_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        tc2_wgrad_kernel<2><<<grid, THREADS, p.smem, st>>>(tmD, tmH, partials, M, N1, N2, p.n1_blocks, p.rows_per_split, p.stages);
+        tc2_wgrad_kernel<2><<<grid, THREADS, p.smem, st>>>(tmD, tmH, tmP, M, N1, N2, p.n1_blocks, p.rows_per_split, p.stages);
     } else {
         cudaFuncSetAttribute(tc2_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        tc2_wgrad_kernel<1><<<grid, THREADS, p.smem, st>>>(tmD, tmH, partials, M, N1, N2, p.n1_blocks, p.rows_per_split, p.stages);
+        tc2_wgrad_kernel<1><<<grid, THREADS, p.smem, st>>>(tmD, tmH, tmP, M, N1, N2, p.n1_blocks, p.rows_per_split, p.stages);
     }
     DPPO_CHECK_LAUNCH(ctx, "tc2_wgrad_kernel");
     return 0;

@@ -152,6 +152,18 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
     }
 }
 
+// row_floats % 4 == 0 and 16-byte aligned bases: one float4 per thread, a row is read by row_floats/4 consecutive threads
+__global__ void gather_rows4_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx, float4* __restrict__ dst,
+                                    int64_t rows, int row_vec)
+{
+    const int64_t total = rows * row_vec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / row_vec;
+        const int c = (int)(i - r * row_vec);
+        dst[i] = __ldg(src + (int64_t)__ldg(idx + r) * row_vec + c);
+    }
+}
+
 // 16 independent 3-register FFMA chains per thread (acc = x*y + acc, the form a GEMM inner loop issues):
 // the FP32 FMA-pipe ceiling of this GPU at its current clocks.  iters FMAs per thread (multiple of 16).
 __global__ void __launch_bounds__(256)
@@ -233,6 +245,15 @@ extern "C" int dppo_gather_rows_f32(dppo_ctx* ctx, const float* src, const int32
 {
     if (!ctx) return 1;
     if (rows <= 0 || row_floats <= 0) return 0;
+    if (row_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int64_t total4 = rows * (row_floats / 4);
+        int blocks4 = (int)((total4 + 255) / 256);
+        if (blocks4 > 16 * ctx->sm_count) blocks4 = 16 * ctx->sm_count;
+        gather_rows4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), idx,
+                                                                      reinterpret_cast<float4*>(dst), rows, row_floats / 4);
+        DPPO_CHECK_LAUNCH(ctx, "gather_rows4_kernel");
+        return 0;
+    }
     const int64_t total = rows * row_floats;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
