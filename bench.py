@@ -27,6 +27,9 @@ T, N_ENVS, D, H, A, E, MB = 128, 4096, 64, 256, 4, 4, 8
 FLOP_PER_SAMPLE_UPDATE = 1_252_864          # 2*(3F - D*H), F = D*H + 3H^2 + H*A + H
 FLOP_PER_SAMPLE_PREPASS = 723_968           # 2*(F + Fc)
 GAE_BYTES_PER_ELEM = 28                     # 5 fp32 reads + 2 fp32 writes
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full, profiles/r1c_*):
+# 67.8 MB read + 16.0 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
+GEMM_DRAM_TRAFFIC = 83.8e6
 
 
 def measured_peaks():
@@ -205,6 +208,43 @@ def bench_gae(ctx, hbm_peak, sets=20, launches=200):
             "bytes_per_launch": bytes_, "launches": launches, "buffer_sets": sets}
 
 
+def bench_dominant_gemm(ctx, tensor_peak, sets=4, reps=12):
+    """The dominant kernel of the update loop, timed alone with CUDA events: the CTA-pair tcgen05 GEMM at the trunk-layer
+    shape of one minibatch ([65536, 256] x [256, 256]^T, bias + tanh epilogue).  `sets` rotating input/output pairs
+    (4 x 134 MB > the 126 MB L2) keep the operands HBM-resident; the weight images are prepared once (they are
+    L2-resident in the real step too)."""
+    M, K, N = T * N_ENVS // MB, H, H
+    g = torch.Generator(device="cuda").manual_seed(7)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    ins = [torch.randn(M, K, device="cuda", generator=g) for _ in range(sets)]
+    outs = [torch.empty(M, N, device="cuda") for _ in range(sets)]
+    ws = torch.empty(ctx.lib.dppo_tc_linear_workspace_bytes(N, K), device="cuda", dtype=torch.uint8)
+    ctx.tc_linear(1, ins[0], W, False, bias=b, out=outs[0], ws=ws)
+    for i in range(sets):
+        ctx.tc_linear(1, ins[i], W, False, bias=b, out=outs[i], ws=ws, prepared=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        ctx.tc_linear(1, ins[i % sets], W, False, bias=b, out=outs[i % sets], ws=ws, prepared=True)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    flops = 2.0 * M * N * K
+    tf = flops / (us * 1e-6) / 1e12
+    return {"bound": "tensor", "kernel": "tc3_gemm_kernel<BIAS_TANH> (3xTF32 tcgen05 cta_group::2), layer base.2 of one minibatch: "
+                                         f"[{M},{K}] x [{N},{K}]^T", "us_per_launch": us, "flops_per_launch": flops,
+            "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak,
+            "bytes_per_launch": 4.0 * M * (K + N), "launches": reps, "buffer_sets": sets}
+
+
+def bench_mma_probe(ctx):
+    """SM cycles per tcgen05.mma (M=256 over a CTA pair, N=256, K=8 tf32, shared-memory operands) on every SM pair."""
+    c = ctx.mma_probe(1, 0, 256, 4000)
+    return float(c.mean())
+
+
 def bench_fma_peak(ctx):
     sink = torch.ones(128, device="cuda")
     iters = 1 << 16
@@ -299,18 +339,28 @@ def run_ours(args, rank, world, local_rank):
     fma_peak = bench_fma_peak(ctx)
     gae = bench_gae(ctx, hbm_peak)
     upd_tflops = E * T * N_ENVS * FLOP_PER_SAMPLE_UPDATE / (t_upd * 1e-3) / 1e12
+    # fp32-accurate products cost three TF32 tensor passes; TF32 runs at half the bf16 rate (same cycles per instruction
+    # at half the K, confirmed by the in-run probe), so the algorithmic peak is bf16 / 2 / 3
+    tensor_peak = bf16_peak / 6.0
+    clk_per_mma = bench_mma_probe(ctx)
+    sm_mhz = clocks.get("sm_max_mhz") or 1965
+    probe_tf32 = 2.0 * 256 * 256 * 8 / clk_per_mma * (ctx.sm_count // 2) * sm_mhz * 1e6 / 1e12
+    gemm = bench_dominant_gemm(ctx, tensor_peak)
+    peak_note = ("3xTF32 algorithmic peak = MEASURED_PEAKS.json bf16_tflops (%.1f, %s) / 2 (tf32) / 3 (passes); in-run tcgen05 probe: "
+                 "%.1f clk per 256x256x8 tf32 MMA = %.0f TF/s tf32 at %d MHz" % (bf16_peak, peak_src, clk_per_mma, probe_tf32, sm_mhz))
     line = {
         "metric": "ppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "phases_ms": {"prepass": t_pre, "gae_and_stats": t_gae, "update_loop": t_upd},
         "update_loop_samples_per_s": E * T * N_ENVS * world / (t_upd * 1e-3),
-        "roofline": {"bound": "fma", "kernel": "gemm_kernel/wgrad_kernel (FP32 FFMA GEMMs of the update loop)",
-                     "achieved": upd_tflops, "peak": fma_peak, "unit": "TFLOP/s", "frac": upd_tflops / fma_peak,
-                     "peak_source": "FP32 FMA-pipe peak measured in this run by dppo_fma_peak_kernel "
-                                    "(MEASURED_PEAKS.json has no fp32 figure; bf16 tensor peak there: %.1f TF/s, %s)" % (bf16_peak, peak_src),
-                     "flop_per_sample_update": FLOP_PER_SAMPLE_UPDATE, "traffic": None},
-        "roofline_gae": dict(gae, kernel="gae_kernel<8>", peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=None),
+        # dominant kernel (52 % of the step in profiles/): algorithmic flops per launch / CUDA-event time of the kernel alone
+        "roofline": dict(gemm, peak_source=peak_note, traffic=GEMM_DRAM_TRAFFIC),
+        # the whole update loop (32 optimiser steps: gather, forward, loss, backward, reduce, clip + Adam)
+        "roofline_update_loop": {"bound": "tensor", "achieved": upd_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                                 "frac": upd_tflops / tensor_peak, "flop_per_sample_update": FLOP_PER_SAMPLE_UPDATE,
+                                 "fp32_fma_peak_tflops": fma_peak, "peak_source": peak_note},
+        "roofline_gae": dict(gae, kernel="gae_tma_kernel<8>", peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=None),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_losses.numel() * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
     }

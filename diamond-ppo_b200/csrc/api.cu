@@ -47,6 +47,7 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->use_tensor_cores = 3;
     c->gae_variant = 0;
     c->tc_debug = 0;
+    c->launch_count = 0;
     c->tm_cache = nullptr;
     c->tm_cache_free = nullptr;
     *out = c;
@@ -68,6 +69,8 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "tc_debug")) { ctx->tc_debug = value; return 0; }
     DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
+
+extern "C" int64_t dppo_launch_count(dppo_ctx* ctx) { return ctx ? ctx->launch_count : 0; }
 
 extern "C" int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
 {
@@ -427,9 +430,11 @@ extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_
     if ((img - (unsigned char*)ws) + dppo_tc_image_bytes(N, K) > ws_bytes) DPPO_FAIL(ctx, "tc_linear: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int rows_w = transpose ? K : N, cols_w = transpose ? N : K;
-    if (variant >= 2 ? !dppo_tc2_gemm_supported(M, N, K) : !dppo_tc_supported(M, N, K))
+    if ((variant & 0xff) >= 2 ? !dppo_tc2_gemm_supported(M, N, K) : !dppo_tc_supported(M, N, K))
         DPPO_FAIL(ctx, "tc_linear: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
-    if (dppo_tc_prep_weights(ctx, W, rows_w, cols_w, transpose, img, st)) return 1;
+    const bool prepared = (variant & 0x100) != 0;       // images already in ws from an earlier call with the same weights
+    variant &= 0xff;
+    if (!prepared && dppo_tc_prep_weights(ctx, W, rows_w, cols_w, transpose, img, st)) return 1;
     if (variant >= 3) return dppo_tc3_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
     if (variant >= 2) return dppo_tc2_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
     return dppo_tc_gemm(ctx, epi, A, K, nullptr, img, bias, Hact, N, C, N, colsum, M, N, K, st);

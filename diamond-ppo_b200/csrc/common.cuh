@@ -14,6 +14,7 @@ struct dppo_ctx {
     char err[512];
     int use_tensor_cores;                 // 1: 3xTF32 tcgen05 GEMMs where the shape allows (default); 0: FP32 FFMA GEMMs only
     int gae_variant;                      // 0: auto, 1: register-staged kernel, 2: TMA-staged kernel
+    long long launch_count;               // kernels launched through this context (bench.py's gpu_launches)
     int tc_debug;                         // bit mask of experiment switches of the tc2 kernels (wrong results; timing only)
     void* tm_cache;                       // tensor-map cache owned by gae.cu
     void (*tm_cache_free)(void*);
@@ -31,6 +32,7 @@ extern char g_dppo_create_error[512];
     do {                                                                                    \
         cudaError_t e_ = cudaGetLastError();                                                \
         if (e_ != cudaSuccess) DPPO_FAIL(ctx, "%s: %s", what, cudaGetErrorString(e_));      \
+        ++(ctx)->launch_count;                                                              \
     } while (0)
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

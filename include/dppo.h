@@ -76,6 +76,7 @@ int dppo_destroy(dppo_ctx* ctx);
 const char* dppo_last_error(dppo_ctx* ctx);          /* ctx may be NULL: last create() error */
 int dppo_version(void);
 int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+int64_t dppo_launch_count(dppo_ctx* ctx);            /* kernels launched through this context so far */
 /* Kernel-variant switches used by tests and bench.py for A/B measurements:
  *   "tensor_cores" 3 (default): CTA-pair (cta_group::2) persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where
  *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 2: the same with single-CTA
@@ -179,7 +180,8 @@ int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
  * partial column sums of C in colsum [dppo_tc_colsum_parts(ctx, M, N, variant), N] (bias-gradient partials).
  * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed);
  * 3: the same roles over CTA pairs (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC).
- * ws (dppo_tc_linear_workspace_bytes) holds the split weight images. */
+ * ws (dppo_tc_linear_workspace_bytes) holds the split weight images; variant | 0x100 re-uses the images an earlier call
+ * with the same W left in ws (kernel-only timing). */
 int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
                        const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
                        int variant, void* stream);
