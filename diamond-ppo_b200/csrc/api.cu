@@ -46,6 +46,7 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->err[0] = 0;
     c->use_tensor_cores = 3;
     c->gae_variant = 0;
+    c->gae_inputs_settled = 0;
     c->tc_debug = 0;
     c->launch_count = 0;
     c->tm_cache = nullptr;
@@ -67,6 +68,7 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value < 0 ? 0 : value > 3 ? 3 : value; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
     if (!strcmp(name, "tc_debug")) { ctx->tc_debug = value; return 0; }
+    if (!strcmp(name, "gae_inputs_settled")) { ctx->gae_inputs_settled = value != 0; return 0; }
     DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
 

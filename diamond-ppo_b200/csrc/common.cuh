@@ -13,7 +13,8 @@ struct dppo_ctx {
     int cc_major, cc_minor;
     char err[512];
     int use_tensor_cores;                 // 1: 3xTF32 tcgen05 GEMMs where the shape allows (default); 0: FP32 FFMA GEMMs only
-    int gae_variant;                      // 0: auto, 1: register-staged kernel, 2: TMA-staged kernel
+    int gae_variant;                      // 0: auto (pipelined TMA kernel for T >= 128), 1: register-staged kernel, 2: single-barrier TMA kernel
+    int gae_inputs_settled;               // 1: caller guarantees the GAE inputs are not written by the kernel just before the GAE launch
     long long launch_count;               // kernels launched through this context (bench.py's gpu_launches)
     int tc_debug;                         // bit mask of experiment switches of the tc2 kernels (wrong results; timing only)
     void* tm_cache;                       // tensor-map cache owned by gae.cu

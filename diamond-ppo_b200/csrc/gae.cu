@@ -83,7 +83,7 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
                double* __restrict__ stats, int T, int N, int epc, int box_rows, int region_bytes, float gamma, float gamma_lambda)
 {
     extern __shared__ __align__(128) unsigned char dyn[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar, mbar_b;
     __shared__ float s_a0[GAE_WARPS][32];
     __shared__ float s_p0[GAE_WARPS][32];
     __shared__ float s_carry[32];
@@ -96,7 +96,7 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
     const bool env_ok = lane < epc && env < N;
     constexpr int SPAN = GAE_WARPS * L;
     const int passes = (T + SPAN - 1) / SPAN;
-    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    if (threadIdx.x == 0) { mbar_init(&mbar, 1); mbar_init(&mbar_b, 1); }
     if (warp == 0) s_carry[lane] = 0.0f;
     __syncthreads();
 
@@ -110,16 +110,28 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
 
     for (int pass = passes - 1; pass >= 0; --pass) {
         const int tbase = pass * SPAN;
+        // Programmatic dependent launch: rewards and the two masks are rollout data that no preceding kernel of the stream
+        // writes, so their tiles are requested before griddepcontrol.wait and stream in while the predecessor (the
+        // pre-update pass that produces values / next_values, or the previous GAE launch) drains; the dependents of this
+        // grid are released at once so that the same overlap continues down the stream.
         if (threadIdx.x == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&mbar, 5u * (uint32_t)(box_rows * epc * 4));
+            mbar_expect_tx(&mbar, 3u * (uint32_t)(box_rows * epc * 4));
             tma_load_2d(dyn, &tm_r, env0, tbase, &mbar);
             tma_load_2d(dyn + region_bytes, &tm_te, env0, tbase, &mbar);
             tma_load_2d(dyn + 2 * region_bytes, &tm_tr, env0, tbase, &mbar);
-            tma_load_2d(dyn + 3 * region_bytes, &tm_v, env0, tbase, &mbar);
-            tma_load_2d(dyn + 4 * region_bytes, &tm_nv, env0, tbase, &mbar);
+        }
+        if (pass == passes - 1) {
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&mbar_b, 2u * (uint32_t)(box_rows * epc * 4));
+            tma_load_2d(dyn + 3 * region_bytes, &tm_v, env0, tbase, &mbar_b);
+            tma_load_2d(dyn + 4 * region_bytes, &tm_nv, env0, tbase, &mbar_b);
         }
         mbar_wait(&mbar, parity);
+        mbar_wait(&mbar_b, parity);
         parity ^= 1u;
         float r[L], te[L], tr[L], v[L], nv[L];
 #pragma unroll
@@ -157,6 +169,147 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
         if (passes > 1) {
             __syncthreads();
             if (warp == 0) s_carry[lane] = sc.a[0] + sc.p[0] * carry;
+            __syncthreads();
+        }
+    }
+
+    if (stats) {
+        double ds = warp_sum_d((double)sum), dq = warp_sum_d((double)sumsq);
+        if (lane == 0) { s_red[0][warp] = ds; s_red[1][warp] = dq; }
+        __syncthreads();
+        if (warp == 0) {
+            ds = lane < GAE_WARPS ? s_red[0][lane] : 0.0;
+            dq = lane < GAE_WARPS ? s_red[1][lane] : 0.0;
+            ds = warp_sum_d(ds); dq = warp_sum_d(dq);
+            if (lane == 0) { atomicAdd(stats, ds); atomicAdd(stats + 1, dq); }
+        }
+    }
+}
+
+// Pipelined variant for horizons of at least 128 steps: the 128 x envs tile of a pass is requested as four 32-step chunks,
+// latest steps first, each with its own mbarrier.  The four warps of a chunk scan and STORE as soon as their chunk has
+// landed -- the reverse-time recurrence only needs the (already finished) later chunk's carry -- so the output stream
+// overlaps the rest of the input stream instead of following it.
+//   settled != 0: the caller guarantees that none of the five inputs is written by the kernel immediately preceding this
+//   launch in the stream (PPO.learn(): that kernel is the 16-byte statistics fill).  All input tiles are then requested
+//   before griddepcontrol.wait, which is only executed before the first global write; back-to-back launches overlap
+//   their load and store phases.  settled == 0: only rewards and the masks (rollout data) are requested early.
+constexpr int GP_CHUNKS = 4, GP_L = 8, GP_ROWS = 32, GP_WPC = GAE_WARPS / GP_CHUNKS;      // 4 warps x 8 steps per chunk
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__global__ void __launch_bounds__(GAE_WARPS * 32)
+gae_pipe_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_te,
+                const __grid_constant__ CUtensorMap tm_tr, const __grid_constant__ CUtensorMap tm_v,
+                const __grid_constant__ CUtensorMap tm_nv, float* __restrict__ adv_out, float* __restrict__ ret_out,
+                double* __restrict__ stats, int T, int N, int epc, int chunk_bytes, float gamma, float gamma_lambda, int settled)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];       // [tensor 0..4][chunk 0..3][32 rows x epc]
+    __shared__ __align__(8) uint64_t cbar[GP_CHUNKS];
+    __shared__ float s_a0[GAE_WARPS][32];
+    __shared__ float s_p0[GAE_WARPS][32];
+    __shared__ float s_ccarry[GP_CHUNKS + 1][32];               // [c]: advantage at the first step of chunk c (= carry into chunk c-1);
+                                                                // [GP_CHUNKS]: carry entering the pass (0, or the later pass's first step)
+    __shared__ double s_red[2][GAE_WARPS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chunk = warp / GP_WPC, wic = warp % GP_WPC;       // chunk of this warp, warp index inside the chunk
+    const int env0 = blockIdx.x * epc;
+    const int env = env0 + lane;
+    const bool env_ok = lane < epc && env < N;
+    constexpr int SPAN = GAE_WARPS * GP_L;                      // 128 steps per pass
+    const int passes = (T + SPAN - 1) / SPAN;
+    const int region = GP_CHUNKS * chunk_bytes;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < GP_CHUNKS; ++c) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&cbar[c])), "r"(1));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) s_ccarry[GP_CHUNKS][lane] = 0.0f;
+    __syncthreads();
+
+    float sum = 0.0f, sumsq = 0.0f;
+    uint32_t parity = 0;
+    bool waited = false;
+    for (int pass = passes - 1; pass >= 0; --pass) {
+        const int tbase = pass * SPAN;
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int c = GP_CHUNKS - 1; c >= 0; --c) {
+                mbar_expect_tx(&cbar[c], 5u * (uint32_t)(GP_ROWS * epc * 4));
+                tma_load_2d(dyn + 0 * region + c * chunk_bytes, &tm_r, env0, tbase + c * GP_ROWS, &cbar[c]);
+                tma_load_2d(dyn + 1 * region + c * chunk_bytes, &tm_te, env0, tbase + c * GP_ROWS, &cbar[c]);
+                tma_load_2d(dyn + 2 * region + c * chunk_bytes, &tm_tr, env0, tbase + c * GP_ROWS, &cbar[c]);
+                if (settled) {
+                    tma_load_2d(dyn + 3 * region + c * chunk_bytes, &tm_v, env0, tbase + c * GP_ROWS, &cbar[c]);
+                    tma_load_2d(dyn + 4 * region + c * chunk_bytes, &tm_nv, env0, tbase + c * GP_ROWS, &cbar[c]);
+                }
+            }
+        }
+        if (pass == passes - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (!settled) {
+            if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
+            if (threadIdx.x == 0) {
+                for (int c = GP_CHUNKS - 1; c >= 0; --c) {
+                    tma_load_2d(dyn + 3 * region + c * chunk_bytes, &tm_v, env0, tbase + c * GP_ROWS, &cbar[c]);
+                    tma_load_2d(dyn + 4 * region + c * chunk_bytes, &tm_nv, env0, tbase + c * GP_ROWS, &cbar[c]);
+                }
+            }
+        }
+        mbar_wait(&cbar[chunk], parity);
+        parity ^= 1u;
+        const float* base = reinterpret_cast<const float*>(dyn + chunk * chunk_bytes);
+        const int fl = region / 4;                                  // floats between tensors
+        float r[GP_L], te[GP_L], tr[GP_L], v[GP_L], nv[GP_L];
+#pragma unroll
+        for (int j = 0; j < GP_L; ++j) {
+            const int i = (wic * GP_L + j) * epc + lane;            // rows past T inside the box are zero-filled by TMA
+            const bool ok = lane < epc;
+            r[j] = ok ? base[i] : 0.0f;
+            te[j] = ok ? base[fl + i] : 0.0f;
+            tr[j] = ok ? base[2 * fl + i] : 0.0f;
+            v[j] = ok ? base[3 * fl + i] : 0.0f;
+            nv[j] = ok ? base[4 * fl + i] : 0.0f;
+        }
+        GaeScan<GP_L> sc;
+        sc.local(r, te, tr, v, nv, gamma, gamma_lambda);
+        s_a0[warp][lane] = sc.a[0];
+        s_p0[warp][lane] = sc.p[0];
+        // the chunk's four warps have published their maps; the later chunk (or the previous pass) has published its carry
+        named_bar_sync(1 + chunk, GP_WPC * 32);
+        if (chunk < GP_CHUNKS - 1) named_bar_sync(1 + GP_CHUNKS + chunk, GP_WPC * 32 + 32);   // released by the first warp of chunk + 1
+        float carry = s_ccarry[chunk + 1][lane];
+#pragma unroll
+        for (int w = GP_WPC - 1; w >= 1; --w)
+            if (w > wic) carry = s_a0[chunk * GP_WPC + w][lane] + s_p0[chunk * GP_WPC + w][lane] * carry;
+        if (wic == 0) {
+            // advantage at the first step of this chunk = carry entering the chunk before it in time
+            s_ccarry[chunk][lane] = sc.a[0] + sc.p[0] * carry;
+            if (chunk > 0) {
+                __threadfence_block();
+                named_bar_arrive(1 + GP_CHUNKS + chunk - 1, GP_WPC * 32 + 32);
+            }
+        }
+        if (settled && !waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
+#pragma unroll
+        for (int j = 0; j < GP_L; ++j) {
+            const int t = tbase + warp * GP_L + j;
+            if (env_ok && t < T) {
+                const int64_t i = (int64_t)t * N + env;
+                const float A = sc.a[j] + sc.p[j] * carry;
+                adv_out[i] = A;
+                if (ret_out) ret_out[i] = v[j] + A;                     // ppo.py:241
+                sum += A;
+                sumsq += A * A;
+            }
+        }
+        if (passes > 1) {
+            __syncthreads();
+            if (warp == 0) s_ccarry[GP_CHUNKS][lane] = s_ccarry[0][lane];
             __syncthreads();
         }
     }
@@ -342,6 +495,29 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
         int epc = (N + ctx->sm_count - 1) / ctx->sm_count;
         epc = (epc + 3) / 4 * 4;
         if (epc > 32) epc = 32;
+        if (T >= GAE_WARPS * GP_L && ctx->gae_variant != 2) {
+            // pipelined kernel: 32-step chunks with their own barriers, stores overlap the remaining loads
+            const int chunk_bytes = (GP_ROWS * epc * 4 + 127) / 128 * 128;
+            CUtensorMap m[5];
+            const float* ptrs[5] = {rewards, terminations, truncations, values, next_values};
+            bool ok = true;
+            for (int i = 0; i < 5 && ok; ++i) ok = get_tensor_map(ctx, ptrs[i], T, N, epc, GP_ROWS, &m[i]);
+            if (ok) {
+                const int grid = (N + epc - 1) / epc;
+                const size_t smem = (size_t)5 * GP_CHUNKS * chunk_bytes;
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3(grid); lc.blockDim = dim3(GAE_WARPS * 32); lc.dynamicSmemBytes = smem; lc.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = attr; lc.numAttrs = 1;
+                cudaFuncSetAttribute(gae_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaLaunchKernelEx(&lc, gae_pipe_kernel, m[0], m[1], m[2], m[3], m[4], advantages, returns, stats, T, N, epc, chunk_bytes,
+                                   g, gl, ctx->gae_inputs_settled);
+                DPPO_CHECK_LAUNCH(ctx, "gae_pipe_kernel");
+                return 0;
+            }
+        }
         const int L = per_warp <= 1 ? 1 : per_warp <= 2 ? 2 : per_warp <= 4 ? 4 : 8;
         const int span = GAE_WARPS * L;
         const int rows = T < span ? T : span;
@@ -353,11 +529,17 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
         if (ok) {
             const int grid = (N + epc - 1) / epc;
             const size_t smem = (size_t)5 * region;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(grid); lc.blockDim = dim3(GAE_WARPS * 32); lc.dynamicSmemBytes = smem; lc.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = attr; lc.numAttrs = 1;
 #define GAE_TMA_LAUNCH(LL)                                                                                              \
             do {                                                                                                        \
                 cudaFuncSetAttribute(gae_tma_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-                gae_tma_kernel<LL><<<grid, GAE_WARPS * 32, smem, st>>>(m[0], m[1], m[2], m[3], m[4], advantages, returns, stats, \
-                                                                       T, N, epc, rows, region, g, gl);                 \
+                cudaLaunchKernelEx(&lc, gae_tma_kernel<LL>, m[0], m[1], m[2], m[3], m[4], advantages, returns, stats,   \
+                                   T, N, epc, rows, region, g, gl);                                                     \
             } while (0)
             if (L == 1) GAE_TMA_LAUNCH(1); else if (L == 2) GAE_TMA_LAUNCH(2); else if (L == 4) GAE_TMA_LAUNCH(4); else GAE_TMA_LAUNCH(8);
 #undef GAE_TMA_LAUNCH

@@ -402,8 +402,9 @@ class FusedMlpEngine(_EngineBase):
         self.prepass(buf, b)
         mark("prepass_end")
         b["stats"].zero_()
+        # the kernel right before the GAE launch is the 16-byte fill above, not the pre-update pass: inputs are settled
         ctx.gae(buf.rewards, buf.terminations, buf.truncations, b["values"], b["next_values"], cfg.gamma, cfg.gae_lambda,
-                advantages=b["adv"], returns=b["ret"], stats=b["stats"])
+                advantages=b["adv"], returns=b["ret"], stats=b["stats"], inputs_settled=True)
         dist.all_reduce_sum(b["stats"])     # global mean/std of the advantages (ppo.py:243)
         mark("gae_end")
 

@@ -82,7 +82,13 @@ int64_t dppo_launch_count(dppo_ctx* ctx);            /* kernels launched through
  *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 2: the same with single-CTA
  *                  GEMMs, 1: first-generation tcgen05
  *                  GEMMs (forward/dgrad only), 0: FP32 FFMA GEMMs everywhere
- *   "gae_variant"  0 (default): TMA-staged GAE kernel when the layout allows, 1: register-staged, 2: TMA */
+ *   "gae_variant"  0 (default): pipelined TMA-staged GAE kernel (T >= 128; chunked loads, stores overlap them) or the
+ *                  single-barrier TMA kernel when the layout allows, 1: register-staged, 2: single-barrier TMA
+ *   "gae_inputs_settled" 0 (default) / 1: promise that none of the five GAE input tensors is written by the kernel launched
+ *                  immediately before dppo_gae_f32 on the stream.  The GAE kernels are launched with programmatic stream
+ *                  serialization; with the promise they request all input tiles before griddepcontrol.wait (which then only
+ *                  guards their global writes), so consecutive launches overlap.  Without it only rewards/terminations/
+ *                  truncations (rollout data) are requested early. */
 int dppo_set_option(dppo_ctx* ctx, const char* name, int value);
 
 /* ---- rollout buffer + batched action sampling (diamond/ppo.py:153-186, 73-82) ---------- */
