@@ -166,7 +166,10 @@ def workload_config(world):
                         f"2x{H} trunk + {H}-wide heads, {A} actions, {E} epochs x {MB} minibatches",
             "envs_per_gpu": N_ENVS, "rollout_steps": T, "global_batch": T * N_ENVS * world, "minibatch": T * N_ENVS * world // MB,
             "parallelism": f"env-sharded dp{world}" if world > 1 else "single GPU",
-            "permutation": "bit-exact numpy MT19937 stream (host thread, overlapped)",
+            "permutation": ("bit-exact numpy MT19937 stream (host thread, overlapped)" if world == 1 else
+                            "rank-local bit-exact numpy MT19937 stream per shard (host thread, overlapped); equal 1/MB slices per rank"),
+            "exchange": None if world == 1 else "per optimiser step: one fused kernel per rank sums all ranks' gradients over NVLink peer "
+                                                "memory (rank order) + global-norm partials, then clip + Adam",
             "l2": "inputs (2 x 134 MB observations) exceed the 126 MB L2; GAE sub-benchmark cycles 20 buffer sets (294 MB)"}
 
 
@@ -274,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
     env_fn.vectorized = True
     cfg = PPOConfig(num_envs=N_ENVS, rollout_steps=T, network_hidden_dim=H, num_epochs=E, num_minibatches=MB, verbose=False,
                     total_steps=T * N_ENVS * 1000)
-    agent = PPO(env_fn, cfg, dp=world > 1)
+    agent = PPO(env_fn, cfg, dp=world > 1, dp_exchange=args.dp_exchange)
     host = synth_host_rollout(1 + rank)
     buf = RolloutBuffer(ctx, T, N_ENVS, D, 1, False, agent.device)
     buf.load_host(*host)
@@ -383,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp-exchange", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

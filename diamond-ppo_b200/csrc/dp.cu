@@ -1,0 +1,199 @@
+// Env-sharded data parallelism: the per-minibatch exchange step.
+//
+// Every rank (one process per GPU) computes the gradient of its shard of the global minibatch; the reference-equivalent
+// update needs their SUM before clip_grad_norm_ (ppo.py:284) and Adam (ppo.py:285).  Instead of an NCCL all-reduce followed
+// by the norm kernel, ONE kernel per rank does the exchange and the first half of the optimiser step over NVLink peer
+// memory: it publishes "my gradient of step s is complete" to every peer, waits for all peers, reads every rank's gradient
+// (+ the 4 loss sums) straight from that rank's HBM over NVLink, adds them in rank order 0..G-1 -- so every rank obtains
+// the bit-identical sum -- writes the reduced gradient locally and emits the partial sums of squares of the global norm.
+// clip_adam_kernel then finishes the step on every replica.  861 KB per rank at config S: latency-bound (one NVLink round
+// trip), which is why it is one fused launch rather than a ring.
+//
+// Exchange buffer per rank (cudaMalloc'ed here because CUDA IPC handles need a base allocation; everything else in libdppo
+// runs on caller-owned memory): [slot 0 | slot 1 | flags], slot = gradient (n floats) + 4 loss sums, padded.  Steps alternate
+// slots; a slot is re-written two steps later, which the flag protocol orders after every peer's read (a peer signals
+// step s+1 only after its step-s kernel, stream order).  flags[q] = last step rank q has published.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "optim.cuh"
+
+struct dppo_dp {
+    int world, rank;
+    int64_t n, slot_floats;
+    float* local;                       // this rank's exchange buffer
+    float* peer[DPPO_MAX_RANKS];        // every rank's buffer as mapped in this process (peer[rank] == local)
+    int opened[DPPO_MAX_RANKS];
+    cudaIpcMemHandle_t handle;
+};
+
+namespace {
+
+struct PeerPtrs { const float* slot[DPPO_MAX_RANKS]; unsigned long long* flags[DPPO_MAX_RANKS]; };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr int DP_THREADS = 256;
+
+// n4: float4 elements of the gradient; the 4 loss sums follow as one more float4 (excluded from the norm)
+__global__ void __launch_bounds__(DP_THREADS)
+dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long step, int64_t n4, float* __restrict__ grads_out,
+                          float* __restrict__ losses_out, double* __restrict__ partials)
+{
+    __shared__ double red[DP_THREADS / 32];
+    // publish: the gradient of this step was written by earlier kernels of this stream, i.e. it is complete
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(pp.flags[threadIdx.x] + rank, step);
+    }
+    // wait until every rank has published this step (flags live in this rank's own buffer)
+    if (threadIdx.x < world) {
+        const unsigned long long* f = pp.flags[rank] + threadIdx.x;
+        while (ld_acquire_sys(f) < step) __nanosleep(64);
+    }
+    __syncthreads();
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < world; ++q) {                                   // fixed rank order: identical sums on every rank
+            const float4 v = __ldcv(reinterpret_cast<const float4*>(pp.slot[q]) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (i < n4) {
+            reinterpret_cast<float4*>(grads_out)[i] = acc;
+            s += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
+        } else if (losses_out) {
+            *reinterpret_cast<float4*>(losses_out) = acc;
+        }
+    }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < DP_THREADS / 32 ? red[threadIdx.x] : 0.0;
+        s = warp_sum_d(s);
+        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    }
+}
+
+int dp_blocks(int64_t n4)
+{
+    int64_t b = (n4 + 1 + DP_THREADS - 1) / DP_THREADS;
+    if (b > 256) b = 256;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" int dppo_dp_create(dppo_ctx* ctx, int world, int rank, int64_t n_floats, dppo_dp** out)
+{
+    if (!ctx || !out) return 1;
+    *out = nullptr;
+    if (world < 1 || world > DPPO_MAX_RANKS || rank < 0 || rank >= world) DPPO_FAIL(ctx, "dp_create: bad world/rank %d/%d", world, rank);
+    if (n_floats <= 0 || n_floats % 4 != 0) DPPO_FAIL(ctx, "dp_create: gradient length must be a positive multiple of 4 floats");
+    dppo_dp* dp = new dppo_dp();
+    dp->world = world; dp->rank = rank; dp->n = n_floats;
+    dp->slot_floats = align_up(n_floats + 4, 64);
+    const size_t bytes = (size_t)(2 * dp->slot_floats) * 4 + DPPO_MAX_RANKS * sizeof(unsigned long long);
+    for (int q = 0; q < DPPO_MAX_RANKS; ++q) { dp->peer[q] = nullptr; dp->opened[q] = 0; }
+    cudaError_t e = cudaMalloc((void**)&dp->local, bytes);
+    if (e == cudaSuccess) e = cudaMemset(dp->local, 0, bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&dp->handle, dp->local);
+    if (e != cudaSuccess) {
+        if (dp->local) cudaFree(dp->local);
+        delete dp;
+        DPPO_FAIL(ctx, "dp_create: %s", cudaGetErrorString(e));
+    }
+    dp->peer[rank] = dp->local;
+    *out = dp;
+    return 0;
+}
+
+extern "C" int dppo_dp_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int dppo_dp_handle(dppo_dp* dp, void* handle_out)
+{
+    if (!dp || !handle_out) return 1;
+    memcpy(handle_out, &dp->handle, sizeof(cudaIpcMemHandle_t));
+    return 0;
+}
+
+// all_handles: world consecutive cudaIpcMemHandle_t, index = rank (as all-gathered by the caller)
+extern "C" int dppo_dp_connect(dppo_ctx* ctx, dppo_dp* dp, const void* all_handles)
+{
+    if (!ctx || !dp || !all_handles) return 1;
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int q = 0; q < dp->world; ++q) {
+        if (q == dp->rank) continue;
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) DPPO_FAIL(ctx, "dp_connect: cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+        dp->peer[q] = static_cast<float*>(p);
+        dp->opened[q] = 1;
+    }
+    return 0;
+}
+
+extern "C" int dppo_dp_destroy(dppo_dp* dp)
+{
+    if (!dp) return 0;
+    for (int q = 0; q < dp->world; ++q)
+        if (dp->opened[q]) cudaIpcCloseMemHandle(dp->peer[q]);
+    if (dp->local) cudaFree(dp->local);
+    delete dp;
+    return 0;
+}
+
+// Device pointer the LOCAL gradient (n floats) and, right after it, the 4 local loss sums of optimiser step `step` must be
+// written to (pass it as `grads` / `losses` to dppo_mlp_grad_minibatch).
+extern "C" float* dppo_dp_slot(dppo_dp* dp, int64_t step) { return dp ? dp->local + (step & 1) * dp->slot_floats : nullptr; }
+
+extern "C" int64_t dppo_dp_workspace_bytes(int64_t n) { return (int64_t)dp_blocks(n / 4) * (int64_t)sizeof(double); }
+
+// Fused exchange + optimiser step: grads_out (n floats, local) receives the rank-ordered sum of every rank's slot, losses_out
+// (4 floats, optional) the summed loss sums; then clip_grad_norm_ + Adam run on this replica exactly as dppo_clip_adam_step.
+extern "C" int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, float* params, float* grads_out, float* exp_avg,
+                                           float* exp_avg_sq, const dppo_hyper* h, float* losses_out, float* grad_norm_out,
+                                           void* ws, int64_t ws_bytes, void* stream)
+{
+    if (!ctx) return 1;
+    if (!dp || !params || !grads_out || !exp_avg || !exp_avg_sq || !h || !ws) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: null argument");
+    if (h->step < 1) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: step must be >= 1");
+    for (int q = 0; q < dp->world; ++q)
+        if (!dp->peer[q]) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: rank %d is not connected (dppo_dp_connect)", q);
+    const int64_t n4 = dp->n / 4;
+    const int nb = dp_blocks(n4);
+    if (ws_bytes < (int64_t)nb * (int64_t)sizeof(double)) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(grads_out) & 15u) || (losses_out && (reinterpret_cast<uintptr_t>(losses_out) & 15u)))
+        DPPO_FAIL(ctx, "dp_allreduce_clip_adam: grads_out / losses_out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    PeerPtrs pp;
+    const int64_t slot_off = (h->step & 1) * dp->slot_floats;
+    for (int q = 0; q < DPPO_MAX_RANKS; ++q) {
+        pp.slot[q] = q < dp->world ? dp->peer[q] + slot_off : nullptr;
+        pp.flags[q] = q < dp->world ? reinterpret_cast<unsigned long long*>(dp->peer[q] + 2 * dp->slot_floats) : nullptr;
+    }
+    double* partials = (double*)ws;
+    dp_allreduce_sumsq_kernel<<<nb, DP_THREADS, 0, st>>>(pp, dp->world, dp->rank, (unsigned long long)h->step, n4, grads_out, losses_out,
+                                                         partials);
+    DPPO_CHECK_LAUNCH(ctx, "dp_allreduce_sumsq_kernel");
+    return launch_clip_adam(ctx, params, grads_out, exp_avg, exp_avg_sq, dp->n, partials, nb, h, grad_norm_out, st);
+}
+
+// A rank that owns no row of a global minibatch contributes zeros
+extern "C" int dppo_dp_zero_slot(dppo_ctx* ctx, dppo_dp* dp, int64_t step, void* stream)
+{
+    if (!ctx || !dp) return 1;
+    if (cudaMemsetAsync(dppo_dp_slot(dp, step), 0, (size_t)dp->slot_floats * 4, (cudaStream_t)stream) != cudaSuccess)
+        DPPO_FAIL(ctx, "dp_zero_slot: cudaMemsetAsync failed");
+    return 0;
+}

@@ -203,6 +203,23 @@ int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int
     return 0;
 }
 
+int launch_clip_adam(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const double* partials,
+                     int nparts, const dppo_hyper* h, float* grad_norm_out, cudaStream_t st)
+{
+    // bias corrections in double on the host exactly as torch does with python floats (adam.py:531-547)
+    const double bc1 = 1.0 - pow(h->beta1, (double)h->step);
+    const double bc2 = 1.0 - pow(h->beta2, (double)h->step);
+    const double step_size = h->lr / bc1;
+    const double bc2_sqrt = sqrt(bc2);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
+    clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, nparts, h->grad_norm_clip,
+                                             (float)(1.0 - h->beta1), (float)h->beta2, (float)(1.0 - h->beta2), (float)bc2_sqrt,
+                                             h->adam_eps, (float)(-step_size), grad_norm_out);
+    DPPO_CHECK_LAUNCH(ctx, "clip_adam_kernel");
+    return 0;
+}
+
 static int sumsq_blocks(int64_t n)
 {
     int64_t b = (n + SUMSQ_THREADS * 4 - 1) / (SUMSQ_THREADS * 4);
@@ -226,18 +243,7 @@ extern "C" int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, f
     double* partials = (double*)ws;
     sumsq_kernel<<<nb, SUMSQ_THREADS, 0, st>>>(grads, n, partials);
     DPPO_CHECK_LAUNCH(ctx, "sumsq_kernel");
-    // bias corrections in double on the host exactly as torch does with python floats (adam.py:531-547)
-    const double bc1 = 1.0 - pow(h->beta1, (double)h->step);
-    const double bc2 = 1.0 - pow(h->beta2, (double)h->step);
-    const double step_size = h->lr / bc1;
-    const double bc2_sqrt = sqrt(bc2);
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
-    clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, nb, h->grad_norm_clip,
-                                             (float)(1.0 - h->beta1), (float)h->beta2, (float)(1.0 - h->beta2), (float)bc2_sqrt,
-                                             h->adam_eps, (float)(-step_size), grad_norm_out);
-    DPPO_CHECK_LAUNCH(ctx, "clip_adam_kernel");
-    return 0;
+    return launch_clip_adam(ctx, params, grads, exp_avg, exp_avg_sq, n, partials, nb, h, grad_norm_out, st);
 }
 
 extern "C" int dppo_gather_rows_f32(dppo_ctx* ctx, const float* src, const int32_t* idx, float* dst, int64_t rows,

@@ -19,3 +19,7 @@ struct GradSegTable {
 // kernel's loss partials into losses[0..3].
 int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int64_t total, const float* loss_partials,
                        int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* losses, cudaStream_t st);
+
+// clip_grad_norm_ + Adam from `nparts` fp64 partial sums of squares of the (already summed) gradient
+int launch_clip_adam(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const double* partials,
+                     int nparts, const dppo_hyper* h, float* grad_norm_out, cudaStream_t st);

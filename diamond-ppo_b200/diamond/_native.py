@@ -45,7 +45,8 @@ EXPORTS = [
     "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_clip_adam_step",
     "dppo_clip_adam_workspace_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
-    "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe",
+    "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy",
+    "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
 ]
 
 _lib = None
@@ -64,8 +65,9 @@ def load_library() -> C.CDLL:
             lib.dppo_last_error.restype = C.c_char_p
             lib.dppo_last_error.argtypes = [C.c_void_p]
             for name in ("dppo_step_record_bytes", "dppo_mlp_workspace_bytes", "dppo_clip_adam_workspace_bytes",
-                         "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count"):
+                         "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes"):
                 getattr(lib, name).restype = C.c_int64
+            lib.dppo_dp_slot.restype = C.c_void_p
             _lib = lib
     return _lib
 
@@ -73,6 +75,8 @@ def load_library() -> C.CDLL:
 def _ptr(t):
     if t is None:
         return C.c_void_p(0)
+    if isinstance(t, int):                      # raw device pointer (e.g. a slot of the DP exchange buffer)
+        return C.c_void_p(t)
     if isinstance(t, torch.Tensor):
         assert t.is_contiguous(), "libdppo takes contiguous tensors"
         return C.c_void_p(t.data_ptr())
@@ -334,6 +338,38 @@ class Context:
         torch.cuda.synchronize()
         o = out[:g.value]
         return o[o > 0].float() / iters
+
+    # ---- data-parallel exchange (dp.cu) --------------------------------------------------------
+    def dp_create(self, world, rank, n_floats):
+        h = C.c_void_p()
+        self._check(self.lib.dppo_dp_create(self.h, C.c_int(world), C.c_int(rank), C.c_int64(n_floats), C.byref(h)), "dppo_dp_create")
+        return h
+
+    def dp_handle(self, dp) -> bytes:
+        buf = C.create_string_buffer(self.lib.dppo_dp_handle_bytes())
+        self.lib.dppo_dp_handle(dp, buf)
+        return buf.raw
+
+    def dp_connect(self, dp, all_handles: bytes):
+        self._check(self.lib.dppo_dp_connect(self.h, dp, C.c_char_p(all_handles)), "dppo_dp_connect")
+
+    def dp_slot(self, dp, step) -> int:
+        return int(self.lib.dppo_dp_slot(dp, C.c_int64(step)))
+
+    def dp_zero_slot(self, dp, step):
+        self._check(self.lib.dppo_dp_zero_slot(self.h, dp, C.c_int64(step), _stream()), "dppo_dp_zero_slot")
+
+    def dp_workspace_bytes(self, n):
+        return int(self.lib.dppo_dp_workspace_bytes(C.c_int64(n)))
+
+    def dp_allreduce_clip_adam(self, dp, params, grads_out, exp_avg, exp_avg_sq, hyper, losses_out, ws, grad_norm_out=None):
+        self._check(self.lib.dppo_dp_allreduce_clip_adam(self.h, dp, _ptr(params), _ptr(grads_out), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                                         C.byref(hyper), _ptr(losses_out), _ptr(grad_norm_out), _ptr(ws),
+                                                         C.c_int64(ws.numel() * ws.element_size()), _stream()),
+                    "dppo_dp_allreduce_clip_adam")
+
+    def dp_destroy(self, dp):
+        self.lib.dppo_dp_destroy(dp)
 
     def fma_peak(self, sink, iters):
         b, t = C.c_int(), C.c_int()

@@ -164,7 +164,15 @@ class RolloutBuffer:
 # Data-parallel plumbing: env-sharded, one process per GPU
 # ------------------------------------------------------------------------------------------------
 class _Dist:
-    def __init__(self, group=None, enabled=False):
+    """permutation: "local" (default) -- every rank permutes its own shard with its own bit-exact numpy stream and takes
+    equal 1/MB slices of it (identical to the reference at one GPU; at G GPUs a valid PPO minibatch scheme that needs no
+    host work proportional to the GLOBAL batch); "global" -- every rank generates the reference's permutation of the
+    concatenated buffer and keeps its shard's members (sample-for-sample the reference's minibatches, used by the
+    equivalence tests; the sequential MT19937 shuffle of G x B indices then runs on every host).
+    exchange: "fused" (default on CUDA/NCCL groups) -- dppo_dp_allreduce_clip_adam over NVLink peer memory;
+    "nccl" -- torch.distributed all_reduce followed by dppo_clip_adam_step."""
+
+    def __init__(self, group=None, enabled=False, permutation="local", exchange="fused"):
         import torch.distributed as dist
         self.dist = dist
         self.enabled = bool(enabled or group is not None) and dist.is_available() and dist.is_initialized()
@@ -173,10 +181,26 @@ class _Dist:
         self.rank = dist.get_rank(group) if self.enabled else 0
         if self.world == 1:
             self.enabled = False
+        if permutation not in ("local", "global") or exchange not in ("fused", "nccl"):
+            raise ValueError("dp_permutation must be 'local' or 'global', dp_exchange 'fused' or 'nccl'")
+        self.permutation, self.exchange = permutation, exchange
+        self.global_perm = self.enabled and permutation == "global"
 
     def all_reduce_sum(self, t: torch.Tensor):
         if self.enabled:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def connect_exchange(self, ctx, n_floats, device):
+        """Creates this rank's exchange buffer and maps every peer's (CUDA IPC handles all-gathered over the group)."""
+        if not self.enabled or self.exchange != "fused" or self.dist.get_backend(self.group) != "nccl":
+            return None
+        dp = ctx.dp_create(self.world, self.rank, n_floats)
+        mine = torch.frombuffer(bytearray(ctx.dp_handle(dp)), dtype=torch.uint8).to(device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(gathered, mine, group=self.group)
+        ctx.dp_connect(dp, b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered))
+        self.dist.barrier(group=self.group)
+        return dp
 
 
 class _PermWorker(threading.Thread):
@@ -256,8 +280,11 @@ class _EngineBase:
                 p.data = view                                            # parameters alias the flat buffer
                 p.grad = self.G[off:off + n].view(*shape)
                 self.param_list.append((name, p, off, n, shape))
-        self.adam_ws = torch.empty(self.ctx.clip_adam_workspace_bytes(total) // 8 + 1, dtype=torch.float64, device=dev)
+        ws_bytes = max(self.ctx.clip_adam_workspace_bytes(total), self.ctx.dp_workspace_bytes(total))
+        self.adam_ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.float64, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.total = total
+        self.dpx = None
         self.adam_step = 0
 
     def bind_optimizer(self, optimizer: torch.optim.Optimizer):
@@ -308,6 +335,7 @@ class FusedMlpEngine(_EngineBase):
         self.network = network
         self.fm = FlatMlp(obs_dim, cfg.network_hidden_dim, act_dim, continuous)
         self._adopt(network, self.fm.slices, self.fm.total)
+        self.dpx = dist.connect_exchange(ctx, self.fm.total, device)    # fused NVLink exchange (None: single GPU / NCCL path)
         self.D, self.A = obs_dim, act_dim
         self.fwd_rows = 65536
         self.fwd_ws = torch.empty(ctx.mlp_workspace_bytes(self.fm.desc, self.fwd_rows, False) // 4 + 256, device=device)
@@ -352,15 +380,16 @@ class FusedMlpEngine(_EngineBase):
             return self._bufs[key]
         dev, B = self.device, T * N_
         B_global = B * self.dist.world
+        B_perm = B_global if (self.dist.global_perm or not self.dist.enabled) else B    # indices generated per epoch
         f = dict(dtype=torch.float32, device=dev)
         b = dict(head=torch.empty(B, self.A, **f), values=torch.empty(T, N_, **f), next_values=torch.empty(T, N_, **f),
                  old_logp=torch.empty(T, N_, **f), adv=torch.empty(T, N_, **f), ret=torch.empty(T, N_, **f),
                  stats=torch.zeros(2, dtype=torch.float64, device=dev), losses=torch.zeros(E * MB, 4, **f),
-                 idx=torch.empty(E, B_global if not self.dist.enabled else B, dtype=torch.int32, device=dev),
-                 h_idx=[torch.empty(B_global if not self.dist.enabled else B, dtype=torch.int32).pin_memory() for _ in range(E)])
-        m_max = B_global // MB if not self.dist.enabled else B      # a rank may own a whole global minibatch in the worst case
-        if self.dist.enabled:
-            m_max = min(B, B_global // MB)
+                 idx=torch.empty(E, B if self.dist.enabled else B_perm, dtype=torch.int32, device=dev),
+                 h_idx=[torch.empty(B if self.dist.enabled else B_perm, dtype=torch.int32).pin_memory() for _ in range(E)])
+        m_max = B_perm // MB
+        if self.dist.global_perm:
+            m_max = min(B, B_global // MB)                          # a rank may own a whole global minibatch in the worst case
         b["train_ws"] = torch.empty(self.ctx.mlp_workspace_bytes(self.fm.desc, m_max, True) // 4 + 256, **f)
         b["m_max"] = m_max
         self._bufs[key] = b
@@ -389,8 +418,11 @@ class FusedMlpEngine(_EngineBase):
         M_global = B_global // MB
         self._resync_optimizer()
         b = self._alloc(T, N_, E, MB)
-        shard = (N_ * dist.world, dist.rank * N_, N_) if dist.enabled else None
-        worker = _PermWorker(B_global, E, MB, [h.numpy() for h in b["h_idx"]], shard)
+        shard = (N_ * dist.world, dist.rank * N_, N_) if dist.global_perm else None
+        B_perm = B_global if (dist.global_perm or not dist.enabled) else B
+        if B_perm % MB != 0:
+            raise ValueError(f"cannot reshape array of size {E * B_perm} into shape ({E},{MB},{B_perm // MB})")
+        worker = _PermWorker(B_perm, E, MB, [h.numpy() for h in b["h_idx"]], shard)
         worker.start()                      # host permutation overlaps the pre-update pass on the GPU
 
         def mark(name):
@@ -418,12 +450,25 @@ class FusedMlpEngine(_EngineBase):
             worker.wait(e)
             b["idx"][e].copy_(b["h_idx"][e], non_blocking=True)
             for k in range(MB):
-                if dist.enabled:
+                if dist.global_perm:
                     off, m = worker.counts[e][k]
                 else:
-                    off, m = k * M_global, M_global
+                    m = B_perm // MB
+                    off = k * m
                 self.adam_step += 1
                 hyper.step = self.adam_step
+                if self.dpx is not None:
+                    # env-sharded DP, fused exchange: the local gradient and loss sums go straight into this step's slot of
+                    # the exchange buffer; one kernel per rank then sums all ranks' slots over NVLink and starts the optimiser step
+                    slot = ctx.dp_slot(self.dpx, self.adam_step)
+                    if m > 0:
+                        ctx.mlp_grad_minibatch(desc, self.P, slot, obs_flat, actions, old_logp, adv, ret, b["stats"],
+                                               b["idx"][e][off:off + m], m, hyper, slot + 4 * self.total, b["train_ws"])
+                    else:
+                        ctx.dp_zero_slot(self.dpx, self.adam_step)
+                    ctx.dp_allreduce_clip_adam(self.dpx, self.P, self.G, self.M, self.V, hyper, losses[e * MB + k], self.adam_ws,
+                                               self.grad_norm)
+                    continue
                 if m > 0:
                     ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"],
                                            b["idx"][e][off:off + m], m, hyper, losses[e * MB + k], b["train_ws"])
@@ -538,13 +583,13 @@ class _PPOBase:
     _continuous = False
     _default_network: Any = None
 
-    def _setup(self, env_fn, cfg, network_cls, process_group=None, dp=False):
+    def _setup(self, env_fn, cfg, network_cls, process_group=None, dp=False, dp_permutation="local", dp_exchange="fused"):
         self.device = _require_cuda()
         self.ctx = N.get_context(self.device.index)
         if cfg.seed is not None:
             np.random.seed(cfg.seed)                                   # ppo.py:120-122
             torch.manual_seed(cfg.seed)
-        self._dist = _Dist(process_group, dp)
+        self._dist = _Dist(process_group, dp, dp_permutation, dp_exchange)
 
         if getattr(env_fn, "vectorized", False):                       # additive: env_fn(num_envs) -> batched vector env
             self.envs = env_fn(cfg.num_envs)
@@ -649,8 +694,8 @@ class PPO(_PPOBase):
     _default_network = ActorCriticNetwork
 
     def __init__(self, env_fn: Callable[[], Any], cfg: PPOConfig = PPOConfig(), network_cls: Any = ActorCriticNetwork,
-                 *, process_group=None, dp: bool = False) -> None:
-        self._setup(env_fn, cfg, network_cls, process_group, dp)
+                 *, process_group=None, dp: bool = False, dp_permutation: str = "local", dp_exchange: str = "fused") -> None:
+        self._setup(env_fn, cfg, network_cls, process_group, dp, dp_permutation, dp_exchange)
         self.current_step = 0
 
 
@@ -660,5 +705,6 @@ class ContinuousPPO(_PPOBase):
     _default_network = ContinuousActorCriticNetwork
 
     def __init__(self, env_fn: Callable[[], Any], cfg: ContinuousPPOConfig = ContinuousPPOConfig(),
-                 network_cls: Any = ContinuousActorCriticNetwork, *, process_group=None, dp: bool = False) -> None:
-        self._setup(env_fn, cfg, network_cls, process_group, dp)
+                 network_cls: Any = ContinuousActorCriticNetwork, *, process_group=None, dp: bool = False,
+                 dp_permutation: str = "local", dp_exchange: str = "fused") -> None:
+        self._setup(env_fn, cfg, network_cls, process_group, dp, dp_permutation, dp_exchange)

@@ -163,6 +163,28 @@ int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, float* exp_a
                         const dppo_hyper* hyper, float* grad_norm_out, void* ws, int64_t ws_bytes, void* stream);
 int64_t dppo_clip_adam_workspace_bytes(int64_t n);
 
+/* ---- env-sharded data parallelism: the per-minibatch exchange step -------- */
+/* One process per GPU.  Each rank writes the gradient of its shard of the global minibatch (and its 4 loss sums) into the
+ * slot dppo_dp_slot() returns for that optimiser step; dppo_dp_allreduce_clip_adam then performs, in ONE kernel per rank,
+ * the cross-GPU sum over NVLink peer memory (every rank reads every rank's slot and adds them in rank order, so all
+ * replicas obtain the bit-identical gradient) together with the partial sums of the global gradient norm, followed by the
+ * clip + Adam kernel of dppo_clip_adam_step.  Set-up: dppo_dp_create (allocates the exchange buffer -- the one device
+ * allocation libdppo makes, CUDA IPC needs a base allocation), all-gather the dppo_dp_handle bytes of every rank
+ * (torch.distributed), dppo_dp_connect.  All ranks must call dppo_dp_allreduce_clip_adam with the same step sequence. */
+#define DPPO_MAX_RANKS 16
+typedef struct dppo_dp dppo_dp;
+int dppo_dp_create(dppo_ctx* ctx, int world, int rank, int64_t n_floats, dppo_dp** out);
+int dppo_dp_handle_bytes(void);
+int dppo_dp_handle(dppo_dp* dp, void* handle_out);
+int dppo_dp_connect(dppo_ctx* ctx, dppo_dp* dp, const void* all_handles);
+int dppo_dp_destroy(dppo_dp* dp);
+float* dppo_dp_slot(dppo_dp* dp, int64_t step);      /* [n_floats gradient | 4 loss sums] of optimiser step `step` */
+int dppo_dp_zero_slot(dppo_ctx* ctx, dppo_dp* dp, int64_t step, void* stream);   /* a rank with no rows contributes zeros */
+int64_t dppo_dp_workspace_bytes(int64_t n_floats);
+int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, float* params, float* grads_out, float* exp_avg,
+                                float* exp_avg_sq, const dppo_hyper* hyper, float* losses_out, float* grad_norm_out,
+                                void* ws, int64_t ws_bytes, void* stream);
+
 /* Standalone loss forward+backward for custom network_cls modules (readme.md:89-111): the user
  * module runs under PyTorch autograd, this provides loss values and d(loss)/d(outputs).
  * Rows are already gathered (M rows).  losses[0..3] = policy, value, entropy, total. */

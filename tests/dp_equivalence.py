@@ -2,8 +2,10 @@
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dp_equivalence.py
 
-Env-sharded data-parallel learn() over G ranks (global permutation, gradient all-reduce) must equal the
-single-GPU learn() on the concatenated buffer up to fp32 summation order."""
+Env-sharded data-parallel learn() over G ranks with the GLOBAL permutation must equal the single-GPU learn() on the
+concatenated buffer up to fp32 summation order -- for both exchange paths: the fused NVLink peer-memory
+kernel (dppo_dp_allreduce_clip_adam) and NCCL all_reduce + dppo_clip_adam_step.  The default rank-local permutation mode
+is checked for replica consistency (bit-identical parameters on every rank) and finite losses."""
 import os
 import sys
 
@@ -33,31 +35,49 @@ def main():
         return envs.BatchedSyntheticVectorEnv(n, D, A)
     env_fn.vectorized = True
     cfg = PPOConfig(num_envs=NL, rollout_steps=T, network_hidden_dim=H, num_epochs=2, num_minibatches=4, verbose=False)
+    ok, same = True, True
+    single_result = None
+    for exchange in ("fused", "nccl"):
+        agent = PPO(env_fn, cfg, dp=True, dp_permutation="global", dp_exchange=exchange)
+        if exchange == "fused":
+            assert agent.engine.dpx is not None, "fused exchange was not set up"
+        init = {k: v.detach().clone() for k, v in agent.network.state_dict().items()}
+        np.random.seed(123)
+        agent.learn(local_exp)
+        torch.cuda.synchronize()
+        if rank == 0:
+            cfg1 = PPOConfig(num_envs=NG, rollout_steps=T, network_hidden_dim=H, num_epochs=2, num_minibatches=4, verbose=False)
+            single = PPO(env_fn, cfg1, dp=False)
+            single.network.load_state_dict(init)
+            np.random.seed(123)
+            single.learn(full)
+            torch.cuda.synchronize()
+            worst = 0.0
+            for (n, p), (_, q) in zip(agent.network.named_parameters(), single.network.named_parameters()):
+                err = float((p - q).abs().max() / q.abs().max().clamp_min(1e-12))
+                worst = max(worst, err)
+            lerr = float((agent.last_losses - single.last_losses).abs().max())
+            good = worst <= 2e-5 and lerr <= 1e-5
+            ok = ok and good
+            print(f"dp{world} [{exchange}] vs single: max param err {worst:.2e}, max loss err {lerr:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+        # every rank holds identical parameters after the update
+        flat = agent.engine.P.clone()
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        same = same and bool(torch.equal(flat, ref))
+    # default mode: rank-local permutations, fused exchange
     agent = PPO(env_fn, cfg, dp=True)
-    init = {k: v.detach().clone() for k, v in agent.network.state_dict().items()}
     np.random.seed(123)
     agent.learn(local_exp)
+    agent.learn(local_exp)
     torch.cuda.synchronize()
-    ok = True
-    if rank == 0:
-        cfg1 = PPOConfig(num_envs=NG, rollout_steps=T, network_hidden_dim=H, num_epochs=2, num_minibatches=4, verbose=False)
-        single = PPO(env_fn, cfg1, dp=False)
-        single.network.load_state_dict(init)
-        np.random.seed(123)
-        single.learn(full)
-        torch.cuda.synchronize()
-        worst = 0.0
-        for (n, p), (_, q) in zip(agent.network.named_parameters(), single.network.named_parameters()):
-            err = float((p - q).abs().max() / q.abs().max().clamp_min(1e-12))
-            worst = max(worst, err)
-        lerr = float((agent.last_losses - single.last_losses).abs().max())
-        ok = worst <= 2e-5 and lerr <= 1e-5
-        print(f"dp{world} vs single: max param err {worst:.2e}, max loss err {lerr:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
-    # every rank holds identical parameters after the update
     flat = agent.engine.P.clone()
     ref = flat.clone()
     dist.broadcast(ref, src=0)
-    same = bool(torch.equal(flat, ref))
+    local_ok = bool(torch.equal(flat, ref)) and bool(torch.isfinite(agent.last_losses).all()) and bool(torch.isfinite(flat).all())
+    if rank == 0:
+        print(f"dp{world} [local permutation, fused]: replicas identical and finite -> {'OK' if local_ok else 'FAIL'}", flush=True)
+    same = same and local_ok
     t = torch.tensor([int(ok and same)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
