@@ -1,0 +1,304 @@
+"""RecurrentPPO (reference: diamond/recurrent_ppo.py) on the libdppo kernels.
+
+Kept from the reference: `RecurrentPPO(env_fn, cfg, network_cls)`, `RecurrentPPOConfig`, `GRUCore`,
+`RecurrentActorCriticNetwork` with `get_values(obs[T,B,D], hx, dones)` /
+`get_logits_values_and_hx(obs, hx, dones) -> (logits, values, hx)` (recurrent_ppo.py:127-149), the attributes
+`current_observations / current_hx / prev_dones` and `rollout() / calculate_advantage() / learn() / train()`.
+
+What runs where: the GRU time loop with done-masked hidden resets and the full-T BPTT per minibatch
+(recurrent_ppo.py:82-87, 337-341) run under torch autograd on the GPU -- restructured as ONE input-projection GEMM over
+all T steps followed by T hidden-state steps, instead of T one-step `nn.GRU` calls; action sampling, GAE + returns,
+advantage normalisation, the bit-exact minibatch permutation, the PPO loss forward/backward, gradient clipping and Adam
+run on the libdppo CUDA kernels.  The reference's `hx or zeros` / `dones or zeros` lines (recurrent_ppo.py:78-79) raise on
+every call; the intended `is None` semantics are implemented.
+"""
+from __future__ import annotations
+
+import time
+from math import sqrt
+from typing import Any, Callable
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import envs as gym
+from .agents import _Dist, _EngineBase, _PermWorker, _require_cuda
+from .config import RecurrentPPOConfig
+from .networks import _obs_dim, network_parameter_init_
+from .utils import Checkpointer, Logger, Ticker, Timer
+
+
+class GRUCore(nn.GRU):
+    """GRU for RL with per-timestep hidden state resets (recurrent_ppo.py:41-91).  Parameters are nn.GRU's
+    (`weight_ih_l0 [3Hg, H]`, `weight_hh_l0 [3Hg, Hg]`, `bias_ih_l0`, `bias_hh_l0`; gate order r, z, n), so state dicts are
+    interchangeable with the reference."""
+
+    def __init__(self, input_dim: int, hidden_dim: int) -> None:
+        super().__init__(input_dim, hidden_dim)
+
+    def forward(self, x: torch.Tensor, hx: torch.Tensor | None, dones: torch.Tensor | None):
+        T, B = x.shape[:2]
+        Hg = self.hidden_size
+        h = torch.zeros(B, Hg, dtype=x.dtype, device=x.device) if hx is None else hx.reshape(B, Hg)
+        # all T input projections in one GEMM; only the hidden-to-hidden product is sequential
+        gi = torch.addmm(self.bias_ih_l0, x.reshape(T * B, -1), self.weight_ih_l0.t()).view(T, B, 3 * Hg)
+        keep = None if dones is None else (~dones.to(torch.bool)).to(x.dtype).unsqueeze(-1)      # [T, B, 1]
+        outs = []
+        for t in range(T):
+            if keep is not None:
+                h = h * keep[t]                                   # reset hidden state at the start of new episodes (:84)
+            gh = torch.addmm(self.bias_hh_l0, h, self.weight_hh_l0.t())
+            i_r, i_z, i_n = gi[t].chunk(3, dim=-1)
+            h_r, h_z, h_n = gh.chunk(3, dim=-1)
+            r = torch.sigmoid(i_r + h_r)
+            z = torch.sigmoid(i_z + h_z)
+            n = torch.tanh(i_n + r * h_n)
+            h = (1.0 - z) * n + z * h
+            outs.append(h)
+        return torch.stack(outs, dim=0), h.unsqueeze(0)
+
+
+class RecurrentActorCriticNetwork(nn.Module):
+    """Linear-Tanh -> GRU -> actor / critic heads (recurrent_ppo.py:94-149)."""
+
+    def __init__(self, observation_space, action_space, cfg: RecurrentPPOConfig) -> None:
+        super().__init__()
+        assert hasattr(action_space, "n"), "Only Discrete action spaces are supported."
+        d, h, hg = _obs_dim(observation_space), int(cfg.network_hidden_dim), int(cfg.gru_hidden_dim)
+        self.base = nn.Sequential(nn.Linear(d, h), nn.Tanh())
+        self.gru = GRUCore(h, hg)
+        self.actor_head = nn.Sequential(nn.Linear(hg, h), nn.Tanh(), nn.Linear(h, int(action_space.n)))
+        self.actor_out_layer = self.actor_head[-1]
+        self.critic_head = nn.Sequential(nn.Linear(hg, h), nn.Tanh(), nn.Linear(h, 1))
+
+    def get_values(self, observations, hx, dones) -> torch.Tensor:
+        x, _ = self.gru.forward(self.base(observations), hx, dones)
+        return self.critic_head(x).squeeze(-1)
+
+    def get_logits_values_and_hx(self, observations, hx, dones):
+        x, hx = self.gru.forward(self.base(observations), hx, dones)
+        return self.actor_head(x), self.critic_head(x).squeeze(-1), hx
+
+
+class RecurrentRollout:
+    """Device-resident rollout of the recurrent agent; iterating yields the reference's 10-item step records
+    (recurrent_ppo.py:234-245)."""
+
+    def __init__(self, T, N_, D, Hg, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.T, self.N = T, N_
+        self.obs = torch.empty(T, N_, D, **f)
+        self.actions = torch.empty(T, N_, dtype=torch.int64, device=device)
+        self.rewards, self.terminations, self.truncations = (torch.empty(T, N_, **f) for _ in range(3))
+        self.prev_dones = torch.empty(T, N_, dtype=torch.bool, device=device)
+        self.log_probs, self.values, self.next_values = (torch.empty(T, N_, **f) for _ in range(3))
+        self.hx0 = torch.zeros(1, N_, Hg, **f)
+        self.filled = 0
+
+    @staticmethod
+    def from_lists(experience, device) -> "RecurrentRollout":
+        cols = list(zip(*experience))
+        dev_t = lambda x, dt: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=device, dtype=dt)
+        obs = torch.stack([dev_t(o, torch.float32) for o in cols[0]])
+        T, N_, D = obs.shape
+        hx0 = dev_t(cols[9][0], torch.float32).clone()                  # recurrent_ppo.py:313
+        r = RecurrentRollout(T, N_, D, hx0.shape[-1], device)
+        r.obs.copy_(obs)
+        r.actions.copy_(torch.stack([dev_t(a, torch.int64) for a in cols[1]]))
+        r.rewards.copy_(dev_t(np.asarray([np.asarray(x) for x in cols[2]]), torch.float32))       # f64 -> f32 (:306)
+        r.terminations.copy_(dev_t(np.asarray([np.asarray(x) for x in cols[3]]), torch.float32))
+        r.truncations.copy_(dev_t(np.asarray([np.asarray(x) for x in cols[4]]), torch.float32))
+        r.prev_dones.copy_(torch.stack([dev_t(p, torch.bool) for p in cols[5]]))
+        r.log_probs.copy_(torch.stack([dev_t(x, torch.float32) for x in cols[6]]))
+        r.values.copy_(torch.stack([dev_t(x, torch.float32) for x in cols[7]]))
+        r.next_values.copy_(torch.stack([dev_t(x, torch.float32) for x in cols[8]]))
+        r.hx0.copy_(hx0.reshape(r.hx0.shape))
+        r.filled = T
+        return r
+
+    def __len__(self):
+        return self.filled
+
+    def __iter__(self):
+        for t in range(self.filled):
+            yield [self.obs[t], self.actions[t], self.rewards[t].cpu().numpy(), self.terminations[t].bool().cpu().numpy(),
+                   self.truncations[t].bool().cpu().numpy(), self.prev_dones[t], self.log_probs[t], self.values[t],
+                   self.next_values[t], self.hx0]
+
+
+class RecurrentEngine(_EngineBase):
+    """learn() of the recurrent agent: sequence forward/backward under autograd, everything else on libdppo kernels."""
+
+    def __init__(self, ctx, network, cfg, device):
+        self.ctx, self.cfg, self.device = ctx, cfg, device
+        self.dist = _Dist(None, False)
+        self.network = network
+        offsets, o = {}, 0
+        for name, p in network.named_parameters():
+            offsets[name] = (o, tuple(p.shape))
+            o += (p.numel() + 3) // 4 * 4
+        self._adopt(network, offsets, max(o, 4))
+        self.last_losses = None
+        self.draws = 0
+        self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+
+    def learn(self, ro: RecurrentRollout):
+        cfg, ctx, net, dev = self.cfg, self.ctx, self.network, self.device
+        T, N_ = ro.T, ro.N
+        E, MB = cfg.num_epochs, cfg.num_minibatches
+        B = T * N_
+        if B % MB != 0:                                                  # the reference's reshape raises here (:329)
+            raise ValueError(f"cannot reshape array of size {E * B} into shape ({E},{MB},{B // MB})")
+        M = B // MB
+        self._resync_optimizer()
+        h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
+        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
+        worker.start()
+        # GAE with the values stored at rollout time, returns, advantage normalisation (recurrent_ppo.py:315-318)
+        stats = torch.zeros(2, dtype=torch.float64, device=dev)
+        adv = torch.empty(T, N_, device=dev)
+        ret = torch.empty(T, N_, device=dev)
+        ctx.gae(ro.rewards, ro.terminations, ro.truncations, ro.values.contiguous(), ro.next_values.contiguous(), cfg.gamma,
+                cfg.gae_lambda, advantages=adv, returns=ret, stats=stats)
+        if cfg.advantage_norm:
+            adv = ctx.adv_normalize(adv, stats, B)
+        hyper = self._hyper(cfg, M, B)
+        hyper.advantage_norm = 0                                         # already normalised above
+        old_logp, adv_f, ret_f = ro.log_probs.reshape(B).contiguous(), adv.view(B), ret.view(B)
+        act_bits = ro.actions.reshape(B).to(torch.int32).view(torch.float32)
+        A = net.actor_out_layer.out_features
+        losses = torch.zeros(E * MB, 4, device=dev)
+        loss_ws = torch.empty(ctx.ppo_loss_workspace_bytes(M, max(A, 32)) // 4 + 64, device=dev)
+        idx = torch.empty(E, B, dtype=torch.int32, device=dev)
+        hx0 = ro.hx0.clone()
+        for e in range(E):
+            worker.wait(e)
+            idx[e].copy_(h_idx[e], non_blocking=True)
+            for k in range(MB):
+                mb = idx[e][k * M:(k + 1) * M]
+                mb64 = mb.to(torch.int64)
+                a_mb = ctx.gather_rows(act_bits, mb)
+                lp_mb, adv_mb, ret_mb = ctx.gather_rows(old_logp, mb), ctx.gather_rows(adv_f, mb), ctx.gather_rows(ret_f, mb)
+                self.adam_step += 1
+                hyper.step = self.adam_step
+                self.G.zero_()
+                # full-sequence forward with the current parameters, then the minibatch rows (recurrent_ppo.py:337-341)
+                logits, values, _ = net.get_logits_values_and_hx(ro.obs, hx0, ro.prev_dones)
+                logits_mb = logits.reshape(B, A).index_select(0, mb64).contiguous()
+                val_mb = values.reshape(B).index_select(0, mb64).contiguous()
+                dlogits, dval = torch.empty_like(logits_mb), torch.empty_like(val_mb)
+                ctx.ppo_loss_discrete(logits_mb.detach(), val_mb.detach(), a_mb.view(torch.int32), lp_mb, adv_mb, ret_mb, hyper,
+                                      losses[e * MB + k], dlogits, dval, loss_ws)
+                torch.autograd.backward([logits_mb, val_mb], [dlogits, dval])
+                ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+        worker.finish()
+        self._publish_steps()
+        self.last_losses = losses
+
+
+class RecurrentPPO:
+    """Recurrent (GRU) discrete-action PPO (reference: diamond/recurrent_ppo.py:164-394)."""
+
+    def __init__(self, env_fn: Callable[[], Any], cfg: RecurrentPPOConfig = RecurrentPPOConfig(),
+                 network_cls: Any = RecurrentActorCriticNetwork) -> None:
+        self.device = _require_cuda()
+        self.ctx = N.get_context(self.device.index)
+        if cfg.seed is not None:
+            np.random.seed(cfg.seed)                                    # recurrent_ppo.py:173-175
+            torch.manual_seed(cfg.seed)
+        if getattr(env_fn, "vectorized", False):
+            self.envs = env_fn(cfg.num_envs)
+        else:
+            self.envs = gym.vector.SyncVectorEnv([env_fn for _ in range(cfg.num_envs)], copy=True, autoreset_mode="Disabled")
+        obs_space, act_space = self.envs.single_observation_space, self.envs.single_action_space
+        self.network = network_cls(obs_space, act_space, cfg=cfg).to(self.device)
+        network_parameter_init_(self.network, gain=sqrt(2.0), small_actor_out=True)     # touches nn.Linear only (:152-161)
+        self.obs_dim = int(np.prod(obs_space.shape))
+        self.engine = RecurrentEngine(self.ctx, self.network, cfg, self.device)
+        self.optimizer = torch.optim.Adam(self.network.parameters(), lr=cfg.lr, eps=cfg.adam_eps)
+        self.engine.bind_optimizer(self.optimizer)
+        self.lr_scheduler = torch.optim.lr_scheduler.LinearLR(
+            self.optimizer, start_factor=1.0, end_factor=0.05 if cfg.decay_lr else 1.0,
+            total_iters=cfg.total_steps // (cfg.num_envs * cfg.rollout_steps))
+        self.logger = Logger()
+        self.timer = Timer()
+        self.checkpointer = Checkpointer(folder="models", run_name="default")
+        self.ticker = Ticker(cfg.total_steps, cfg.num_envs, cfg.rollout_steps, verbose=cfg.verbose)
+        self.cfg = cfg
+
+    # ---- rollout (recurrent_ppo.py:205-263) ----------------------------------------------------------
+    def rollout(self) -> RecurrentRollout:
+        cfg, dev = self.cfg, self.device
+        T, N_ = cfg.rollout_steps, cfg.num_envs
+        ro = RecurrentRollout(T, N_, self.obs_dim, cfg.gru_hidden_dim, dev)
+        observations, hx, prev_dones = self.current_observations, self.current_hx, self.prev_dones
+        ro.hx0.copy_(hx)
+        for t in range(T):
+            obs_t = torch.as_tensor(np.asarray(observations, dtype=np.float32)[None, ...], device=dev)
+            pd_t = torch.as_tensor(np.asarray(prev_dones)[None, ...], dtype=torch.bool, device=dev)
+            with torch.inference_mode():
+                logits, values, new_hx = self.network.get_logits_values_and_hx(obs_t, hx, pd_t)
+            # Categorical(logits).sample() + log_prob on the device (counter-based generator, dppo_sample_categorical)
+            actions = torch.empty(N_, dtype=torch.int64, device=dev)
+            self.ctx.sample_categorical(logits.squeeze(0).contiguous(), self.engine.seed, self.engine.draws, 0, actions, ro.log_probs[t])
+            self.engine.draws += 1
+            next_observations, rewards, terminations, truncations, infos = self.envs.step(actions.cpu().numpy())
+            final_t = torch.as_tensor(np.asarray(next_observations, dtype=np.float32)[None, ...], device=dev)
+            with torch.inference_mode():
+                next_values = self.network.get_values(final_t, new_hx, None)      # V(final obs | h_{t+1}), no reset (:226-232)
+            ro.obs[t].copy_(obs_t.squeeze(0)); ro.actions[t].copy_(actions)
+            ro.rewards[t].copy_(torch.as_tensor(np.asarray(rewards, dtype=np.float32), device=dev))
+            ro.terminations[t].copy_(torch.as_tensor(np.asarray(terminations, dtype=np.float32), device=dev))
+            ro.truncations[t].copy_(torch.as_tensor(np.asarray(truncations, dtype=np.float32), device=dev))
+            ro.prev_dones[t].copy_(pd_t.squeeze(0)); ro.values[t].copy_(values.squeeze(0)); ro.next_values[t].copy_(next_values.squeeze(0))
+            dones = np.logical_or(terminations, truncations)
+            if np.any(dones):
+                observations, infos = self.envs.reset(options={"reset_mask": dones})
+            else:
+                observations = next_observations
+            hx = new_hx
+            prev_dones = dones
+            if self.ticker is not None:
+                self.ticker.tick(rewards, dones)
+        ro.filled = T
+        self.current_observations, self.current_hx, self.prev_dones = observations, hx, prev_dones
+        return ro
+
+    # ---- GAE (recurrent_ppo.py:265-299) ----------------------------------------------------------------
+    def calculate_advantage(self, rewards, terminations, truncations, values, next_values) -> torch.Tensor:
+        args = [torch.as_tensor(x).to(self.device, torch.float32).contiguous() for x in
+                (rewards, terminations, truncations, values, next_values)]
+        return self.ctx.gae(*args, self.cfg.gamma, self.cfg.gae_lambda)
+
+    # ---- learn (recurrent_ppo.py:301-367) ---------------------------------------------------------------
+    def learn(self, experience) -> None:
+        ro = experience if isinstance(experience, RecurrentRollout) else RecurrentRollout.from_lists(experience, self.device)
+        self.engine.learn(ro)
+        self.optimizer._opt_called = True
+        self.lr_scheduler.step()
+
+    @property
+    def last_losses(self):
+        return self.engine.last_losses
+
+    # ---- train (recurrent_ppo.py:369-394) ---------------------------------------------------------------
+    def train(self) -> None:
+        cfg = self.cfg
+        self.current_observations, _ = self.envs.reset(seed=cfg.seed)
+        self.prev_dones = np.zeros(cfg.num_envs, dtype=bool)
+        self.current_hx = torch.zeros(1, cfg.num_envs, cfg.gru_hidden_dim, device=self.device)
+        last_checkpoint_time = time.time()
+        total_rollouts = cfg.total_steps // (cfg.rollout_steps * cfg.num_envs)
+        env_steps = 0
+        for rollout_idx in range(total_rollouts):
+            experience = self.rollout()
+            self.learn(experience)
+            env_steps = (rollout_idx + 1) * cfg.rollout_steps * cfg.num_envs
+            if cfg.checkpoint and time.time() - last_checkpoint_time >= cfg.save_interval:
+                self.checkpointer.save(env_steps, self.network, self.optimizer)
+                last_checkpoint_time = time.time()
+        if cfg.checkpoint and total_rollouts > 0:
+            self.checkpointer.save(env_steps, self.network, self.optimizer)
+        self.envs.close()

@@ -244,3 +244,41 @@ def test_checkpoint_roundtrip(tmp_path):
     np.random.seed(5); agent2.learn(experience_from(g))
     for k, v in agent.network.state_dict().items():
         assert torch.allclose(v, agent2.network.state_dict()[k], rtol=0, atol=0), k
+
+
+def test_recurrent_learn_matches_reference():
+    """RecurrentPPO.learn() vs the reference (+ the documented 2-line `is None` fix) on the recorded rollout:
+    2 epochs x 1 minibatch of full-sequence BPTT (recurrent_ppo.py:301-367)."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig, envs
+    g = np.load(os.path.join(GOLDEN, "learn_R.npz"))
+    D, A, H, Hg, N_, T, E, MB = (int(x) for x in g["meta"])
+    cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, num_epochs=E, num_minibatches=MB, verbose=False,
+                             network_hidden_dim=H, gru_hidden_dim=Hg, seed=42)
+    agent = RecurrentPPO(lambda: envs.SyntheticEnv(D, A), cfg)
+    sd = {k[len("init."):]: torch.as_tensor(g[k]) for k in g.files if k.startswith("init.")}
+    agent.network.load_state_dict(sd)
+    hx0 = torch.as_tensor(g["hx0"])
+    exp = [[torch.as_tensor(g["obs"][t]), torch.as_tensor(g["actions"][t]), g["rewards"][t], g["terminations"][t], g["truncations"][t],
+            torch.as_tensor(g["prev_dones"][t]), torch.as_tensor(g["log_probs"][t]), torch.as_tensor(g["values"][t]),
+            torch.as_tensor(g["next_values"][t]), hx0] for t in range(T)]
+    np.random.seed(123)
+    agent.learn(exp)
+    check(agent, g, f"e{E}")
+    # state_dict / optimizer state keep working (Checkpointer payload, utils.py:584-600)
+    st = agent.optimizer.state_dict()["state"]
+    assert len(st) == len(list(agent.network.parameters())) and all(float(v["step"]) == E * MB for v in st.values())
+
+
+def test_recurrent_train_runs_on_cartpole():
+    """Plumbing run of config 4 (RecurrentPPO on CartPole-v1): rollout with done-masked hidden resets, learn, LR schedule."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig, envs
+    cfg = RecurrentPPOConfig(num_envs=8, rollout_steps=16, num_epochs=2, num_minibatches=1, total_steps=8 * 16 * 3, verbose=False, seed=1)
+    agent = RecurrentPPO(lambda: envs.make("CartPole-v1"), cfg)
+    before = {k: v.detach().clone() for k, v in agent.network.state_dict().items()}
+    agent.train()
+    after = agent.network.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before)
+    assert all(torch.isfinite(v).all() for v in after.values())
+    assert torch.isfinite(agent.last_losses).all()
+    ro_like = agent.engine.last_losses.shape
+    assert ro_like == (2, 4)

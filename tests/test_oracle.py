@@ -139,3 +139,36 @@ def test_gru_restatement_matches_nn_gru():
     ref_out, ref_h = gru(x, h0.unsqueeze(0))
     np.testing.assert_allclose(out.numpy(), ref_out.detach().numpy(), atol=1e-6)
     np.testing.assert_allclose(h.numpy(), ref_h[0].detach().numpy(), atol=1e-6)
+
+
+def test_recurrent_core_matches_stepwise_nn_gru():
+    """GRUCore (one input-projection GEMM + T hidden steps, functional done-masking) equals the reference's loop of one-step
+    nn.GRU calls with in-place hidden resets (recurrent_ppo.py:82-87, with the documented `is None` fix), values and gradients."""
+    import torch
+    from diamond.recurrent import GRUCore
+    torch.manual_seed(0)
+    T, B, H, Hg = 9, 5, 12, 7
+    core = GRUCore(H, Hg)
+    x = torch.randn(T, B, H, requires_grad=True)
+    hx0 = torch.randn(1, B, Hg)
+    dones = torch.rand(T, B) < 0.3
+    out, hT = core.forward(x, hx0.clone(), dones)
+    # reference-style evaluation
+    x2 = x.detach().clone().requires_grad_(True)
+    h = hx0.clone()
+    outs = []
+    for t in range(T):
+        h = h.clone()
+        h[:, dones[t]] = 0.0
+        o, h = torch.nn.GRU.forward(core, x2[t:t + 1], h)
+        outs.append(o)
+    ref = torch.cat(outs, 0)
+    assert torch.allclose(out, ref, atol=1e-6) and torch.allclose(hT, h, atol=1e-6)
+    w = torch.randn_like(out)
+    g1 = torch.autograd.grad((out * w).sum(), [x] + list(core.parameters()))
+    g2 = torch.autograd.grad((ref * w).sum(), [x2] + list(core.parameters()))
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, atol=2e-6)
+    # None handling (the reference's `or` raises here)
+    o3, _ = core.forward(x.detach(), None, None)
+    assert o3.shape == (T, B, Hg)
