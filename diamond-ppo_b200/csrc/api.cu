@@ -74,6 +74,13 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
 
 extern "C" int64_t dppo_launch_count(dppo_ctx* ctx) { return ctx ? ctx->launch_count : 0; }
 
+extern "C" int dppo_count_launches(dppo_ctx* ctx, int64_t n)
+{
+    if (!ctx) return 1;
+    ctx->launch_count += n;
+    return 0;
+}
+
 extern "C" int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
 {
     if (!ctx) return 1;

@@ -221,10 +221,11 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr) {
                     // Bias-gradient partials: one row of column sums per (CTA, lane quadrant), accumulated over all tiles of
-                    // this CTA (the row is owned by this warp pair; the launcher zeroes the buffer).  Rows >= M hold exact
-                    // zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
+                    // this CTA (the row is owned by this warp pair).  With a single column tile every CTA covers all N
+                    // columns in its first tile, which then initialises the row; otherwise the launcher zeroes the buffer.
+                    // Rows >= M hold exact zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
                     float* cp = colsum + ((int64_t)blockIdx.x * 4 + q) * N + n + lane;
-                    const float prev = *cp;
+                    const float prev = (n_tiles == 1 && it == 0) ? 0.0f : *cp;
                     // warp transpose-reduce: afterwards lane l holds the sum over the warp's 32 rows of column l
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) {
@@ -293,7 +294,7 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     const size_t smem = (size_t)STAGES * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK + 1024;
     const int grid = tc3_grid(ctx, M, N);
     (void)total;
-    if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr &&
+    if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && N / n_tile > 1 &&
         cudaMemsetAsync(colsum, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {

@@ -114,9 +114,12 @@ sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partia
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                  const double* __restrict__ norm_partials, int nparts, float max_norm, float w1, float beta2, float w2,
-                 float bc2_sqrt, float eps, float neg_step_size, float* __restrict__ grad_norm_out)
+                 float bc2_sqrt, float eps, float neg_step_size, float* __restrict__ grad_norm_out,
+                 const float* __restrict__ step_consts)
 {
     __shared__ float s_coef;
+    // device-resident step constants (CUDA-graph replay of the update loop): [0] = sqrt(1 - beta2^t), [1] = -lr / (1 - beta1^t)
+    if (step_consts != nullptr) { bc2_sqrt = __ldg(step_consts); neg_step_size = __ldg(step_consts + 1); }
     if (threadIdx.x < 32) {
         double s = 0.0;
         for (int i = threadIdx.x; i < nparts; i += 32) s += norm_partials[i];
@@ -215,7 +218,7 @@ int launch_clip_adam(dppo_ctx* ctx, float* params, float* grads, float* exp_avg,
     if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
     clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, nparts, h->grad_norm_clip,
                                              (float)(1.0 - h->beta1), (float)h->beta2, (float)(1.0 - h->beta2), (float)bc2_sqrt,
-                                             h->adam_eps, (float)(-step_size), grad_norm_out);
+                                             h->adam_eps, (float)(-step_size), grad_norm_out, h->step_consts);
     DPPO_CHECK_LAUNCH(ctx, "clip_adam_kernel");
     return 0;
 }

@@ -33,12 +33,12 @@ class Hyper(C.Structure):
                 ("grad_norm_clip", C.c_float), ("adam_eps", C.c_float), ("pad0", C.c_float),
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("step", C.c_int64),
                 ("advantage_norm", C.c_int32), ("pad1", C.c_int32), ("adv_count", C.c_int64),
-                ("loss_denominator", C.c_int64)]
+                ("loss_denominator", C.c_int64), ("step_consts", C.c_void_p)]
 
 
 # every symbol include/dppo.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
-    "dppo_create", "dppo_destroy", "dppo_last_error", "dppo_version", "dppo_device_info", "dppo_set_option", "dppo_launch_count",
+    "dppo_create", "dppo_destroy", "dppo_last_error", "dppo_version", "dppo_device_info", "dppo_set_option", "dppo_launch_count", "dppo_count_launches",
     "dppo_buffer_store_step", "dppo_step_record_bytes", "dppo_sample_categorical", "dppo_sample_gaussian",
     "dppo_gae_f32", "dppo_adv_normalize_f32", "dppo_permutation_mt19937", "dppo_mt19937_seed",
     "dppo_gather_rows_f32", "dppo_mlp_layout_compute", "dppo_mlp_workspace_bytes", "dppo_mlp_forward",
@@ -168,6 +168,10 @@ class Context:
     @launches.setter
     def launches(self, _):          # the old Python-side estimates (`self.launches += n`) are ignored
         pass
+
+    def count_launches(self, n: int):
+        """Adds launches that were replayed from a CUDA graph captured through this context."""
+        self.lib.dppo_count_launches(self.h, C.c_int64(int(n)))
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.dppo_set_option(self.h, name.encode(), C.c_int(int(value))), "dppo_set_option")

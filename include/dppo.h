@@ -68,6 +68,9 @@ typedef struct dppo_hyper {
     int32_t pad1;
     int64_t adv_count;        /* number of samples behind adv_stats (global batch T*N) */
     int64_t loss_denominator; /* rows the loss means divide by (global minibatch size) */
+    const float* step_consts; /* optional DEVICE pointer to {sqrt(1 - beta2^step), -lr / (1 - beta1^step)}: when set, the Adam
+                                 kernel reads the two step-dependent constants from it instead of deriving them from
+                                 lr / step on the host, so a captured CUDA graph of an optimiser step can be replayed */
 } dppo_hyper;
 
 /* ---- context -------------------------------------------------------------------------- */
@@ -77,6 +80,7 @@ const char* dppo_last_error(dppo_ctx* ctx);          /* ctx may be NULL: last cr
 int dppo_version(void);
 int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
 int64_t dppo_launch_count(dppo_ctx* ctx);            /* kernels launched through this context so far */
+int dppo_count_launches(dppo_ctx* ctx, int64_t n);   /* add n: launches replayed from a CUDA graph captured through this context */
 /* Kernel-variant switches used by tests and bench.py for A/B measurements:
  *   "tensor_cores" 3 (default): CTA-pair (cta_group::2) persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where
  *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 2: the same with single-CTA

@@ -282,3 +282,37 @@ def test_recurrent_train_runs_on_cartpole():
     assert torch.isfinite(agent.last_losses).all()
     ro_like = agent.engine.last_losses.shape
     assert ro_like == (2, 4)
+
+
+def test_graph_replay_of_update_loop_is_bit_identical_to_eager():
+    """From the second consecutive learn() on the same device buffer the optimiser steps of an epoch are replayed as a CUDA
+    graph (device-resident indices and Adam step constants); parameters, Adam state and losses must equal the eager path
+    bit for bit, and the numpy stream must advance identically."""
+    from diamond import PPO, PPOConfig, envs
+    from diamond.agents import RolloutBuffer
+    D, A, H, N_, T = 16, 4, 256, 64, 64                      # 4096 rows, minibatches of 1024: tensor-core path
+    rng = np.random.default_rng(3)
+    exp = [[rng.standard_normal((N_, D)).astype(np.float32), rng.standard_normal((N_, D)).astype(np.float32),
+            rng.integers(0, A, N_), rng.standard_normal(N_), rng.random(N_) < 0.05, rng.random(N_) < 0.05] for _ in range(T)]
+
+    def run(use_graphs):
+        cfg = PPOConfig(num_envs=N_, rollout_steps=T, network_hidden_dim=H, num_epochs=3, num_minibatches=4, verbose=False, seed=7,
+                        total_steps=N_ * T * 10)
+        agent = PPO(lambda: envs.SyntheticEnv(D, A), cfg)
+        agent.engine.use_graphs = use_graphs
+        buf = RolloutBuffer.from_lists(agent.ctx, exp, False, agent.device)
+        np.random.seed(99)
+        all_losses = []
+        for _ in range(3):
+            agent.learn(buf)
+            all_losses.append(agent.last_losses.clone())
+        torch.cuda.synchronize()
+        return agent, torch.cat(all_losses), np.random.randint(0, 2 ** 31, 2)
+
+    a0, l0, r0 = run(False)
+    a1, l1, r1 = run(True)
+    assert a1.engine._bufs and any("graph" in b for b in a1.engine._bufs.values()), "graph path was not taken"
+    assert torch.equal(l0, l1)
+    assert torch.equal(a0.engine.P, a1.engine.P) and torch.equal(a0.engine.M, a1.engine.M) and torch.equal(a0.engine.V, a1.engine.V)
+    assert a0.engine.adam_step == a1.engine.adam_step == 3 * 3 * 4
+    np.testing.assert_array_equal(r0, r1)
