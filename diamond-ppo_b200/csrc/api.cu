@@ -244,6 +244,7 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
     {
         PrepJobs jobs;
         jobs.n = 0;
+        jobs.gather = GatherJob{nullptr, nullptr, nullptr, 0, 0};
         auto job = [&](bool on, const float* W, int rows_w, int cols_w, unsigned char* im) {
             if (on) { jobs.job[jobs.n].W = W; jobs.job[jobs.n].rows_w = rows_w; jobs.job[jobs.n].cols_w = cols_w;
                       jobs.job[jobs.n].transpose = 0; jobs.job[jobs.n].n_tile = 0; jobs.job[jobs.n].img = im; ++jobs.n; }
@@ -306,9 +307,20 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     WImages img = carve_images(d, img_base);
     const bool tc1 = tc_on && dppo_tc_supported(M, H, D), tc2 = tc_on && dppo_tc_supported(M, H, H),
                tc3 = tc_on && dppo_tc_supported(M, 2 * H, H), tcb3 = tc_on && dppo_tc_supported(M, H, 2 * H), tcb2 = tc2;
+    const bool v2 = ctx->use_tensor_cores >= 2;
+    const bool g1 = tc1 && v2 && dppo_tc2_gemm_supported(M, H, D), g2 = tc2 && v2 && dppo_tc2_gemm_supported(M, H, H),
+               g3 = tc3 && v2 && dppo_tc2_gemm_supported(M, 2 * H, H), gb3 = tcb3 && v2 && dppo_tc2_gemm_supported(M, H, 2 * H), gb2 = g2;
+    const bool wg3 = tc_on && v2 && w.t3 > 0, wg2 = tc_on && v2 && w.t2 > 0, wg1 = tc_on && v2 && w.t1 > 0;
+    // the TMA-fed kernels read contiguous rows: gather the minibatch observations once (ppo.py:261 observations[mb])
+    const float* x1 = obs;
+    const int32_t* x1_idx = idx;
+    bool gather_pending = idx && (g1 || wg1);
+    if (gather_pending) { x1 = w.xg; x1_idx = nullptr; }
     {
+        // one launch: the hi/lo weight images of this step + the observation gather
         PrepJobs jobs;
         jobs.n = 0;
+        jobs.gather = GatherJob{nullptr, nullptr, nullptr, 0, 0};
         auto job = [&](bool on, const float* W, int rows_w, int cols_w, int transpose, unsigned char* im) {
             if (on) { jobs.job[jobs.n].W = W; jobs.job[jobs.n].rows_w = rows_w; jobs.job[jobs.n].cols_w = cols_w;
                       jobs.job[jobs.n].transpose = transpose; jobs.job[jobs.n].n_tile = 0; jobs.job[jobs.n].img = im; ++jobs.n; }
@@ -318,20 +330,13 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
         job(tc3, params + L.w3, 2 * H, H, 0, img.w3f);
         job(tcb3, params + L.w3, 2 * H, H, 1, img.w3b);
         job(tcb2, params + L.w2, H, H, 1, img.w2b);
+        if (gather_pending && D % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w.xg) & 15u) == 0) {
+            jobs.gather = GatherJob{reinterpret_cast<const float4*>(obs), idx, reinterpret_cast<float4*>(w.xg), M, D / 4};
+            gather_pending = false;
+        }
         if (dppo_tc_prep_weights_multi(ctx, jobs, st)) return 1;
     }
-
-    const bool v2 = ctx->use_tensor_cores >= 2;
-    const bool g1 = tc1 && v2 && dppo_tc2_gemm_supported(M, H, D), g2 = tc2 && v2 && dppo_tc2_gemm_supported(M, H, H),
-               g3 = tc3 && v2 && dppo_tc2_gemm_supported(M, 2 * H, H), gb3 = tcb3 && v2 && dppo_tc2_gemm_supported(M, H, 2 * H), gb2 = g2;
-    const bool wg3 = tc_on && v2 && w.t3 > 0, wg2 = tc_on && v2 && w.t2 > 0, wg1 = tc_on && v2 && w.t1 > 0;
-    // the TMA-fed kernels read contiguous rows: gather the minibatch observations once (ppo.py:261 observations[mb])
-    const float* x1 = obs;
-    const int32_t* x1_idx = idx;
-    if (idx && (g1 || wg1)) {
-        if (dppo_gather_rows_f32(ctx, obs, idx, w.xg, M, D, stream)) return 1;
-        x1 = w.xg; x1_idx = nullptr;
-    }
+    if (gather_pending && dppo_gather_rows_f32(ctx, obs, idx, w.xg, M, D, stream)) return 1;
 
     // forward (ppo.py:261), activations kept for the backward pass
     if (g1) {
@@ -415,7 +420,7 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     if (d->continuous) seg(L.log_std, A, w.hp + off_dls, w.head_stride, w.head_blocks);
     tab.nseg = n;
     return launch_grad_reduce(ctx, tab, grads, L.total, w.hp + off_loss, w.head_blocks, w.head_stride, hy->value_loss_weight,
-                              hy->entropy_beta, inv_m, losses, st);
+                              hy->entropy_beta, inv_m, losses, hy->grad_sumsq, st);
 }
 
 // ---- tensor-core building blocks exposed for unit tests and A/B measurements ----------------------
@@ -470,5 +475,5 @@ extern "C" int dppo_tc_wgrad_f32(dppo_ctx* ctx, const float* Dm, const float* Hm
     tab.seg[0].dst = 0; tab.seg[0].count = (int64_t)N1 * N2; tab.seg[0].src = parts; tab.seg[0].stride = (int64_t)N1 * N2;
     tab.seg[0].nparts = splits; tab.seg[0].pad = 0;
     tab.nseg = 1;
-    return launch_grad_reduce(ctx, tab, dW, (int64_t)N1 * N2, nullptr, 0, 0, 0.f, 0.f, 0.f, nullptr, st);
+    return launch_grad_reduce(ctx, tab, dW, (int64_t)N1 * N2, nullptr, 0, 0, 0.f, 0.f, 0.f, nullptr, nullptr, st);
 }

@@ -145,6 +145,17 @@ __global__ void prep_weights_kernel(const float* __restrict__ W, int rows_w, int
 // All weight images of one optimiser step in a single launch: blockIdx.y selects the job.
 __global__ void prep_weights_multi_kernel(PrepJobs jobs)
 {
+    if ((int)blockIdx.y == jobs.n) {
+        // the minibatch observation gather (ppo.py:261 observations[mb]) shares the launch: it is independent of the weights
+        const GatherJob& g = jobs.gather;
+        const int64_t total = g.rows * g.row_vec;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / g.row_vec;
+            const int c = (int)(i - r * g.row_vec);
+            g.dst[i] = __ldg(g.src + (int64_t)__ldg(g.idx + r) * g.row_vec + c);
+        }
+        return;
+    }
     const PrepJob& j = jobs.job[blockIdx.y];
     const int N = j.transpose ? j.cols_w : j.rows_w;
     const int K = j.transpose ? j.rows_w : j.cols_w;
@@ -364,16 +375,18 @@ int dppo_tc_prep_weights(dppo_ctx* ctx, const float* W, int rows_w, int cols_w, 
 
 int dppo_tc_prep_weights_multi(dppo_ctx* ctx, PrepJobs jobs, cudaStream_t st)
 {
-    if (jobs.n < 1) return 0;
-    int64_t most = 0;
+    const bool with_gather = jobs.gather.rows > 0 && jobs.gather.dst != nullptr;
+    if (jobs.n < 1 && !with_gather) return 0;
+    int64_t most = with_gather ? jobs.gather.rows * jobs.gather.row_vec / 8 : 0;
     for (int i = 0; i < jobs.n; ++i) {
         const int64_t t = (int64_t)jobs.job[i].rows_w * jobs.job[i].cols_w;
         jobs.job[i].n_tile = dppo_tc_n_tile(jobs.job[i].transpose ? jobs.job[i].cols_w : jobs.job[i].rows_w);
         if (t > most) most = t;
     }
     int blocks = (int)((most + 255) / 256);
-    if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
-    prep_weights_multi_kernel<<<dim3(blocks, jobs.n), 256, 0, st>>>(jobs);
+    if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
+    if (blocks < 1) blocks = 1;
+    prep_weights_multi_kernel<<<dim3(blocks, jobs.n + (with_gather ? 1 : 0)), 256, 0, st>>>(jobs);
     DPPO_CHECK_LAUNCH(ctx, "prep_weights_multi_kernel");
     return 0;
 }

@@ -7,7 +7,9 @@ int dppo_tc_n_tile(int N);
 int64_t dppo_tc_image_bytes(int N, int K);        // bytes of the hi/lo weight images of an [N, K] B operand
 int dppo_tc_prep_weights(dppo_ctx* ctx, const float* W, int rows_w, int cols_w, int transpose, unsigned char* img, cudaStream_t st);
 struct PrepJob { const float* W; int rows_w, cols_w, transpose, n_tile; unsigned char* img; };
-struct PrepJobs { PrepJob job[8]; int n; };
+// optional row gather riding in the same launch (blockIdx.y == n): dst[i, :] = src[idx[i], :], row_vec float4 per row
+struct GatherJob { const float4* src; const int32_t* idx; float4* dst; int64_t rows; int row_vec; };
+struct PrepJobs { PrepJob job[8]; int n; GatherJob gather; };
 int dppo_tc_prep_weights_multi(dppo_ctx* ctx, PrepJobs jobs, cudaStream_t st);      // every job in one launch
 int dppo_tc_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const int32_t* a_rows, const unsigned char* Wimg, const float* bias,
                  const float* Hact, int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);

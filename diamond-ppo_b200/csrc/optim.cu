@@ -13,11 +13,13 @@ constexpr int RED_X = 32, RED_Y = 8;
 
 __global__ void __launch_bounds__(RED_X * RED_Y)
 grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, const float* __restrict__ loss_partials,
-                   int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* __restrict__ losses)
+                   int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* __restrict__ losses,
+                   double* __restrict__ sumsq_out)
 {
     __shared__ float4 s_part[RED_Y][RED_X];
     const int x = threadIdx.x, y = threadIdx.y;
     const int64_t total4 = (total + 3) / 4;
+    double sq = 0.0;                       // this thread's share of the squared gradient norm (y == 0 threads)
     for (int64_t base = (int64_t)blockIdx.x * RED_X; base < total4; base += (int64_t)gridDim.x * RED_X) {
         const int64_t i = (base + x) * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -67,10 +69,19 @@ grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, c
             float4 r = s_part[0][x];
 #pragma unroll
             for (int k = 1; k < RED_Y; ++k) { const float4 v = s_part[k][x]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
-            if (i + 4 <= total) *reinterpret_cast<float4*>(grads + i) = r;
-            else { const float rr[4] = {r.x, r.y, r.z, r.w}; for (int e = 0; i + e < total; ++e) grads[i + e] = rr[e]; }
+            if (i + 4 <= total) {
+                *reinterpret_cast<float4*>(grads + i) = r;
+                sq += (double)r.x * r.x + (double)r.y * r.y + (double)r.z * r.z + (double)r.w * r.w;
+            } else {
+                const float rr[4] = {r.x, r.y, r.z, r.w};
+                for (int e = 0; i + e < total; ++e) { grads[i + e] = rr[e]; sq += (double)rr[e] * rr[e]; }
+            }
         }
         __syncthreads();
+    }
+    if (sumsq_out != nullptr && y == 0) {          // y == 0 is exactly warp 0 of the block
+        sq = warp_sum_d(sq);
+        if (x == 0) sumsq_out[blockIdx.x] = sq;
     }
     if (blockIdx.x == 0 && losses != nullptr) {
         __shared__ float l[3];
@@ -194,14 +205,21 @@ fma_peak_kernel(float* __restrict__ sink, int64_t iters)
 
 }  // namespace
 
-int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int64_t total, const float* loss_partials,
-                       int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* losses, cudaStream_t st)
+int grad_reduce_blocks(dppo_ctx* ctx, int64_t total)
 {
-    if ((reinterpret_cast<uintptr_t>(grads) & 15u) != 0) DPPO_FAIL(ctx, "grad_reduce: gradient buffer must be 16-byte aligned");
     int64_t want = ((total + 3) / 4 + RED_X - 1) / RED_X;
     int blocks = (int)(want < 16 * (int64_t)ctx->sm_count ? want : 16 * (int64_t)ctx->sm_count);
-    if (blocks < 1) blocks = 1;
-    grad_reduce_kernel<<<blocks, dim3(RED_X, RED_Y), 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses);
+    return blocks < 1 ? 1 : blocks;
+}
+
+int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int64_t total, const float* loss_partials,
+                       int loss_nparts, int64_t loss_stride, float vw, float beta, float inv_m, float* losses, double* sumsq_out,
+                       cudaStream_t st)
+{
+    if ((reinterpret_cast<uintptr_t>(grads) & 15u) != 0) DPPO_FAIL(ctx, "grad_reduce: gradient buffer must be 16-byte aligned");
+    const int blocks = grad_reduce_blocks(ctx, total);
+    grad_reduce_kernel<<<blocks, dim3(RED_X, RED_Y), 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses,
+                                                              sumsq_out);
     DPPO_CHECK_LAUNCH(ctx, "grad_reduce_kernel");
     return 0;
 }
@@ -233,16 +251,20 @@ static int sumsq_blocks(int64_t n)
 
 extern "C" int64_t dppo_clip_adam_workspace_bytes(int64_t n) { return (int64_t)sumsq_blocks(n) * (int64_t)sizeof(double); }
 
+extern "C" int64_t dppo_grad_sumsq_bytes(dppo_ctx* ctx, int64_t n) { return ctx ? (int64_t)grad_reduce_blocks(ctx, n) * (int64_t)sizeof(double) : 0; }
+
 extern "C" int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                                    const dppo_hyper* h, float* grad_norm_out, void* ws, int64_t ws_bytes, void* stream)
 {
     if (!ctx) return 1;
     if (n <= 0) DPPO_FAIL(ctx, "clip_adam: empty parameter buffer");
     if (h->step < 1) DPPO_FAIL(ctx, "clip_adam: step must be >= 1 (got %lld)", (long long)h->step);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->grad_sumsq != nullptr)          // dppo_mlp_grad_minibatch already left the partial sums of squares there
+        return launch_clip_adam(ctx, params, grads, exp_avg, exp_avg_sq, n, h->grad_sumsq, grad_reduce_blocks(ctx, n), h, grad_norm_out, st);
     const int nb = sumsq_blocks(n);
     if (ws_bytes < (int64_t)nb * (int64_t)sizeof(double)) DPPO_FAIL(ctx, "clip_adam: workspace too small");
     if ((reinterpret_cast<uintptr_t>(ws) & 7u) != 0) DPPO_FAIL(ctx, "clip_adam: workspace must be 8-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
     double* partials = (double*)ws;
     sumsq_kernel<<<nb, SUMSQ_THREADS, 0, st>>>(grads, n, partials);
     DPPO_CHECK_LAUNCH(ctx, "sumsq_kernel");

@@ -33,7 +33,7 @@ class Hyper(C.Structure):
                 ("grad_norm_clip", C.c_float), ("adam_eps", C.c_float), ("pad0", C.c_float),
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("step", C.c_int64),
                 ("advantage_norm", C.c_int32), ("pad1", C.c_int32), ("adv_count", C.c_int64),
-                ("loss_denominator", C.c_int64), ("step_consts", C.c_void_p)]
+                ("loss_denominator", C.c_int64), ("step_consts", C.c_void_p), ("grad_sumsq", C.c_void_p)]
 
 
 # every symbol include/dppo.h declares (tests/test_abi.py checks the header against this list)
@@ -43,7 +43,7 @@ EXPORTS = [
     "dppo_gae_f32", "dppo_adv_normalize_f32", "dppo_permutation_mt19937", "dppo_mt19937_seed",
     "dppo_gather_rows_f32", "dppo_mlp_layout_compute", "dppo_mlp_workspace_bytes", "dppo_mlp_forward",
     "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_clip_adam_step",
-    "dppo_clip_adam_workspace_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
+    "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
     "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy",
     "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
@@ -64,8 +64,8 @@ def load_library() -> C.CDLL:
             lib = C.CDLL(LIB_PATH)
             lib.dppo_last_error.restype = C.c_char_p
             lib.dppo_last_error.argtypes = [C.c_void_p]
-            for name in ("dppo_step_record_bytes", "dppo_mlp_workspace_bytes", "dppo_clip_adam_workspace_bytes",
-                         "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes"):
+            for name in ("dppo_step_record_bytes", "dppo_mlp_workspace_bytes", "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes",
+                         "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes", "dppo_grad_sumsq_bytes"):
                 getattr(lib, name).restype = C.c_int64
             lib.dppo_dp_slot.restype = C.c_void_p
             _lib = lib
@@ -261,6 +261,9 @@ class Context:
                                                      _ptr(losses), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()),
                                                      _stream()), "dppo_mlp_grad_minibatch")
         self.launches += 10
+
+    def grad_sumsq_bytes(self, n):
+        return int(self.lib.dppo_grad_sumsq_bytes(self.h, C.c_int64(n)))
 
     def clip_adam_workspace_bytes(self, n):
         return int(self.lib.dppo_clip_adam_workspace_bytes(C.c_int64(n)))

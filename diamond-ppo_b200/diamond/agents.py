@@ -285,6 +285,7 @@ class _EngineBase:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.total = total
         self.dpx = None
+        self.grad_sumsq = torch.zeros(self.ctx.grad_sumsq_bytes(total) // 8 + 1, dtype=torch.float64, device=dev)
         self.adam_step = 0
 
     def bind_optimizer(self, optimizer: torch.optim.Optimizer):
@@ -516,6 +517,8 @@ class FusedMlpEngine(_EngineBase):
                    cfg.entropy_beta, cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm))
         use_graph = self.use_graphs and not dist.enabled and self._seen_key == ptr_key and B % MB == 0
         self._seen_key = ptr_key
+        if not dist.enabled:
+            hyper.grad_sumsq = self.grad_sumsq.data_ptr()    # gradient assembly leaves the norm partials for the Adam kernel
         if use_graph:
             self._learn_epochs_graphed(b, worker, hyper, desc, obs_flat, actions, old_logp, adv, ret, losses, E, MB, B // MB, ptr_key)
             mark("update_end")

@@ -71,6 +71,9 @@ typedef struct dppo_hyper {
     const float* step_consts; /* optional DEVICE pointer to {sqrt(1 - beta2^step), -lr / (1 - beta1^step)}: when set, the Adam
                                  kernel reads the two step-dependent constants from it instead of deriving them from
                                  lr / step on the host, so a captured CUDA graph of an optimiser step can be replayed */
+    double* grad_sumsq;       /* optional DEVICE buffer of dppo_grad_sumsq_bytes(): dppo_mlp_grad_minibatch leaves the fp64 partial
+                                 sums of squares of the gradient it assembled there and dppo_clip_adam_step reads them instead of
+                                 launching its own norm kernel (single-GPU path; under DP the norm is taken after the exchange) */
 } dppo_hyper;
 
 /* ---- context -------------------------------------------------------------------------- */
@@ -166,6 +169,7 @@ int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* desc, const floa
 int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                         const dppo_hyper* hyper, float* grad_norm_out, void* ws, int64_t ws_bytes, void* stream);
 int64_t dppo_clip_adam_workspace_bytes(int64_t n);
+int64_t dppo_grad_sumsq_bytes(dppo_ctx* ctx, int64_t n);
 
 /* ---- env-sharded data parallelism: the per-minibatch exchange step -------- */
 /* One process per GPU.  Each rank writes the gradient of its shard of the global minibatch (and its 4 loss sums) into the
