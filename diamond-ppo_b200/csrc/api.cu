@@ -143,6 +143,7 @@ struct TrainWs {
     float *p3, *p2, *p1, *c2, *c1, *hp;
     int s3, s2, s1, tiles2, tiles1, head_blocks, head_stride;
     int t3, t2, t1;          // split counts of the tcgen05 weight-gradient kernels (0: shape unsupported)
+    bool multi;              // the three weight gradients run as one balanced launch (t3/t2/t1 then come from the joint plan)
     int64_t img_off;
     int64_t bytes;
 };
@@ -164,6 +165,13 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     w.t3 = dppo_tc2_wgrad_supported(M, (int)(2 * H), (int)H) ? dppo_tc2_wgrad_splits(&fake, M, (int)(2 * H), (int)H) : 0;
     w.t2 = dppo_tc2_wgrad_supported(M, (int)H, (int)H) ? dppo_tc2_wgrad_splits(&fake, M, (int)H, (int)H) : 0;
     w.t1 = dppo_tc2_wgrad_supported(M, (int)H, (int)D) ? dppo_tc2_wgrad_splits(&fake, M, (int)H, (int)D) : 0;
+    w.multi = w.t3 > 0 && w.t2 > 0 && w.t1 > 0 && H % 256 == 0;      // all three in one balanced launch
+    if (w.multi) {
+        const int n1s[3] = {(int)(2 * H), (int)H, (int)H}, n2s[3] = {(int)H, (int)H, (int)D};
+        int sp[3];
+        dppo_tc2_wgrad_multi_splits(&fake, M, 3, n1s, n2s, sp);
+        w.t3 = sp[0]; w.t2 = sp[1]; w.t1 = sp[2];
+    }
     auto mx = [](int a, int b) { return a > b ? a : b; };
     w.p3 = take((int64_t)mx(w.s3, w.t3) * 2 * H * H);
     w.p2 = take((int64_t)mx(w.s2, w.t2) * H * H);
@@ -388,6 +396,14 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     // weight gradients: deterministic split-K partials
     const int n3p = wg3 ? w.t3 : w.s3, n2p = wg2 ? w.t2 : w.s2, n1p = wg1 ? w.t1 : w.s1;
+    if (w.multi && wg3 && wg2 && wg1) {
+        const float* Ds[3] = {w.d3, w.d2, w.d1};
+        const float* Hs[3] = {w.h2, w.h1, x1};
+        float* Ps[3] = {w.p3, w.p2, w.p1};
+        const int ldds[3] = {2 * H, H, H}, ldhs[3] = {H, H, D}, sps[3] = {w.t3, w.t2, w.t1}, n1s[3] = {2 * H, H, H}, n2s[3] = {H, H, D};
+        if (dppo_tc2_wgrad_multi(ctx, 3, Ds, ldds, Hs, ldhs, Ps, sps, M, n1s, n2s, st)) return 1;
+    } else {
+    // (tensor-core levels < 2 take the FFMA kernels with their own split counts; wg3/wg2/wg1 are all on or all off)
     if (wg3) {
         if (dppo_tc2_wgrad(ctx, w.d3, 2 * H, w.h2, H, w.p3, w.t3, M, 2 * H, H, st)) return 1;
     } else if (dppo_wgrad(ctx, w.d3, 2 * H, w.h2, H, nullptr, w.p3, w.s3, M, 2 * H, H, st)) return 1;
@@ -397,6 +413,7 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     if (wg1) {
         if (dppo_tc2_wgrad(ctx, w.d1, H, x1, D, w.p1, w.t1, M, H, D, st)) return 1;
     } else if (dppo_wgrad(ctx, w.d1, H, x1, D, x1_idx, w.p1, w.s1, M, H, D, st)) return 1;
+    }
 
     // assemble the flat gradient
     GradSegTable tab;

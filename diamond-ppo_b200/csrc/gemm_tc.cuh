@@ -24,6 +24,10 @@ bool dppo_tc2_wgrad_supported(int64_t M, int N1, int N2);
 int dppo_tc2_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2);
 int dppo_tc2_wgrad(dppo_ctx* ctx, const float* Dm, int ldd, const float* Hm, int ldh, float* partials, int splits, int64_t M, int N1,
                    int N2, cudaStream_t st);
+// up to three weight gradients over the same M rows in ONE launch, row ranges balanced so that all CTAs carry equal work
+void dppo_tc2_wgrad_multi_splits(dppo_ctx* ctx, int64_t M, int n, const int* N1, const int* N2, int* splits_out);
+int dppo_tc2_wgrad_multi(dppo_ctx* ctx, int n, const float* const* Dm, const int* ldd, const float* const* Hm, const int* ldh,
+                         float* const* partials, const int* splits, int64_t M, const int* N1, const int* N2, cudaStream_t st);
 
 // CTA-pair (cta_group::2) variant of the forward / dgrad GEMM (gemm_tc3.cu); same contract as dppo_tc2_gemm
 bool dppo_tc3_gemm_supported(int64_t M, int N, int K);

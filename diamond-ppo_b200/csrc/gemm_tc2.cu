@@ -275,10 +275,23 @@ constexpr int GRP = WKC * 128;             // bytes of one 32-column group of a 
 //   partials[split][n1_blk*NACC*128 + i][j] = sum_m D[m, n1_0 + i] * H[m, j],   i < NACC*128, j < N2
 // in NACC TMEM accumulators of N2 columns.  Stage layout: [D_hi | H_hi | D_lo | H_lo]; each operand is stored as
 // 32-column groups of WKC rows x 128 B, exactly what a SWIZZLE_128B_ATOM_32B TMA box of 32 x WKC floats delivers.
+// Up to three weight gradients share one launch (WgradJobs): CTA ranges [cta_begin, cta_begin + n1_blocks * splits) belong to
+// job j, and the host plan (wgrad_multi_plan) sizes the row ranges so that every CTA of the launch carries the same tensor
+// work -- one wave over all SMs instead of one wave per gradient, and ~2.6x fewer row-range partials to reduce.
+struct WgradJob {
+    CUtensorMap tmD, tmH, tmP;
+    int N1, N2, n1_blocks, rows_per_split, cta_begin, cta_count;
+};
+struct WgradJobs {
+    WgradJob j[3];
+    int n;
+    int smem_bytes;            // dynamic shared memory of the launch (each job derives its own stage count from it)
+    int64_t M;
+};
+
 template <int NACC>
 __global__ void __launch_bounds__(THREADS, 1)
-tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmP,
-                 int64_t M, int N1, int N2, int n1_blocks, int rows_per_split, int stages)
+tc2_wgrad_kernel(const __grid_constant__ WgradJobs jobs)
 {
     extern __shared__ unsigned char dyn_raw[];
     __shared__ __align__(8) uint64_t full[MAX_STAGES], ready[MAX_STAGES], empty[MAX_STAGES], tfull;
@@ -286,13 +299,24 @@ tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant_
 
     unsigned char* dyn = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int ji = 0;
+    while (ji + 1 < jobs.n && (int)blockIdx.x >= jobs.j[ji].cta_begin + jobs.j[ji].cta_count) ++ji;
+    const WgradJob& job = jobs.j[ji];
+    const CUtensorMap& tmD = job.tmD;
+    const CUtensorMap& tmH = job.tmH;
+    const CUtensorMap& tmP = job.tmP;
+    const int64_t M = jobs.M;
+    const int N1 = job.N1, N2 = job.N2, n1_blocks = job.n1_blocks, rows_per_split = job.rows_per_split;
+    const int local_cta = (int)blockIdx.x - job.cta_begin;
     constexpr int gA = NACC * 4;
     const int gB = N2 / 32;
     constexpr int a_bytes = gA * GRP;
     const int b_bytes = gB * GRP;
     const int hi_bytes = a_bytes + b_bytes;
     const int stage_bytes = 2 * hi_bytes;
-    const int n1_blk = blockIdx.x % n1_blocks, split = blockIdx.x / n1_blocks;
+    int stages = (jobs.smem_bytes - 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    const int n1_blk = local_cta % n1_blocks, split = local_cta / n1_blocks;
     const int n1_0 = n1_blk * NACC * 128;
     const int64_t r0 = (int64_t)split * rows_per_split;
     const int64_t r1 = r0 + rows_per_split < M ? r0 + rows_per_split : M;
@@ -529,49 +553,106 @@ bool dppo_tc2_wgrad_supported(int64_t M, int N1, int N2)
 }
 
 namespace {
-struct WgradPlan { int nacc, n1_blocks, rows_per_split, splits, stages; size_t smem; };
-WgradPlan wgrad_plan(int sm_count, int64_t M, int N1, int N2)
+struct WgradPlan { int nacc, n1_blocks, rows_per_split, splits; };
+
+// measured cycles of one tcgen05.mma (M = 128, K = 8 tf32, shared-memory operands) as a function of N (dppo_tc_mma_probe)
+double mma_clk(int n2) { return n2 >= 256 ? 171.0 : n2 >= 128 ? 107.0 + (n2 - 128) * (64.0 / 128.0) : 96.0 + (n2 - 64) * (11.0 / 64.0); }
+
+int stage_bytes_of(int nacc, int N2) { return 2 * (nacc * 4 + N2 / 32) * GRP; }
+
+// Row-range plan of `n` weight gradients sharing one launch on `sm_count` CTAs: equal tensor work per CTA.
+void wgrad_multi_plan(int sm_count, int64_t M, int n, const int* N1, const int* N2, WgradPlan* out)
 {
-    WgradPlan p;
-    // two accumulators share every H chunk: one accumulator per CTA (N1 spread over CTAs) was measured slower -- the
-    // H tile is then streamed by twice as many CTAs and the kernel becomes L2-bound
-    p.nacc = (N1 % 256 == 0) ? 2 : 1;
-    p.n1_blocks = N1 / (128 * p.nacc);
-    int splits = sm_count / p.n1_blocks;
-    if (splits < 1) splits = 1;
-    int64_t rps = (M + splits - 1) / splits;
-    rps = (rps + WKC - 1) / WKC * WKC;
-    p.rows_per_split = (int)rps;
-    p.splits = (int)((M + rps - 1) / rps);
-    const int stage_bytes = 2 * (p.nacc * 4 + N2 / 32) * GRP;
-    p.stages = (200 * 1024) / stage_bytes;
-    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    p.smem = (size_t)p.stages * stage_bytes + 1024;
-    return p;
+    double denom = 0.0;
+    for (int j = 0; j < n; ++j) {
+        out[j].nacc = (N1[j] % 256 == 0) ? 2 : 1;
+        out[j].n1_blocks = N1[j] / (128 * out[j].nacc);
+        denom += out[j].n1_blocks * out[j].nacc * mma_clk(N2[j]);
+    }
+    int used = 0;
+    for (int j = 0; j < n; ++j) {
+        int sp = (int)(sm_count * out[j].nacc * mma_clk(N2[j]) / denom);
+        if (sp < 1) sp = 1;
+        out[j].splits = sp;
+        used += sp * out[j].n1_blocks;
+    }
+    // hand the leftover CTAs to the job whose CTAs currently carry the most work
+    for (;;) {
+        int best = -1;
+        double worst = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double cost = (double)M / out[j].splits * out[j].nacc * mma_clk(N2[j]);
+            if (used + out[j].n1_blocks <= sm_count && cost > worst) { worst = cost; best = j; }
+        }
+        if (best < 0) break;
+        ++out[best].splits;
+        used += out[best].n1_blocks;
+    }
+    for (int j = 0; j < n; ++j) {
+        int64_t rps = (M + out[j].splits - 1) / out[j].splits;
+        rps = (rps + WKC - 1) / WKC * WKC;
+        out[j].rows_per_split = (int)rps;
+        out[j].splits = (int)((M + rps - 1) / rps);
+    }
 }
 }  // namespace
 
-int dppo_tc2_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2) { return wgrad_plan(ctx->sm_count, M, N1, N2).splits; }
+int dppo_tc2_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2)
+{
+    WgradPlan p;
+    wgrad_multi_plan(ctx->sm_count, M, 1, &N1, &N2, &p);
+    return p.splits;
+}
+
+void dppo_tc2_wgrad_multi_splits(dppo_ctx* ctx, int64_t M, int n, const int* N1, const int* N2, int* splits_out)
+{
+    WgradPlan p[3];
+    wgrad_multi_plan(ctx->sm_count, M, n, N1, N2, p);
+    for (int j = 0; j < n; ++j) splits_out[j] = p[j].splits;
+}
+
+int dppo_tc2_wgrad_multi(dppo_ctx* ctx, int n, const float* const* Dm, const int* ldd, const float* const* Hm, const int* ldh,
+                         float* const* partials, const int* splits, int64_t M, const int* N1, const int* N2, cudaStream_t st)
+{
+    if (n < 1 || n > 3) DPPO_FAIL(ctx, "tc2_wgrad: 1..3 jobs per launch");
+    WgradPlan p[3];
+    wgrad_multi_plan(ctx->sm_count, M, n, N1, N2, p);
+    WgradJobs jobs;
+    jobs.n = n;
+    jobs.M = M;
+    int cta = 0, max_stage = 0;
+    for (int j = 0; j < n; ++j) {
+        if (!dppo_tc2_wgrad_supported(M, N1[j], N2[j])) DPPO_FAIL(ctx, "tc2_wgrad: unsupported shape M=%lld N1=%d N2=%d", (long long)M, N1[j], N2[j]);
+        if (ldd[j] % 4 != 0 || ldh[j] % 4 != 0 || !al16(Dm[j]) || !al16(Hm[j]) || !al16(partials[j])) DPPO_FAIL(ctx, "tc2_wgrad: operands must be 16-byte aligned");
+        if (p[j].splits != splits[j]) DPPO_FAIL(ctx, "tc2_wgrad: caller sized the partials of job %d for %d splits, plan has %d", j, splits[j], p[j].splits);
+        if (p[j].nacc != p[0].nacc) DPPO_FAIL(ctx, "tc2_wgrad: jobs of one launch must agree on N1 %% 256");
+        WgradJob& q = jobs.j[j];
+        if (!dppo_make_tensor_map_2d(&q.tmD, Dm[j], M, N1[j], ldd[j], 32, WKC, 4) || !dppo_make_tensor_map_2d(&q.tmH, Hm[j], M, N2[j], ldh[j], 32, WKC, 4) ||
+            !dppo_make_tensor_map_2d(&q.tmP, partials[j], (int64_t)p[j].splits * N1[j], N2[j], N2[j], 32, 32, 3))
+            DPPO_FAIL(ctx, "tc2_wgrad: cuTensorMapEncodeTiled failed");
+        q.N1 = N1[j]; q.N2 = N2[j]; q.n1_blocks = p[j].n1_blocks; q.rows_per_split = p[j].rows_per_split;
+        q.cta_begin = cta; q.cta_count = p[j].n1_blocks * p[j].splits;
+        cta += q.cta_count;
+        const int sb = stage_bytes_of(p[j].nacc, N2[j]);
+        if (sb > max_stage) max_stage = sb;
+    }
+    int stages = (200 * 1024) / max_stage;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    const size_t smem = (size_t)stages * max_stage + 1024;
+    jobs.smem_bytes = (int)smem;
+    if (p[0].nacc == 2) {
+        cudaFuncSetAttribute(tc2_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc2_wgrad_kernel<2><<<cta, THREADS, smem, st>>>(jobs);
+    } else {
+        cudaFuncSetAttribute(tc2_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc2_wgrad_kernel<1><<<cta, THREADS, smem, st>>>(jobs);
+    }
+    DPPO_CHECK_LAUNCH(ctx, "tc2_wgrad_kernel");
+    return 0;
+}
 
 int dppo_tc2_wgrad(dppo_ctx* ctx, const float* Dm, int ldd, const float* Hm, int ldh, float* partials, int splits, int64_t M, int N1,
                    int N2, cudaStream_t st)
 {
-    if (!dppo_tc2_wgrad_supported(M, N1, N2)) DPPO_FAIL(ctx, "tc2_wgrad: unsupported shape M=%lld N1=%d N2=%d", (long long)M, N1, N2);
-    if (ldd % 4 != 0 || ldh % 4 != 0 || !al16(Dm) || !al16(Hm) || !al16(partials)) DPPO_FAIL(ctx, "tc2_wgrad: operands must be 16-byte aligned");
-    const WgradPlan p = wgrad_plan(ctx->sm_count, M, N1, N2);
-    if (p.splits != splits) DPPO_FAIL(ctx, "tc2_wgrad: caller sized the partials for %d splits, plan has %d", splits, p.splits);
-    CUtensorMap tmD, tmH, tmP;
-    if (!dppo_make_tensor_map_2d(&tmD, Dm, M, N1, ldd, 32, WKC, 4) || !dppo_make_tensor_map_2d(&tmH, Hm, M, N2, ldh, 32, WKC, 4) ||
-        !dppo_make_tensor_map_2d(&tmP, partials, (int64_t)p.splits * N1, N2, N2, 32, 32, 3))
-        DPPO_FAIL(ctx, "tc2_wgrad: cuTensorMapEncodeTiled failed");
-    const int grid = p.n1_blocks * p.splits;
-    if (p.nacc == 2) {
-        cudaFuncSetAttribute(tc2_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        tc2_wgrad_kernel<2><<<grid, THREADS, p.smem, st>>>(tmD, tmH, tmP, M, N1, N2, p.n1_blocks, p.rows_per_split, p.stages);
-    } else {
-        cudaFuncSetAttribute(tc2_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        tc2_wgrad_kernel<1><<<grid, THREADS, p.smem, st>>>(tmD, tmH, tmP, M, N1, N2, p.n1_blocks, p.rows_per_split, p.stages);
-    }
-    DPPO_CHECK_LAUNCH(ctx, "tc2_wgrad_kernel");
-    return 0;
+    return dppo_tc2_wgrad_multi(ctx, 1, &Dm, &ldd, &Hm, &ldh, &partials, &splits, M, &N1, &N2, st);
 }
