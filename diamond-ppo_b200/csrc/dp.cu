@@ -46,10 +46,11 @@ constexpr int DP_THREADS = 256;
 
 // n4: float4 elements of the gradient; the 4 loss sums follow as one more float4 (excluded from the norm)
 __global__ void __launch_bounds__(DP_THREADS)
-dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long step, int64_t n4, float* __restrict__ grads_out,
-                          float* __restrict__ losses_out, double* __restrict__ partials)
+dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long step, const unsigned long long* __restrict__ step_dev,
+                          int64_t n4, float* __restrict__ grads_out, float* __restrict__ losses_out, double* __restrict__ partials)
 {
     __shared__ double red[DP_THREADS / 32];
+    if (step_dev != nullptr) step = *step_dev;      // CUDA-graph replay: the step number is device-resident
     // publish: the gradient of this step was written by earlier kernels of this stream, i.e. it is complete
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
@@ -183,8 +184,10 @@ extern "C" int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, float* pa
         pp.flags[q] = q < dp->world ? reinterpret_cast<unsigned long long*>(dp->peer[q] + 2 * dp->slot_floats) : nullptr;
     }
     double* partials = (double*)ws;
-    dp_allreduce_sumsq_kernel<<<nb, DP_THREADS, 0, st>>>(pp, dp->world, dp->rank, (unsigned long long)h->step, n4, grads_out, losses_out,
-                                                         partials);
+    // h->step_consts (optional, device): {2 floats for the Adam kernel, then the 64-bit step number of this launch}
+    const unsigned long long* step_dev = h->step_consts ? reinterpret_cast<const unsigned long long*>(h->step_consts + 2) : nullptr;
+    dp_allreduce_sumsq_kernel<<<nb, DP_THREADS, 0, st>>>(pp, dp->world, dp->rank, (unsigned long long)h->step, step_dev, n4, grads_out,
+                                                         losses_out, partials);
     DPPO_CHECK_LAUNCH(ctx, "dp_allreduce_sumsq_kernel");
     return launch_clip_adam(ctx, params, grads_out, exp_avg, exp_avg_sq, dp->n, partials, nb, h, grad_norm_out, st);
 }

@@ -84,15 +84,16 @@ grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, c
         if (x == 0) sumsq_out[blockIdx.x] = sq;
     }
     if (blockIdx.x == 0 && losses != nullptr) {
+        // warp w < 3 sums loss term w: lane-strided partial sums in a fixed order, then a fixed shuffle tree
         __shared__ float l[3];
-        const int t = y * RED_X + x;
-        if (t < 3) {
+        if (y < 3) {
             float s = 0.f;
-            for (int p = 0; p < loss_nparts; ++p) s += loss_partials[(int64_t)p * loss_stride + t];
-            l[t] = s;
+            for (int p = x; p < loss_nparts; p += RED_X) s += __ldg(loss_partials + (int64_t)p * loss_stride + y);
+            s = warp_sum(s);
+            if (x == 0) l[y] = s;
         }
         __syncthreads();
-        if (t == 0) {
+        if (x == 0 && y == 0) {
             const float pol = l[0] * inv_m, val = 0.5f * l[1] * inv_m, ent = l[2] * inv_m;    // ppo.py:270-274
             losses[0] = pol; losses[1] = val; losses[2] = ent;
             losses[3] = pol + vw * val + -beta * ent;                                          // ppo.py:276-280

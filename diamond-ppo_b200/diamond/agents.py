@@ -406,8 +406,8 @@ class FusedMlpEngine(_EngineBase):
             B = M * MB
             gs = dict(key=key, graphs=[], launches=0,
                       idx=[torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)],
-                      consts=[torch.zeros(MB, 2, dtype=torch.float32, device=dev) for _ in range(2)],
-                      h_consts=[torch.zeros(MB, 2, dtype=torch.float32).pin_memory() for _ in range(2)],
+                      consts=[torch.zeros(MB, 4, dtype=torch.float32, device=dev) for _ in range(2)],
+                      h_consts=[torch.zeros(MB, 4, dtype=torch.float32).pin_memory() for _ in range(2)],
                       losses=[torch.zeros(MB, 4, dtype=torch.float32, device=dev) for _ in range(2)],
                       copy_stream=torch.cuda.Stream(), copied=[torch.cuda.Event() for _ in range(2)],
                       done=[torch.cuda.Event() for _ in range(2)])
@@ -418,11 +418,19 @@ class FusedMlpEngine(_EngineBase):
                 l0 = ctx.launches
                 with torch.cuda.graph(g, stream=cap):
                     for k in range(MB):
-                        hyper.step = 1                                   # ignored: the Adam kernel reads consts[p][k]
+                        # only the parity of `step` is baked in (exchange slot); the kernels read consts[p][k]
+                        hyper.step = 2 + ((self.adam_step + k + 1) & 1)
                         hyper.step_consts = gs["consts"][p][k].data_ptr()
-                        ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"],
-                                               gs["idx"][p][k * M:(k + 1) * M], M, hyper, gs["losses"][p][k], b["train_ws"])
-                        ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+                        if self.dpx is not None:
+                            slot = ctx.dp_slot(self.dpx, hyper.step)
+                            ctx.mlp_grad_minibatch(desc, self.P, slot, obs_flat, actions, old_logp, adv, ret, b["stats"],
+                                                   gs["idx"][p][k * M:(k + 1) * M], M, hyper, slot + 4 * self.total, b["train_ws"])
+                            ctx.dp_allreduce_clip_adam(self.dpx, self.P, self.G, self.M, self.V, hyper, gs["losses"][p][k],
+                                                       self.adam_ws, self.grad_norm)
+                        else:
+                            ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"],
+                                                   gs["idx"][p][k * M:(k + 1) * M], M, hyper, gs["losses"][p][k], b["train_ws"])
+                            ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
                 gs["launches"] = ctx.launches - l0
                 gs["graphs"].append(g)
             hyper.step_consts = None
@@ -437,10 +445,12 @@ class FusedMlpEngine(_EngineBase):
             worker.wait(e)
             gs["copied"][p].synchronize()                                # the previous copy out of h_consts[p] has been issued and is done
             hc = gs["h_consts"][p].numpy()
+            hc_step = hc.view(np.uint64)                                 # [MB, 2]: column 1 aliases floats 2..3
             for k in range(MB):
                 step = self.adam_step + k + 1                            # torch/optim/adam.py:531-547, python-float bias corrections
                 hc[k, 0] = np.float32(np.sqrt(1.0 - b2 ** step))
                 hc[k, 1] = np.float32(-(hyper.lr / (1.0 - b1 ** step)))
+                hc_step[k, 1] = step
             cs = gs["copy_stream"]
             cs.wait_event(gs["done"][p])                                 # the graph that last read idx[p] / consts[p] has finished
             with torch.cuda.stream(cs):
@@ -515,7 +525,9 @@ class FusedMlpEngine(_EngineBase):
         # keyed on the data pointers it bakes in and only used from the second consecutive learn() on the same buffers.
         ptr_key = (buf.obs.data_ptr(), buf.actions.data_ptr(), buf.T, buf.N, E, MB, cfg.ppo_clip, cfg.value_loss_weight,
                    cfg.entropy_beta, cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm))
-        use_graph = self.use_graphs and not dist.enabled and self._seen_key == ptr_key and B % MB == 0
+        # under DP: rank-local permutations + fused exchange only, and an even MB so that the baked slot parity repeats
+        dp_ok = not dist.enabled or (self.dpx is not None and not dist.global_perm and MB % 2 == 0 and self.adam_step % 2 == 0)
+        use_graph = self.use_graphs and dp_ok and self._seen_key == ptr_key and B % MB == 0
         self._seen_key = ptr_key
         if not dist.enabled:
             hyper.grad_sumsq = self.grad_sumsq.data_ptr()    # gradient assembly leaves the norm partials for the Adam kernel

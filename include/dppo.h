@@ -68,9 +68,11 @@ typedef struct dppo_hyper {
     int32_t pad1;
     int64_t adv_count;        /* number of samples behind adv_stats (global batch T*N) */
     int64_t loss_denominator; /* rows the loss means divide by (global minibatch size) */
-    const float* step_consts; /* optional DEVICE pointer to {sqrt(1 - beta2^step), -lr / (1 - beta1^step)}: when set, the Adam
-                                 kernel reads the two step-dependent constants from it instead of deriving them from
-                                 lr / step on the host, so a captured CUDA graph of an optimiser step can be replayed */
+    const float* step_consts; /* optional DEVICE pointer to 16 bytes {f32 sqrt(1 - beta2^step), f32 -lr / (1 - beta1^step), u64 step}:
+                                 when set, the Adam kernel reads its two step-dependent constants (and the data-parallel exchange
+                                 kernel the step number it publishes / waits for) from device memory instead of from lr / step,
+                                 so a captured CUDA graph of an optimiser step can be replayed.  `step` must still carry the
+                                 parity (step & 1) of the launch: it selects the exchange slot */
     double* grad_sumsq;       /* optional DEVICE buffer of dppo_grad_sumsq_bytes(): dppo_mlp_grad_minibatch leaves the fp64 partial
                                  sums of squares of the gradient it assembled there and dppo_clip_adam_step reads them instead of
                                  launching its own norm kernel (single-GPU path; under DP the norm is taken after the exchange) */

@@ -78,6 +78,24 @@ def main():
     if rank == 0:
         print(f"dp{world} [local permutation, fused]: replicas identical and finite -> {'OK' if local_ok else 'FAIL'}", flush=True)
     same = same and local_ok
+    # graph replay under DP (device-resident step numbers for the exchange flags) equals the eager DP path bit for bit
+    finals = []
+    for use_graphs in (False, True):
+        ag = PPO(env_fn, cfg, dp=True)
+        ag.engine.use_graphs = use_graphs
+        from diamond.agents import RolloutBuffer
+        buf = RolloutBuffer.from_lists(ag.ctx, local_exp, False, ag.device)
+        np.random.seed(77)
+        for _ in range(3):
+            ag.learn(buf)
+        torch.cuda.synchronize()
+        finals.append(ag.engine.P.clone())
+        if use_graphs:
+            assert any("graph" in b_ for b_ in ag.engine._bufs.values()), "graph path was not taken under DP"
+    graph_ok = bool(torch.equal(finals[0], finals[1]))
+    if rank == 0:
+        print(f"dp{world} [graph replay vs eager]: bit-identical -> {'OK' if graph_ok else 'FAIL'}", flush=True)
+    same = same and graph_ok
     t = torch.tensor([int(ok and same)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
