@@ -27,9 +27,9 @@ T, N_ENVS, D, H, A, E, MB = 128, 4096, 64, 256, 4, 4, 8
 FLOP_PER_SAMPLE_UPDATE = 1_252_864          # 2*(3F - D*H), F = D*H + 3H^2 + H*A + H
 FLOP_PER_SAMPLE_PREPASS = 723_968           # 2*(F + Fc)
 GAE_BYTES_PER_ELEM = 28                     # 5 fp32 reads + 2 fp32 writes
-# dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full, profiles/r1c_*):
-# 67.8 MB read + 16.0 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
-GEMM_DRAM_TRAFFIC = 83.8e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full,
+# profiles/r1e_kernels.csv): 67.7 MB read + 15.2 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
+GEMM_DRAM_TRAFFIC = 82.9e6
 
 
 def measured_peaks():

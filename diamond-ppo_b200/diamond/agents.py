@@ -67,6 +67,8 @@ class RolloutBuffer:
         self._dev_rec = torch.empty(padded, dtype=torch.uint8, device=device)
         self._views = [self._carve(p.numpy()) for p in self._pinned]
         self.h2d_bytes = 0
+        self._copy_stream = None        # side stream of load_host
+        self._h2d = None                # pending sliced load: {"bounds", "events"}
         self.filled = 0
 
     def _carve(self, raw: np.ndarray):
@@ -118,6 +120,7 @@ class RolloutBuffer:
         A = int(np.prod(act.shape[2:])) if continuous else 1
         buf = cls.__new__(cls)
         buf.ctx, buf.T, buf.N, buf.D, buf.A, buf.continuous, buf.device = ctx, T, N_, D, A, continuous, device
+        buf._copy_stream, buf._h2d = None, None
 
         def up(x, dtype):
             t = torch.as_tensor(np.ascontiguousarray(x)).to(dtype)
@@ -131,17 +134,61 @@ class RolloutBuffer:
         buf.filled = T
         return buf
 
+    H2D_CHUNKS = 4
+
     def load_host(self, obs, next_obs, actions, rewards, terminations, truncations) -> int:
-        """Fill the whole buffer from host tensors already in this buffer's dtypes/shapes (pinned
-        memory makes the copies asynchronous).  Returns the bytes copied host->device."""
+        """Fill the whole buffer from host tensors already in this buffer's dtypes/shapes (pinned memory makes the copies
+        asynchronous).  The copies run on a side stream in the order the learner consumes them -- scalars, observations,
+        final observations, each observation tensor in H2D_CHUNKS time slices with an event per slice -- so that the
+        pre-update pass of slice c overlaps the transfer of slice c+1 (`wait_slice`).  Returns the bytes copied."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream())            # everything enqueued so far may still read the old contents
         n = 0
-        for dst, src in ((self.obs, obs), (self.next_obs, next_obs), (self.actions, actions), (self.rewards, rewards),
-                         (self.terminations, terminations), (self.truncations, truncations)):
-            dst.copy_(src.view(dst.shape), non_blocking=True)
-            n += dst.numel() * dst.element_size()
+        T, nch = self.T, min(self.H2D_CHUNKS, self.T)
+        bounds = [T * c // nch for c in range(nch + 1)]
+        events = {"obs": [], "next_obs": []}
+        with torch.cuda.stream(cs):
+            for dst, src in ((self.actions, actions), (self.rewards, rewards), (self.terminations, terminations),
+                             (self.truncations, truncations)):
+                dst.copy_(src.view(dst.shape), non_blocking=True)
+                n += dst.numel() * dst.element_size()
+            for name, dst, src in (("obs", self.obs, obs), ("next_obs", self.next_obs, next_obs)):
+                src = src.view(dst.shape)
+                for c in range(nch):
+                    dst[bounds[c]:bounds[c + 1]].copy_(src[bounds[c]:bounds[c + 1]], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    events[name].append(ev)
+                n += dst.numel() * dst.element_size()
+        self._h2d = dict(bounds=bounds, events=events)
         self.filled = self.T
         self.h2d_bytes += n
         return n
+
+    def time_slices(self):
+        """[(t0, t1)] row ranges in which a pending load_host delivers the observation tensors (one slice otherwise)."""
+        if self._h2d is None:
+            return [(0, self.T)]
+        b = self._h2d["bounds"]
+        return [(b[c], b[c + 1]) for c in range(len(b) - 1)]
+
+    def wait_slice(self, name: str, c: int):
+        """Makes the current stream wait for slice c of `obs` / `next_obs` of a pending load_host (no-op otherwise)."""
+        if self._h2d is not None:
+            torch.cuda.current_stream().wait_event(self._h2d["events"][name][c])
+
+    def wait_all(self):
+        """Current stream waits for every slice of a pending load_host."""
+        if self._h2d is not None:
+            for name in ("obs", "next_obs"):
+                torch.cuda.current_stream().wait_event(self._h2d["events"][name][-1])
+            self._h2d = None
+
+    def h2d_done(self):
+        """All slices have been waited for by the consumer: later readers need no further event waits."""
+        self._h2d = None
 
     # ---- list-like view for user code ---------------------------------------------------------
     def __len__(self) -> int:
@@ -150,6 +197,7 @@ class RolloutBuffer:
     def __getitem__(self, t: int):
         if not -self.filled <= t < self.filled:
             raise IndexError(t)
+        self.wait_all()
         act = self.actions[t].cpu().numpy()
         return [self.obs[t].cpu().numpy(), self.next_obs[t].cpu().numpy(),
                 act if self.continuous else act.astype(np.int64),
@@ -469,14 +517,26 @@ class FusedMlpEngine(_EngineBase):
     def prepass(self, buf: RolloutBuffer, b):
         """ppo.py:235-238: old log-probs, values, next_values with the pre-update parameters."""
         B = buf.T * buf.N
+        N_ = buf.N
         ctx, desc = self.ctx, self.fm.desc
-        ctx.mlp_forward(desc, self.P, buf.obs, B, 3, b["head"], b["values"], self.fwd_ws)
+        # time slices: one for a resident buffer; a pending load_host delivers the observations slice by slice and the
+        # forward pass of slice c overlaps the transfer of slice c+1
+        slices = buf.time_slices()
+        values, next_values = b["values"].view(B), b["next_values"].view(B)
+        for c, (t0, t1) in enumerate(slices):
+            buf.wait_slice("obs", c)
+            r0, r1 = t0 * N_, t1 * N_
+            ctx.mlp_forward(desc, self.P, buf.obs[t0:t1], r1 - r0, 3, b["head"][r0:r1], values[r0:r1], self.fwd_ws)
         if self.continuous:
             lay = self.fm.layout
             ctx.logprob_gaussian(b["head"], self.P[lay.log_std:lay.log_std + self.A], buf.actions.view(B, self.A), b["old_logp"].view(B))
         else:
             ctx.logprob_categorical(b["head"], buf.actions.view(B), b["old_logp"].view(B))
-        ctx.mlp_forward(desc, self.P, buf.next_obs, B, 2, None, b["next_values"], self.fwd_ws)
+        for c, (t0, t1) in enumerate(slices):
+            buf.wait_slice("next_obs", c)
+            r0, r1 = t0 * N_, t1 * N_
+            ctx.mlp_forward(desc, self.P, buf.next_obs[t0:t1], r1 - r0, 2, None, next_values[r0:r1], self.fwd_ws)
+        buf.h2d_done()
 
     def learn(self, buf: RolloutBuffer, events=None):
         cfg, ctx, dist = self.cfg, self.ctx, self.dist
@@ -608,6 +668,7 @@ class AutogradEngine(_EngineBase):
         h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
         worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
         worker.start()
+        buf.wait_all()
         obs, nobs = buf.obs, buf.next_obs
         A = buf.A
         old_logp = torch.empty(B, device=dev)
