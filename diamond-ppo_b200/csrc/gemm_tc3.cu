@@ -36,7 +36,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, const unsigned char* __restrict__ Wimg,
                 const float* __restrict__ bias, const float* __restrict__ Hact, int ldh, float* __restrict__ colsum, int64_t M,
-                int N, int K, int n_tile, int pair_tiles, int dbg)
+                int N, int K, int n_tile, int pair_tiles, int tail_halves, int dbg)
 {
     extern __shared__ unsigned char dyn_raw[];
     __shared__ __align__(8) uint64_t full[STAGES], ready[STAGES], empty[STAGES], tfull[2], tempty[2];
@@ -53,6 +53,17 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int n_tiles = N / n_tile;
     const int total = pair_tiles * n_tiles;
     const int chunks = K / KC;
+    // Tile schedule of this cluster: `base` full 256 x n_tile tiles (round robin), then the remainder.  When the remainder
+    // R satisfies 2R <= clusters (tail_halves), each leftover tile is split into two half-width (n_tile/2 columns) tiles
+    // that go to different clusters: the makespan drops from base + 1 to base + ~0.63 tiles.
+    const int base_tiles = total / n_clusters, rem_tiles = total - base_tiles * n_clusters;
+    const int extra = tail_halves ? (cluster_id < 2 * rem_tiles ? 1 : 0) : (cluster_id < rem_tiles ? 1 : 0);
+    const int n_my = base_tiles + extra;
+    auto tile_of = [&](int i, int& tile, int& half) {
+        if (i < base_tiles) { tile = i * n_clusters + cluster_id; half = -1; }
+        else if (tail_halves) { tile = base_tiles * n_clusters + (cluster_id >> 1); half = cluster_id & 1; }
+        else { tile = base_tiles * n_clusters + cluster_id; half = -1; }
+    };
 
     if (tid == 0) {
 #pragma unroll
@@ -72,24 +83,29 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_prefetch_desc(&tmA);
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = cluster_id; tile < total; tile += n_clusters) {
+            for (int i = 0; i < n_my; ++i) {
+                int tile, half;
+                tile_of(i, tile, half);
                 const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
                 const int m0 = m_pair * 2 * BM + (int)rank * BM;
-                const unsigned char* wsrc = Wimg + (int64_t)n_blk * chunks * 2 * b_img + (int64_t)rank * b_half;
-                const int next = tile + n_clusters;
-                const int next_m = next < total ? next / n_tiles : -1;
+                const int n_eff = half < 0 ? n_tile : n_tile / 2;                  // columns of this tile
+                const int hb = (n_eff / 2) * KC * 4;                               // bytes of this CTA's rows of one image
+                const int row_off = (half < 0 ? 0 : half * (n_tile / 2)) + (int)rank * (n_eff / 2);
+                const unsigned char* wsrc = Wimg + (int64_t)n_blk * chunks * 2 * b_img + (int64_t)row_off * KC * 4;
+                int next_m = -1;
+                if (i + 1 < n_my) { int nt, nh; tile_of(i + 1, nt, nh); next_m = nt / n_tiles; }
                 for (int c = 0; c < chunks; ++c) {
                     // pull the next tile's activations into L2 while this tile computes
                     if (next_m >= 0 && next_m != m_pair) tma_prefetch_2d(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM);
                     mbar_wait(&empty[s], ph ^ 1);
-                    const bool skip_b = (dbg & 1) && (tile != cluster_id || c >= STAGES);
-                    mbar_expect_tx(&full[s], (uint32_t)(A_IMG + (skip_b ? 0 : 2 * b_half)));
+                    const bool skip_b = (dbg & 1) && (i != 0 || c >= STAGES);
+                    mbar_expect_tx(&full[s], (uint32_t)(A_IMG + (skip_b ? 0 : 2 * hb)));
                     unsigned char* st = dyn + s * stage_bytes;
                     tma_load_2d(st, &tmA, c * KC, m0, &full[s]);
                     if (!skip_b) {
                         const unsigned char* w = wsrc + (int64_t)c * 2 * b_img;
-                        bulk_copy_g2s(st + 2 * A_IMG, w, (uint32_t)b_half, &full[s]);                    // hi rows of this half
-                        bulk_copy_g2s(st + 2 * A_IMG + b_half, w + b_img, (uint32_t)b_half, &full[s]);   // lo rows of this half
+                        bulk_copy_g2s(st + 2 * A_IMG, w, (uint32_t)hb, &full[s]);                        // hi rows of this CTA
+                        bulk_copy_g2s(st + 2 * A_IMG + b_half, w + b_img, (uint32_t)hb, &full[s]);       // lo rows of this CTA
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -98,10 +114,13 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
     } else if (warp == W_MMA) {
         if (rank == 0 && lane == 0) {
-            const uint32_t idesc = idesc_tf32(2 * BM, n_tile, 0, 0);
+            const uint32_t idesc_full = idesc_tf32(2 * BM, n_tile, 0, 0), idesc_half = idesc_tf32(2 * BM, n_tile / 2, 0, 0);
             int s = 0;
-            uint32_t ph = 0, it = 0;
-            for (int tile = cluster_id; tile < total; tile += n_clusters, ++it) {
+            uint32_t ph = 0;
+            for (uint32_t it = 0; it < (uint32_t)n_my; ++it) {
+                int tile, half;
+                tile_of((int)it, tile, half);
+                const uint32_t idesc = half < 0 ? idesc_full : idesc_half;
                 const uint32_t set = it & 1;
                 mbar_wait(&tempty[set], ((it >> 1) & 1) ^ 1);            // both CTAs' epilogues have drained this accumulator
                 fence_after();
@@ -135,7 +154,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr int PER = A_IMG / 16 / SPLIT_THREADS;
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = cluster_id; tile < total; tile += n_clusters) {
+        for (int i = 0; i < n_my; ++i) {
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(&full[s], ph);
                 const uint32_t hi = smem_u32(dyn + s * stage_bytes) + ct * 16;
@@ -159,16 +178,18 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // per-warp 32x32 staging block in the SWIZZLE_128B layout and a TMA store (full 128-byte row segments reach HBM).
         const int ew = warp - W_EPI0;
         const int q = warp & 3, grp = ew >> 2;
-        const int ncols = n_tile / 2;
-        const int col0 = grp * ncols;
-        const int nblk = ncols / 32;
         const uint32_t stg = smem_u32(dyn + STAGES * stage_bytes) + (uint32_t)ew * STG_BLK;
         const uint32_t row_off = (uint32_t)lane * 128, sw = (uint32_t)(lane & 7);
-        uint32_t it = 0;
         if (lane == 0) tma_prefetch_desc(&tmC);
-        for (int tile = cluster_id; tile < total; tile += n_clusters, ++it) {
+        for (uint32_t it = 0; it < (uint32_t)n_my; ++it) {
+            int tile, half;
+            tile_of((int)it, tile, half);
             const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
-            const int n0 = n_blk * n_tile + col0;
+            const int n_eff = half < 0 ? n_tile : n_tile / 2;
+            const int ncols = n_eff / 2;                                 // columns of this warp group
+            const int col0 = grp * ncols;                                // first accumulator column of this warp group
+            const int nblk = ncols / 32;
+            const int n0 = n_blk * n_tile + (half < 0 ? 0 : half * (n_tile / 2)) + col0;
             const int m0 = m_pair * 2 * BM + (int)rank * BM + q * 32;
             const int64_t m = (int64_t)m0 + lane;
             const uint32_t set = it & 1;
@@ -225,7 +246,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     // columns in its first tile, which then initialises the row; otherwise the launcher zeroes the buffer.
                     // Rows >= M hold exact zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
                     float* cp = colsum + ((int64_t)blockIdx.x * 4 + q) * N + n + lane;
-                    const float prev = (n_tiles == 1 && it == 0) ? 0.0f : *cp;
+                    const float prev = (n_tiles == 1 && it == 0 && half < 0) ? 0.0f : *cp;
                     // warp transpose-reduce: afterwards lane l holds the sum over the warp's 32 rows of column l
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) {
@@ -293,18 +314,20 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     const int total = pair_tiles * (N / n_tile);
     const size_t smem = (size_t)STAGES * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK + 1024;
     const int grid = tc3_grid(ctx, M, N);
-    (void)total;
+    const int clusters = grid / 2, base_tiles = total / clusters, rem = total - base_tiles * clusters;
+    // half-width tail tiles: only when every cluster still starts with a full tile and the halves fit one per cluster
+    const int tail_halves = (!(ctx->tc_debug & 128) && n_tile == 256 && base_tiles >= 1 && rem > 0 && 2 * rem <= clusters) ? 1 : 0;
     if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && N / n_tile > 1 &&
         cudaMemsetAsync(colsum, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tc3_gemm_kernel<DPPO_EPI_BIAS_TANH><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,
-                                                                          ctx->tc_debug);
+                                                                          tail_halves, ctx->tc_debug);
     } else if (epi == DPPO_EPI_TANH_BWD) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tc3_gemm_kernel<DPPO_EPI_TANH_BWD><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,
-                                                                         ctx->tc_debug);
+                                                                         tail_halves, ctx->tc_debug);
     } else {
         DPPO_FAIL(ctx, "tc3_gemm: unknown epilogue %d", epi);
     }
