@@ -178,7 +178,7 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     w.p1 = take((int64_t)mx(w.s1, w.t1) * H * D);
     w.tiles2 = dppo_gemm_row_tiles(M, (int)H);
     w.tiles1 = dppo_gemm_row_tiles(M, (int)H);
-    const int cparts = mx(mx(dppo_tc2_colsum_parts(M), dppo_tc3_colsum_parts(&fake, M, (int)H)), w.tiles2);
+    const int cparts = mx(mx(dppo_tc2_colsum_parts(M), dppo_tc3_colsum_rows(&fake, M, (int)H)), w.tiles2);
     w.c2 = take((int64_t)cparts * H);
     w.c1 = take((int64_t)cparts * H);
     w.head_blocks = head_train_blocks(&fake, M);
@@ -427,8 +427,8 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     seg(L.w2, (int64_t)H * H, w.p2, (int64_t)H * H, n2p);
     seg(L.b2, H, w.c2, H, tiles2);
     seg(L.w3, (int64_t)2 * H * H, w.p3, (int64_t)2 * H * H, n3p);
-    const int off_dba = A * H, off_dwc = A * H + A, off_dbc = off_dwc + H, off_dls = off_dbc + 1, off_b3 = off_dls + A,
-              off_loss = off_b3 + 2 * H;
+    const HeadOffsets ho = head_offsets(H, A);
+    const int off_dba = ho.dba, off_dwc = ho.dwc, off_dbc = ho.dbc, off_dls = ho.dls, off_b3 = ho.b3, off_loss = ho.loss;
     seg(L.b3, 2 * H, w.hp + off_b3, w.head_stride, w.head_blocks);
     seg(L.wa, (int64_t)A * H, w.hp, w.head_stride, w.head_blocks);
     seg(L.ba, A, w.hp + off_dba, w.head_stride, w.head_blocks);
@@ -445,7 +445,7 @@ extern "C" int64_t dppo_tc_linear_workspace_bytes(int N, int K) { return dppo_tc
 
 extern "C" int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N, int variant)
 {
-    if (variant >= 3 && ctx) return dppo_tc3_colsum_parts(ctx, M, N);
+    if (variant >= 3 && ctx) return dppo_tc3_colsum_rows(ctx, M, N);
     return variant >= 2 ? dppo_tc2_colsum_parts(M) : (int)((M + 127) / 128);
 }
 

@@ -245,7 +245,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     // this CTA (the row is owned by this warp pair).  With a single column tile every CTA covers all N
                     // columns in its first tile, which then initialises the row; otherwise the launcher zeroes the buffer.
                     // Rows >= M hold exact zeros (TMA zero-fills the out-of-range A rows), so they do not disturb the sums.
-                    float* cp = colsum + ((int64_t)blockIdx.x * 4 + q) * N + n + lane;
+                    float* cp = colsum + ((int64_t)gridDim.x + (int64_t)blockIdx.x * 4 + q) * N + n + lane;      // working row of (CTA, quadrant)
                     const float prev = (n_tiles == 1 && it == 0 && half < 0) ? 0.0f : *cp;
                     // warp transpose-reduce: afterwards lane l holds the sum over the warp's 32 rows of column l
 #pragma unroll
@@ -267,6 +267,15 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (lane == 0) bulk_wait<0>();             // staging memory must outlive the last store's read
         __syncwarp();
+        if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr) {
+            // fold the four quadrant rows of this CTA into its one partial row (fixed order): rows [0, grid) are what the
+            // gradient reduction reads, rows [grid, 5 grid) the per-quadrant working rows
+            __threadfence_block();
+            asm volatile("bar.sync 1, 256;" ::: "memory");                       // the eight epilogue warps
+            const float* wr = colsum + ((int64_t)gridDim.x + (int64_t)blockIdx.x * 4) * N;
+            for (int col = tid - W_EPI0 * 32; col < N; col += N_EPI * 32)
+                colsum[(int64_t)blockIdx.x * N + col] = (__ldcg(wr + col) + __ldcg(wr + N + col)) + (__ldcg(wr + 2 * N + col) + __ldcg(wr + 3 * N + col));
+        }
     }
 
     // no CTA may exit (or free TMEM) while its peer can still touch its shared memory, barriers or TMEM
@@ -293,7 +302,8 @@ int tc3_grid(dppo_ctx* ctx, int64_t M, int N)
 }
 }  // namespace
 
-int dppo_tc3_colsum_parts(dppo_ctx* ctx, int64_t M, int N) { return 4 * tc3_grid(ctx, M, N); }
+int dppo_tc3_colsum_parts(dppo_ctx* ctx, int64_t M, int N) { return tc3_grid(ctx, M, N); }      // one partial row per CTA
+int dppo_tc3_colsum_rows(dppo_ctx* ctx, int64_t M, int N) { return 5 * tc3_grid(ctx, M, N); }       // + 4 working rows per CTA
 
 bool dppo_tc3_gemm_supported(int64_t M, int N, int K)
 {
@@ -318,7 +328,7 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     // half-width tail tiles: only when every cluster still starts with a full tile and the halves fit one per cluster
     const int tail_halves = (!(ctx->tc_debug & 128) && n_tile == 256 && base_tiles >= 1 && rem > 0 && 2 * rem <= clusters) ? 1 : 0;
     if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && N / n_tile > 1 &&
-        cudaMemsetAsync(colsum, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
+        cudaMemsetAsync(colsum + (size_t)grid * N, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -290,7 +290,7 @@ head_train_kernel(HeadTrainArgs a)
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < HEAD_WARPS; ++w) s += s_acc[(size_t)w * (A + 1) * H + i];
-        if (i < A * H) out[i] = s; else out[A * H + A + (i - A * H)] = s;
+        if (i < A * H) out[i] = s; else out[head_offsets(H, A).dwc + (i - A * H)] = s;
     }
     __syncthreads();
     // reuse s_acc as scratch for the small per-warp vectors
@@ -308,7 +308,8 @@ head_train_kernel(HeadTrainArgs a)
         mine[2 * H + 64] = acc_dbc; mine[2 * H + 65] = l_pol; mine[2 * H + 66] = l_val; mine[2 * H + 67] = l_ent;
     }
     __syncthreads();
-    const int off_dba = A * H, off_dbc = A * H + A + H, off_dls = off_dbc + 1, off_b3 = off_dls + A, off_loss = off_b3 + 2 * H;
+    const HeadOffsets ho = head_offsets(H, A);
+    const int off_dba = ho.dba, off_dbc = ho.dbc, off_dls = ho.dls, off_b3 = ho.b3, off_loss = ho.loss;
     for (int i = threadIdx.x; i < 2 * H + 68; i += blockDim.x) {
         float s = 0.f;
 #pragma unroll
@@ -476,7 +477,7 @@ int launch_head_train(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int
 
 }  // namespace
 
-int head_partial_floats(int H, int A) { return A * H + A + H + 1 + A + 2 * H + 4; }
+int head_partial_floats(int H, int A) { return head_offsets(H, A).total; }
 
 int head_train_blocks(dppo_ctx* ctx, int64_t M)
 {

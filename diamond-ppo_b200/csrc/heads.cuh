@@ -21,6 +21,23 @@ struct HeadTrainArgs {
     int partial_stride;
 };
 
+// Layout of one head-kernel partial: [dWa A*H | dba A | dWc H | dbc 1 | dlog_std A | db3 2H | losses 4], every block starting on a
+// multiple of 4 floats so that the gradient reduction reads all of them as float4 (an unaligned db3 block took the scalar path
+// and was the long pole of grad_reduce_kernel).
+struct HeadOffsets { int dba, dwc, dbc, dls, b3, loss, total; };
+__host__ __device__ inline HeadOffsets head_offsets(int H, int A)
+{
+    auto up4 = [](int x) { return (x + 3) / 4 * 4; };
+    HeadOffsets o;
+    o.dba = up4(A * H);
+    o.dwc = up4(o.dba + A);
+    o.dbc = up4(o.dwc + H);
+    o.dls = up4(o.dbc + 1);
+    o.b3 = up4(o.dls + A);
+    o.loss = up4(o.b3 + 2 * H);
+    o.total = o.loss + 4;
+    return o;
+}
 int head_partial_floats(int H, int A);
 int head_train_blocks(dppo_ctx* ctx, int64_t M);
 int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int blocks, cudaStream_t st);

@@ -215,7 +215,8 @@ int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
 /* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate).
  * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).
  * epi 1: C = tanh(A W^T + bias); epi 2: C = (A W) * (1 - Hact^2) with Hact [M,N], and, if colsum != NULL,
- * partial column sums of C in colsum [dppo_tc_colsum_parts(ctx, M, N, variant), N] (bias-gradient partials).
+ * partial column sums of C in colsum [dppo_tc_colsum_parts(ctx, M, N, variant), N] (variant 3: the first fifth of the
+ * rows are the per-CTA partials, the rest per-quadrant working rows; sum only rows [0, parts/5)) (bias-gradient partials).
  * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed);
  * 3: the same roles over CTA pairs (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC).
  * ws (dppo_tc_linear_workspace_bytes) holds the split weight images; variant | 0x100 re-uses the images an earlier call

@@ -32,7 +32,7 @@ for (Nn, K) in [(256, 512), (256, 256)]:
     for dbg in (0, 128, 0, 128):
         ctx.set_option("tc_debug", dbg)
         C, cs = ctx.tc_linear(2, A, W, True, Hact=Hact, colsum=True)
-        err = (C.double() - ref).abs().max().item(); ce = (cs.double().sum(0) - ref.sum(0)).abs().max().item()
+        err = (C.double() - ref).abs().max().item(); cs = cs[:cs.shape[0] // 5]; ce = (cs.double().sum(0) - ref.sum(0)).abs().max().item()
         us = t(lambda: ctx.tc_linear(2, A, W, True, Hact=Hact, colsum=True))
         print(f"dgrad N={Nn} K={K} tails={'full' if dbg else 'half'}: {us:.1f} us (incl. prep)  err {err:.2e} colsum {ce:.2e}", flush=True)
 ctx.set_option("tc_debug", 0)

@@ -458,6 +458,8 @@ def test_tc_linear_dgrad_vs_fp64(ctx, variant, M, N, K):
     ref = (A.double() @ W.double()) * (1.0 - Hact.double() ** 2)
     assert (C.double() - ref).abs().max().item() <= TC_TOL * max(1.0, ref.abs().max().item())
     col = ref.sum(0)
+    if variant == 3:
+        cs = cs[:cs.shape[0] // 5]                          # per-CTA partial rows; the rest are per-quadrant working rows
     assert (cs.double().sum(0) - col).abs().max().item() <= 3e-5 * max(1.0, col.abs().max().item())
 
 
