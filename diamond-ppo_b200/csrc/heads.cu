@@ -86,6 +86,53 @@ __device__ __forceinline__ Dist<CONT> eval_dist(float z, int lane, int A, int ac
     return d;
 }
 
+// Per-CTA partial [dWa A*H | dba A | dWc H | dbc 1 | dlog_std A | db3 2H | losses 4] (head_offsets): sums the per-warp
+// accumulators held in s_acc ([HEAD_WARPS][(A+1)][H]) and the per-lane sums in fixed order and writes one partial per CTA.
+template <int KPL, int VEC>
+__device__ __forceinline__ void head_train_flush(const HeadTrainArgs& a, float* s_acc, const float (&acc_b3)[2 * KPL], float acc_dba,
+                                                 float acc_dbc, float acc_dls, float l_pol, float l_val, float l_ent)
+{
+    const int H = a.H, A = a.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto kof = [&](int e) { return VEC == 4 ? ((e >> 2) * 128 + 4 * lane + (e & 3)) : lane + 32 * e; };
+    __syncthreads();
+    float* out = a.partials + (int64_t)blockIdx.x * a.partial_stride;
+    for (int i = threadIdx.x; i < (A + 1) * H; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < HEAD_WARPS; ++w) s += s_acc[(size_t)w * (A + 1) * H + i];
+        if (i < A * H) out[i] = s; else out[head_offsets(H, A).dwc + (i - A * H)] = s;
+    }
+    __syncthreads();
+    // reuse s_acc as scratch for the small per-warp vectors
+    float* scratch = s_acc;                    // [HEAD_WARPS][2H + 3*32 + 4]
+    const int sw = 2 * H + 100;
+    float* mine = scratch + warp * sw;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int k = kof(i);
+        if (k < H) { mine[k] = acc_b3[i]; mine[H + k] = acc_b3[KPL + i]; }
+    }
+    mine[2 * H + lane] = acc_dba;
+    mine[2 * H + 32 + lane] = acc_dls;
+    if (lane == 0) {
+        mine[2 * H + 64] = acc_dbc; mine[2 * H + 65] = l_pol; mine[2 * H + 66] = l_val; mine[2 * H + 67] = l_ent;
+    }
+    __syncthreads();
+    const HeadOffsets ho = head_offsets(H, A);
+    const int off_dba = ho.dba, off_dbc = ho.dbc, off_dls = ho.dls, off_b3 = ho.b3, off_loss = ho.loss;
+    for (int i = threadIdx.x; i < 2 * H + 68; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < HEAD_WARPS; ++w) s += scratch[w * sw + i];
+        if (i < 2 * H) out[off_b3 + i] = s;
+        else if (i < 2 * H + 32) { if (i - 2 * H < A) out[off_dba + (i - 2 * H)] = s; }
+        else if (i < 2 * H + 64) { if (i - 2 * H - 32 < A) out[off_dls + (i - 2 * H - 32)] = s; }
+        else if (i == 2 * H + 64) out[off_dbc] = s;
+        else out[off_loss + (i - 2 * H - 65)] = s;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Training kernel: heads forward + loss + backward into the first head layers.
 // ---------------------------------------------------------------------------------------------
@@ -283,43 +330,200 @@ head_train_kernel(HeadTrainArgs a)
         }
     }
 
-    // ---- per-CTA partial: [dWa A*H | dba A | dWc H | dbc 1 | dlog_std A | db3 2H | losses 4] ----
+    head_train_flush<KPL, VEC>(a, s_acc, acc_b3, acc_dba, acc_dbc, acc_dls, l_pol, l_val, l_ent);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-accumulator variant of the training kernel (H a multiple of 128, A <= AMAX, float4 columns).
+// The per-warp head weight gradients live in registers (the shared-memory read-modify-write of the generic kernel moved
+// 20 KB through shared memory per row — the kernel ran at half of HBM speed), and the R rows of an iteration share
+// every weight load.  Same per-element arithmetic and the same partial layout as head_train_kernel.
+// ---------------------------------------------------------------------------------------------
+template <bool CONT, int KPL, int R, int AMAX>
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 2)
+head_train_reg_kernel(HeadTrainArgs a)
+{
+    extern __shared__ float smem[];
+    const int H = a.H, A = a.A;
+    constexpr int G = KPL / 4;                  // float4 groups per half row
+    float* s_wa = smem;                         // [A][H]
+    float* s_wc = s_wa + A * H;                 // [H]
+    float* s_acc = s_wc + H;                    // [HEAD_WARPS][(A+1)][H]  flushed once at the end
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = a.wa[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_wc[i] = a.wc[i];
     __syncthreads();
-    float* out = a.partials + (int64_t)blockIdx.x * a.partial_stride;
-    for (int i = threadIdx.x; i < (A + 1) * H; i += blockDim.x) {
-        float s = 0.f;
+
+    float mean, denom;
+    adv_norm_consts(a.adv_stats, a.adv_count, a.advantage_norm, mean, denom);
+    const float bias_a = lane < A ? a.ba[lane] : 0.f;
+    const float bias_c = a.bc[0];
+    const float log_std = (CONT && lane < A) ? a.log_std[lane] : 0.f;
+
+    float4 gwa[AMAX][G], gwc[G];                // this lane's columns of dWa / dWc
 #pragma unroll
-        for (int w = 0; w < HEAD_WARPS; ++w) s += s_acc[(size_t)w * (A + 1) * H + i];
-        if (i < A * H) out[i] = s; else out[head_offsets(H, A).dwc + (i - A * H)] = s;
-    }
-    __syncthreads();
-    // reuse s_acc as scratch for the small per-warp vectors
-    float* scratch = s_acc;                    // [HEAD_WARPS][2H + 3*32 + 4]
-    const int sw = 2 * H + 100;
-    float* mine = scratch + warp * sw;
+    for (int j = 0; j < AMAX; ++j)
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-        const int k = kof(i);
-        if (k < H) { mine[k] = acc_b3[i]; mine[H + k] = acc_b3[KPL + i]; }
-    }
-    mine[2 * H + lane] = acc_dba;
-    mine[2 * H + 32 + lane] = acc_dls;
-    if (lane == 0) {
-        mine[2 * H + 64] = acc_dbc; mine[2 * H + 65] = l_pol; mine[2 * H + 66] = l_val; mine[2 * H + 67] = l_ent;
-    }
-    __syncthreads();
-    const HeadOffsets ho = head_offsets(H, A);
-    const int off_dba = ho.dba, off_dbc = ho.dbc, off_dls = ho.dls, off_b3 = ho.b3, off_loss = ho.loss;
-    for (int i = threadIdx.x; i < 2 * H + 68; i += blockDim.x) {
-        float s = 0.f;
+        for (int g = 0; g < G; ++g) gwa[j][g] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int w = 0; w < HEAD_WARPS; ++w) s += scratch[w * sw + i];
-        if (i < 2 * H) out[off_b3 + i] = s;
-        else if (i < 2 * H + 32) { if (i - 2 * H < A) out[off_dba + (i - 2 * H)] = s; }
-        else if (i < 2 * H + 64) { if (i - 2 * H - 32 < A) out[off_dls + (i - 2 * H - 32)] = s; }
-        else if (i == 2 * H + 64) out[off_dbc] = s;
-        else out[off_loss + (i - 2 * H - 65)] = s;
+    for (int g = 0; g < G; ++g) gwc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc_b3[2 * KPL];
+#pragma unroll
+    for (int i = 0; i < 2 * KPL; ++i) acc_b3[i] = 0.f;
+    float acc_dba = 0.f, acc_dbc = 0.f, acc_dls = 0.f;
+    float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+
+    const int64_t warp_global = (int64_t)blockIdx.x * HEAD_WARPS + warp;
+    const int64_t warp_stride = (int64_t)gridDim.x * HEAD_WARPS;
+    for (int64_t mb = warp_global * R; mb < a.M; mb += warp_stride * R) {
+        float4 ha[R][G], hc[R][G];
+        float old_lp[R], advv[R], ret[R], act_f[R];
+        int act_i[R];
+        bool ok[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t m = mb + r;
+            ok[r] = m < a.M;
+            const int64_t src = ok[r] ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
+            const float4* h3 = reinterpret_cast<const float4*>(a.h3 + (ok[r] ? m : 0) * (int64_t)(2 * H));
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                ha[r][g] = __ldg(h3 + g * 32 + lane);
+                hc[r][g] = __ldg(h3 + (H / 4) + g * 32 + lane);
+            }
+            old_lp[r] = __ldg(a.old_logp + src);
+            advv[r] = (__ldg(a.adv + src) - mean) / denom;
+            ret[r] = __ldg(a.ret + src);
+            act_i[r] = 0; act_f[r] = 0.f;
+            if (CONT) act_f[r] = lane < A ? __ldg(a.actions_f + src * A + lane) : 0.f;
+            else act_i[r] = __ldg(a.actions_i + src);
+        }
+
+        // head products: each weight vector is read once for the R rows
+        float z[R], v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < AMAX; ++j) {
+            if (j < A) {
+                float part[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) part[r] = 0.f;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        part[r] = fmaf(ha[r][g].x, w.x, part[r]); part[r] = fmaf(ha[r][g].y, w.y, part[r]);
+                        part[r] = fmaf(ha[r][g].z, w.z, part[r]); part[r] = fmaf(ha[r][g].w, w.w, part[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    part[r] = warp_sum(part[r]);
+                    if (lane == j) z[r] = part[r];
+                }
+            }
+        }
+        float4 wcv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) wcv[g] = reinterpret_cast<const float4*>(s_wc + g * 128)[lane];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float vp = 0.f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                vp = fmaf(hc[r][g].x, wcv[g].x, vp); vp = fmaf(hc[r][g].y, wcv[g].y, vp);
+                vp = fmaf(hc[r][g].z, wcv[g].z, vp); vp = fmaf(hc[r][g].w, wcv[g].w, vp);
+            }
+            v[r] = warp_sum(vp) + bias_c;
+            z[r] += bias_a;
+        }
+
+        // distribution, loss terms, d(loss)/d(head outputs); rows past the end contribute exact zeros
+        float dz[R], dv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const Dist<CONT> d = eval_dist<CONT>(z[r], lane, A, act_i[r], act_f[r], log_std);
+            const RowTerms t = policy_terms(d.new_lp, old_lp[r], advv[r], a.clip, a.inv_m);
+            dz[r] = 0.f;
+            float dls = 0.f;
+            if (lane < A) {
+                if (!CONT) {
+                    dz[r] = t.dlogp * ((lane == act_i[r] ? 1.0f : 0.0f) - d.p) + (a.beta * a.inv_m) * d.p * (d.lsm + d.entropy);
+                } else {
+                    dz[r] = t.dlogp * d.diff / d.var;
+                    dls = t.dlogp * (d.diff * d.diff / d.var - 1.0f) - a.beta * a.inv_m;
+                }
+            }
+            const float verr = v[r] - ret[r];
+            dv[r] = a.vw * verr * a.inv_m;
+            if (ok[r]) {
+                l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
+                acc_dba += dz[r]; acc_dbc += dv[r]; acc_dls += dls;
+            } else {
+                dz[r] = 0.f; dv[r] = 0.f;
+            }
+        }
+
+        // backward into the first head layers + head weight gradients
+        float4 ga[R][G];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int g = 0; g < G; ++g) ga[r][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < AMAX; ++j) {
+            if (j < A) {
+                float dzj[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) dzj[r] = __shfl_sync(0xffffffffu, dz[r], j);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        ga[r][g].x = fmaf(dzj[r], w.x, ga[r][g].x); ga[r][g].y = fmaf(dzj[r], w.y, ga[r][g].y);
+                        ga[r][g].z = fmaf(dzj[r], w.z, ga[r][g].z); ga[r][g].w = fmaf(dzj[r], w.w, ga[r][g].w);
+                        gwa[j][g].x = fmaf(dzj[r], ha[r][g].x, gwa[j][g].x); gwa[j][g].y = fmaf(dzj[r], ha[r][g].y, gwa[j][g].y);
+                        gwa[j][g].z = fmaf(dzj[r], ha[r][g].z, gwa[j][g].z); gwa[j][g].w = fmaf(dzj[r], ha[r][g].w, gwa[j][g].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float* d3 = a.d3 + (mb + r) * (int64_t)(2 * H);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float4 da, dc;
+                da.x = ga[r][g].x * (1.0f - ha[r][g].x * ha[r][g].x); da.y = ga[r][g].y * (1.0f - ha[r][g].y * ha[r][g].y);
+                da.z = ga[r][g].z * (1.0f - ha[r][g].z * ha[r][g].z); da.w = ga[r][g].w * (1.0f - ha[r][g].w * ha[r][g].w);
+                dc.x = dv[r] * wcv[g].x * (1.0f - hc[r][g].x * hc[r][g].x); dc.y = dv[r] * wcv[g].y * (1.0f - hc[r][g].y * hc[r][g].y);
+                dc.z = dv[r] * wcv[g].z * (1.0f - hc[r][g].z * hc[r][g].z); dc.w = dv[r] * wcv[g].w * (1.0f - hc[r][g].w * hc[r][g].w);
+                acc_b3[4 * g] += da.x; acc_b3[4 * g + 1] += da.y; acc_b3[4 * g + 2] += da.z; acc_b3[4 * g + 3] += da.w;
+                acc_b3[KPL + 4 * g] += dc.x; acc_b3[KPL + 4 * g + 1] += dc.y; acc_b3[KPL + 4 * g + 2] += dc.z; acc_b3[KPL + 4 * g + 3] += dc.w;
+                gwc[g].x = fmaf(dv[r], hc[r][g].x, gwc[g].x); gwc[g].y = fmaf(dv[r], hc[r][g].y, gwc[g].y);
+                gwc[g].z = fmaf(dv[r], hc[r][g].z, gwc[g].z); gwc[g].w = fmaf(dv[r], hc[r][g].w, gwc[g].w);
+                if (ok[r]) {
+                    __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, da);
+                    __stcs(reinterpret_cast<float4*>(d3 + H + g * 128) + lane, dc);
+                }
+            }
+        }
     }
+
+    // hand the register accumulators to the common flush
+    float* acc = s_acc + (size_t)warp * (A + 1) * H;
+#pragma unroll
+    for (int j = 0; j < AMAX; ++j)
+        if (j < A) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) reinterpret_cast<float4*>(acc + j * H + g * 128)[lane] = gwa[j][g];
+        }
+#pragma unroll
+    for (int g = 0; g < G; ++g) reinterpret_cast<float4*>(acc + A * H + g * 128)[lane] = gwc[g];
+    head_train_flush<KPL, 4>(a, s_acc, acc_b3, acc_dba, acc_dbc, acc_dls, l_pol, l_val, l_ent);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -497,6 +701,22 @@ int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuo
     const size_t smem = ((size_t)(A + 1) * H + accf) * sizeof(float);
     if (smem > 200 * 1024) DPPO_FAIL(ctx, "head kernel: (A+1)*H = %d too large for shared memory", (A + 1) * H);
     const bool vec = (H % 128 == 0) && ((reinterpret_cast<uintptr_t>(a.h3) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.d3) & 15u) == 0);
+    if (vec && A <= 4 && H <= 256 && !(ctx->tc_debug & 256)) {        // register-accumulator kernel (wider rows spill)
+#define HTR(KPL, R)                                                                                                              \
+    do {                                                                                                                         \
+        if (continuous) {                                                                                                        \
+            cudaFuncSetAttribute(head_train_reg_kernel<true, KPL, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            head_train_reg_kernel<true, KPL, R, 4><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);                                    \
+        } else {                                                                                                                 \
+            cudaFuncSetAttribute(head_train_reg_kernel<false, KPL, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            head_train_reg_kernel<false, KPL, R, 4><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);                                   \
+        }                                                                                                                        \
+    } while (0)
+        if (H == 128) HTR(4, 2); else HTR(8, 2);
+#undef HTR
+        DPPO_CHECK_LAUNCH(ctx, "head_train_reg_kernel");
+        return 0;
+    }
     if (H <= 64) return launch_head_train<2, 1, 2>(ctx, a, continuous, blocks, smem, st);
     if (H <= 128) return vec ? launch_head_train<4, 4, 2>(ctx, a, continuous, blocks, smem, st) : launch_head_train<4, 1, 2>(ctx, a, continuous, blocks, smem, st);
     if (H <= 256) return vec ? launch_head_train<8, 4, 2>(ctx, a, continuous, blocks, smem, st) : launch_head_train<8, 1, 2>(ctx, a, continuous, blocks, smem, st);
