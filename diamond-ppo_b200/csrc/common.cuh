@@ -56,7 +56,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---- internal launchers shared between translation units ----------------------------------
 // C[M,N] = epi(A[M,K] * op(B)); see gemm_simt.cu
-enum { DPPO_EPI_BIAS = 0, DPPO_EPI_BIAS_TANH = 1, DPPO_EPI_TANH_BWD = 2 };
+enum { DPPO_EPI_BIAS = 0, DPPO_EPI_BIAS_TANH = 1, DPPO_EPI_TANH_BWD = 2, DPPO_EPI_NONE = 3 };
 // NT: B is [N,K] row-major (a torch Linear weight used in the forward direction)
 int dppo_gemm_nt(dppo_ctx* ctx, int epi, const float* A, int lda, const int32_t* a_rows, const float* B, int ldb,
                  const float* bias, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st);
@@ -64,6 +64,9 @@ int dppo_gemm_nt(dppo_ctx* ctx, int epi, const float* A, int lda, const int32_t*
 // C = (A*B) .* (1 - Hact^2); colsum (optional) receives per-row-tile column sums of C: [tiles_m, N]
 int dppo_gemm_nn_tanh_bwd(dppo_ctx* ctx, const float* A, int lda, const float* B, int ldb, const float* Hact, int ldh,
                           float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);
+// plain C = A*B with B [K,N] row-major (gradient w.r.t. the input of a Linear layer that is not followed by tanh')
+int dppo_gemm_nn(dppo_ctx* ctx, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                 cudaStream_t st);
 int dppo_gemm_row_tiles(int64_t M, int N);     // number of row tiles the NN kernel uses (colsum partial count)
 // TN split-K weight gradient: partials[s][n1][n2] = sum over the rows of split s of A[m,n1]*B[m,n2]
 int dppo_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2);

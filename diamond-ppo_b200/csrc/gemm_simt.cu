@@ -379,6 +379,12 @@ int dppo_gemm_nn_tanh_bwd(dppo_ctx* ctx, const float* A, int lda, const float* B
     return launch_gemm<1, DPPO_EPI_TANH_BWD>(ctx, A, lda, nullptr, B, ldb, nullptr, Hact, ldh, C, ldc, colsum, M, N, K, st);
 }
 
+int dppo_gemm_nn(dppo_ctx* ctx, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                 cudaStream_t st)
+{
+    return launch_gemm<1, DPPO_EPI_NONE>(ctx, A, lda, nullptr, B, ldb, nullptr, nullptr, 0, C, ldc, nullptr, M, N, K, st);
+}
+
 static inline bool wgrad_large(int N1, int N2) { return N1 >= 128 && N2 >= 128; }
 
 int dppo_wgrad_splits(dppo_ctx* ctx, int64_t M, int N1, int N2)

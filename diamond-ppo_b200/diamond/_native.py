@@ -28,6 +28,14 @@ class MlpLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("w1", "b1", "w2", "b2", "w3", "b3", "wa", "ba", "wc", "bc", "log_std", "total")]
 
 
+class RnnDesc(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("hidden", C.c_int32), ("gru_hidden", C.c_int32), ("act_dim", C.c_int32)]
+
+
+class RnnLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("w1", "b1", "wih", "whh", "bih", "bhh", "w3", "b3", "wa", "ba", "wc", "bc", "total")]
+
+
 class Hyper(C.Structure):
     _fields_ = [("ppo_clip", C.c_float), ("value_loss_weight", C.c_float), ("entropy_beta", C.c_float),
                 ("grad_norm_clip", C.c_float), ("adam_eps", C.c_float), ("pad0", C.c_float),
@@ -47,6 +55,7 @@ EXPORTS = [
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
     "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy",
     "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
+    "dppo_rnn_layout_compute", "dppo_rnn_workspace_bytes", "dppo_rnn_forward", "dppo_rnn_grad_minibatch",
 ]
 
 _lib = None
@@ -65,7 +74,8 @@ def load_library() -> C.CDLL:
             lib.dppo_last_error.restype = C.c_char_p
             lib.dppo_last_error.argtypes = [C.c_void_p]
             for name in ("dppo_step_record_bytes", "dppo_mlp_workspace_bytes", "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes",
-                         "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes", "dppo_grad_sumsq_bytes"):
+                         "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes", "dppo_grad_sumsq_bytes",
+                         "dppo_rnn_workspace_bytes"):
                 getattr(lib, name).restype = C.c_int64
             lib.dppo_dp_slot.restype = C.c_void_p
             _lib = lib
@@ -94,6 +104,13 @@ def mlp_layout(desc: MlpDesc) -> MlpLayout:
     lay = MlpLayout()
     if load_library().dppo_mlp_layout_compute(C.byref(desc), C.byref(lay)):
         raise NativeError("dppo_mlp_layout_compute: bad descriptor")
+    return lay
+
+
+def rnn_layout(desc: RnnDesc) -> RnnLayout:
+    lay = RnnLayout()
+    if load_library().dppo_rnn_layout_compute(C.byref(desc), C.byref(lay)):
+        raise NativeError("dppo_rnn_layout_compute: bad descriptor")
     return lay
 
 
@@ -261,6 +278,23 @@ class Context:
                                                      _ptr(losses), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()),
                                                      _stream()), "dppo_mlp_grad_minibatch")
         self.launches += 10
+
+    # ---- recurrent actor-critic (recurrent_ppo.py) -----------------------------------------------
+    def rnn_workspace_bytes(self, desc, T, N, M, training):
+        return int(self.lib.dppo_rnn_workspace_bytes(C.byref(desc), C.c_int(T), C.c_int(N), C.c_int64(M), C.c_int(int(training))))
+
+    def rnn_forward(self, desc, params, obs, prev_dones, hx0, T, N, heads, logits, values, hx_out, ws):
+        self._check(self.lib.dppo_rnn_forward(self.h, C.byref(desc), _ptr(params), _ptr(obs), _ptr(prev_dones), _ptr(hx0),
+                                              C.c_int(T), C.c_int(N), C.c_int(heads), _ptr(logits), _ptr(values), _ptr(hx_out),
+                                              _ptr(ws), C.c_int64(ws.numel() * ws.element_size()), _stream()), "dppo_rnn_forward")
+
+    def rnn_grad_minibatch(self, desc, params, grads, obs, prev_dones, hx0, T, N, actions, old_logp, adv, returns, adv_stats, idx, M,
+                           hyper, losses, ws):
+        self._check(self.lib.dppo_rnn_grad_minibatch(self.h, C.byref(desc), _ptr(params), _ptr(grads), _ptr(obs), _ptr(prev_dones),
+                                                     _ptr(hx0), C.c_int(T), C.c_int(N), _ptr(actions), _ptr(old_logp), _ptr(adv),
+                                                     _ptr(returns), _ptr(adv_stats), _ptr(idx), C.c_int64(M), C.byref(hyper),
+                                                     _ptr(losses), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()), _stream()),
+                    "dppo_rnn_grad_minibatch")
 
     def grad_sumsq_bytes(self, n):
         return int(self.lib.dppo_grad_sumsq_bytes(self.h, C.c_int64(n)))

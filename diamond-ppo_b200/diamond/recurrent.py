@@ -5,11 +5,14 @@ Kept from the reference: `RecurrentPPO(env_fn, cfg, network_cls)`, `RecurrentPPO
 `get_logits_values_and_hx(obs, hx, dones) -> (logits, values, hx)` (recurrent_ppo.py:127-149), the attributes
 `current_observations / current_hx / prev_dones` and `rollout() / calculate_advantage() / learn() / train()`.
 
-What runs where: the GRU time loop with done-masked hidden resets and the full-T BPTT per minibatch
-(recurrent_ppo.py:82-87, 337-341) run under torch autograd on the GPU -- restructured as ONE input-projection GEMM over
-all T steps followed by T hidden-state steps, instead of T one-step `nn.GRU` calls; action sampling, GAE + returns,
-advantage normalisation, the bit-exact minibatch permutation, the PPO loss forward/backward, gradient clipping and Adam
-run on the libdppo CUDA kernels.  The reference's `hx or zeros` / `dones or zeros` lines (recurrent_ppo.py:78-79) raise on
+What runs where.  Default network class (`RecurrentActorCriticNetwork`): everything on libdppo kernels -- the base layer, the
+input projection of all T steps, the GRU recurrence with done-masked hidden resets (forward scan), the heads + PPO loss,
+back-propagation through all T steps (backward scan), weight gradients, clip and Adam (`FusedRecurrentEngine`,
+csrc/rnn.cu: `dppo_rnn_forward`, `dppo_rnn_grad_minibatch`); parameters are views of one flat buffer.
+Custom `network_cls`: the user module runs under torch autograd (its GRU time loop restructured as ONE input-projection
+GEMM over all T steps followed by T hidden-state steps, instead of T one-step `nn.GRU` calls) and only GAE + returns,
+advantage normalisation, the bit-exact minibatch permutation, the PPO loss forward/backward, gradient clipping and Adam run
+on the libdppo kernels (`RecurrentEngine`).  The reference's `hx or zeros` / `dones or zeros` lines (recurrent_ppo.py:78-79) raise on
 every call; the intended `is None` semantics are implemented.
 """
 from __future__ import annotations
@@ -198,6 +201,97 @@ class RecurrentEngine(_EngineBase):
         self.last_losses = losses
 
 
+def rnn_param_slices(desc: N.RnnDesc, lay: N.RnnLayout):
+    """name (reference module naming, recurrent_ppo.py:101-125) -> (offset, shape) in the flat buffers (dppo_rnn_layout)."""
+    D, H, Hg, A = desc.obs_dim, desc.hidden, desc.gru_hidden, desc.act_dim
+    return {
+        "base.0.weight": (lay.w1, (H, D)), "base.0.bias": (lay.b1, (H,)),
+        "gru.weight_ih_l0": (lay.wih, (3 * Hg, H)), "gru.weight_hh_l0": (lay.whh, (3 * Hg, Hg)),
+        "gru.bias_ih_l0": (lay.bih, (3 * Hg,)), "gru.bias_hh_l0": (lay.bhh, (3 * Hg,)),
+        "actor_head.0.weight": (lay.w3, (H, Hg)), "actor_head.0.bias": (lay.b3, (H,)),
+        "actor_head.2.weight": (lay.wa, (A, H)), "actor_head.2.bias": (lay.ba, (A,)),
+        "critic_head.0.weight": (lay.w3 + H * Hg, (H, Hg)), "critic_head.0.bias": (lay.b3 + H, (H,)),
+        "critic_head.2.weight": (lay.wc, (1, H)), "critic_head.2.bias": (lay.bc, (1,)),
+    }
+
+
+class FusedRecurrentEngine(_EngineBase):
+    """learn() / forward of the default recurrent network on the libdppo kernels only (csrc/rnn.cu)."""
+
+    fused = True
+
+    def __init__(self, ctx, network, cfg, obs_dim, act_dim, device):
+        self.ctx, self.cfg, self.device = ctx, cfg, device
+        self.dist = _Dist(None, False)
+        self.network = network
+        self.desc = N.RnnDesc(int(obs_dim), int(cfg.network_hidden_dim), int(cfg.gru_hidden_dim), int(act_dim))
+        self.layout = N.rnn_layout(self.desc)
+        self._adopt(network, rnn_param_slices(self.desc, self.layout), int(self.layout.total))
+        self.last_losses = None
+        self.draws = 0
+        self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        self._ws = {}
+
+    def _workspace(self, T, N_, M, training):
+        key = (T, N_, M, bool(training))
+        if key not in self._ws:
+            self._ws[key] = torch.empty(self.ctx.rnn_workspace_bytes(self.desc, T, N_, M, training) // 4 + 64, device=self.device)
+        return self._ws[key]
+
+    def forward(self, obs, hx, prev_dones, heads=3):
+        """(logits [T,N,A], values [T,N], hx [1,N,Hg]) of get_logits_values_and_hx / get_values (recurrent_ppo.py:127-149)."""
+        T, N_ = obs.shape[:2]
+        dev, A, Hg = self.device, self.desc.act_dim, self.desc.gru_hidden
+        logits = torch.empty(T, N_, A, device=dev) if heads & 1 else None
+        values = torch.empty(T, N_, device=dev) if heads & 2 else None
+        hx_out = torch.empty(1, N_, Hg, device=dev)
+        pd = None if prev_dones is None else prev_dones.to(torch.uint8).contiguous()
+        self.ctx.rnn_forward(self.desc, self.P, obs.contiguous(), pd, None if hx is None else hx.contiguous(), T, N_, heads,
+                             logits, values, hx_out, self._workspace(T, N_, T * N_, False))
+        return logits, values, hx_out
+
+    def learn(self, ro: RecurrentRollout):
+        cfg, ctx, dev = self.cfg, self.ctx, self.device
+        T, N_ = ro.T, ro.N
+        E, MB = cfg.num_epochs, cfg.num_minibatches
+        B = T * N_
+        if B % MB != 0:                                                  # the reference's reshape raises here (:329)
+            raise ValueError(f"cannot reshape array of size {E * B} into shape ({E},{MB},{B // MB})")
+        M = B // MB
+        self._resync_optimizer()
+        h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
+        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
+        worker.start()
+        # GAE with the values stored at rollout time + returns + advantage sums (recurrent_ppo.py:315-318); the normalisation
+        # itself is applied while the head kernel gathers the advantages
+        stats = torch.zeros(2, dtype=torch.float64, device=dev)
+        adv = torch.empty(T, N_, device=dev)
+        ret = torch.empty(T, N_, device=dev)
+        ctx.gae(ro.rewards, ro.terminations, ro.truncations, ro.values.contiguous(), ro.next_values.contiguous(), cfg.gamma,
+                cfg.gae_lambda, advantages=adv, returns=ret, stats=stats)
+        hyper = self._hyper(cfg, M, B)
+        hyper.grad_sumsq = self.grad_sumsq.data_ptr()
+        old_logp = ro.log_probs.reshape(B).contiguous()
+        actions = ro.actions.reshape(B).to(torch.int32)
+        pd = ro.prev_dones.to(torch.uint8).contiguous()
+        hx0 = ro.hx0.reshape(N_, -1).contiguous()
+        losses = torch.zeros(E * MB, 4, device=dev)
+        ws = self._workspace(T, N_, M, True)
+        idx = torch.empty(E, B, dtype=torch.int32, device=dev)
+        for e in range(E):
+            worker.wait(e)
+            idx[e].copy_(h_idx[e], non_blocking=True)
+            for k in range(MB):
+                self.adam_step += 1
+                hyper.step = self.adam_step
+                ctx.rnn_grad_minibatch(self.desc, self.P, self.G, ro.obs, pd, hx0, T, N_, actions, old_logp, adv.view(B), ret.view(B),
+                                       stats, idx[e][k * M:(k + 1) * M], M, hyper, losses[e * MB + k], ws)
+                ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+        worker.finish()
+        self._publish_steps()
+        self.last_losses = losses
+
+
 class RecurrentPPO:
     """Recurrent (GRU) discrete-action PPO (reference: diamond/recurrent_ppo.py:164-394)."""
 
@@ -216,7 +310,10 @@ class RecurrentPPO:
         self.network = network_cls(obs_space, act_space, cfg=cfg).to(self.device)
         network_parameter_init_(self.network, gain=sqrt(2.0), small_actor_out=True)     # touches nn.Linear only (:152-161)
         self.obs_dim = int(np.prod(obs_space.shape))
-        self.engine = RecurrentEngine(self.ctx, self.network, cfg, self.device)
+        if type(self.network) is RecurrentActorCriticNetwork:            # default network: libdppo kernels end to end
+            self.engine = FusedRecurrentEngine(self.ctx, self.network, cfg, self.obs_dim, int(act_space.n), self.device)
+        else:                                                            # custom network_cls: the module runs under autograd
+            self.engine = RecurrentEngine(self.ctx, self.network, cfg, self.device)
         self.optimizer = torch.optim.Adam(self.network.parameters(), lr=cfg.lr, eps=cfg.adam_eps)
         self.engine.bind_optimizer(self.optimizer)
         self.lr_scheduler = torch.optim.lr_scheduler.LinearLR(
@@ -238,16 +335,22 @@ class RecurrentPPO:
         for t in range(T):
             obs_t = torch.as_tensor(np.asarray(observations, dtype=np.float32)[None, ...], device=dev)
             pd_t = torch.as_tensor(np.asarray(prev_dones)[None, ...], dtype=torch.bool, device=dev)
-            with torch.inference_mode():
-                logits, values, new_hx = self.network.get_logits_values_and_hx(obs_t, hx, pd_t)
+            if getattr(self.engine, "fused", False):
+                logits, values, new_hx = self.engine.forward(obs_t, hx, pd_t)
+            else:
+                with torch.inference_mode():
+                    logits, values, new_hx = self.network.get_logits_values_and_hx(obs_t, hx, pd_t)
             # Categorical(logits).sample() + log_prob on the device (counter-based generator, dppo_sample_categorical)
             actions = torch.empty(N_, dtype=torch.int64, device=dev)
             self.ctx.sample_categorical(logits.squeeze(0).contiguous(), self.engine.seed, self.engine.draws, 0, actions, ro.log_probs[t])
             self.engine.draws += 1
             next_observations, rewards, terminations, truncations, infos = self.envs.step(actions.cpu().numpy())
             final_t = torch.as_tensor(np.asarray(next_observations, dtype=np.float32)[None, ...], device=dev)
-            with torch.inference_mode():
-                next_values = self.network.get_values(final_t, new_hx, None)      # V(final obs | h_{t+1}), no reset (:226-232)
+            if getattr(self.engine, "fused", False):
+                _, next_values, _ = self.engine.forward(final_t, new_hx, None, heads=2)
+            else:
+                with torch.inference_mode():
+                    next_values = self.network.get_values(final_t, new_hx, None)  # V(final obs | h_{t+1}), no reset (:226-232)
             ro.obs[t].copy_(obs_t.squeeze(0)); ro.actions[t].copy_(actions)
             ro.rewards[t].copy_(torch.as_tensor(np.asarray(rewards, dtype=np.float32), device=dev))
             ro.terminations[t].copy_(torch.as_tensor(np.asarray(terminations, dtype=np.float32), device=dev))

@@ -211,6 +211,43 @@ int dppo_ppo_loss_gaussian(dppo_ctx* ctx, const float* mean, const float* log_st
                            float* dvalues, void* ws, int64_t ws_bytes, void* stream);
 int64_t dppo_ppo_loss_workspace_bytes(int64_t M, int A);
 
+/* ---- recurrent actor-critic (RecurrentPPO, diamond/recurrent_ppo.py) --------------------------------- */
+/* Default RecurrentActorCriticNetwork (recurrent_ppo.py:94-125): base Linear(D,H)+Tanh -> GRU(H,Hg) -> actor head
+ * Linear(Hg,H)+Tanh+Linear(H,A) and critic head Linear(Hg,H)+Tanh+Linear(H,1). */
+typedef struct dppo_rnn_desc {
+    int32_t obs_dim;      /* D */
+    int32_t hidden;       /* H  = cfg.network_hidden_dim */
+    int32_t gru_hidden;   /* Hg = cfg.gru_hidden_dim (<= 128) */
+    int32_t act_dim;      /* A  = Discrete.n */
+} dppo_rnn_desc;
+/* Offsets (floats, multiples of 4) in the flat parameter / gradient / Adam buffers; the GRU tensors are nn.GRU's
+ * weight_ih_l0 [3Hg,H], weight_hh_l0 [3Hg,Hg], bias_ih_l0, bias_hh_l0 (gate order r,z,n); w3/b3 = actor_head.0 | critic_head.0. */
+typedef struct dppo_rnn_layout {
+    int64_t w1, b1;
+    int64_t wih, whh, bih, bhh;
+    int64_t w3, b3;
+    int64_t wa, ba;
+    int64_t wc, bc;
+    int64_t total;
+} dppo_rnn_layout;
+int dppo_rnn_layout_compute(const dppo_rnn_desc* desc, dppo_rnn_layout* out);
+int64_t dppo_rnn_workspace_bytes(const dppo_rnn_desc* desc, int T, int N, int64_t M, int training);
+/* get_logits_values_and_hx / get_values (recurrent_ppo.py:127-149) over a [T,N] sequence: obs [T,N,D]; prev_dones uint8 [T,N]
+ * (NULL: no resets) zeroes the hidden state of an environment BEFORE step t (recurrent_ppo.py:84); hx0 [N,Hg] (NULL: zeros).
+ * heads bit0: logits [T*N,A]; bit1: values [T*N]; hx_out (optional) [N,Hg] final hidden state. */
+int dppo_rnn_forward(dppo_ctx* ctx, const dppo_rnn_desc* desc, const float* params, const float* obs,
+                     const unsigned char* prev_dones, const float* hx0, int T, int N, int heads, float* logits,
+                     float* values, float* hx_out, void* ws, int64_t ws_bytes, void* stream);
+/* One optimiser step's gradient (recurrent_ppo.py:335-362): full-sequence forward with the current parameters, the rows
+ * idx[0..M) of the flattened [T*N] outputs enter the PPO loss (idx NULL: all rows in order, M = T*N), back-propagation
+ * through all T steps.  actions int32 [T*N]; old_log_probs / adv / returns f32 [T*N]; flat gradient -> grads,
+ * (policy, value, entropy, total) -> losses[0..3]. */
+int dppo_rnn_grad_minibatch(dppo_ctx* ctx, const dppo_rnn_desc* desc, const float* params, float* grads, const float* obs,
+                            const unsigned char* prev_dones, const float* hx0, int T, int N, const int32_t* actions,
+                            const float* old_log_probs, const float* adv, const float* returns, const double* adv_stats,
+                            const int32_t* idx, int64_t M, const dppo_hyper* hyper, float* losses, void* ws,
+                            int64_t ws_bytes, void* stream);
+
 /* ---- tensor-core building blocks of the fused update (unit tests, A/B measurements) ---------- */
 /* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate).
  * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).

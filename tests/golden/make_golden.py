@@ -231,14 +231,13 @@ def perm_cases():
     print("perm s42 n524288 head", out["s42_n524288.head"][:6])
 
 
-def recurrent_case():
-    D, A, H, Hg, N, T, E = 4, 2, 64, 16, 8, 16, 2
+def recurrent_case(name="R", D=4, A=2, H=64, Hg=16, N=8, T=16, E=2, MB=1):
     diamond = import_reference(D, A, False)
     patch_recurrent_none_checks(diamond)
-    cfg = diamond.RecurrentPPOConfig(num_envs=N, rollout_steps=T, num_epochs=E, num_minibatches=1, verbose=False,
+    cfg = diamond.RecurrentPPOConfig(num_envs=N, rollout_steps=T, num_epochs=E, num_minibatches=MB, verbose=False,
                                      network_hidden_dim=H, gru_hidden_dim=Hg)
     agent = diamond.RecurrentPPO(lambda: None, cfg)
-    out = {"meta": np.array([D, A, H, Hg, N, T, E, 1], dtype=np.int64)}
+    out = {"meta": np.array([D, A, H, Hg, N, T, E, MB], dtype=np.int64)}
     out.update(sd_np(agent.network.state_dict(), "init."))
     rng = np.random.default_rng(11)
     # Build experience as RecurrentPPO.rollout() does (recurrent_ppo.py:214-245) with synthetic env outputs.
@@ -281,12 +280,22 @@ def recurrent_case():
         agent.learn(exp)
     out.update(sd_np(agent.network.state_dict(), f"e{E}.params."))
     out[f"e{E}.losses"] = np.asarray(lh.rows, dtype=np.float64)
-    np.savez_compressed(os.path.join(HERE, "learn_R.npz"), **out)
-    print("R losses", out[f"e{E}.losses"])
+    np.savez_compressed(os.path.join(HERE, f"learn_{name}.npz"), **out)
+    print(name, "losses", out[f"e{E}.losses"])
+
+
+def recurrent_extra_cases():
+    # minibatch gather/scatter around the full-sequence BPTT (MB > 1), a GRU width off the warp-shuffle fast path, wider nets
+    recurrent_case("R4", D=4, A=2, H=64, Hg=16, N=8, T=16, E=2, MB=4)
+    recurrent_case("Rg", D=6, A=3, H=32, Hg=24, N=12, T=10, E=2, MB=2)
+    recurrent_case("Rw", D=8, A=4, H=128, Hg=32, N=16, T=32, E=1, MB=2)
 
 
 if __name__ == "__main__":
     torch.set_num_threads(1)      # deterministic summation order for the pin
+    if len(sys.argv) > 1 and sys.argv[1] == "recurrent_extra":   # added later: leaves the other fixtures untouched
+        recurrent_extra_cases()
+        sys.exit(0)
     gae_cases()
     perm_cases()
     learn_case("C", "discrete", D=4, act=2, H=64, N=8, T=128, E=4, MB=8, seed_exp=1, save_adam=True)
@@ -298,3 +307,4 @@ if __name__ == "__main__":
                extra_cfg=dict(decay_lr=True, total_steps=8 * 32 * 10, advantage_norm=False, ppo_clip=0.1,
                               value_loss_weight=0.5, entropy_beta=0.02, grad_norm_clip=0.3, gamma=0.97, gae_lambda=0.9))
     recurrent_case()
+    recurrent_extra_cases()

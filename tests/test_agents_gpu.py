@@ -246,27 +246,77 @@ def test_checkpoint_roundtrip(tmp_path):
         assert torch.allclose(v, agent2.network.state_dict()[k], rtol=0, atol=0), k
 
 
-def test_recurrent_learn_matches_reference():
-    """RecurrentPPO.learn() vs the reference (+ the documented 2-line `is None` fix) on the recorded rollout:
-    2 epochs x 1 minibatch of full-sequence BPTT (recurrent_ppo.py:301-367)."""
+def _recurrent_agent_and_experience(name, network_cls=None):
     from diamond import RecurrentPPO, RecurrentPPOConfig, envs
-    g = np.load(os.path.join(GOLDEN, "learn_R.npz"))
+    g = np.load(os.path.join(GOLDEN, f"learn_{name}.npz"))
     D, A, H, Hg, N_, T, E, MB = (int(x) for x in g["meta"])
     cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, num_epochs=E, num_minibatches=MB, verbose=False,
                              network_hidden_dim=H, gru_hidden_dim=Hg, seed=42)
-    agent = RecurrentPPO(lambda: envs.SyntheticEnv(D, A), cfg)
+    kw = {} if network_cls is None else dict(network_cls=network_cls)
+    agent = RecurrentPPO(lambda: envs.SyntheticEnv(D, A), cfg, **kw)
     sd = {k[len("init."):]: torch.as_tensor(g[k]) for k in g.files if k.startswith("init.")}
     agent.network.load_state_dict(sd)
     hx0 = torch.as_tensor(g["hx0"])
     exp = [[torch.as_tensor(g["obs"][t]), torch.as_tensor(g["actions"][t]), g["rewards"][t], g["terminations"][t], g["truncations"][t],
             torch.as_tensor(g["prev_dones"][t]), torch.as_tensor(g["log_probs"][t]), torch.as_tensor(g["values"][t]),
             torch.as_tensor(g["next_values"][t]), hx0] for t in range(T)]
+    return agent, exp, g, E, MB
+
+
+@pytest.mark.parametrize("name", ["R", "R4", "Rg", "Rw"])
+def test_recurrent_learn_matches_reference(name):
+    """RecurrentPPO.learn() on the fused recurrent kernels (csrc/rnn.cu) vs the reference (+ the documented 2-line `is None`
+    fix) on recorded rollouts: full-sequence BPTT per minibatch (recurrent_ppo.py:301-367).  R: default sizes,
+    one minibatch; R4: four minibatches (row gather / gradient scatter around the scan); Rg: GRU width 24 (shared-memory scan
+    kernels); Rw: GRU width 32, 128-wide layers."""
+    from diamond.recurrent import FusedRecurrentEngine
+    agent, exp, g, E, MB = _recurrent_agent_and_experience(name)
+    assert isinstance(agent.engine, FusedRecurrentEngine)
     np.random.seed(123)
     agent.learn(exp)
     check(agent, g, f"e{E}")
     # state_dict / optimizer state keep working (Checkpointer payload, utils.py:584-600)
     st = agent.optimizer.state_dict()["state"]
     assert len(st) == len(list(agent.network.parameters())) and all(float(v["step"]) == E * MB for v in st.values())
+
+
+def test_recurrent_custom_network_runs_under_autograd_and_matches_reference():
+    """A user-supplied network_cls (here: a subclass of the default) is run under torch autograd, with GAE, permutation, loss,
+    clip and Adam on the libdppo kernels (RecurrentEngine)."""
+    from diamond.recurrent import RecurrentActorCriticNetwork, RecurrentEngine
+
+    class MyNet(RecurrentActorCriticNetwork):
+        pass
+
+    agent, exp, g, E, MB = _recurrent_agent_and_experience("R4", network_cls=MyNet)
+    assert isinstance(agent.engine, RecurrentEngine)
+    np.random.seed(123)
+    agent.learn(exp)
+    check(agent, g, f"e{E}")
+
+
+@pytest.mark.parametrize("Hg", [16, 24, 64])
+def test_rnn_forward_matches_torch_module(Hg):
+    """dppo_rnn_forward (base layer, input projection, forward scan with done-masked resets, heads) vs the torch module the
+    reference would run (stepwise nn.GRU semantics are pinned by tests/test_oracle.py::test_recurrent_core_matches_stepwise_nn_gru)."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig, envs
+    D, A, H, N_, T = 5, 3, 64, 37, 19
+    cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, verbose=False, network_hidden_dim=H, gru_hidden_dim=Hg, seed=3)
+    agent = RecurrentPPO(lambda: envs.SyntheticEnv(D, A), cfg)
+    gen = torch.Generator().manual_seed(Hg)
+    obs = torch.randn(T, N_, D, generator=gen).cuda()
+    dones = (torch.rand(T, N_, generator=gen) < 0.15).cuda()
+    hx0 = torch.randn(1, N_, Hg, generator=gen).cuda()
+    with torch.no_grad():
+        ref_logits, ref_values, ref_hx = agent.network.get_logits_values_and_hx(obs, hx0.clone(), dones)
+    logits, values, hx = agent.engine.forward(obs, hx0, dones)
+    for got, ref in ((logits, ref_logits), (values, ref_values), (hx, ref_hx)):
+        assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    # no resets, zero initial state, critic only (get_values with dones=None, recurrent_ppo.py:127-136)
+    with torch.no_grad():
+        ref_v = agent.network.get_values(obs, None, None)
+    _, v, _ = agent.engine.forward(obs, None, None, heads=2)
+    assert (v - ref_v).abs().max().item() <= 1e-5 * max(1.0, ref_v.abs().max().item())
 
 
 def test_recurrent_train_runs_on_cartpole():
