@@ -38,6 +38,36 @@ extern char g_dppo_create_error[512];
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch along the kernels of an optimiser step (opt-in: tc_debug bit 512) ---------------
+// MEASURED NEGATIVE on B200 for this chain (graph replay, config S: 605-615 us per optimiser step with the attribute,
+// 580-600 us without), so the attribute is off by default and the instructions below are no-ops; kept for A/B.
+// With the bit set every kernel of the update loop is launched with programmatic stream serialisation and starts with DPPO_PDL_ENTER():
+// it releases its own dependents at once and then waits for its predecessor grid to complete (and its writes to become
+// visible) before touching global memory.  The work itself stays fully ordered; what overlaps is the launch latency and the
+// per-CTA set-up (barrier init, TMEM allocation, tensor-map fetch) of kernel i+1 with the tail of kernel i: CTAs of the
+// next grid become resident as soon as an SM is free.  A kernel launched without the attribute sees both instructions as
+// no-ops.  Every kernel launched with the attribute MUST execute the wait (completion of a grid then implies completion of
+// all its predecessors).
+#define DPPO_PDL_ENTER()                                                    \
+    do {                                                                    \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                  \
+    } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dppo_launch_pdl(dppo_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args)
+{
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = (ctx->tc_debug & 512) ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -145,6 +145,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ W, int rows_w, int
 // All weight images of one optimiser step in a single launch: blockIdx.y selects the job.
 __global__ void prep_weights_multi_kernel(PrepJobs jobs)
 {
+    DPPO_PDL_ENTER();
     if ((int)blockIdx.y == jobs.n) {
         // the minibatch observation gather (ppo.py:261 observations[mb]) shares the launch: it is independent of the weights
         const GatherJob& g = jobs.gather;
@@ -386,7 +387,7 @@ int dppo_tc_prep_weights_multi(dppo_ctx* ctx, PrepJobs jobs, cudaStream_t st)
     int blocks = (int)((most + 255) / 256);
     if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
     if (blocks < 1) blocks = 1;
-    prep_weights_multi_kernel<<<dim3(blocks, jobs.n + (with_gather ? 1 : 0)), 256, 0, st>>>(jobs);
+    dppo_launch_pdl(ctx, prep_weights_multi_kernel, dim3(blocks, jobs.n + (with_gather ? 1 : 0)), dim3(256), 0, st, jobs);
     DPPO_CHECK_LAUNCH(ctx, "prep_weights_multi_kernel");
     return 0;
 }

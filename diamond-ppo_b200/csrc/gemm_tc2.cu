@@ -332,6 +332,7 @@ tc2_wgrad_kernel(const __grid_constant__ WgradJobs jobs)
     __syncthreads();
     fence_after();
     const uint32_t tmem = s_tmem;
+    DPPO_PDL_ENTER();                                    // set-up done; global memory only after the predecessor grid completed
 
     if (warp == W_PROD) {
         if (lane == 0) {
@@ -642,10 +643,10 @@ int dppo_tc2_wgrad_multi(dppo_ctx* ctx, int n, const float* const* Dm, const int
     jobs.smem_bytes = (int)smem;
     if (p[0].nacc == 2) {
         cudaFuncSetAttribute(tc2_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc2_wgrad_kernel<2><<<cta, THREADS, smem, st>>>(jobs);
+        dppo_launch_pdl(ctx, tc2_wgrad_kernel<2>, dim3(cta), dim3(THREADS), smem, st, jobs);
     } else {
         cudaFuncSetAttribute(tc2_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc2_wgrad_kernel<1><<<cta, THREADS, smem, st>>>(jobs);
+        dppo_launch_pdl(ctx, tc2_wgrad_kernel<1>, dim3(cta), dim3(THREADS), smem, st, jobs);
     }
     DPPO_CHECK_LAUNCH(ctx, "tc2_wgrad_kernel");
     return 0;

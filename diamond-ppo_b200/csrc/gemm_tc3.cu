@@ -77,6 +77,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync();                                      // barriers of both CTAs initialised before any remote arrival
     fence_after();
     const uint32_t tmem = s_tmem;
+    DPPO_PDL_ENTER();                                    // set-up done; global memory only after the predecessor grid completed
 
     if (warp == W_PROD) {
         if (lane == 0) {
@@ -332,12 +333,12 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc3_gemm_kernel<DPPO_EPI_BIAS_TANH><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,
-                                                                          tail_halves, ctx->tc_debug);
+        dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, Wimg, bias, Hact, ldh, colsum, M,
+                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug);
     } else if (epi == DPPO_EPI_TANH_BWD) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc3_gemm_kernel<DPPO_EPI_TANH_BWD><<<grid, THREADS, smem, st>>>(tmA, tmC, Wimg, bias, Hact, ldh, colsum, M, N, K, n_tile, pair_tiles,
-                                                                         tail_halves, ctx->tc_debug);
+        dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, Wimg, bias, Hact, ldh, colsum, M,
+                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug);
     } else {
         DPPO_FAIL(ctx, "tc3_gemm: unknown epilogue %d", epi);
     }

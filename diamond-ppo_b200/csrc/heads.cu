@@ -148,6 +148,7 @@ head_train_kernel(HeadTrainArgs a)
     float* s_wc = s_wa + A * H;                 // [H]
     float* s_acc = s_wc + H;                    // [HEAD_WARPS][(A+1)][H]  per-warp dWa | dWc
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DPPO_PDL_ENTER();
     for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = a.wa[i];
     for (int i = threadIdx.x; i < H; i += blockDim.x) s_wc[i] = a.wc[i];
     float* acc = s_acc + (size_t)warp * (A + 1) * H;
@@ -350,6 +351,7 @@ head_train_reg_kernel(HeadTrainArgs a)
     float* s_wc = s_wa + A * H;                 // [H]
     float* s_acc = s_wc + H;                    // [HEAD_WARPS][(A+1)][H]  flushed once at the end
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DPPO_PDL_ENTER();
     for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = a.wa[i];
     for (int i = threadIdx.x; i < H; i += blockDim.x) s_wc[i] = a.wc[i];
     __syncthreads();
@@ -670,10 +672,10 @@ int launch_head_train(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int
 {
     if (continuous) {
         cudaFuncSetAttribute(head_train_kernel<true, KPL, VEC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_train_kernel<true, KPL, VEC, R><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
+        dppo_launch_pdl(ctx, head_train_kernel<true, KPL, VEC, R>, dim3(blocks), dim3(HEAD_WARPS * 32), smem, st, a);
     } else {
         cudaFuncSetAttribute(head_train_kernel<false, KPL, VEC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_train_kernel<false, KPL, VEC, R><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);
+        dppo_launch_pdl(ctx, head_train_kernel<false, KPL, VEC, R>, dim3(blocks), dim3(HEAD_WARPS * 32), smem, st, a);
     }
     DPPO_CHECK_LAUNCH(ctx, "head_train_kernel");
     return 0;
@@ -706,10 +708,10 @@ int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuo
     do {                                                                                                                         \
         if (continuous) {                                                                                                        \
             cudaFuncSetAttribute(head_train_reg_kernel<true, KPL, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            head_train_reg_kernel<true, KPL, R, 4><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);                                    \
+            dppo_launch_pdl(ctx, head_train_reg_kernel<true, KPL, R, 4>, dim3(blocks), dim3(HEAD_WARPS * 32), smem, st, a);     \
         } else {                                                                                                                 \
             cudaFuncSetAttribute(head_train_reg_kernel<false, KPL, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            head_train_reg_kernel<false, KPL, R, 4><<<blocks, HEAD_WARPS * 32, smem, st>>>(a);                                   \
+            dppo_launch_pdl(ctx, head_train_reg_kernel<false, KPL, R, 4>, dim3(blocks), dim3(HEAD_WARPS * 32), smem, st, a);    \
         }                                                                                                                        \
     } while (0)
         if (H == 128) HTR(4, 2); else HTR(8, 2);

@@ -17,6 +17,7 @@ grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, c
                    double* __restrict__ sumsq_out)
 {
     __shared__ float4 s_part[RED_Y][RED_X];
+    DPPO_PDL_ENTER();
     const int x = threadIdx.x, y = threadIdx.y;
     const int64_t total4 = (total + 3) / 4;
     double sq = 0.0;                       // this thread's share of the squared gradient norm (y == 0 threads)
@@ -130,6 +131,7 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
                  const float* __restrict__ step_consts)
 {
     __shared__ float s_coef;
+    DPPO_PDL_ENTER();
     // device-resident step constants (CUDA-graph replay of the update loop): [0] = sqrt(1 - beta2^t), [1] = -lr / (1 - beta1^t)
     if (step_consts != nullptr) { bc2_sqrt = __ldg(step_consts); neg_step_size = __ldg(step_consts + 1); }
     if (threadIdx.x < 32) {
@@ -219,8 +221,8 @@ int launch_grad_reduce(dppo_ctx* ctx, const GradSegTable& tab, float* grads, int
 {
     if ((reinterpret_cast<uintptr_t>(grads) & 15u) != 0) DPPO_FAIL(ctx, "grad_reduce: gradient buffer must be 16-byte aligned");
     const int blocks = grad_reduce_blocks(ctx, total);
-    grad_reduce_kernel<<<blocks, dim3(RED_X, RED_Y), 0, st>>>(tab, grads, total, loss_partials, loss_nparts, loss_stride, vw, beta, inv_m, losses,
-                                                              sumsq_out);
+    dppo_launch_pdl(ctx, grad_reduce_kernel, dim3(blocks), dim3(RED_X, RED_Y), 0, st, tab, grads, total, loss_partials, loss_nparts, loss_stride,
+                    vw, beta, inv_m, losses, sumsq_out);
     DPPO_CHECK_LAUNCH(ctx, "grad_reduce_kernel");
     return 0;
 }
@@ -235,9 +237,9 @@ int launch_clip_adam(dppo_ctx* ctx, float* params, float* grads, float* exp_avg,
     const double bc2_sqrt = sqrt(bc2);
     int blocks = (int)((n + 255) / 256);
     if (blocks > 2 * ctx->sm_count) blocks = 2 * ctx->sm_count;
-    clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, nparts, h->grad_norm_clip,
-                                             (float)(1.0 - h->beta1), (float)h->beta2, (float)(1.0 - h->beta2), (float)bc2_sqrt,
-                                             h->adam_eps, (float)(-step_size), grad_norm_out, h->step_consts);
+    dppo_launch_pdl(ctx, clip_adam_kernel, dim3(blocks), dim3(256), 0, st, params, grads, exp_avg, exp_avg_sq, n, partials, nparts,
+                    h->grad_norm_clip, (float)(1.0 - h->beta1), (float)h->beta2, (float)(1.0 - h->beta2), (float)bc2_sqrt, h->adam_eps,
+                    (float)(-step_size), grad_norm_out, h->step_consts);
     DPPO_CHECK_LAUNCH(ctx, "clip_adam_kernel");
     return 0;
 }
