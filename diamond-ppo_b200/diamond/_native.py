@@ -36,6 +36,15 @@ class RnnLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("w1", "b1", "wih", "whh", "bih", "bhh", "w3", "b3", "wa", "ba", "wc", "bc", "total")]
 
 
+class EnvDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("num_envs", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("seed", C.c_uint64),
+                ("env_offset", C.c_int64), ("p_term", C.c_float), ("p_trunc", C.c_float)]
+
+
+class EnvState(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("steps", C.c_void_p), ("episode", C.c_void_p), ("ep_return", C.c_void_p), ("cur_obs", C.c_void_p)]
+
+
 class Hyper(C.Structure):
     _fields_ = [("ppo_clip", C.c_float), ("value_loss_weight", C.c_float), ("entropy_beta", C.c_float),
                 ("grad_norm_clip", C.c_float), ("adam_eps", C.c_float), ("pad0", C.c_float),
@@ -55,6 +64,7 @@ EXPORTS = [
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
     "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy",
     "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
+    "dppo_env_reset", "dppo_env_step",
     "dppo_rnn_layout_compute", "dppo_rnn_workspace_bytes", "dppo_rnn_forward", "dppo_rnn_grad_minibatch",
 ]
 
@@ -278,6 +288,16 @@ class Context:
                                                      _ptr(losses), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()),
                                                      _stream()), "dppo_mlp_grad_minibatch")
         self.launches += 10
+
+    # ---- device-resident vector environments -----------------------------------------------------
+    def env_reset(self, desc, state, mask=None):
+        self._check(self.lib.dppo_env_reset(self.h, C.byref(desc), C.byref(state), _ptr(mask), _stream()), "dppo_env_reset")
+
+    def env_step(self, desc, state, actions, t, auto_reset, obs, next_obs, buf_actions, rewards, terminations, truncations,
+                 done_return=None):
+        self._check(self.lib.dppo_env_step(self.h, C.byref(desc), C.byref(state), _ptr(actions), C.c_int(t), C.c_int(int(auto_reset)),
+                                           _ptr(obs), _ptr(next_obs), _ptr(buf_actions), _ptr(rewards), _ptr(terminations),
+                                           _ptr(truncations), _ptr(done_return), _stream()), "dppo_env_step")
 
     # ---- recurrent actor-critic (recurrent_ppo.py) -----------------------------------------------
     def rnn_workspace_bytes(self, desc, T, N, M, training):

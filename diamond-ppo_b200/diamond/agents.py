@@ -425,6 +425,26 @@ class FusedMlpEngine(_EngineBase):
         torch.cuda.current_stream().synchronize()
         return st["h_act"].numpy().copy()
 
+    def sample_actions_device(self, d_obs: torch.Tensor) -> torch.Tensor:
+        """get_actions for observations that already live on the device (DeviceVectorEnv): forward + sampling kernels only,
+        no host round trip and no synchronisation.  Returns int64 [N] / f32 [N, A] on the device."""
+        n = d_obs.shape[0]
+        st = self._act_stage.get(("dev", n))
+        if st is None:
+            st = dict(head=torch.empty(n, self.A, dtype=torch.float32, device=self.device),
+                      d_act=(torch.empty(n, self.A, dtype=torch.float32, device=self.device) if self.continuous
+                             else torch.empty(n, dtype=torch.int64, device=self.device)))
+            self._act_stage[("dev", n)] = st
+        self.ctx.mlp_forward(self.fm.desc, self.P, d_obs, n, 1, st["head"], None, self.fwd_ws)
+        env_offset = self.dist.rank * n
+        if self.continuous:
+            lay = self.fm.layout
+            self.ctx.sample_gaussian(st["head"], self.P[lay.log_std:lay.log_std + self.A], self.seed, self.draws, env_offset, st["d_act"])
+        else:
+            self.ctx.sample_categorical(st["head"], self.seed, self.draws, env_offset, st["d_act"])
+        self.draws += 1
+        return st["d_act"]
+
     # ---- learn (ppo.py:224-287) ---------------------------------------------------------------------
     def _alloc(self, T, N_, E, MB):
         key = (T, N_, E, MB)
@@ -788,6 +808,18 @@ class _PPOBase:
                                          self.act_dim if self._continuous else 1, self._continuous, self.device)
         buf = self._buffer
         buf.filled = 0
+        if getattr(self.envs, "device_resident", False) and isinstance(self.engine, FusedMlpEngine):
+            # device-resident environments: sampling kernel -> environment kernel per step, nothing crosses PCIe
+            envs = self.envs
+            for step_idx in range(cfg.rollout_steps):
+                envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs))
+            if self.ticker is not None:                                # episode statistics: one read-back per rollout
+                rew = buf.rewards.double().cpu().numpy()
+                dones = ((buf.terminations + buf.truncations) > 0).cpu().numpy()
+                for step_idx in range(cfg.rollout_steps):
+                    self.ticker.tick(rew[step_idx], dones[step_idx])
+            self.current_observations = envs.cur_obs
+            return buf
         observations = self.current_observations
         for step_idx in range(cfg.rollout_steps):
             actions = self.network.get_actions(observations, device=self.device)

@@ -213,6 +213,102 @@ class BatchedSyntheticVectorEnv:
         pass
 
 
+class DeviceVectorEnv:
+    """Vector environment that lives on the GPU (csrc/envs.cu: dppo_env_step / dppo_env_reset): CartPole-v1, Pendulum-v1
+    (Gymnasium classic-control dynamics, float64 state) and the synthetic shape stand-ins.  Same vector API and
+    autoreset-DISABLED semantics as SyncVectorEnv, so any agent or user code can drive it through `step` / `reset` with host
+    arrays; the default-network agents use `step_into`, which writes the step straight into the device rollout buffer and
+    resets finished environments inside the same kernel (diamond/ppo.py:160-182 without a PCIe crossing).
+
+    Use as `env_fn = DeviceVectorEnv.factory("CartPole-v1")` (an `env_fn.vectorized` factory taking num_envs)."""
+
+    device_resident = True
+    _KINDS = {"CartPole-v1": (0, 4, 2, False), "Pendulum-v1": (1, 3, 1, True)}
+
+    def __init__(self, env_id: str, num_envs: int, seed: int = 0, device=None, obs_dim: int = 64, n_actions: int = 4,
+                 continuous: bool = False, p_term: float = 0.01, p_trunc: float = 0.01, env_offset: int = 0):
+        import torch
+        from . import _native as N
+        self._torch, self._N = torch, N
+        if env_id in self._KINDS:
+            kind, D, A, cont = self._KINDS[env_id]
+        elif env_id in ("Synthetic", "LunarLander-v3"):                   # Box2D unavailable: shape stand-in
+            D, A, cont = (8, 4, False) if env_id == "LunarLander-v3" else (int(obs_dim), int(n_actions), bool(continuous))
+            kind = 3 if cont else 2
+        else:
+            raise KeyError(f"unknown device env id {env_id!r}; available: {sorted(self._KINDS) + ['LunarLander-v3', 'Synthetic']}")
+        self.env_id, self.num_envs, self.continuous = env_id, int(num_envs), cont
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ctx = N.get_context(self.device.index)
+        if kind == 0:
+            high = np.array([4.8, np.inf, 24 * math.pi / 360 * 2, np.inf], dtype=np.float32)
+            self.single_observation_space, self.single_action_space = Box(-high, high, (4,)), Discrete(2)
+        elif kind == 1:
+            high = np.array([1.0, 1.0, 8.0], dtype=np.float32)
+            self.single_observation_space, self.single_action_space = Box(-high, high, (3,)), Box(-2.0, 2.0, (1,))
+        else:
+            self.single_observation_space = Box(-np.inf, np.inf, (D,))
+            self.single_action_space = Box(-1.0, 1.0, (A,)) if cont else Discrete(A)
+        self.obs_dim, self.act_dim = D, A
+        self.desc = N.EnvDesc(kind, self.num_envs, D, A, int(seed) & (2 ** 64 - 1), int(env_offset), float(p_term), float(p_trunc))
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+        self.steps = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.cur_obs = torch.zeros(n, D, dtype=torch.float32, device=dev)
+        self._st = N.EnvState(self.state.data_ptr(), self.steps.data_ptr(), self.episode.data_ptr(), self.ep_return.data_ptr(),
+                              self.cur_obs.data_ptr())
+        f = dict(dtype=torch.float32, device=dev)
+        self._row = dict(next_obs=torch.empty(1, n, D, **f), rew=torch.empty(1, n, **f), term=torch.empty(1, n, **f),
+                         trunc=torch.empty(1, n, **f))
+        self.ctx.env_reset(self.desc, self._st, None)
+
+    @classmethod
+    def factory(cls, env_id: str, **kwargs):
+        def env_fn(num_envs):
+            return cls(env_id, num_envs, **kwargs)
+        env_fn.vectorized = True
+        return env_fn
+
+    def reset(self, *, seed: int | None = None, options: dict | None = None):
+        torch = self._torch
+        mask = None if options is None else options.get("reset_mask")
+        if seed is not None:
+            self.desc.seed = int(seed) & (2 ** 64 - 1)
+            if mask is None:
+                self.episode.zero_()
+        m = None if mask is None else torch.as_tensor(np.asarray(mask, dtype=np.uint8) if not torch.is_tensor(mask) else mask).to(
+            self.device, torch.uint8).contiguous()
+        self.ctx.env_reset(self.desc, self._st, m)
+        return self.cur_obs.cpu().numpy(), {}
+
+    def _actions(self, actions):
+        torch = self._torch
+        a = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
+        if self.continuous:
+            return a.to(self.device, torch.float32).reshape(self.num_envs, self.act_dim).contiguous()
+        return a.to(self.device, torch.int64).reshape(self.num_envs).contiguous()
+
+    def step(self, actions):
+        """Gymnasium vector API with host arrays (autoreset disabled: the caller resets through reset(options=...))."""
+        r = self._row
+        self.ctx.env_step(self.desc, self._st, self._actions(actions), 0, False, None, r["next_obs"], None, r["rew"], r["term"],
+                          r["trunc"])
+        return (r["next_obs"][0].cpu().numpy(), r["rew"][0].double().cpu().numpy(), r["term"][0].bool().cpu().numpy(),
+                r["trunc"][0].bool().cpu().numpy(), {})
+
+    def step_into(self, buf, t: int, actions) -> None:
+        """Fused rollout step: row t of the device rollout buffer (obs, next_obs, actions, rewards, terminations, truncations)
+        is written by the kernel, finished environments are reset, `cur_obs` becomes the next step's observations."""
+        self.ctx.env_step(self.desc, self._st, self._actions(actions), t, True, buf.obs, buf.next_obs, buf.actions, buf.rewards,
+                          buf.terminations, buf.truncations)
+        buf.filled = max(buf.filled, t + 1)
+
+    def close(self):
+        pass
+
+
 _REGISTRY = {"CartPole-v1": CartPoleEnv, "Pendulum-v1": PendulumEnv,
              "LunarLander-v3": lambda: SyntheticEnv(8, 4)}       # Box2D unavailable: shape stand-in
 

@@ -248,6 +248,38 @@ int dppo_rnn_grad_minibatch(dppo_ctx* ctx, const dppo_rnn_desc* desc, const floa
                             const int32_t* idx, int64_t M, const dppo_hyper* hyper, float* losses, void* ws,
                             int64_t ws_bytes, void* stream);
 
+/* ---- device-resident vectorised environments ------------------------------------ */
+/* Replaces the host `envs.step(actions)` + `envs.reset(options={"reset_mask": dones})` + list append of a rollout step
+ * (diamond/ppo.py:160-182): one kernel steps all environments and writes row t of the time-major rollout buffers.
+ * kind 0: CartPole-v1, 1: Pendulum-v1 (Gymnasium classic-control dynamics, float64 state), 2 / 3: synthetic discrete /
+ * continuous (i.i.d. normal observations; the scale benchmark's shape stand-in).  Autoreset-DISABLED contract: next_obs[t]
+ * is the true final observation; with auto_reset != 0 finished environments are then reset inside the same kernel and
+ * cur_obs holds the post-reset observation (ppo.py:174-179), else the caller resets them with dppo_env_reset(mask). */
+typedef struct dppo_env_desc {
+    int32_t kind;
+    int32_t num_envs;
+    int32_t obs_dim;        /* 4 (CartPole), 3 (Pendulum), any (synthetic) */
+    int32_t act_dim;        /* Discrete.n, or action dims when continuous */
+    uint64_t seed;          /* reset / synthetic draws: Philox4x32-10 keyed by (seed, env_offset + env, episode or step) */
+    int64_t env_offset;     /* global id of env 0 (env-sharded data parallelism) */
+    float p_term, p_trunc;  /* synthetic kinds only */
+} dppo_env_desc;
+typedef struct dppo_env_state {  /* caller-allocated device buffers */
+    double* state;          /* [N, 4] */
+    int32_t* steps;         /* [N] steps taken in the current episode */
+    int64_t* episode;       /* [N] episodes started */
+    double* ep_return;      /* [N] running return of the current episode */
+    float* cur_obs;         /* [N, D] observation the next sampling step reads */
+} dppo_env_state;
+/* mask: uint8 [N] (NULL: reset every environment). */
+int dppo_env_reset(dppo_ctx* ctx, const dppo_env_desc* desc, const dppo_env_state* state, const unsigned char* mask, void* stream);
+/* actions: int64 [N] (what dppo_sample_categorical writes) or f32 [N, A].  obs / next_obs / buf_actions / rewards /
+ * terminations / truncations are the BASES of the [T, N, ...] buffers (obs and buf_actions may be NULL); row t is written with
+ * the casts of ppo.py:229-232.  done_return (optional, f32 [N]) receives the return of every episode that ended at this step. */
+int dppo_env_step(dppo_ctx* ctx, const dppo_env_desc* desc, const dppo_env_state* state, const void* actions, int t, int auto_reset,
+                  float* obs, float* next_obs, void* buf_actions, float* rewards, float* terminations, float* truncations,
+                  float* done_return, void* stream);
+
 /* ---- tensor-core building blocks of the fused update (unit tests, A/B measurements) ---------- */
 /* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate).
  * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).

@@ -1,0 +1,99 @@
+"""GPU: device-resident vector environments (csrc/envs.cu) against oracle/env_oracle.py, and the PCIe-free rollout path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1"])
+def test_device_env_steps_match_oracle(env_id):
+    """Every step of 600 vector steps: the kernel's next state / observation / reward / flags equal the oracle's step from the
+    same float64 state and actions (flags bit-exact, floats to 1e-12); autoreset-disabled contract of the vector API."""
+    from diamond.envs import DeviceVectorEnv
+    from oracle import env_oracle as EO
+    N_ = 96
+    env = DeviceVectorEnv(env_id, N_, seed=5)
+    step_fn = EO.cartpole_step if env_id == "CartPole-v1" else EO.pendulum_step
+    rng = np.random.default_rng(1)
+    obs0, _ = env.reset(seed=5)
+    s = env.state.cpu().numpy()
+    if env_id == "CartPole-v1":
+        assert np.all(np.abs(s) <= 0.05) and np.array_equal(obs0, s.astype(np.float32))
+    else:
+        assert np.all(np.abs(s[:, 0]) <= np.pi) and np.all(np.abs(s[:, 1]) <= 1.0)
+        np.testing.assert_allclose(obs0, np.stack([np.cos(s[:, 0]), np.sin(s[:, 0]), s[:, 1]], 1).astype(np.float32), atol=1e-7)
+    n_done = 0
+    for it in range(600):
+        state = env.state.cpu().numpy().copy()
+        steps = env.steps.cpu().numpy().copy()
+        actions = rng.integers(0, 2, N_) if env_id == "CartPole-v1" else rng.uniform(-2.5, 2.5, (N_, 1)).astype(np.float32)
+        nobs, rew, term, trunc, _ = env.step(actions)
+        ref_next, ref_obs, ref_rew, ref_term, ref_trunc = step_fn(state, actions, steps)
+        np.testing.assert_array_equal(term, ref_term)
+        np.testing.assert_array_equal(trunc, ref_trunc)
+        np.testing.assert_allclose(env.state.cpu().numpy()[:, :ref_next.shape[1]], ref_next, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(nobs, ref_obs, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(rew, ref_rew, rtol=1e-6, atol=1e-6)            # rewards are stored as f32 (ppo.py:230)
+        dones = term | trunc
+        if dones.any():
+            n_done += int(dones.sum())
+            before = env.state.cpu().numpy().copy()
+            obs, _ = env.reset(options={"reset_mask": dones})
+            after = env.state.cpu().numpy()
+            assert np.array_equal(after[~dones], before[~dones])                     # only the masked environments are reset
+            assert np.all(env.steps.cpu().numpy()[dones] == 0)
+            assert np.array_equal(obs[~dones], nobs[~dones])
+    assert n_done > 0
+
+
+def test_device_env_reset_draws_are_keyed_by_seed_and_global_env_id():
+    from diamond.envs import DeviceVectorEnv
+    a = DeviceVectorEnv("CartPole-v1", 32, seed=9)
+    b = DeviceVectorEnv("CartPole-v1", 16, seed=9, env_offset=16)          # the second shard of a 32-env run
+    c = DeviceVectorEnv("CartPole-v1", 32, seed=10)
+    assert torch.equal(a.state[16:], b.state)
+    assert not torch.equal(a.state, c.state)
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1", "LunarLander-v3"])
+def test_rollout_on_device_envs_keeps_rollout_semantics(env_id):
+    """agent.rollout() with a DeviceVectorEnv: no host env stepping; the buffer obeys ppo.py:165-185 (obs[t+1] is next_obs[t]
+    unless the env finished at t, in which case it is a freshly reset observation), and learn() consumes it."""
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig
+    from diamond.envs import DeviceVectorEnv
+    cont = env_id == "Pendulum-v1"
+    Agent, Cfg = (ContinuousPPO, ContinuousPPOConfig) if cont else (PPO, PPOConfig)
+    T, N_ = 64 if cont else 128, 64
+    extra = dict(p_term=0.03, p_trunc=0.02) if env_id == "LunarLander-v3" else {}
+    cfg = Cfg(num_envs=N_, rollout_steps=T, verbose=False, seed=3, total_steps=T * N_ * 4)
+    agent = Agent(DeviceVectorEnv.factory(env_id, seed=3, **extra), cfg)
+    agent.current_observations, _ = agent.envs.reset(seed=3)
+    first = agent.envs.cur_obs.clone()
+    buf = agent.rollout()
+    torch.cuda.synchronize()
+    assert torch.equal(buf.obs[0], first)
+    done = (buf.terminations + buf.truncations) > 0
+    cont_rows = ~done[:-1]
+    assert torch.equal(buf.obs[1:][cont_rows], buf.next_obs[:-1][cont_rows])
+    if done[:-1].any():
+        assert not torch.equal(buf.obs[1:][done[:-1]], buf.next_obs[:-1][done[:-1]])
+    assert torch.equal(agent.envs.cur_obs[~done[-1]], buf.next_obs[-1][~done[-1]])
+    if env_id == "CartPole-v1":
+        assert done.any() and torch.all(buf.rewards == 1.0)
+        assert torch.all((buf.next_obs[..., 0].abs() > 2.4) | (buf.next_obs[..., 2].abs() > 12 * 2 * np.pi / 360) == (buf.terminations > 0))
+    before = {k: v.detach().clone() for k, v in agent.network.state_dict().items()}
+    agent.learn(buf)
+    assert torch.isfinite(agent.last_losses).all()
+    assert any(not torch.equal(before[k], v) for k, v in agent.network.state_dict().items())
+
+
+def test_cartpole_learns_on_device():
+    """End-to-end train() on device-resident CartPole-v1: the mean episode length grows well beyond the random policy's ~22."""
+    from diamond import PPO, PPOConfig
+    from diamond.envs import DeviceVectorEnv
+    cfg = PPOConfig(num_envs=64, rollout_steps=128, verbose=False, seed=1, total_steps=64 * 128 * 40)
+    agent = PPO(DeviceVectorEnv.factory("CartPole-v1", seed=1), cfg)
+    agent.train()
+    lengths = list(agent.ticker.recent_lengths)
+    assert len(lengths) > 10 and np.mean(lengths) > 100.0, np.mean(lengths)

@@ -172,3 +172,35 @@ def test_recurrent_core_matches_stepwise_nn_gru():
     # None handling (the reference's `or` raises here)
     o3, _ = core.forward(x.detach(), None, None)
     assert o3.shape == (T, B, Hg)
+
+
+def test_env_oracle_matches_per_env_host_implementation():
+    """oracle/env_oracle.py (vectorised restatement of Gymnasium's CartPole-v1 / Pendulum-v1 steps) against the independent
+    per-environment host classes in diamond/envs.py, plus a hand-computed CartPole step."""
+    from diamond import envs
+    from oracle import env_oracle as EO
+    rng = np.random.default_rng(0)
+    # hand-computed: state 0, action 1 -> temp = 10/1.1, th_acc = -temp / (0.5 (4/3 - 0.1/1.1)), x_acc = temp - 0.05 th_acc / 1.1
+    nxt, obs, r, term, trunc = EO.cartpole_step(np.zeros((1, 4)), np.array([1]), np.array([0]))
+    temp = 10.0 / 1.1
+    th_acc = -temp / (0.5 * (4.0 / 3.0 - 0.1 / 1.1))
+    np.testing.assert_allclose(nxt[0], [0.0, 0.02 * (temp - 0.05 * th_acc / 1.1), 0.0, 0.02 * th_acc], rtol=1e-14)
+    assert r[0] == 1.0 and not term[0] and not trunc[0]
+    for _ in range(200):
+        e = envs.CartPoleEnv()
+        e.state = rng.uniform(-1, 1, 4) * np.array([2.6, 2.0, 0.25, 2.0])
+        e.t = int(rng.integers(0, 500))
+        s0, t0, a = e.state.copy(), e.t, int(rng.integers(0, 2))
+        o, rew, te, tr, _ = e.step(a)
+        nxt, obs, r, term, trunc = EO.cartpole_step(s0[None], np.array([a]), np.array([t0]))
+        np.testing.assert_allclose(nxt[0], e.state, rtol=1e-13, atol=1e-15)
+        np.testing.assert_array_equal(obs[0], o)
+        assert (bool(term[0]), bool(trunc[0]), float(r[0])) == (te, tr, rew)
+        p = envs.PendulumEnv()
+        p.th, p.thdot, p.t = float(rng.uniform(-7, 7)), float(rng.uniform(-8, 8)), int(rng.integers(0, 200))
+        s0, t0, u = np.array([[p.th, p.thdot]]), p.t, rng.uniform(-3, 3, (1, 1)).astype(np.float32)
+        o, rew, te, tr, _ = p.step(u[0])
+        nxt, obs, r, term, trunc = EO.pendulum_step(s0, u, np.array([t0]))
+        np.testing.assert_allclose(nxt[0], [p.th, p.thdot], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(obs[0], o, rtol=0, atol=1e-7)
+        assert abs(r[0] - rew) <= 1e-12 * max(1.0, abs(rew)) and bool(trunc[0]) == tr and not te
