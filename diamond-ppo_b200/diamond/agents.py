@@ -398,6 +398,7 @@ class FusedMlpEngine(_EngineBase):
         self.use_graphs = True          # replay the optimiser steps of an epoch as a CUDA graph (single GPU, steady state)
         self._seen_key = None
         self._idx_consumed = None       # event after the last async copy out of the pinned per-epoch index buffers
+        self.reuse_rollout_values = True   # learn() takes log-probs / values recorded at sampling time when they are still valid
 
     # ---- rollout side: fused forward + sampling (ppo.py:73-82) -----------------------------------
     def sample_actions(self, observations: np.ndarray) -> np.ndarray:
@@ -425,9 +426,11 @@ class FusedMlpEngine(_EngineBase):
         torch.cuda.current_stream().synchronize()
         return st["h_act"].numpy().copy()
 
-    def sample_actions_device(self, d_obs: torch.Tensor) -> torch.Tensor:
+    def sample_actions_device(self, d_obs: torch.Tensor, values_out: torch.Tensor | None = None,
+                              logp_out: torch.Tensor | None = None) -> torch.Tensor:
         """get_actions for observations that already live on the device (DeviceVectorEnv): forward + sampling kernels only,
-        no host round trip and no synchronisation.  Returns int64 [N] / f32 [N, A] on the device."""
+        no host round trip and no synchronisation.  Returns int64 [N] / f32 [N, A] on the device.  values_out / logp_out
+        (f32 [N]) additionally receive V(obs) and log_prob(action) of the sampling policy."""
         n = d_obs.shape[0]
         st = self._act_stage.get(("dev", n))
         if st is None:
@@ -435,15 +438,20 @@ class FusedMlpEngine(_EngineBase):
                       d_act=(torch.empty(n, self.A, dtype=torch.float32, device=self.device) if self.continuous
                              else torch.empty(n, dtype=torch.int64, device=self.device)))
             self._act_stage[("dev", n)] = st
-        self.ctx.mlp_forward(self.fm.desc, self.P, d_obs, n, 1, st["head"], None, self.fwd_ws)
+        self.ctx.mlp_forward(self.fm.desc, self.P, d_obs, n, 1 if values_out is None else 3, st["head"], values_out, self.fwd_ws)
         env_offset = self.dist.rank * n
         if self.continuous:
             lay = self.fm.layout
-            self.ctx.sample_gaussian(st["head"], self.P[lay.log_std:lay.log_std + self.A], self.seed, self.draws, env_offset, st["d_act"])
+            self.ctx.sample_gaussian(st["head"], self.P[lay.log_std:lay.log_std + self.A], self.seed, self.draws, env_offset, st["d_act"],
+                                     logp_out)
         else:
-            self.ctx.sample_categorical(st["head"], self.seed, self.draws, env_offset, st["d_act"])
+            self.ctx.sample_categorical(st["head"], self.seed, self.draws, env_offset, st["d_act"], logp_out)
         self.draws += 1
         return st["d_act"]
+
+    def policy_stamp(self):
+        """Identifies the parameter values: optimiser steps taken by the kernels + torch-side in-place writes to the flat buffer."""
+        return (self.adam_step, self.P._version, self.P.data_ptr(), sum(p._version for _, p, *_ in self.param_list))
 
     # ---- learn (ppo.py:224-287) ---------------------------------------------------------------------
     def _alloc(self, T, N_, E, MB):
@@ -558,6 +566,27 @@ class FusedMlpEngine(_EngineBase):
             ctx.mlp_forward(desc, self.P, buf.next_obs[t0:t1], r1 - r0, 2, None, next_values[r0:r1], self.fwd_ws)
         buf.h2d_done()
 
+    def prepass_from_rollout(self, buf: RolloutBuffer, b):
+        """the pre-update pass (ppo.py:235-238) re-evaluates the policy that sampled the rollout, with unchanged
+        parameters.  When the rollout recorded log_prob(action) and V(obs) at sampling time, only V(final observation) is
+        missing, and `next_obs[t] == obs[t+1]` wherever the environment did not finish at t: next_values[t] = values[t+1]
+        there, and the critic is evaluated only on the final observations of finished steps and on the last row --
+        ~3 % of the 2 B rows the full pass touches."""
+        T, N_ = buf.T, buf.N
+        B = T * N_
+        b["values"].copy_(buf.values)
+        b["old_logp"].copy_(buf.logp)
+        nv = b["next_values"]
+        if T > 1:
+            nv[:-1].copy_(buf.values[1:])
+        need = (buf.terminations + buf.truncations) > 0
+        need[-1] = True
+        idx = need.view(B).nonzero().squeeze(1)
+        n = int(idx.numel())
+        tmp = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.ctx.mlp_forward(self.fm.desc, self.P, buf.next_obs.view(B, self.D), n, 2, None, tmp, self.fwd_ws, idx=idx.to(torch.int32))
+        nv.view(B).index_copy_(0, idx, tmp)
+
     def learn(self, buf: RolloutBuffer, events=None):
         cfg, ctx, dist = self.cfg, self.ctx, self.dist
         T, N_ = buf.T, buf.N
@@ -584,7 +613,10 @@ class FusedMlpEngine(_EngineBase):
                 ev.record()
                 events[name] = ev
         mark("start")
-        self.prepass(buf, b)
+        if self.reuse_rollout_values and getattr(buf, "policy_stamp", None) == self.policy_stamp():
+            self.prepass_from_rollout(buf, b)
+        else:
+            self.prepass(buf, b)
         mark("prepass_end")
         b["stats"].zero_()
         # the kernel right before the GAE launch is the 16-byte fill above, not the pre-update pass: inputs are settled
@@ -811,8 +843,15 @@ class _PPOBase:
         if getattr(self.envs, "device_resident", False) and isinstance(self.engine, FusedMlpEngine):
             # device-resident environments: sampling kernel -> environment kernel per step, nothing crosses PCIe
             envs = self.envs
+            if getattr(buf, "values", None) is None:
+                buf.values = torch.empty(buf.T, buf.N, dtype=torch.float32, device=self.device)
+                buf.logp = torch.empty(buf.T, buf.N, dtype=torch.float32, device=self.device)
+            buf.policy_stamp = None
+            stamp = self.engine.policy_stamp()
             for step_idx in range(cfg.rollout_steps):
-                envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs))
+                envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs, buf.values[step_idx], buf.logp[step_idx]))
+            if self.engine.policy_stamp() == stamp:
+                buf.policy_stamp = stamp                               # V(obs), log_prob(action) of exactly these parameters
             if self.ticker is not None:                                # episode statistics: one read-back per rollout
                 rew = buf.rewards.double().cpu().numpy()
                 dones = ((buf.terminations + buf.truncations) > 0).cpu().numpy()

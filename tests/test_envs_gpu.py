@@ -97,3 +97,62 @@ def test_cartpole_learns_on_device():
     agent.train()
     lengths = list(agent.ticker.recent_lengths)
     assert len(lengths) > 10 and np.mean(lengths) > 100.0, np.mean(lengths)
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1", "Synthetic"])
+def test_learn_reuses_rollout_values_and_matches_full_prepass(env_id):
+    """with log_prob(action) / V(obs) recorded at sampling time and next_values[t] = values[t+1] where the env did
+    not finish, learn() skips the pre-update pass; the result equals the full pass (ppo.py:235-238) on the same buffer."""
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig
+    from diamond.envs import DeviceVectorEnv
+    cont = env_id == "Pendulum-v1"
+    Agent, Cfg = (ContinuousPPO, ContinuousPPOConfig) if cont else (PPO, PPOConfig)
+    N_, T, H = (2048, 32, 128) if env_id == "Synthetic" else (64, 64, 64)           # Synthetic: tensor-core forward path
+    kw = dict(obs_dim=32, n_actions=4, p_term=0.03, p_trunc=0.02) if env_id == "Synthetic" else {}
+
+    def make_agent():
+        cfg = Cfg(num_envs=N_, rollout_steps=T, network_hidden_dim=H, verbose=False, seed=11, total_steps=T * N_ * 8)
+        agent = Agent(DeviceVectorEnv.factory(env_id, seed=11, **kw), cfg)
+        agent.current_observations, _ = agent.envs.reset(seed=11)
+        return agent, cfg
+
+    def run(reuse):
+        agent, cfg = make_agent()
+        agent.engine.reuse_rollout_values = reuse
+        buf = agent.rollout()
+        assert buf.policy_stamp == agent.engine.policy_stamp()
+        np.random.seed(4)
+        agent.learn(buf)
+        torch.cuda.synchronize()
+        return agent.last_losses.clone(), torch.cat([q.detach().flatten() for q in agent.network.parameters()]).clone()
+
+    # identical parameters and seeds -> identical rollouts; one learn() with and without the recorded values
+    (la, pa), (lf, pf) = run(True), run(False)
+    assert torch.allclose(la, lf, rtol=1e-4, atol=5e-6)
+    err = (pa - pf).abs().max().item() / pf.abs().max().item()
+    assert err <= 1e-4, err
+
+    # GAE inputs of the two pre-update passes on the same buffers, over several rollout / learn iterations
+    agent, cfg = make_agent()
+    eng = agent.engine
+    for it in range(3):
+        buf = agent.rollout()
+        b = eng._alloc(T, N_, cfg.num_epochs, cfg.num_minibatches)
+        eng.prepass(buf, b)
+        full = {k: b[k].clone() for k in ("values", "next_values", "old_logp")}
+        for k in full:
+            b[k].fill_(float("nan"))
+        eng.prepass_from_rollout(buf, b)
+        for k, ref in full.items():
+            assert (b[k] - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), (it, k)
+        agent.learn(buf)
+
+    # a buffer whose sampling policy is no longer the current one falls back to the full pass
+    from diamond.agents import FusedMlpEngine
+    cfg = Cfg(num_envs=N_, rollout_steps=T, network_hidden_dim=H, verbose=False, seed=11, total_steps=T * N_ * 8)
+    agent = Agent(DeviceVectorEnv.factory(env_id, seed=11, **kw), cfg)
+    agent.current_observations, _ = agent.envs.reset(seed=11)
+    buf = agent.rollout()
+    with torch.no_grad():
+        next(agent.network.parameters()).mul_(1.01)
+    assert buf.policy_stamp != agent.engine.policy_stamp()
