@@ -287,6 +287,7 @@ struct WgradJobs {
     int n;
     int smem_bytes;            // dynamic shared memory of the launch (each job derives its own stage count from it)
     int64_t M;
+    int rn_hi;                 // A/B: store a round-to-nearest hi image instead of using the raw chunk as hi
 };
 
 template <int NACC>
@@ -406,13 +407,19 @@ tc2_wgrad_kernel(const __grid_constant__ WgradJobs jobs)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (i + j * SPLIT_THREADS < n4) x[j] = lds128(hi + (i + j * SPLIT_THREADS) * 16);
+                if (jobs.rn_hi) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (i + j * SPLIT_THREADS < n4) {
-                        const float4 l = split_tf32x4(x[j]);
-                        sts128(hi + (i + j * SPLIT_THREADS) * 16, x[j]);
-                        sts128(hi + hi_bytes + (i + j * SPLIT_THREADS) * 16, l);
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (i + j * SPLIT_THREADS < n4) {
+                            const float4 l = split_tf32x4(x[j]);
+                            sts128(hi + (i + j * SPLIT_THREADS) * 16, x[j]);
+                            sts128(hi + hi_bytes + (i + j * SPLIT_THREADS) * 16, l);
+                        }
+                } else {                                                // the raw chunk is the hi image; only lo is written
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i + j * SPLIT_THREADS < n4) sts128(hi + hi_bytes + (i + j * SPLIT_THREADS) * 16, lo_of_trunc_x4(x[j]));
+                }
             }
             fence_proxy_async();
             mbar_arrive(&ready[s]);
@@ -621,6 +628,7 @@ int dppo_tc2_wgrad_multi(dppo_ctx* ctx, int n, const float* const* Dm, const int
     WgradJobs jobs;
     jobs.n = n;
     jobs.M = M;
+    jobs.rn_hi = (ctx->tc_debug & 1024) ? 1 : 0;
     int cta = 0, max_stage = 0;
     for (int j = 0; j < n; ++j) {
         if (!dppo_tc2_wgrad_supported(M, N1[j], N2[j])) DPPO_FAIL(ctx, "tc2_wgrad: unsupported shape M=%lld N1=%d N2=%d", (long long)M, N1[j], N2[j]);

@@ -162,11 +162,16 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float4 x[PER];
 #pragma unroll
                 for (int j = 0; j < PER; ++j) x[j] = lds128(hi + j * SPLIT_THREADS * 16);
+                if (dbg & 1024) {                                       // A/B: round-to-nearest hi image stored in place
 #pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const float4 l = split_tf32x4(x[j]);
-                    sts128(hi + j * SPLIT_THREADS * 16, x[j]);
-                    sts128(hi + A_IMG + j * SPLIT_THREADS * 16, l);
+                    for (int j = 0; j < PER; ++j) {
+                        const float4 l = split_tf32x4(x[j]);
+                        sts128(hi + j * SPLIT_THREADS * 16, x[j]);
+                        sts128(hi + A_IMG + j * SPLIT_THREADS * 16, l);
+                    }
+                } else {                                                // the raw chunk is the hi image; only lo is written
+#pragma unroll
+                    for (int j = 0; j < PER; ++j) sts128(hi + A_IMG + j * SPLIT_THREADS * 16, lo_of_trunc_x4(x[j]));
                 }
                 fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core
                 __syncwarp();

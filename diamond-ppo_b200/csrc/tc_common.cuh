@@ -252,6 +252,21 @@ __device__ __forceinline__ float4 split_tf32x4(float4& x)
     return lo;
 }
 
+// The raw fp32 operand as its own hi image: kind::tf32 reads the upper 19 bits of each fp32 word (the 13 low mantissa bits are
+// ignored), i.e. hi = trunc_tf32(x) costs no shared-memory store.  lo = rn_tf32(x - trunc(x)); the difference is exact in fp32
+// (13 significant bits) and |lo| < 2^-10 |x|.  Halves the shared-memory write traffic of the split warps (the weight-gradient
+// kernel, which splits BOTH operands, is shared-memory-bandwidth bound: 64 KB read + 128 KB written + 64 KB TMA + operand
+// fetch per chunk).
+__device__ __forceinline__ float lo_of_trunc(float x)
+{
+    const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float4 lo_of_trunc_x4(const float4& x)
+{
+    return make_float4(lo_of_trunc(x.x), lo_of_trunc(x.y), lo_of_trunc(x.z), lo_of_trunc(x.w));
+}
+
 }  // namespace tc
 
 // ---- host: tensor maps (gemm_tc2.cu) -------------------------------------------------------------
