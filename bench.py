@@ -28,8 +28,8 @@ FLOP_PER_SAMPLE_UPDATE = 1_252_864          # 2*(3F - D*H), F = 
 FLOP_PER_SAMPLE_PREPASS = 723_968           # 2*(F + Fc)
 GAE_BYTES_PER_ELEM = 28                     # 5 fp32 reads + 2 fp32 writes
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full,
-# profiles/r1e_kernels.csv): 67.7 MB read + 15.2 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
-GEMM_DRAM_TRAFFIC = 82.9e6
+# profiles/r1f_kernels.csv): 67.7 MB read + 16.5 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
+GEMM_DRAM_TRAFFIC = 84.2e6
 
 
 def measured_peaks():
@@ -90,7 +90,8 @@ def synth_host_rollout(seed):
     rewards = torch.randn(T, N_ENVS, generator=g)
     term = (torch.rand(T, N_ENVS, generator=g) < 0.01).float()
     trunc = ((torch.rand(T, N_ENVS, generator=g) < 0.01) & (term == 0)).float()
-    return [x.pin_memory() for x in (obs, next_obs, actions, rewards, term, trunc)]
+    pin = torch.cuda.is_available()                       # the reference arm also runs on hosts without a GPU
+    return [x.pin_memory() if pin else x for x in (obs, next_obs, actions, rewards, term, trunc)]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -264,6 +265,35 @@ def bench_fma_peak(ctx):
     return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
+def bench_train_iteration(reps=3):
+    """One full training iteration of config S with the environments on the device (diamond/envs.py DeviceVectorEnv, synthetic
+    shape stand-in): rollout() (sampling kernel + environment kernel per step, nothing crosses PCIe, log-probs / values recorded)
+    followed by learn() (which then skips the pre-update pass).  Wall clock around synchronised iterations."""
+    from diamond import PPO, PPOConfig
+    from diamond.envs import DeviceVectorEnv
+    cfg = PPOConfig(num_envs=N_ENVS, rollout_steps=T, network_hidden_dim=H, num_epochs=E, num_minibatches=MB, verbose=False,
+                    total_steps=T * N_ENVS * 1000, seed=1)
+    agent = PPO(DeviceVectorEnv.factory("Synthetic", obs_dim=D, n_actions=A, seed=1), cfg)
+    agent.ticker = None
+    agent.current_observations, _ = agent.envs.reset(seed=1)
+    for _ in range(3):
+        agent.learn(agent.rollout())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        buf = agent.rollout()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        agent.learn(agent.rollout())
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    ms_roll, ms_iter = (t1 - t0) * 1e3 / reps, (t2 - t1) * 1e3 / reps
+    return {"workload": "device-resident synthetic envs: rollout() + learn() per iteration, config S", "rollout_ms": ms_roll,
+            "iteration_ms": ms_iter, "env_steps_per_s": T * N_ENVS / (ms_iter * 1e-3), "rollout_env_steps_per_s": T * N_ENVS / (ms_roll * 1e-3),
+            "sample_updates_per_s": E * T * N_ENVS / (ms_iter * 1e-3)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from diamond import PPO, PPOConfig, envs, _native
@@ -372,6 +402,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_losses.numel() * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if world == 1:
+        line["train_iteration"] = bench_train_iteration()
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(4, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
