@@ -30,6 +30,9 @@ GAE_BYTES_PER_ELEM = 28                     # 5 fp32 reads + 2 fp32 writes
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full,
 # profiles/r1f_kernels.csv): 67.7 MB read + 16.5 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
 GEMM_DRAM_TRAFFIC = 84.2e6
+# one gae_pipe_kernel launch on a cold buffer set (profiles/r1f_gae_kernels.csv): 10.5 MB read; the 4.2 MB of advantages / returns are
+# still in L2 when the kernel ends (dram__bytes_write.sum = 0) and reach DRAM by eviction as the benchmark cycles its 20 buffer sets
+GAE_DRAM_TRAFFIC = 10.5e6
 
 
 def measured_peaks():
@@ -396,7 +399,7 @@ def run_ours(args, rank, world, local_rank):
                                  "frac": upd_tflops / tensor_peak, "flop_per_sample_update": FLOP_PER_SAMPLE_UPDATE,
                                  "fp32_fma_peak_tflops": fma_peak, "peak_source": peak_note},
         "roofline_gae": dict(gae, kernel="gae_pipe_kernel (chunked TMA loads, programmatic dependent launch)",
-                             peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=None,
+                             peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=GAE_DRAM_TRAFFIC,
                              without_settled_promise={"us_per_launch": gae_cons["us_per_launch"], "achieved": gae_cons["achieved"],
                                                       "frac": gae_cons["frac"]}),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_losses.numel() * 4)},
