@@ -334,6 +334,36 @@ head_train_kernel(HeadTrainArgs a)
     head_train_flush<KPL, VEC>(a, s_acc, acc_b3, acc_dba, acc_dbc, acc_dls, l_pol, l_val, l_ent);
 }
 
+// ---- packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction) -------------------------
+// Element-wise results are identical to the scalar forms nvcc emits (fmaf, *, fma(-h, h, 1)); only dot4 changes the summation order (even and odd
+// columns are accumulated separately and added at the end).
+__device__ __forceinline__ void axpy4(float4& acc, float s, const float4& x)              // acc += s * x
+{
+    const float2 ss = make_float2(s, s);
+    const float2 lo = __ffma2_rn(ss, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(ss, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void dot4(float2& acc, const float4& a, const float4& b)       // acc.{x,y} += a.{x,y}*b.{x,y} + a.{z,w}*b.{z,w}
+{
+    acc = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+    acc = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
+}
+__device__ __forceinline__ float4 mul4(const float4& a, const float4& b)
+{
+    const float2 lo = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fmul2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 scale4(float s, const float4& a) { return mul4(make_float4(s, s, s, s), a); }
+__device__ __forceinline__ float4 one_minus_sq4(const float4& h)                           // fma(-h, h, 1), as nvcc contracts 1 - h*h
+{
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 lo = __ffma2_rn(make_float2(-h.x, -h.y), make_float2(h.x, h.y), one);
+    const float2 hi = __ffma2_rn(make_float2(-h.z, -h.w), make_float2(h.z, h.w), one);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Register-accumulator variant of the training kernel (H a multiple of 128, A <= AMAX, float4 columns).
 // The per-warp head weight gradients live in registers (the shared-memory read-modify-write of the generic kernel moved
@@ -408,22 +438,19 @@ head_train_reg_kernel(HeadTrainArgs a)
 #pragma unroll
         for (int j = 0; j < AMAX; ++j) {
             if (j < A) {
-                float part[R];
+                float2 part2[R];                                 // even / odd column partial sums (packed FFMA2)
 #pragma unroll
-                for (int r = 0; r < R; ++r) part[r] = 0.f;
+                for (int r = 0; r < R; ++r) part2[r] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        part[r] = fmaf(ha[r][g].x, w.x, part[r]); part[r] = fmaf(ha[r][g].y, w.y, part[r]);
-                        part[r] = fmaf(ha[r][g].z, w.z, part[r]); part[r] = fmaf(ha[r][g].w, w.w, part[r]);
-                    }
+                    for (int r = 0; r < R; ++r) dot4(part2[r], ha[r][g], w);
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    part[r] = warp_sum(part[r]);
-                    if (lane == j) z[r] = part[r];
+                    const float part = warp_sum(part2[r].x + part2[r].y);
+                    if (lane == j) z[r] = part;
                 }
             }
         }
@@ -432,13 +459,10 @@ head_train_reg_kernel(HeadTrainArgs a)
         for (int g = 0; g < G; ++g) wcv[g] = reinterpret_cast<const float4*>(s_wc + g * 128)[lane];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float vp = 0.f;
+            float2 vp = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                vp = fmaf(hc[r][g].x, wcv[g].x, vp); vp = fmaf(hc[r][g].y, wcv[g].y, vp);
-                vp = fmaf(hc[r][g].z, wcv[g].z, vp); vp = fmaf(hc[r][g].w, wcv[g].w, vp);
-            }
-            v[r] = warp_sum(vp) + bias_c;
+            for (int g = 0; g < G; ++g) dot4(vp, hc[r][g], wcv[g]);
+            v[r] = warp_sum(vp.x + vp.y) + bias_c;
             z[r] += bias_a;
         }
 
@@ -485,10 +509,8 @@ head_train_reg_kernel(HeadTrainArgs a)
                     const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        ga[r][g].x = fmaf(dzj[r], w.x, ga[r][g].x); ga[r][g].y = fmaf(dzj[r], w.y, ga[r][g].y);
-                        ga[r][g].z = fmaf(dzj[r], w.z, ga[r][g].z); ga[r][g].w = fmaf(dzj[r], w.w, ga[r][g].w);
-                        gwa[j][g].x = fmaf(dzj[r], ha[r][g].x, gwa[j][g].x); gwa[j][g].y = fmaf(dzj[r], ha[r][g].y, gwa[j][g].y);
-                        gwa[j][g].z = fmaf(dzj[r], ha[r][g].z, gwa[j][g].z); gwa[j][g].w = fmaf(dzj[r], ha[r][g].w, gwa[j][g].w);
+                        axpy4(ga[r][g], dzj[r], w);
+                        axpy4(gwa[j][g], dzj[r], ha[r][g]);
                     }
                 }
             }
@@ -498,15 +520,12 @@ head_train_reg_kernel(HeadTrainArgs a)
             float* d3 = a.d3 + (mb + r) * (int64_t)(2 * H);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                float4 da, dc;
-                da.x = ga[r][g].x * (1.0f - ha[r][g].x * ha[r][g].x); da.y = ga[r][g].y * (1.0f - ha[r][g].y * ha[r][g].y);
-                da.z = ga[r][g].z * (1.0f - ha[r][g].z * ha[r][g].z); da.w = ga[r][g].w * (1.0f - ha[r][g].w * ha[r][g].w);
-                dc.x = dv[r] * wcv[g].x * (1.0f - hc[r][g].x * hc[r][g].x); dc.y = dv[r] * wcv[g].y * (1.0f - hc[r][g].y * hc[r][g].y);
-                dc.z = dv[r] * wcv[g].z * (1.0f - hc[r][g].z * hc[r][g].z); dc.w = dv[r] * wcv[g].w * (1.0f - hc[r][g].w * hc[r][g].w);
+                // same per-element operations as the scalar form, two columns per instruction
+                const float4 da = mul4(ga[r][g], one_minus_sq4(ha[r][g]));
+                const float4 dc = mul4(scale4(dv[r], wcv[g]), one_minus_sq4(hc[r][g]));
                 acc_b3[4 * g] += da.x; acc_b3[4 * g + 1] += da.y; acc_b3[4 * g + 2] += da.z; acc_b3[4 * g + 3] += da.w;
                 acc_b3[KPL + 4 * g] += dc.x; acc_b3[KPL + 4 * g + 1] += dc.y; acc_b3[KPL + 4 * g + 2] += dc.z; acc_b3[KPL + 4 * g + 3] += dc.w;
-                gwc[g].x = fmaf(dv[r], hc[r][g].x, gwc[g].x); gwc[g].y = fmaf(dv[r], hc[r][g].y, gwc[g].y);
-                gwc[g].z = fmaf(dv[r], hc[r][g].z, gwc[g].z); gwc[g].w = fmaf(dv[r], hc[r][g].w, gwc[g].w);
+                axpy4(gwc[g], dv[r], hc[r][g]);
                 if (ok[r]) {
                     __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, da);
                     __stcs(reinterpret_cast<float4*>(d3 + H + g * 128) + lane, dc);
