@@ -212,7 +212,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        aux[j] = m < M ? __ldg(reinterpret_cast<const float4*>(Hact + m * (int64_t)ldh + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        aux[j] = (m < M && !(dbg & 8192)) ? __ldg(reinterpret_cast<const float4*>(Hact + m * (int64_t)ldh + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 tmem_ld32_wait(r);
                 float v[32];
@@ -246,7 +246,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_store_2d(&tmC, n, m0, stg);                     // rows >= M are clipped by the tensor map
                     bulk_commit();
                 }
-                if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr) {
+                if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr && !(dbg & 16384)) {
                     // Bias-gradient partials: one row of column sums per (CTA, lane quadrant), accumulated over all tiles of
                     // this CTA (the row is owned by this warp pair).  With a single column tile every CTA covers all N
                     // columns in its first tile, which then initialises the row; otherwise the launcher zeroes the buffer.

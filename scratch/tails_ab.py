@@ -23,7 +23,7 @@ for (Nn, K) in [(256, 64), (256, 256), (512, 256)]:
         ctx.set_option("tc_debug", dbg)
         us = t(lambda: ctx.tc_linear(1, A, W, False, bias=b, out=out, ws=ws, prepared=True))
         err = (out.double() - ref).abs().max().item()
-        print(f"fwd N={Nn} K={K} tails={'full' if dbg else 'half'}: {us:.1f} us  err {err:.2e}", flush=True)
+        print(f"fwd N={Nn} K={K} tc_debug={dbg}: {us:.1f} us  err {err:.2e}", flush=True)
 ctx.set_option("tc_debug", 0)
 for (Nn, K) in [(256, 512), (256, 256)]:
     A = torch.randn(M, K, device="cuda", generator=g); W = torch.randn(K, Nn, device="cuda", generator=g) / K ** 0.5
