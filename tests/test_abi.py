@@ -94,3 +94,20 @@ def test_step_record_bytes():
     lib = N.load_library()
     assert lib.dppo_step_record_bytes(8, 4, 2, 0) == 2 * 8 * 4 * 4 + 8 * 8 + 8 * 8 + 2 * 8
     assert lib.dppo_step_record_bytes(3, 3, 2, 1) == 2 * 9 * 4 + 3 * 8 + 3 * 2 * 4 + 2 * 3
+
+
+def test_rnn_layout_matches_reference_parameter_count():
+    """SURVEY §8c KAT 4: the recurrent network of config R has 6 627 parameters; dppo_rnn_layout places the 14 tensors of
+    recurrent_ppo.py:101-125 (nn.GRU names, gate order r,z,n) without overlap, every offset a multiple of 4 floats."""
+    from diamond import _native as N
+    from diamond.recurrent import rnn_param_slices
+    desc = N.RnnDesc(4, 64, 16, 2)
+    lay = N.rnn_layout(desc)
+    sl = rnn_param_slices(desc, lay)
+    assert len(sl) == 14
+    assert sum(int(np.prod(shape)) for _, shape in sl.values()) == 6627
+    offs = sorted((off, int(np.prod(shape))) for off, shape in sl.values())
+    for (o1, n1), (o2, _) in zip(offs, offs[1:]):
+        assert o1 + n1 <= o2 and o1 % 4 == 0
+    assert lay.total >= offs[-1][0] + offs[-1][1]
+    assert sl["critic_head.0.weight"][0] == sl["actor_head.0.weight"][0] + 64 * 16       # one [2H, Hg] product

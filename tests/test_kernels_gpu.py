@@ -51,6 +51,61 @@ def test_gae_golden(ctx, case, tag, gam, lam):
         assert np.abs(an.cpu().numpy() - refn).max() <= 2e-5 * max(1.0, np.abs(refn).max())
 
 
+def test_gae_known_answer_vectors(ctx):
+    """SURVEY §8c KATs: rewards = 1 geometric sums; termination (no bootstrap, trace cut) vs truncation (bootstrap, trace cut)."""
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    adv = ctx.gae(torch.ones(8, 1, device="cuda"), z(8, 1), z(8, 1), z(8, 1), z(8, 1), 0.99, 0.95).cpu().numpy()[:, 0]
+    np.testing.assert_allclose(adv, [6.5182, 5.8673, 5.1752, 4.4394, 3.6570, 2.8250, 1.9405, 1.0000], atol=5e-5)
+    r, v, nv = torch.ones(4, 3, device="cuda"), torch.full((4, 3), 0.5, device="cuda"), torch.full((4, 3), 2.0, device="cuda")
+    te, tr = z(4, 3), z(4, 3)
+    te[1, 1] = 1.0
+    tr[1, 2] = 1.0
+    ret = torch.empty(4, 3, device="cuda")
+    adv = ctx.gae(r, te, tr, v, nv, 0.99, 0.95, returns=ret).cpu().numpy()
+    ref = np.array([[9.069237, 2.950250, 4.812440], [7.006100, 0.500000, 2.480000], [4.812440] * 3, [2.480000] * 3])
+    np.testing.assert_allclose(adv, ref, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ret.cpu().numpy(), ref + 0.5, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("T,N", [(1, 1), (1, 4096), (2, 1), (2048, 3), (129, 4097), (128, 28), (128, 29)])
+def test_gae_edge_shapes_vs_c_oracle(ctx, T, N):
+    """Single step / single env, sizes straddling the 28-env CTA tile and the 128-step chunking of the pipelined kernel, every
+    step finished (all masks set), and no step finished."""
+    rng = np.random.default_rng(T * 7 + N)
+    r, v, nv = (rng.standard_normal((T, N)).astype(np.float32) for _ in range(3))
+    for mode in ("mixed", "all_done", "none"):
+        te = {"mixed": (rng.random((T, N)) < 0.3), "all_done": np.ones((T, N), bool), "none": np.zeros((T, N), bool)}[mode].astype(np.float32)
+        tr = ((rng.random((T, N)) < 0.3) & (te == 0)).astype(np.float32) if mode == "mixed" else np.zeros((T, N), np.float32)
+        ref, _ = CO.gae(r, te, tr, v, nv)
+        ret = torch.empty(T, N, device="cuda")
+        adv = ctx.gae(dev(r), dev(te), dev(tr), dev(v), dev(nv), 0.99, 0.95, returns=ret).cpu().numpy()
+        assert nerr(adv, ref) <= 1e-5, mode
+        np.testing.assert_allclose(ret.cpu().numpy(), v + ref, rtol=1e-5, atol=1e-5)
+
+
+def test_gae_linearity_and_time_locality_at_full_size(ctx):
+    """Size-independent properties at BASELINE.json's 4096 x 128: GAE is linear in (rewards, values, next_values) for fixed masks,
+    and a finished step cuts the trace -- advantages before a done step do not depend on anything after it."""
+    T, N = 128, 4096
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda: torch.randn(T, N, device="cuda", generator=g)
+    te = (torch.rand(T, N, device="cuda", generator=g) < 0.01).float()
+    tr = ((torch.rand(T, N, device="cuda", generator=g) < 0.01) & (te == 0)).float()
+    r1, v1, n1, r2, v2, n2 = rnd(), rnd(), rnd(), rnd(), rnd(), rnd()
+    a1 = ctx.gae(r1, te, tr, v1, n1, 0.99, 0.95)
+    a2 = ctx.gae(r2, te, tr, v2, n2, 0.99, 0.95)
+    a12 = ctx.gae(r1 + 2 * r2, te, tr, v1 + 2 * v2, n1 + 2 * n2, 0.99, 0.95)
+    assert (a12 - (a1 + 2 * a2)).abs().max().item() <= 1e-5 * a12.abs().max().item()
+    # cut: make every env finish at step 63; perturbing steps >= 64 must leave steps <= 63 bit-identical
+    te2 = te.clone(); te2[63] = 1.0
+    base = ctx.gae(r1, te2, tr * (1 - te2), v1, n1, 0.99, 0.95)
+    r3, v3, n3 = r1.clone(), v1.clone(), n1.clone()
+    r3[64:] += 3.0; v3[64:] -= 1.0; n3[64:] *= 2.0
+    pert = ctx.gae(r3, te2, tr * (1 - te2), v3, n3, 0.99, 0.95)
+    assert torch.equal(base[:64], pert[:64])
+    assert not torch.equal(base[64:], pert[64:])
+
+
 @pytest.mark.parametrize("T,N", [(128, 4096), (128, 1000), (300, 77), (5, 33), (128, 8)])
 def test_gae_random_vs_c_oracle(ctx, T, N):
     rng = np.random.default_rng(T * 1000 + N)
