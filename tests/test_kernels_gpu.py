@@ -234,6 +234,50 @@ def test_mlp_grad_minibatch_vs_oracle(ctx, D, H, A, cont, B, M):
     assert float(grads.cpu()[~used].abs().sum()) == 0.0
 
 
+def test_update_gradient_is_additive_over_samples_at_full_size(ctx):
+    """Size-independent property at BASELINE.json's full minibatch (65 536 rows of the 4096 x 128 buffer, D = 64, 2x256 + heads):
+    with a fixed loss denominator the minibatch gradient is the sum of the gradients of its two halves, the losses are the sums of
+    the halves' losses, and the result does not depend on the order of the rows (up to fp32 summation order) -- through
+    the tensor-core path (tcgen05 GEMMs, joint weight-gradient launch, head kernel, deterministic reduction)."""
+    from diamond import _native as N
+    from diamond.flat import FlatMlp
+    D, H, A, B, M = 64, 256, 4, 524288, 65536
+    rng = np.random.default_rng(21)
+    p = rand_params(rng, O.DISCRETE_PARAM_NAMES, D, H, A, False)
+    fm = FlatMlp(D, H, A, False)
+    flat = fm.pack(p, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    obs = torch.randn(B, D, device="cuda", generator=g)
+    act = torch.randint(0, A, (B,), device="cuda", generator=g, dtype=torch.int32)
+    old_lp = torch.randn(B, device="cuda", generator=g) * 0.3 - 1.0
+    adv, ret = torch.randn(B, device="cuda", generator=g), torch.randn(B, device="cuda", generator=g)
+    idx = torch.randperm(B, device="cuda", generator=g)[:M].to(torch.int32)
+    hyper, _ = make_hyper(N, M)
+    ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, M, True) // 4 + 512, device="cuda")
+
+    def run(rows):
+        grads = torch.zeros(fm.total, device="cuda"); losses = torch.zeros(4, device="cuda")
+        ctx.mlp_grad_minibatch(fm.desc, flat, grads, obs, act, old_lp, adv, ret, None, rows.contiguous(), rows.numel(), hyper, losses, ws)
+        torch.cuda.synchronize()
+        return grads.double(), losses.double()
+
+    g_all, l_all = run(idx)
+    g_a, l_a = run(idx[:M // 2])
+    g_b, l_b = run(idx[M // 2:])
+    g_perm, l_perm = run(idx[torch.randperm(M, device="cuda", generator=g)])
+    g_again, l_again = run(idx)
+    assert torch.equal(g_all, g_again) and torch.equal(l_all, l_again)                   # bit-reproducible
+    views = lambda x: fm.views(x)
+    for name in O.DISCRETE_PARAM_NAMES:
+        ref = views(g_all)[name]
+        scale = ref.abs().max().item()
+        assert (views(g_a)[name] + views(g_b)[name] - ref).abs().max().item() <= 2e-5 * scale, name
+        assert (views(g_perm)[name] - ref).abs().max().item() <= 2e-5 * scale, name
+    # policy / value / entropy terms are means over the fixed denominator: halves add up
+    assert torch.allclose(l_a[:3] + l_b[:3], l_all[:3], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(l_perm, l_all, rtol=1e-5, atol=1e-7)
+
+
 def test_mlp_grad_advantage_norm_on_the_fly(ctx):
     from diamond import _native as N
     from diamond.flat import FlatMlp
