@@ -1,5 +1,5 @@
 """learn() latency of the small (launch-latency-bound) configurations of BASELINE.json next to the CPU port of the reference
-algorithm (oracle/ppo_oracle.py learn(), 1 host thread: more threads are slower at these sizes).  scratch/ only."""
+algorithm (oracle/ppo_oracle.py learn(), 1 host thread: more threads are slower at these sizes).  lives under tests/ because it runs the oracle (checker / CPU baseline only)."""
 import sys, os, time, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "diamond-ppo_b200"))
