@@ -48,6 +48,7 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->gae_variant = 0;
     c->gae_inputs_settled = 0;
     c->tc_debug = 0;
+    c->draw_base = nullptr;
     c->launch_count = 0;
     c->tm_cache = nullptr;
     c->tm_cache_free = nullptr;

@@ -17,6 +17,7 @@ struct dppo_ctx {
     int gae_inputs_settled;               // 1: caller guarantees the GAE inputs are not written by the kernel just before the GAE launch
     long long launch_count;               // kernels launched through this context (bench.py's gpu_launches)
     int tc_debug;                         // bit mask of experiment switches of the tc2 kernels (wrong results; timing only)
+    const unsigned long long* draw_base;  // optional device counter added to every sampling draw counter (CUDA-graph replay of rollouts)
     void* tm_cache;                       // tensor-map cache owned by gae.cu
     void (*tm_cache_free)(void*);
 };

@@ -23,10 +23,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
 
 __global__ void sample_categorical_kernel(const float* __restrict__ logits, int N, int A, uint64_t seed, uint64_t counter,
-                                          int64_t env_offset, int64_t* __restrict__ actions, float* __restrict__ logp)
+                                          const unsigned long long* __restrict__ counter_base, int64_t env_offset,
+                                          int64_t* __restrict__ actions, float* __restrict__ logp)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
+    if (counter_base) counter += *counter_base;
     const float* z = logits + (int64_t)e * A;
     float mx = -CUDART_INF_F;
     for (int j = 0; j < A; ++j) mx = fmaxf(mx, z[j]);
@@ -47,11 +49,12 @@ __global__ void sample_categorical_kernel(const float* __restrict__ logits, int 
 }
 
 __global__ void sample_gaussian_kernel(const float* __restrict__ mean, const float* __restrict__ log_std, int N, int A,
-                                       uint64_t seed, uint64_t counter, int64_t env_offset, float* __restrict__ actions,
-                                       float* __restrict__ logp)
+                                       uint64_t seed, uint64_t counter, const unsigned long long* __restrict__ counter_base,
+                                       int64_t env_offset, float* __restrict__ actions, float* __restrict__ logp)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
+    if (counter_base) counter += *counter_base;
     const uint64_t env = (uint64_t)(env_offset + e);
     float lp = 0.f;
     for (int j0 = 0; j0 < A; j0 += 2) {
@@ -143,7 +146,7 @@ extern "C" int dppo_sample_categorical(dppo_ctx* ctx, const float* logits, int N
 {
     if (!ctx) return 1;
     if (N <= 0 || A <= 0) DPPO_FAIL(ctx, "sample_categorical: bad shape N=%d A=%d", N, A);
-    sample_categorical_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, N, A, seed, counter, env_offset, actions, log_probs);
+    sample_categorical_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, N, A, seed, counter, ctx->draw_base, env_offset, actions, log_probs);
     DPPO_CHECK_LAUNCH(ctx, "sample_categorical_kernel");
     return 0;
 }
@@ -153,7 +156,14 @@ extern "C" int dppo_sample_gaussian(dppo_ctx* ctx, const float* mean, const floa
 {
     if (!ctx) return 1;
     if (N <= 0 || A <= 0) DPPO_FAIL(ctx, "sample_gaussian: bad shape N=%d A=%d", N, A);
-    sample_gaussian_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, log_std, N, A, seed, counter, env_offset, actions, log_probs);
+    sample_gaussian_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, log_std, N, A, seed, counter, ctx->draw_base, env_offset, actions, log_probs);
     DPPO_CHECK_LAUNCH(ctx, "sample_gaussian_kernel");
+    return 0;
+}
+
+extern "C" int dppo_set_draw_counter_base(dppo_ctx* ctx, const unsigned long long* counter_base_dev)
+{
+    if (!ctx) return 1;
+    ctx->draw_base = counter_base_dev;
     return 0;
 }

@@ -64,7 +64,7 @@ EXPORTS = [
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
     "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy",
     "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
-    "dppo_env_reset", "dppo_env_step",
+    "dppo_env_reset", "dppo_env_step", "dppo_set_draw_counter_base",
     "dppo_rnn_layout_compute", "dppo_rnn_workspace_bytes", "dppo_rnn_forward", "dppo_rnn_grad_minibatch",
 ]
 
@@ -255,6 +255,10 @@ class Context:
                                                   _ptr(actions), _ptr(log_probs), _stream()), "dppo_sample_gaussian")
         self.launches += 1
         return actions
+
+    def set_draw_counter_base(self, counter_base):
+        """counter_base: device int64/uint64 tensor [1] (None clears); added to every sampling draw counter at run time."""
+        self._check(self.lib.dppo_set_draw_counter_base(self.h, _ptr(counter_base)), "dppo_set_draw_counter_base")
 
     # ---- MLP -------------------------------------------------------------------------------
     def mlp_workspace_bytes(self, desc, rows, training):

@@ -427,7 +427,7 @@ class FusedMlpEngine(_EngineBase):
         return st["h_act"].numpy().copy()
 
     def sample_actions_device(self, d_obs: torch.Tensor, values_out: torch.Tensor | None = None,
-                              logp_out: torch.Tensor | None = None) -> torch.Tensor:
+                              logp_out: torch.Tensor | None = None, counter: int | None = None) -> torch.Tensor:
         """get_actions for observations that already live on the device (DeviceVectorEnv): forward + sampling kernels only,
         no host round trip and no synchronisation.  Returns int64 [N] / f32 [N, A] on the device.  values_out / logp_out
         (f32 [N]) additionally receive V(obs) and log_prob(action) of the sampling policy."""
@@ -440,13 +440,15 @@ class FusedMlpEngine(_EngineBase):
             self._act_stage[("dev", n)] = st
         self.ctx.mlp_forward(self.fm.desc, self.P, d_obs, n, 1 if values_out is None else 3, st["head"], values_out, self.fwd_ws)
         env_offset = self.dist.rank * n
+        draw = self.draws if counter is None else counter      # counter: relative draw index of a captured rollout (see _PPOBase.rollout)
         if self.continuous:
             lay = self.fm.layout
-            self.ctx.sample_gaussian(st["head"], self.P[lay.log_std:lay.log_std + self.A], self.seed, self.draws, env_offset, st["d_act"],
+            self.ctx.sample_gaussian(st["head"], self.P[lay.log_std:lay.log_std + self.A], self.seed, draw, env_offset, st["d_act"],
                                      logp_out)
         else:
-            self.ctx.sample_categorical(st["head"], self.seed, self.draws, env_offset, st["d_act"], logp_out)
-        self.draws += 1
+            self.ctx.sample_categorical(st["head"], self.seed, draw, env_offset, st["d_act"], logp_out)
+        if counter is None:
+            self.draws += 1
         return st["d_act"]
 
     def policy_stamp(self):
@@ -830,6 +832,7 @@ class _PPOBase:
         self.ticker = Ticker(cfg.total_steps, cfg.num_envs, cfg.rollout_steps, verbose=cfg.verbose)
         self.cfg = cfg
         self._buffer = None
+        self._rollout_graph, self._rollout_seen = None, None
 
     # ---- rollout (ppo.py:153-186) -------------------------------------------------------------------
     def rollout(self) -> RolloutBuffer:
@@ -848,8 +851,36 @@ class _PPOBase:
                 buf.logp = torch.empty(buf.T, buf.N, dtype=torch.float32, device=self.device)
             buf.policy_stamp = None
             stamp = self.engine.policy_stamp()
-            for step_idx in range(cfg.rollout_steps):
-                envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs, buf.values[step_idx], buf.logp[step_idx]))
+            # From the third rollout into the same buffers the T x (forward, head, sampling, environment) launches are replayed
+            # as ONE CUDA graph; the draw counters baked into it are relative, their base lives on the device.
+            gkey = (buf.obs.data_ptr(), buf.values.data_ptr(), envs.cur_obs.data_ptr(), self.engine.P.data_ptr(), cfg.rollout_steps)
+            rg = self._rollout_graph
+            if rg is not None and rg["key"] == gkey:
+                rg["base"].fill_(self.engine.draws)
+                rg["graph"].replay()
+                self.engine.draws += cfg.rollout_steps
+                self.ctx.count_launches(rg["launches"])
+            elif self.engine.use_graphs and self._rollout_seen == gkey:
+                base = torch.zeros(1, dtype=torch.int64, device=self.device)
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                l0 = self.ctx.launches
+                self.ctx.set_draw_counter_base(base)
+                try:
+                    with torch.cuda.graph(graph):
+                        for step_idx in range(cfg.rollout_steps):
+                            envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs, buf.values[step_idx],
+                                                                                            buf.logp[step_idx], counter=step_idx))
+                finally:
+                    self.ctx.set_draw_counter_base(None)
+                self._rollout_graph = rg = dict(key=gkey, graph=graph, base=base, launches=self.ctx.launches - l0)
+                base.fill_(self.engine.draws)
+                graph.replay()
+                self.engine.draws += cfg.rollout_steps
+            else:
+                self._rollout_seen = gkey
+                for step_idx in range(cfg.rollout_steps):
+                    envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs, buf.values[step_idx], buf.logp[step_idx]))
             if self.engine.policy_stamp() == stamp:
                 buf.policy_stamp = stamp                               # V(obs), log_prob(action) of exactly these parameters
             if self.ticker is not None:                                # episode statistics: one read-back per rollout

@@ -119,6 +119,10 @@ int dppo_sample_categorical(dppo_ctx* ctx, const float* logits, int N, int A, ui
 int dppo_sample_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, int N, int A, uint64_t seed,
                          uint64_t counter, int64_t env_offset, float* actions, float* log_probs, void* stream);
 
+/* counter_base_dev (device uint64, NULL to clear): while set, every dppo_sample_* launch adds *counter_base_dev to its draw
+ * counter at run time -- a captured rollout (counters 0..T-1 baked into the CUDA graph) then draws fresh numbers on every replay. */
+int dppo_set_draw_counter_base(dppo_ctx* ctx, const unsigned long long* counter_base_dev);
+
 /* ---- GAE (diamond/ppo.py:188-222) + returns/normalisation (ppo.py:241-243) -------------- */
 /* advantages[t,e], returns[t,e] = values + advantages (returns may be NULL).  If stats != NULL,
  * adds sum(A) and sum(A^2) (fp64) to stats[0..1] (caller zeroes them; under env-sharded data

@@ -10,7 +10,8 @@ def run(name, env_fn, N, T, H, reps=3):
     agent = PPO(env_fn, cfg)
     agent.ticker = None
     agent.current_observations, _ = agent.envs.reset(seed=1)
-    agent.rollout(); torch.cuda.synchronize()
+    for _ in range(4): agent.rollout()          # eager, eager, capture, replay
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps): agent.rollout()
     torch.cuda.synchronize()

@@ -156,3 +156,38 @@ def test_learn_reuses_rollout_values_and_matches_full_prepass(env_id):
     with torch.no_grad():
         next(agent.network.parameters()).mul_(1.01)
     assert buf.policy_stamp != agent.engine.policy_stamp()
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1", "Synthetic"])
+def test_rollout_graph_replay_is_bit_identical_to_eager(env_id):
+    """From the third rollout on, the T x (forward, head, sampling, environment) launches of rollout() are replayed as one CUDA graph
+    whose draw counters are relative to a device-resident base: buffers, recorded values / log-probs, environment state and
+    the parameters after learn() must equal the eagerly launched run bit for bit."""
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig
+    from diamond.envs import DeviceVectorEnv
+    cont = env_id == "Pendulum-v1"
+    Agent, Cfg = (ContinuousPPO, ContinuousPPOConfig) if cont else (PPO, PPOConfig)
+    N_, T, H = (2048, 16, 128) if env_id == "Synthetic" else (64, 32, 64)
+    kw = dict(obs_dim=32, n_actions=4, p_term=0.03, p_trunc=0.02) if env_id == "Synthetic" else {}
+
+    def run(use_graphs):
+        cfg = Cfg(num_envs=N_, rollout_steps=T, network_hidden_dim=H, verbose=False, seed=13, total_steps=T * N_ * 16)
+        agent = Agent(DeviceVectorEnv.factory(env_id, seed=13, **kw), cfg)
+        agent.engine.use_graphs = use_graphs
+        agent.current_observations, _ = agent.envs.reset(seed=13)
+        out = []
+        for it in range(5):
+            buf = agent.rollout()
+            out.append([x.clone() for x in (buf.obs, buf.next_obs, buf.actions, buf.rewards, buf.terminations, buf.truncations,
+                                            buf.values, buf.logp, agent.envs.state, agent.envs.cur_obs)])
+            np.random.seed(it)
+            agent.learn(buf)
+            out[-1].append(torch.cat([q.detach().flatten() for q in agent.network.parameters()]).clone())
+        replayed = agent._rollout_graph is not None
+        return out, replayed, agent.engine.draws
+
+    (a, ra, da), (b, rb, db) = run(True), run(False)
+    assert ra and not rb and da == db == 5 * T
+    for it, (xa, xb) in enumerate(zip(a, b)):
+        for k, (u, v) in enumerate(zip(xa, xb)):
+            assert torch.equal(u, v), (it, k)
