@@ -134,11 +134,21 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
     DPPO_PDL_ENTER();
     // device-resident step constants (CUDA-graph replay of the update loop): [0] = sqrt(1 - beta2^t), [1] = -lr / (1 - beta1^t)
     if (step_consts != nullptr) { bc2_sqrt = __ldg(step_consts); neg_step_size = __ldg(step_consts + 1); }
-    if (threadIdx.x < 32) {
+    // every block needs the global norm: all 256 threads share the nparts fp64 partials (one warp alone spent ~4 us of this
+    // 10 us kernel on 53 dependent-latency loads per lane); fixed order: strided per thread, shuffle tree, then warp 0..7
+    __shared__ double s_norm[8];
+    {
         double s = 0.0;
-        for (int i = threadIdx.x; i < nparts; i += 32) s += norm_partials[i];
+        for (int i = threadIdx.x; i < nparts; i += 256) s += norm_partials[i];
         s = warp_sum_d(s);
+        if ((threadIdx.x & 31) == 0) s_norm[threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += s_norm[w];
             const float total = (float)sqrt(s);
             float coef = max_norm / (total + 1e-6f);
             s_coef = coef > 1.0f ? 1.0f : coef;
