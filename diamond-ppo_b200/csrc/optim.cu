@@ -21,7 +21,12 @@ grad_reduce_kernel(GradSegTable tab, float* __restrict__ grads, int64_t total, c
     const int x = threadIdx.x, y = threadIdx.y;
     const int64_t total4 = (total + 3) / 4;
     double sq = 0.0;                       // this thread's share of the squared gradient norm (y == 0 threads)
-    for (int64_t base = (int64_t)blockIdx.x * RED_X; base < total4; base += (int64_t)gridDim.x * RED_X) {
+    // blocks walk the flat gradient from its END: the segments with the most partials per output (per-CTA head and column-sum
+    // partials: 296 / 148 deep, against ~42 for the weight matrices) sit at the end of the layout and would otherwise start last
+    // (22 -> 15.5 us)
+    const int64_t nchunks = (total4 + RED_X - 1) / RED_X;
+    for (int64_t chunk = nchunks - 1 - (int64_t)blockIdx.x; chunk >= 0; chunk -= (int64_t)gridDim.x) {
+        const int64_t base = chunk * RED_X;
         const int64_t i = (base + x) * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < total) {
