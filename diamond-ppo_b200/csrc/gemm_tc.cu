@@ -146,14 +146,24 @@ __global__ void prep_weights_kernel(const float* __restrict__ W, int rows_w, int
 __global__ void prep_weights_multi_kernel(PrepJobs jobs)
 {
     DPPO_PDL_ENTER();
-    if ((int)blockIdx.y == jobs.n) {
-        // the minibatch observation gather (ppo.py:261 observations[mb]) shares the launch: it is independent of the weights
+    if ((int)blockIdx.y >= jobs.n) {
+        // the minibatch observation gather (ppo.py:261 observations[mb]) shares the launch: it is independent of the weights.
+        // It takes the remaining gridDim.y - jobs.n slices of the grid (index -> row is a dependent pair of DRAM latencies, so the
+        // work is spread over more threads instead of more iterations per thread); two items in flight per thread
         const GatherJob& g = jobs.gather;
         const int64_t total = g.rows * g.row_vec;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t r = i / g.row_vec;
-            const int c = (int)(i - r * g.row_vec);
-            g.dst[i] = __ldg(g.src + (int64_t)__ldg(g.idx + r) * g.row_vec + c);
+        const int64_t nthreads = (int64_t)(gridDim.y - jobs.n) * gridDim.x * blockDim.x;
+        const int64_t t0 = ((int64_t)(blockIdx.y - jobs.n) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        for (int64_t i = t0; i < total; i += 2 * nthreads) {
+            const int64_t i2 = i + nthreads;
+            const int64_t r = i / g.row_vec, r2 = i2 / g.row_vec;
+            const int32_t s1 = __ldg(g.idx + r), s2 = i2 < total ? __ldg(g.idx + r2) : 0;
+            const float4 v1 = __ldg(g.src + (int64_t)s1 * g.row_vec + (int)(i - r * g.row_vec));
+            if (i2 < total) {
+                const float4 v2 = __ldg(g.src + (int64_t)s2 * g.row_vec + (int)(i2 - r2 * g.row_vec));
+                g.dst[i2] = v2;
+            }
+            g.dst[i] = v1;
         }
         return;
     }
@@ -387,7 +397,7 @@ int dppo_tc_prep_weights_multi(dppo_ctx* ctx, PrepJobs jobs, cudaStream_t st)
     int blocks = (int)((most + 255) / 256);
     if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
     if (blocks < 1) blocks = 1;
-    dppo_launch_pdl(ctx, prep_weights_multi_kernel, dim3(blocks, jobs.n + (with_gather ? 1 : 0)), dim3(256), 0, st, jobs);
+    dppo_launch_pdl(ctx, prep_weights_multi_kernel, dim3(blocks, jobs.n + (with_gather ? 4 : 0)), dim3(256), 0, st, jobs);
     DPPO_CHECK_LAUNCH(ctx, "prep_weights_multi_kernel");
     return 0;
 }
