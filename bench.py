@@ -180,8 +180,9 @@ def workload_config(world):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def bench_gae(ctx, hbm_peak, sets=20, launches=200, settled=True):
+def bench_gae(ctx, hbm_peak, sets=20, launches=200, settled=True, n_envs=None):
     f = dict(device="cuda", dtype=torch.float32)
+    N_ENVS = n_envs or globals()["N_ENVS"]
     bufs = []
     for s in range(sets):
         r, v, nv = (torch.randn(T, N_ENVS, **f) for _ in range(3))
@@ -376,6 +377,8 @@ def run_ours(args, rank, world, local_rank):
     fma_peak = bench_fma_peak(ctx)
     gae = bench_gae(ctx, hbm_peak)
     gae_cons = bench_gae(ctx, hbm_peak, settled=False)
+    # a shape where launch latency amortises: 65 536 envs x 128 steps = 235 MB per launch, two buffer sets (470 MB > L2)
+    gae_large = bench_gae(ctx, hbm_peak, sets=2, launches=10, settled=False, n_envs=65536)
     upd_tflops = E * T * N_ENVS * FLOP_PER_SAMPLE_UPDATE / (t_upd * 1e-3) / 1e12
     # fp32-accurate products cost three TF32 tensor passes; TF32 runs at half the bf16 rate (same cycles per instruction
     # at half the K, confirmed by the in-run probe), so the algorithmic peak is bf16 / 2 / 3
@@ -401,7 +404,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline_gae": dict(gae, kernel="gae_pipe_kernel (chunked TMA loads, programmatic dependent launch)",
                              peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=GAE_DRAM_TRAFFIC,
                              without_settled_promise={"us_per_launch": gae_cons["us_per_launch"], "achieved": gae_cons["achieved"],
-                                                      "frac": gae_cons["frac"]}),
+                                                      "frac": gae_cons["frac"]},
+                             large_shape_65536x128={"us_per_launch": gae_large["us_per_launch"], "achieved": gae_large["achieved"],
+                                                    "frac": gae_large["frac"], "bytes_per_launch": gae_large["bytes_per_launch"],
+                                                    "inputs_settled": False}),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_losses.numel() * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
