@@ -96,6 +96,25 @@ def main():
     if rank == 0:
         print(f"dp{world} [graph replay vs eager]: bit-identical -> {'OK' if graph_ok else 'FAIL'}", flush=True)
     same = same and graph_ok
+    # end to end under DP with device-resident environments: every rank owns envs [rank*N, (rank+1)*N) of the global run (reset and
+    # sampling draws keyed by global env id), rollout() on the device with recorded values, learn() with the fused exchange
+    from diamond.envs import DeviceVectorEnv
+    n_loc, t_roll = 64, 64
+    cfg_e = PPOConfig(num_envs=n_loc, rollout_steps=t_roll, verbose=False, seed=5, total_steps=n_loc * t_roll * 6)
+    ag = PPO(DeviceVectorEnv.factory("CartPole-v1", seed=5, env_offset=rank * n_loc), cfg_e, dp=True)
+    ag.train()
+    torch.cuda.synchronize()
+    flat = ag.engine.P.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    st0 = ag.envs.state.clone()
+    gathered = [torch.empty_like(st0) for _ in range(world)]
+    dist.all_gather(gathered, st0)
+    distinct = all(not torch.equal(gathered[0], g_) for g_ in gathered[1:])        # shards simulate different environments
+    env_ok = bool(torch.equal(flat, ref)) and bool(torch.isfinite(flat).all()) and bool(torch.isfinite(ag.last_losses).all()) and distinct
+    if rank == 0:
+        print(f"dp{world} [device envs, train()]: replicas identical, shards distinct, finite -> {'OK' if env_ok else 'FAIL'}", flush=True)
+    same = same and env_ok
     t = torch.tensor([int(ok and same)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
