@@ -66,9 +66,16 @@ extern "C" int dppo_destroy(dppo_ctx* ctx)
 extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
 {
     if (!ctx || !name) return 1;
-    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value < 0 ? 0 : value > 3 ? 3 : value; return 0; }
+    if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value != 0 ? 3 : 0; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
-    if (!strcmp(name, "tc_debug")) { ctx->tc_debug = value; return 0; }
+    if (!strcmp(name, "tc_debug")) {
+#ifdef DPPO_TIMING_SWITCHES
+        ctx->tc_debug = value;
+        return 0;
+#else
+        DPPO_FAIL(ctx, "dppo_set_option: 'tc_debug' needs a library built with -DDPPO_TIMING_SWITCHES (timing experiments only)");
+#endif
+    }
     if (!strcmp(name, "gae_inputs_settled")) { ctx->gae_inputs_settled = value != 0; return 0; }
     DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
@@ -108,15 +115,6 @@ extern "C" int dppo_mlp_layout_compute(const dppo_mlp_desc* d, dppo_mlp_layout* 
 }
 
 namespace {
-
-// persistent tcgen05 GEMM: CTA pairs (level 3) or single CTAs (level 2)
-int tc_gemm_v23(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact, int ldh,
-                float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st)
-{
-    if (ctx->use_tensor_cores >= 3 && dppo_tc3_gemm_supported(M, N, K))
-        return dppo_tc3_gemm(ctx, epi, A, lda, Wimg, bias, Hact, ldh, C, ldc, colsum, M, N, K, st);
-    return dppo_tc2_gemm(ctx, epi, A, lda, Wimg, bias, Hact, ldh, C, ldc, colsum, M, N, K, st);
-}
 
 struct WImages {
     unsigned char *w1f, *w2f, *w3f, *w3b, *w2b;
@@ -179,7 +177,7 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     w.p1 = take((int64_t)mx(w.s1, w.t1) * H * D);
     w.tiles2 = dppo_gemm_row_tiles(M, (int)H);
     w.tiles1 = dppo_gemm_row_tiles(M, (int)H);
-    const int cparts = mx(mx(dppo_tc2_colsum_parts(M), dppo_tc3_colsum_rows(&fake, M, (int)H)), w.tiles2);
+    const int cparts = mx(dppo_tc3_colsum_rows(&fake, M, (int)H), w.tiles2);
     w.c2 = take((int64_t)cparts * H);
     w.c1 = take((int64_t)cparts * H);
     w.head_blocks = head_train_blocks(&fake, M);
@@ -205,7 +203,9 @@ extern "C" int64_t dppo_mlp_workspace_bytes(const dppo_mlp_desc* d, int64_t rows
 {
     if (!d || rows <= 0) return 0;
     const int64_t H = d->hidden;
-    if (!training) return align_up(rows * H * 4, 256) * 2 + align_up(rows * 2 * H * 4, 256) + 1024 + carve_images(d, nullptr).bytes;
+    if (!training)      // h1 | h2 | h3 | gathered observations (idx != NULL) | weight images
+        return align_up(rows * H * 4, 256) * 2 + align_up(rows * 2 * H * 4, 256) + align_up(rows * (int64_t)d->obs_dim * 4, 256) + 1024 +
+               carve_images(d, nullptr).bytes;
     // sized for the B200's 148 SMs or the current device, whichever is larger
     int sms = current_sm_count();
     if (sms < 148) sms = 148;
@@ -234,22 +234,23 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
     WImages img = carve_images(d, aligned);
     char* base = tc_on ? aligned + img_bytes : base0;
     const int64_t avail = tc_on ? ws_bytes - head_room : ws_bytes;
-    // chunk the rows so that h1 | h2 | h3 fit the workspace
-    const int64_t per_row = (int64_t)4 * H * 4;
-    int64_t chunk = (avail - 3 * 256) / per_row;
+    // chunk the rows so that h1 | h2 | h3 (| gathered observations) fit the workspace
+    const int64_t per_row = (int64_t)4 * H * 4 + (idx ? (int64_t)D * 4 : 0);
+    int64_t chunk = (avail - 4 * 256) / per_row;
     if (chunk > rows) chunk = rows;
     if (chunk < 1) DPPO_FAIL(ctx, "mlp_forward: workspace too small (%lld bytes, need >= %lld per row)", (long long)ws_bytes, (long long)per_row);
     float* h1 = (float*)base;
     float* h2 = (float*)(base + align_up(chunk * H * 4, 256));
     float* h3 = (float*)(base + 2 * align_up(chunk * H * 4, 256));
+    float* xg = (float*)(base + 2 * align_up(chunk * H * 4, 256) + align_up(chunk * 2 * H * 4, 256));
     const bool actor = heads & 1, critic = heads & 2;
     const int64_t w3off = actor ? 0 : (int64_t)H * H;
     const int b3off = actor ? 0 : H;
     const int n3 = (actor && critic) ? 2 * H : H;
+    // the tensor-core path is decided once from the first (largest) chunk; a smaller tail chunk takes the FFMA kernels
     const int64_t first = rows < chunk ? rows : chunk;
-    const bool tc1 = tc_on && dppo_tc_supported(first, H, D), tc2 = tc_on && dppo_tc_supported(first, H, H),
-               tc3 = tc_on && dppo_tc_supported(first, n3, H);
-    const bool v2 = ctx->use_tensor_cores >= 2;
+    const bool tc1 = tc_on && dppo_tc3_gemm_supported(first, H, D), tc2 = tc_on && dppo_tc3_gemm_supported(first, H, H),
+               tc3 = tc_on && dppo_tc3_gemm_supported(first, n3, H);
     {
         PrepJobs jobs;
         jobs.n = 0;
@@ -267,21 +268,19 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
         const int64_t n = rows - r0 < chunk ? rows - r0 : chunk;
         const float* x = idx ? obs : obs + r0 * D;
         const int32_t* rowsel = idx ? idx + r0 : nullptr;
-        if (tc1 && v2 && !rowsel && dppo_tc2_gemm_supported(n, H, D)) {
-            if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
-        } else if (tc1 && dppo_tc_supported(n, H, D)) {
-            if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
+        if (tc1 && dppo_tc3_gemm_supported(n, H, D)) {
+            if (rowsel) {       // the TMA-fed GEMM reads contiguous rows: gather this chunk's observations first
+                if (dppo_gather_rows_f32(ctx, obs, rowsel, xg, n, D, stream)) return 1;
+                x = xg;
+            }
+            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
-        if (tc2 && v2 && dppo_tc2_gemm_supported(n, H, H)) {
-            if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
-        } else if (tc2 && dppo_tc_supported(n, H, H)) {
-            if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
+        if (tc2 && dppo_tc3_gemm_supported(n, H, H)) {
+            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
         // first head layers: both (one [2H,H] product) or only the requested half
-        if (tc3 && v2 && dppo_tc2_gemm_supported(n, n3, H)) {
-            if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
-        } else if (tc3 && dppo_tc_supported(n, n3, H)) {
-            if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
+        if (tc3 && dppo_tc3_gemm_supported(n, n3, H)) {
+            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
         const float* ha = actor ? h3 : nullptr;
         const float* hc = critic ? (actor ? h3 + H : h3) : nullptr;
@@ -314,12 +313,9 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     const bool img_fits = (img_base - (char*)ws) + carve_images(d, nullptr).bytes <= ws_bytes;
     const bool tc_on = ctx->use_tensor_cores && img_fits;
     WImages img = carve_images(d, img_base);
-    const bool tc1 = tc_on && dppo_tc_supported(M, H, D), tc2 = tc_on && dppo_tc_supported(M, H, H),
-               tc3 = tc_on && dppo_tc_supported(M, 2 * H, H), tcb3 = tc_on && dppo_tc_supported(M, H, 2 * H), tcb2 = tc2;
-    const bool v2 = ctx->use_tensor_cores >= 2;
-    const bool g1 = tc1 && v2 && dppo_tc2_gemm_supported(M, H, D), g2 = tc2 && v2 && dppo_tc2_gemm_supported(M, H, H),
-               g3 = tc3 && v2 && dppo_tc2_gemm_supported(M, 2 * H, H), gb3 = tcb3 && v2 && dppo_tc2_gemm_supported(M, H, 2 * H), gb2 = g2;
-    const bool wg3 = tc_on && v2 && w.t3 > 0, wg2 = tc_on && v2 && w.t2 > 0, wg1 = tc_on && v2 && w.t1 > 0;
+    const bool g1 = tc_on && dppo_tc3_gemm_supported(M, H, D), g2 = tc_on && dppo_tc3_gemm_supported(M, H, H),
+               g3 = tc_on && dppo_tc3_gemm_supported(M, 2 * H, H), gb3 = tc_on && dppo_tc3_gemm_supported(M, H, 2 * H), gb2 = g2;
+    const bool wg3 = tc_on && w.t3 > 0, wg2 = tc_on && w.t2 > 0, wg1 = tc_on && w.t1 > 0;
     // the TMA-fed kernels read contiguous rows: gather the minibatch observations once (ppo.py:261 observations[mb])
     const float* x1 = obs;
     const int32_t* x1_idx = idx;
@@ -334,11 +330,11 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
             if (on) { jobs.job[jobs.n].W = W; jobs.job[jobs.n].rows_w = rows_w; jobs.job[jobs.n].cols_w = cols_w;
                       jobs.job[jobs.n].transpose = transpose; jobs.job[jobs.n].n_tile = 0; jobs.job[jobs.n].img = im; ++jobs.n; }
         };
-        job(tc1, params + L.w1, H, D, 0, img.w1f);
-        job(tc2, params + L.w2, H, H, 0, img.w2f);
-        job(tc3, params + L.w3, 2 * H, H, 0, img.w3f);
-        job(tcb3, params + L.w3, 2 * H, H, 1, img.w3b);
-        job(tcb2, params + L.w2, H, H, 1, img.w2b);
+        job(g1, params + L.w1, H, D, 0, img.w1f);
+        job(g2, params + L.w2, H, H, 0, img.w2f);
+        job(g3, params + L.w3, 2 * H, H, 0, img.w3f);
+        job(gb3, params + L.w3, 2 * H, H, 1, img.w3b);
+        job(gb2, params + L.w2, H, H, 1, img.w2b);
         if (gather_pending && D % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w.xg) & 15u) == 0) {
             jobs.gather = GatherJob{reinterpret_cast<const float4*>(obs), idx, reinterpret_cast<float4*>(w.xg), M, D / 4};
             gather_pending = false;
@@ -349,19 +345,13 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
 
     // forward (ppo.py:261), activations kept for the backward pass
     if (g1) {
-        if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
-    } else if (tc1) {
-        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
     if (g2) {
-        if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
-    } else if (tc2) {
-        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
     if (g3) {
-        if (tc_gemm_v23(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
-    } else if (tc3) {
-        if (dppo_tc_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
 
     // heads + loss (ppo.py:264-280) + backward into the first head layers
@@ -382,18 +372,12 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused
     int tiles2 = w.tiles2, tiles1 = w.tiles1;
     if (gb3) {
-        tiles2 = (ctx->use_tensor_cores >= 3 && dppo_tc3_gemm_supported(M, H, 2 * H)) ? dppo_tc3_colsum_parts(ctx, M, H) : dppo_tc2_colsum_parts(M);
-        if (tc_gemm_v23(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
-    } else if (tcb3) {
-        tiles2 = (int)((M + 127) / 128);
-        if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, nullptr, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+        tiles2 = dppo_tc3_colsum_parts(ctx, M, H);
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     if (gb2) {
-        tiles1 = (ctx->use_tensor_cores >= 3 && dppo_tc3_gemm_supported(M, H, H)) ? dppo_tc3_colsum_parts(ctx, M, H) : dppo_tc2_colsum_parts(M);
-        if (tc_gemm_v23(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
-    } else if (tcb2) {
-        tiles1 = (int)((M + 127) / 128);
-        if (dppo_tc_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, nullptr, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+        tiles1 = dppo_tc3_colsum_parts(ctx, M, H);
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     // weight gradients: deterministic split-K partials
     const int n3p = wg3 ? w.t3 : w.s3, n2p = wg2 ? w.t2 : w.s2, n1p = wg1 ? w.t1 : w.s1;
@@ -404,7 +388,6 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
         const int ldds[3] = {2 * H, H, H}, ldhs[3] = {H, H, D}, sps[3] = {w.t3, w.t2, w.t1}, n1s[3] = {2 * H, H, H}, n2s[3] = {H, H, D};
         if (dppo_tc2_wgrad_multi(ctx, 3, Ds, ldds, Hs, ldhs, Ps, sps, M, n1s, n2s, st)) return 1;
     } else {
-    // (tensor-core levels < 2 take the FFMA kernels with their own split counts; wg3/wg2/wg1 are all on or all off)
     if (wg3) {
         if (dppo_tc2_wgrad(ctx, w.d3, 2 * H, w.h2, H, w.p3, w.t3, M, 2 * H, H, st)) return 1;
     } else if (dppo_wgrad(ctx, w.d3, 2 * H, w.h2, H, nullptr, w.p3, w.s3, M, 2 * H, H, st)) return 1;
@@ -444,15 +427,14 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
 // ---- tensor-core building blocks exposed for unit tests and A/B measurements ----------------------
 extern "C" int64_t dppo_tc_linear_workspace_bytes(int N, int K) { return dppo_tc_image_bytes(N, K) + 1024; }
 
-extern "C" int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N, int variant)
+extern "C" int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N)
 {
-    if (variant >= 3 && ctx) return dppo_tc3_colsum_rows(ctx, M, N);
-    return variant >= 2 ? dppo_tc2_colsum_parts(M) : (int)((M + 127) / 128);
+    return ctx ? dppo_tc3_colsum_rows(ctx, M, N) : 0;
 }
 
 extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
                                   const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
-                                  int variant, void* stream)
+                                  int prepared, void* stream)
 {
     if (!ctx) return 1;
     if (!A || !W || !C || !ws) DPPO_FAIL(ctx, "tc_linear: null argument");
@@ -462,14 +444,10 @@ extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_
     if ((img - (unsigned char*)ws) + dppo_tc_image_bytes(N, K) > ws_bytes) DPPO_FAIL(ctx, "tc_linear: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int rows_w = transpose ? K : N, cols_w = transpose ? N : K;
-    if ((variant & 0xff) >= 2 ? !dppo_tc2_gemm_supported(M, N, K) : !dppo_tc_supported(M, N, K))
-        DPPO_FAIL(ctx, "tc_linear: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
-    const bool prepared = (variant & 0x100) != 0;       // images already in ws from an earlier call with the same weights
-    variant &= 0xff;
+    if (!dppo_tc3_gemm_supported(M, N, K)) DPPO_FAIL(ctx, "tc_linear: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+    // prepared != 0: the images an earlier call with the same weights left in ws are re-used (kernel-only timing)
     if (!prepared && dppo_tc_prep_weights(ctx, W, rows_w, cols_w, transpose, img, st)) return 1;
-    if (variant >= 3) return dppo_tc3_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
-    if (variant >= 2) return dppo_tc2_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
-    return dppo_tc_gemm(ctx, epi, A, K, nullptr, img, bias, Hact, N, C, N, colsum, M, N, K, st);
+    return dppo_tc3_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
 }
 
 extern "C" int64_t dppo_tc_wgrad_workspace_bytes(dppo_ctx* ctx, int64_t M, int N1, int N2)

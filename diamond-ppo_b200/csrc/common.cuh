@@ -12,11 +12,11 @@ struct dppo_ctx {
     int sm_count;
     int cc_major, cc_minor;
     char err[512];
-    int use_tensor_cores;                 // 1: 3xTF32 tcgen05 GEMMs where the shape allows (default); 0: FP32 FFMA GEMMs only
+    int use_tensor_cores;                 // != 0: 3xTF32 tcgen05 GEMMs where the shape allows (default); 0: FP32 FFMA GEMMs only
     int gae_variant;                      // 0: auto (pipelined TMA kernel for T >= 128), 1: register-staged kernel, 2: single-barrier TMA kernel
     int gae_inputs_settled;               // 1: caller guarantees the GAE inputs are not written by the kernel just before the GAE launch
     long long launch_count;               // kernels launched through this context (bench.py's gpu_launches)
-    int tc_debug;                         // bit mask of experiment switches of the tc2 kernels (wrong results; timing only)
+    int tc_debug;                         // timing-experiment switches; only honoured by builds with -DDPPO_TIMING_SWITCHES (see DPPO_DBG)
     const unsigned long long* draw_base;  // optional device counter added to every sampling draw counter (CUDA-graph replay of rollouts)
     void* tm_cache;                       // tensor-map cache owned by gae.cu
     void (*tm_cache_free)(void*);
@@ -37,9 +37,18 @@ extern char g_dppo_create_error[512];
         ++(ctx)->launch_count;                                                              \
     } while (0)
 
+// Work-skipping / A-B switches of the tensor-core kernels (skip weight copies, single-pass TF32, no epilogue, ...) give WRONG
+// results and exist for timing experiments only.  They are compiled out of the release library: DPPO_DBG() is a constant
+// false unless the library is built with `make EXTRA=-DDPPO_TIMING_SWITCHES`, and dppo_set_option("tc_debug") then fails.
+#ifdef DPPO_TIMING_SWITCHES
+#define DPPO_DBG(mask, bit) (((mask) & (bit)) != 0)
+#else
+#define DPPO_DBG(mask, bit) false
+#endif
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-// ---- programmatic dependent launch along the kernels of an optimiser step (opt-in: tc_debug bit 512) ---------------
+// ---- programmatic dependent launch along the kernels of an optimiser step (opt-in: timing builds, tc_debug bit 512) ---------------
 // MEASURED NEGATIVE on B200 for this chain (graph replay, config S: 605-615 us per optimiser step with the attribute,
 // 580-600 us without), so the attribute is off by default and the instructions below are no-ops; kept for A/B.
 // With the bit set every kernel of the update loop is launched with programmatic stream serialisation and starts with DPPO_PDL_ENTER():
@@ -65,7 +74,7 @@ static inline cudaError_t dppo_launch_pdl(dppo_ctx* ctx, void (*kern)(KArgs...),
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = (ctx->tc_debug & 512) ? 1 : 0;
+    lc.numAttrs = DPPO_DBG(ctx->tc_debug, 512) ? 1 : 0;
     return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
 }
 

@@ -99,7 +99,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     // pull the next tile's activations into L2 while this tile computes
                     if (next_m >= 0 && next_m != m_pair) tma_prefetch_2d(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM);
                     mbar_wait(&empty[s], ph ^ 1);
-                    const bool skip_b = (dbg & 1) && (i != 0 || c >= STAGES);
+                    const bool skip_b = DPPO_DBG(dbg, 1) && (i != 0 || c >= STAGES);
                     mbar_expect_tx(&full[s], (uint32_t)(A_IMG + (skip_b ? 0 : 2 * hb)));
                     unsigned char* st = dyn + s * stage_bytes;
                     tma_load_2d(st, &tmA, c * KC, m0, &full[s]);
@@ -134,7 +134,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
                         const uint32_t ko = ks * 32;                    // 8 tf32 = 32 bytes along K inside the swizzle atom
-                        if (!(dbg & 4)) {
+                        if (!DPPO_DBG(dbg, 4)) {
                             umma_tf32_2cta(d, desc_k_sw64(a_hi + ko), desc_k_sw64(b_lo + ko), idesc, (c | ks) != 0);
                             umma_tf32_2cta(d, desc_k_sw64(a_lo + ko), desc_k_sw64(b_hi + ko), idesc, 1u);
                             umma_tf32_2cta(d, desc_k_sw64(a_hi + ko), desc_k_sw64(b_hi + ko), idesc, 1u);
@@ -162,7 +162,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float4 x[PER];
 #pragma unroll
                 for (int j = 0; j < PER; ++j) x[j] = lds128(hi + j * SPLIT_THREADS * 16);
-                if (dbg & 1024) {                                       // A/B: round-to-nearest hi image stored in place
+                if (DPPO_DBG(dbg, 1024)) {                                       // A/B: round-to-nearest hi image stored in place
 #pragma unroll
                     for (int j = 0; j < PER; ++j) {
                         const float4 l = split_tf32x4(x[j]);
@@ -201,7 +201,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t set = it & 1;
             mbar_wait(&tfull[set], (it >> 1) & 1);
             fence_after();
-            for (int k = 0; k < ((dbg & 8) ? 0 : nblk); ++k) {
+            for (int k = 0; k < (DPPO_DBG(dbg, 8) ? 0 : nblk); ++k) {
                 const int n = n0 + k * 32;
                 uint32_t r[32];
                 tmem_ld32_issue(tmem + set * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + k * 32), r);
@@ -212,7 +212,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        aux[j] = (m < M && !(dbg & 8192)) ? __ldg(reinterpret_cast<const float4*>(Hact + m * (int64_t)ldh + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        aux[j] = (m < M && !DPPO_DBG(dbg, 8192)) ? __ldg(reinterpret_cast<const float4*>(Hact + m * (int64_t)ldh + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 tmem_ld32_wait(r);
                 float v[32];
@@ -221,7 +221,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (EPI == DPPO_EPI_BIAS_TANH) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        if (dbg & 32) {
+                        if (DPPO_DBG(dbg, 32)) {
                             v[4 * j] += aux[j].x; v[4 * j + 1] += aux[j].y; v[4 * j + 2] += aux[j].z; v[4 * j + 3] += aux[j].w;
                         } else {
                             v[4 * j] = tanhf(v[4 * j] + aux[j].x); v[4 * j + 1] = tanhf(v[4 * j + 1] + aux[j].y);
@@ -242,11 +242,11 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     sts128(stg + row_off + ((((uint32_t)j) ^ sw) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0 && !(dbg & 16)) {
+                if (lane == 0 && !DPPO_DBG(dbg, 16)) {
                     tma_store_2d(&tmC, n, m0, stg);                     // rows >= M are clipped by the tensor map
                     bulk_commit();
                 }
-                if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr && !(dbg & 16384)) {
+                if (EPI == DPPO_EPI_TANH_BWD && colsum != nullptr && !DPPO_DBG(dbg, 16384)) {
                     // Bias-gradient partials: one row of column sums per (CTA, lane quadrant), accumulated over all tiles of
                     // this CTA (the row is owned by this warp pair).  With a single column tile every CTA covers all N
                     // columns in its first tile, which then initialises the row; otherwise the launcher zeroes the buffer.
@@ -332,7 +332,7 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     const int grid = tc3_grid(ctx, M, N);
     const int clusters = grid / 2, base_tiles = total / clusters, rem = total - base_tiles * clusters;
     // half-width tail tiles: only when every cluster still starts with a full tile and the halves fit one per cluster
-    const int tail_halves = (!(ctx->tc_debug & 128) && n_tile == 256 && base_tiles >= 1 && rem > 0 && 2 * rem <= clusters) ? 1 : 0;
+    const int tail_halves = (!DPPO_DBG(ctx->tc_debug, 128) && n_tile == 256 && base_tiles >= 1 && rem > 0 && 2 * rem <= clusters) ? 1 : 0;
     if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && N / n_tile > 1 &&
         cudaMemsetAsync(colsum + (size_t)grid * N, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");

@@ -722,7 +722,7 @@ int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuo
     const size_t smem = ((size_t)(A + 1) * H + accf) * sizeof(float);
     if (smem > 200 * 1024) DPPO_FAIL(ctx, "head kernel: (A+1)*H = %d too large for shared memory", (A + 1) * H);
     const bool vec = (H % 128 == 0) && ((reinterpret_cast<uintptr_t>(a.h3) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.d3) & 15u) == 0);
-    if (vec && A <= 4 && H <= 256 && !(ctx->tc_debug & 256)) {        // register-accumulator kernel (wider rows spill)
+    if (vec && A <= 4 && H <= 256 && !DPPO_DBG(ctx->tc_debug, 256)) {        // register-accumulator kernel (wider rows spill)
 #define HTR(KPL, R)                                                                                                              \
     do {                                                                                                                         \
         if (continuous) {                                                                                                        \

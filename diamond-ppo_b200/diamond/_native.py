@@ -364,19 +364,19 @@ class Context:
                     "dppo_ppo_loss_gaussian")
         self.launches += 2
 
-    def tc_linear(self, epi, A, W, transpose, bias=None, Hact=None, colsum=False, variant=3, out=None, ws=None, prepared=False):
+    def tc_linear(self, epi, A, W, transpose, bias=None, Hact=None, colsum=False, out=None, ws=None, prepared=False):
         """C = epi(A op(W)) on the tensor cores (dppo_tc_linear_f32); returns (C, colsum partials or None).
         ws + prepared=True re-uses the weight images an earlier call left in ws (kernel-only timing)."""
         M, K = A.shape
         N = W.shape[1] if transpose else W.shape[0]
         Cm = torch.empty(M, N, device=A.device, dtype=torch.float32) if out is None else out
-        parts = self.lib.dppo_tc_colsum_parts(self.h, C.c_int64(M), C.c_int(N), C.c_int(variant))
+        parts = self.lib.dppo_tc_colsum_parts(self.h, C.c_int64(M), C.c_int(N))
         cs = torch.zeros(parts, N, device=A.device, dtype=torch.float32) if colsum else None
         if ws is None:
             ws = torch.empty(self.lib.dppo_tc_linear_workspace_bytes(C.c_int(N), C.c_int(K)), device=A.device, dtype=torch.uint8)
         self._check(self.lib.dppo_tc_linear_f32(self.h, C.c_int(epi), _ptr(A), C.c_int64(M), C.c_int(K), _ptr(W), C.c_int(N),
                                                 C.c_int(int(transpose)), _ptr(bias), _ptr(Hact), _ptr(Cm), _ptr(cs), _ptr(ws),
-                                                C.c_int64(ws.numel()), C.c_int(variant | (0x100 if prepared else 0)), _stream()),
+                                                C.c_int64(ws.numel()), C.c_int(int(prepared)), _stream()),
                     "dppo_tc_linear_f32")
         self.launches += 2
         return Cm, cs

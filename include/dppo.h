@@ -87,10 +87,8 @@ int dppo_device_info(dppo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor)
 int64_t dppo_launch_count(dppo_ctx* ctx);            /* kernels launched through this context so far */
 int dppo_count_launches(dppo_ctx* ctx, int64_t n);   /* add n: launches replayed from a CUDA graph captured through this context */
 /* Kernel-variant switches used by tests and bench.py for A/B measurements:
- *   "tensor_cores" 3 (default): CTA-pair (cta_group::2) persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where
- *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128), 2: the same with single-CTA
- *                  GEMMs, 1: first-generation tcgen05
- *                  GEMMs (forward/dgrad only), 0: FP32 FFMA GEMMs everywhere
+ *   "tensor_cores" 1 (default): CTA-pair (cta_group::2) persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where
+ *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128); 0: FP32 FFMA GEMMs everywhere
  *   "gae_variant"  0 (default): pipelined TMA-staged GAE kernel (T >= 128; chunked loads, stores overlap them) or the
  *                  single-barrier TMA kernel when the layout allows, 1: register-staged, 2: single-barrier TMA
  *   "gae_inputs_settled" 0 (default) / 1: promise that none of the five GAE input tensors is written by the kernel launched
@@ -285,20 +283,19 @@ int dppo_env_step(dppo_ctx* ctx, const dppo_env_desc* desc, const dppo_env_state
                   float* done_return, void* stream);
 
 /* ---- tensor-core building blocks of the fused update (unit tests, A/B measurements) ---------- */
-/* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate).
+/* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate) on CTA pairs
+ * (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC; persistent, TMA-fed, warp-specialised).
  * transpose 0: W is [N,K] row-major (nn.Linear forward, ppo.py:91-96); 1: W is [K,N] (its backward, ppo.py:283).
  * epi 1: C = tanh(A W^T + bias); epi 2: C = (A W) * (1 - Hact^2) with Hact [M,N], and, if colsum != NULL,
- * partial column sums of C in colsum [dppo_tc_colsum_parts(ctx, M, N, variant), N] (variant 3: the first fifth of the
- * rows are the per-CTA partials, the rest per-quadrant working rows; sum only rows [0, parts/5)) (bias-gradient partials).
- * variant 1: one CTA per tile, all threads share the k loop; 2: persistent warp-specialised kernel (TMA-fed);
- * 3: the same roles over CTA pairs (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC).
- * ws (dppo_tc_linear_workspace_bytes) holds the split weight images; variant | 0x100 re-uses the images an earlier call
+ * partial column sums of C in colsum [dppo_tc_colsum_parts(ctx, M, N), N]: the first fifth of the rows are the per-CTA
+ * partials, the rest per-quadrant working rows; sum only rows [0, parts/5) (bias-gradient partials).
+ * ws (dppo_tc_linear_workspace_bytes) holds the split weight images; prepared != 0 re-uses the images an earlier call
  * with the same W left in ws (kernel-only timing). */
 int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_t M, int K, const float* W, int N, int transpose,
                        const float* bias, const float* Hact, float* C, float* colsum, void* ws, int64_t ws_bytes,
-                       int variant, void* stream);
+                       int prepared, void* stream);
 int64_t dppo_tc_linear_workspace_bytes(int N, int K);
-int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N, int variant);
+int dppo_tc_colsum_parts(dppo_ctx* ctx, int64_t M, int N);
 /* dW[N1,N2] = sum_m D[m,N1] * H[m,N2]  (weight gradient of a Linear layer, ppo.py:283): split over row
  * ranges on tcgen05, partials summed in a fixed order (bit-reproducible). */
 int dppo_tc_wgrad_f32(dppo_ctx* ctx, const float* D, const float* H, int64_t M, int N1, int N2, float* dW, void* ws,

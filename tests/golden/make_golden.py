@@ -163,6 +163,47 @@ def learn_case(name, kind, D, act, H, N, T, E, MB, seed_exp, save_adam=False, ex
     print(name, "losses[0]", out["e1.losses"][0], "n_mb", len(out["e1.losses"]))
 
 
+def seeded_learn_case(name, D, act, H, N, T, E, MB, seed):
+    """Large discrete fixtures (configs Smid / S): inputs and initial parameters are regenerated from
+    `seed` (tests/golden/seeded.py), only the reference's outputs are stored: per-minibatch losses and the 12 updated
+    parameter tensors after one epoch and after E epochs, plus a thin slice of the advantages."""
+    from seeded import seeded_experience, seeded_params, checksum, state_dict_of
+    diamond = import_reference(D, act, False)
+    obs, nobs, actions, rew, term, trunc = seeded_experience(seed, T, N, D, act)
+    init = seeded_params(seed + 1, D, H, act)
+    exp = [[obs[t], nobs[t], actions[t], rew[t], term[t], trunc[t]] for t in range(T)]
+    out = {"meta": np.array([D, act, H, N, T, E, MB, 0], dtype=np.int64), "seed": np.int64(seed),
+           "checksum": np.float64(checksum([obs, nobs, actions, rew, term, trunc] + [init[k] for k in sorted(init)]))}
+    for epochs, tag in ((1, "e1"), (E, f"e{E}")):
+        agent = diamond.PPO(lambda: None, diamond.PPOConfig(num_envs=N, rollout_steps=T, network_hidden_dim=H, num_epochs=epochs,
+                                                            num_minibatches=MB, verbose=False, seed=42))
+        agent.network.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict_of(init).items()})
+        captured = {}
+        orig_adv = agent.calculate_advantage
+
+        def adv_hook(r, te, tr, v, nv):
+            a = orig_adv(r, te, tr, v, nv)
+            captured.update(values=v.numpy()[:, :16].copy(), next_values=nv.numpy()[:, :16].copy(), advantages=a.numpy()[:, :16].copy())
+            return a
+
+        agent.calculate_advantage = adv_hook
+        np.random.seed(123)
+        with LossHooks(False) as lh:
+            agent.learn(exp)
+        out.update({k: v for k, v in sd_np(agent.network.state_dict(), f"{tag}.params.").items() if "actor_out_layer" not in k})
+        out[f"{tag}.losses"] = np.asarray(lh.rows, dtype=np.float64)
+        if tag == "e1":
+            out["gae.values16"], out["gae.next_values16"], out["gae.advantages16"] = (captured[k] for k in ("values", "next_values", "advantages"))
+    np.savez_compressed(os.path.join(HERE, f"learn_{name}.npz"), **out)
+    print(name, "losses[0]", out["e1.losses"][0], "n_mb", len(out["e1.losses"]))
+
+
+def seeded_cases():
+    # the tensor-core path's shapes: minibatches of 4096 rows (Smid) and the named scale configuration itself (S: 65536-row minibatches)
+    seeded_learn_case("Smid", D=64, act=4, H=256, N=256, T=128, E=4, MB=8, seed=101)
+    seeded_learn_case("S", D=64, act=4, H=256, N=4096, T=128, E=4, MB=8, seed=202)
+
+
 def gae_cases():
     diamond = import_reference(4, 2, False)
     out = {}
@@ -293,6 +334,10 @@ def recurrent_extra_cases():
 
 if __name__ == "__main__":
     torch.set_num_threads(1)      # deterministic summation order for the pin
+    if len(sys.argv) > 1 and sys.argv[1] == "seeded":            # round 2: config S / Smid through the reference (minutes of CPU time)
+        sys.path.insert(0, HERE)
+        seeded_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "recurrent_extra":   # added later: leaves the other fixtures untouched
         recurrent_extra_cases()
         sys.exit(0)

@@ -484,19 +484,18 @@ def test_tensor_core_forward_matches_fp32_path_and_oracle(ctx, D, H, A, rows):
     ref_out, ref_v = O.mlp_forward(p, torch.as_tensor(obs), False)
     ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, rows, False) // 4 + 512, device="cuda")
     res = {}
-    for tc in (3, 2, 1, 0):
+    for tc in (1, 0):
         ctx.set_option("tensor_cores", tc)
         out = torch.empty(rows, A, device="cuda"); val = torch.empty(rows, device="cuda")
         ctx.mlp_forward(fm.desc, flat, dev(obs), rows, 3, out, val, ws)
         torch.cuda.synchronize()
         res[tc] = (out.cpu().numpy(), val.cpu().numpy())
-    ctx.set_option("tensor_cores", 3)
-    for tc in (3, 2, 1, 0):
+    ctx.set_option("tensor_cores", 1)
+    for tc in (1, 0):
         assert nerr(res[tc][0], ref_out.numpy()) <= 1e-5, tc
         assert nerr(res[tc][1], ref_v.numpy()) <= 1e-5, tc
-    for tc in (3, 2, 1):
-        assert nerr(res[tc][0], res[0][0]) <= 1e-5
-        assert nerr(res[tc][1], res[0][1]) <= 1e-5
+    assert nerr(res[1][0], res[0][0]) <= 1e-5
+    assert nerr(res[1][1], res[0][1]) <= 1e-5
 
 
 def test_tensor_core_training_step_matches_fp32_path(ctx):
@@ -514,15 +513,15 @@ def test_tensor_core_training_step_matches_fp32_path(ctx):
     hyper, cfg = make_hyper(N, M)
     ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, M, True) // 4 + 512, device="cuda")
     out = {}
-    for tc in (3, 2, 1, 0):
+    for tc in (1, 0):
         ctx.set_option("tensor_cores", tc)
         grads = torch.zeros(fm.total, device="cuda"); losses = torch.zeros(4, device="cuda")
         ctx.mlp_grad_minibatch(fm.desc, flat, grads, obs, act, old_lp, adv, ret, None, idx, M, hyper, losses, ws)
         torch.cuda.synchronize()
         out[tc] = (grads.cpu().numpy(), losses.cpu().numpy())
-    ctx.set_option("tensor_cores", 3)
+    ctx.set_option("tensor_cores", 1)
     gv0 = fm.views(torch.as_tensor(out[0][0]))
-    for tc in (3, 2, 1):
+    for tc in (1,):
         np.testing.assert_allclose(out[tc][1], out[0][1], rtol=1e-5, atol=1e-7)
         gv = fm.views(torch.as_tensor(out[tc][0]))
         for n in O.DISCRETE_PARAM_NAMES:
@@ -533,32 +532,29 @@ def test_tensor_core_training_step_matches_fp32_path(ctx):
 TC_TOL = 3e-5
 
 
-@pytest.mark.parametrize("variant", [3, 2, 1])
 @pytest.mark.parametrize("M,N,K", [(4096, 256, 64), (4096, 256, 256), (4096, 512, 256), (5000, 256, 512), (1024, 128, 64),
                                    (65536, 256, 256)])
-def test_tc_linear_forward_vs_fp64(ctx, variant, M, N, K):
+def test_tc_linear_forward_vs_fp64(ctx, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g)
     W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
     b = torch.randn(N, device="cuda", generator=g)
-    C, _ = ctx.tc_linear(1, A, W, False, bias=b, variant=variant)
+    C, _ = ctx.tc_linear(1, A, W, False, bias=b)
     ref = torch.tanh(A.double() @ W.double().T + b.double())
     assert (C.double() - ref).abs().max().item() <= TC_TOL
 
 
-@pytest.mark.parametrize("variant", [3, 2, 1])
 @pytest.mark.parametrize("M,N,K", [(4096, 256, 512), (4096, 256, 256), (5000, 256, 256), (65536, 256, 512)])
-def test_tc_linear_dgrad_vs_fp64(ctx, variant, M, N, K):
+def test_tc_linear_dgrad_vs_fp64(ctx, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
     A = torch.randn(M, K, device="cuda", generator=g)
     W = torch.randn(K, N, device="cuda", generator=g) / K ** 0.5
     Hact = torch.tanh(torch.randn(M, N, device="cuda", generator=g))
-    C, cs = ctx.tc_linear(2, A, W, True, Hact=Hact, colsum=True, variant=variant)
+    C, cs = ctx.tc_linear(2, A, W, True, Hact=Hact, colsum=True)
     ref = (A.double() @ W.double()) * (1.0 - Hact.double() ** 2)
     assert (C.double() - ref).abs().max().item() <= TC_TOL * max(1.0, ref.abs().max().item())
     col = ref.sum(0)
-    if variant == 3:
-        cs = cs[:cs.shape[0] // 5]                          # per-CTA partial rows; the rest are per-quadrant working rows
+    cs = cs[:cs.shape[0] // 5]                          # per-CTA partial rows; the rest are per-quadrant working rows
     assert (cs.double().sum(0) - col).abs().max().item() <= 3e-5 * max(1.0, col.abs().max().item())
 
 

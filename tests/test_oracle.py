@@ -104,6 +104,33 @@ def test_learn_oracle_one_epoch(name):
             np.testing.assert_allclose(state["exp_avg_sq"][n].numpy(), g[f"e1.exp_avg_sq.{n}"], rtol=1e-4, atol=1e-12)
 
 
+def test_learn_oracle_one_epoch_config_Smid_seeded():
+    """The oracle at the tensor-core path's shapes (H = 256, 4096-row minibatches) against the reference's outputs on the seeded
+    inputs of tests/golden/seeded.py (the same fixture the GPU parity test of config S uses)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from seeded import seeded_experience, seeded_params, checksum
+    g = _load("learn_Smid.npz")
+    D, act, H, N, T, E, MB, _ = (int(x) for x in g["meta"])
+    seed = int(g["seed"])
+    obs, nobs, actions, rew, term, trunc = seeded_experience(seed, T, N, D, act)
+    init = seeded_params(seed + 1, D, H, act)
+    assert checksum([obs, nobs, actions, rew, term, trunc] + [init[k] for k in sorted(init)]) == float(g["checksum"])
+    names = O.DISCRETE_PARAM_NAMES
+    p = {n: torch.as_tensor(init[n]).clone() for n in names}
+    state = O.new_adam_state(p, names)
+    mt = C.MT(123)
+    perms = np.stack([mt.permutation(T * N)])
+    losses, inter = O.learn(p, state, obs, nobs, actions, rew, term, trunc, O.default_cfg(num_epochs=1, num_minibatches=MB), perms)
+    assert np.abs(inter["advantages"][:, :16] - g["gae.advantages16"]).max() / np.abs(g["gae.advantages16"]).max() <= 1e-5
+    got = np.array([[l[k] for k in ("policy", "value", "entropy", "total")] for l in losses])
+    np.testing.assert_allclose(got, g["e1.losses"], rtol=1e-4, atol=5e-6)
+    for n in names:
+        ref = g[f"e1.params.{n}"]
+        err = np.abs(p[n].numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        assert err <= 1e-4, (n, err)
+
+
 @pytest.mark.parametrize("name", ["C", "Pn"])
 def test_learn_oracle_four_epochs(name):
     g, p, state, losses, inter, names = _run_learn(name, "e4")
