@@ -12,7 +12,11 @@
 // Exchange buffer per rank (cudaMalloc'ed here because CUDA IPC handles need a base allocation; everything else in libdppo
 // runs on caller-owned memory): [slot 0 | slot 1 | flags], slot = gradient (n floats) + 4 loss sums, padded.  Steps alternate
 // slots; a slot is re-written two steps later, which the flag protocol orders after every peer's read (a peer signals
-// step s+1 only after its step-s kernel, stream order).  flags[q] = last step rank q has published.
+// exchange s+1 only after its exchange-s kernel, stream order).  flags[q] = last exchange rank q has published.
+// Exchanges are numbered by their own monotonic sequence (1, 2, ...; the caller passes it), NOT by the Adam step: restoring an
+// optimiser checkpoint may move the Adam step backwards, the sequence never does.  The wait is bounded: a peer that does not
+// publish within ~10 s (crashed or desynchronised rank) makes the kernel give up and raise a flag in host-mapped memory that
+// dppo_dp_status() reports, instead of hanging the GPU.
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -25,6 +29,8 @@ struct dppo_dp {
     float* peer[DPPO_MAX_RANKS];        // every rank's buffer as mapped in this process (peer[rank] == local)
     int opened[DPPO_MAX_RANKS];
     cudaIpcMemHandle_t handle;
+    int* status_host;                   // host-mapped: 0 ok, else 1 + rank the kernel timed out waiting for
+    int* status_dev;
 };
 
 namespace {
@@ -43,14 +49,16 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 
 constexpr int DP_THREADS = 256;
+constexpr long long DP_WAIT_CYCLES = 20000000000ll;      // ~10 s at 1.9 GHz
 
 // n4: float4 elements of the gradient; the 4 loss sums follow as one more float4 (excluded from the norm)
 __global__ void __launch_bounds__(DP_THREADS)
 dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long step, const unsigned long long* __restrict__ step_dev,
-                          int64_t n4, float* __restrict__ grads_out, float* __restrict__ losses_out, double* __restrict__ partials)
+                          int64_t n4, float* __restrict__ grads_out, float* __restrict__ losses_out, double* __restrict__ partials,
+                          int* __restrict__ status)
 {
     __shared__ double red[DP_THREADS / 32];
-    if (step_dev != nullptr) step = *step_dev;      // CUDA-graph replay: the step number is device-resident
+    if (step_dev != nullptr) step = *step_dev;      // CUDA-graph replay: the sequence number is device-resident
     // publish: the gradient of this step was written by earlier kernels of this stream, i.e. it is complete
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
@@ -59,7 +67,14 @@ dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long s
     // wait until every rank has published this step (flags live in this rank's own buffer)
     if (threadIdx.x < world) {
         const unsigned long long* f = pp.flags[rank] + threadIdx.x;
-        while (ld_acquire_sys(f) < step) __nanosleep(64);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < step) {
+            __nanosleep(64);
+            if (clock64() - t0 > DP_WAIT_CYCLES) {             // peer never published: report instead of hanging the GPU
+                if (blockIdx.x == 0) *status = 1 + (int)threadIdx.x;
+                break;
+            }
+        }
     }
     __syncthreads();
     double s = 0.0;
@@ -106,10 +121,14 @@ extern "C" int dppo_dp_create(dppo_ctx* ctx, int world, int rank, int64_t n_floa
     dp->slot_floats = align_up(n_floats + 4, 64);
     const size_t bytes = (size_t)(2 * dp->slot_floats) * 4 + DPPO_MAX_RANKS * sizeof(unsigned long long);
     for (int q = 0; q < DPPO_MAX_RANKS; ++q) { dp->peer[q] = nullptr; dp->opened[q] = 0; }
+    dp->status_host = nullptr; dp->status_dev = nullptr;
     cudaError_t e = cudaMalloc((void**)&dp->local, bytes);
     if (e == cudaSuccess) e = cudaMemset(dp->local, 0, bytes);
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&dp->handle, dp->local);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&dp->status_host, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *dp->status_host = 0; e = cudaHostGetDevicePointer((void**)&dp->status_dev, dp->status_host, 0); }
     if (e != cudaSuccess) {
+        if (dp->status_host) cudaFreeHost(dp->status_host);
         if (dp->local) cudaFree(dp->local);
         delete dp;
         DPPO_FAIL(ctx, "dp_create: %s", cudaGetErrorString(e));
@@ -150,25 +169,30 @@ extern "C" int dppo_dp_destroy(dppo_dp* dp)
     for (int q = 0; q < dp->world; ++q)
         if (dp->opened[q]) cudaIpcCloseMemHandle(dp->peer[q]);
     if (dp->local) cudaFree(dp->local);
+    if (dp->status_host) cudaFreeHost(dp->status_host);
     delete dp;
     return 0;
 }
 
-// Device pointer the LOCAL gradient (n floats) and, right after it, the 4 local loss sums of optimiser step `step` must be
+// 0: every exchange so far found its peers; 1 + q: an exchange kernel gave up waiting for rank q (no device synchronisation:
+// the kernels write the flag to host-mapped memory)
+extern "C" int dppo_dp_status(dppo_dp* dp) { return dp && dp->status_host ? *(volatile int*)dp->status_host : -1; }
+
+// Device pointer the LOCAL gradient (n floats) and, right after it, the 4 local loss sums of exchange number `seq` must be
 // written to (pass it as `grads` / `losses` to dppo_mlp_grad_minibatch).
-extern "C" float* dppo_dp_slot(dppo_dp* dp, int64_t step) { return dp ? dp->local + (step & 1) * dp->slot_floats : nullptr; }
+extern "C" float* dppo_dp_slot(dppo_dp* dp, int64_t seq) { return dp ? dp->local + (seq & 1) * dp->slot_floats : nullptr; }
 
 extern "C" int64_t dppo_dp_workspace_bytes(int64_t n) { return (int64_t)dp_blocks(n / 4) * (int64_t)sizeof(double); }
 
 // Fused exchange + optimiser step: grads_out (n floats, local) receives the rank-ordered sum of every rank's slot, losses_out
 // (4 floats, optional) the summed loss sums; then clip_grad_norm_ + Adam run on this replica exactly as dppo_clip_adam_step.
-extern "C" int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, float* params, float* grads_out, float* exp_avg,
+extern "C" int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, int64_t seq, float* params, float* grads_out, float* exp_avg,
                                            float* exp_avg_sq, const dppo_hyper* h, float* losses_out, float* grad_norm_out,
                                            void* ws, int64_t ws_bytes, void* stream)
 {
     if (!ctx) return 1;
     if (!dp || !params || !grads_out || !exp_avg || !exp_avg_sq || !h || !ws) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: null argument");
-    if (h->step < 1) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: step must be >= 1");
+    if (h->step < 1 || seq < 1) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: step and seq must be >= 1");
     for (int q = 0; q < dp->world; ++q)
         if (!dp->peer[q]) DPPO_FAIL(ctx, "dp_allreduce_clip_adam: rank %d is not connected (dppo_dp_connect)", q);
     const int64_t n4 = dp->n / 4;
@@ -178,25 +202,25 @@ extern "C" int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, float* pa
         DPPO_FAIL(ctx, "dp_allreduce_clip_adam: grads_out / losses_out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     PeerPtrs pp;
-    const int64_t slot_off = (h->step & 1) * dp->slot_floats;
+    const int64_t slot_off = (seq & 1) * dp->slot_floats;
     for (int q = 0; q < DPPO_MAX_RANKS; ++q) {
         pp.slot[q] = q < dp->world ? dp->peer[q] + slot_off : nullptr;
         pp.flags[q] = q < dp->world ? reinterpret_cast<unsigned long long*>(dp->peer[q] + 2 * dp->slot_floats) : nullptr;
     }
     double* partials = (double*)ws;
-    // h->step_consts (optional, device): {2 floats for the Adam kernel, then the 64-bit step number of this launch}
+    // h->step_consts (optional, device): {2 floats for the Adam kernel, then the 64-bit exchange sequence number of this launch}
     const unsigned long long* step_dev = h->step_consts ? reinterpret_cast<const unsigned long long*>(h->step_consts + 2) : nullptr;
-    dp_allreduce_sumsq_kernel<<<nb, DP_THREADS, 0, st>>>(pp, dp->world, dp->rank, (unsigned long long)h->step, step_dev, n4, grads_out,
-                                                         losses_out, partials);
+    dp_allreduce_sumsq_kernel<<<nb, DP_THREADS, 0, st>>>(pp, dp->world, dp->rank, (unsigned long long)seq, step_dev, n4, grads_out,
+                                                         losses_out, partials, dp->status_dev);
     DPPO_CHECK_LAUNCH(ctx, "dp_allreduce_sumsq_kernel");
     return launch_clip_adam(ctx, params, grads_out, exp_avg, exp_avg_sq, dp->n, partials, nb, h, grad_norm_out, st);
 }
 
 // A rank that owns no row of a global minibatch contributes zeros
-extern "C" int dppo_dp_zero_slot(dppo_ctx* ctx, dppo_dp* dp, int64_t step, void* stream)
+extern "C" int dppo_dp_zero_slot(dppo_ctx* ctx, dppo_dp* dp, int64_t seq, void* stream)
 {
     if (!ctx || !dp) return 1;
-    if (cudaMemsetAsync(dppo_dp_slot(dp, step), 0, (size_t)dp->slot_floats * 4, (cudaStream_t)stream) != cudaSuccess)
+    if (cudaMemsetAsync(dppo_dp_slot(dp, seq), 0, (size_t)dp->slot_floats * 4, (cudaStream_t)stream) != cudaSuccess)
         DPPO_FAIL(ctx, "dp_zero_slot: cudaMemsetAsync failed");
     return 0;
 }

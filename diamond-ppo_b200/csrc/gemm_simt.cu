@@ -102,7 +102,7 @@ gemm_kernel(const float* __restrict__ A, int lda, const int32_t* __restrict__ a_
         const int64_t m = m0 + row;
         a_ok[v] = (e < A_VECS) && (m < M);
         int64_t src = m;
-        if (a_ok[v] && a_rows) src = a_rows[m];
+        if (a_ok[v] && a_rows) { src = a_rows[m]; if (src < 0) src = 0; }      // padding rows read row 0 (masked in the head kernel)
         a_ptr[v] = A + (a_ok[v] ? src : 0) * (int64_t)lda;
     }
 
@@ -275,7 +275,7 @@ wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, 
             const int64_t m = k0 + krow;
             const bool ok = (e < B_VECS) && m < r1;
             int64_t src = ok ? m : 0;
-            if (ok && b_rows) src = b_rows[m];
+            if (ok && b_rows) { src = b_rows[m]; if (src < 0) src = 0; }
             rb[v] = ld4_guard(B + src * (int64_t)ldb, ok, n2_0 + q * 4, N2, vecB);
         }
     };

@@ -175,11 +175,14 @@ head_train_kernel(HeadTrainArgs a)
     for (int64_t mb = warp_global * R; mb < a.M; mb += warp_stride * R) {
         float ha[R][KPL], hc[R][KPL], old_lp[R], advv[R], ret[R], act_f[R];
         int act_i[R];
+        bool live[R];                                                // false: padding row (idx < 0), contributes nothing
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int64_t m = mb + r;
             const bool ok = m < a.M;
-            const int64_t src = ok ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
+            const int64_t sidx = ok ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
+            live[r] = ok && sidx >= 0;
+            const int64_t src = live[r] ? sidx : 0;
             const float* h3 = a.h3 + (ok ? m : 0) * (int64_t)(2 * H);
             if (VEC == 4) {
 #pragma unroll
@@ -250,7 +253,7 @@ head_train_kernel(HeadTrainArgs a)
             const Dist<CONT> d = eval_dist<CONT>(z, lane, A, act_i[r], act_f[r], log_std);
             const RowTerms t = policy_terms(d.new_lp, old_lp[r], advv[r], a.clip, a.inv_m);
             float dz = 0.f;
-            if (lane < A) {
+            if (lane < A && live[r]) {
                 if (!CONT) {
                     dz = t.dlogp * ((lane == act_i[r] ? 1.0f : 0.0f) - d.p) + (a.beta * a.inv_m) * d.p * (d.lsm + d.entropy);
                 } else {
@@ -259,8 +262,8 @@ head_train_kernel(HeadTrainArgs a)
                 }
             }
             const float verr = v - ret[r];
-            const float dv = a.vw * verr * a.inv_m;
-            l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
+            const float dv = live[r] ? a.vw * verr * a.inv_m : 0.f;
+            if (live[r]) { l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy; }
             acc_dba += dz;
             acc_dbc += dv;
 
@@ -411,12 +414,14 @@ head_train_reg_kernel(HeadTrainArgs a)
         float4 ha[R][G], hc[R][G];
         float old_lp[R], advv[R], ret[R], act_f[R];
         int act_i[R];
-        bool ok[R];
+        bool ok[R], live[R];                        // ok: row exists; live: and is not a padding row (idx < 0 contributes nothing)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int64_t m = mb + r;
             ok[r] = m < a.M;
-            const int64_t src = ok[r] ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
+            const int64_t sidx = ok[r] ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
+            live[r] = ok[r] && sidx >= 0;
+            const int64_t src = live[r] ? sidx : 0;
             const float4* h3 = reinterpret_cast<const float4*>(a.h3 + (ok[r] ? m : 0) * (int64_t)(2 * H));
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -484,7 +489,7 @@ head_train_reg_kernel(HeadTrainArgs a)
             }
             const float verr = v[r] - ret[r];
             dv[r] = a.vw * verr * a.inv_m;
-            if (ok[r]) {
+            if (live[r]) {
                 l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
                 acc_dba += dz[r]; acc_dbc += dv[r]; acc_dls += dls;
             } else {

@@ -180,7 +180,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / row_floats;
         const int c = (int)(i - r * row_floats);
-        dst[i] = __ldg(src + (int64_t)idx[r] * row_floats + c);
+        dst[i] = __ldg(src + (int64_t)(idx[r] < 0 ? 0 : idx[r]) * row_floats + c);
     }
 }
 
@@ -192,7 +192,8 @@ __global__ void gather_rows4_kernel(const float4* __restrict__ src, const int32_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / row_vec;
         const int c = (int)(i - r * row_vec);
-        dst[i] = __ldg(src + (int64_t)__ldg(idx + r) * row_vec + c);
+        const int32_t s = __ldg(idx + r);
+        dst[i] = __ldg(src + (int64_t)(s < 0 ? 0 : s) * row_vec + c);
     }
 }
 

@@ -73,7 +73,8 @@ __global__ void prep_weights_multi_kernel(PrepJobs jobs)
         for (int64_t i = t0; i < total; i += 2 * nthreads) {
             const int64_t i2 = i + nthreads;
             const int64_t r = i / g.row_vec, r2 = i2 / g.row_vec;
-            const int32_t s1 = __ldg(g.idx + r), s2 = i2 < total ? __ldg(g.idx + r2) : 0;
+            int32_t s1 = __ldg(g.idx + r), s2 = i2 < total ? __ldg(g.idx + r2) : 0;
+            s1 = s1 < 0 ? 0 : s1; s2 = s2 < 0 ? 0 : s2;            // padding rows (idx < 0) read row 0: finite values, masked in the head kernel
             const float4 v1 = __ldg(g.src + (int64_t)s1 * g.row_vec + (int)(i - r * g.row_vec));
             if (i2 < total) {
                 const float4 v2 = __ldg(g.src + (int64_t)s2 * g.row_vec + (int)(i2 - r2 * g.row_vec));

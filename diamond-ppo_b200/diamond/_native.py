@@ -62,8 +62,8 @@ EXPORTS = [
     "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_clip_adam_step",
     "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
-    "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy",
-    "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
+    "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy", "dppo_dp_status",
+    "dppo_permutation_device", "dppo_perm_shard_filter", "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
     "dppo_env_reset", "dppo_env_step", "dppo_set_draw_counter_base",
     "dppo_rnn_layout_compute", "dppo_rnn_workspace_bytes", "dppo_rnn_forward", "dppo_rnn_grad_minibatch",
 ]
@@ -332,6 +332,20 @@ class Context:
                                                  C.c_int64(ws.numel() * ws.element_size()), _stream()), "dppo_clip_adam_step")
         self.launches += 2
 
+    # ---- device permutation generator / shard filter ------------------------------------------
+    def permutation_device(self, seed, counter, n, out):
+        """out[0..n) (int32, device) = keyed-bijection permutation of [0, n) (dppo_permutation_device)."""
+        self._check(self.lib.dppo_permutation_device(self.h, C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(counter), C.c_int64(n),
+                                                     _ptr(out), _stream()), "dppo_permutation_device")
+        self.launches += 1
+        return out
+
+    def perm_shard_filter(self, perm, B_global, n_global_envs, env_lo, n_local, MB, M_pad, idx_out, counts, overflow):
+        self._check(self.lib.dppo_perm_shard_filter(self.h, _ptr(perm), C.c_int64(B_global), C.c_int(n_global_envs), C.c_int(env_lo),
+                                                    C.c_int(n_local), C.c_int(MB), C.c_int64(M_pad), _ptr(idx_out), _ptr(counts),
+                                                    _ptr(overflow), _stream()), "dppo_perm_shard_filter")
+        self.launches += 1
+
     # ---- standalone pieces for custom networks ------------------------------------------------
     def gather_rows(self, src, idx, out=None):
         rows = idx.numel()
@@ -418,20 +432,25 @@ class Context:
     def dp_connect(self, dp, all_handles: bytes):
         self._check(self.lib.dppo_dp_connect(self.h, dp, C.c_char_p(all_handles)), "dppo_dp_connect")
 
-    def dp_slot(self, dp, step) -> int:
-        return int(self.lib.dppo_dp_slot(dp, C.c_int64(step)))
+    def dp_slot(self, dp, seq) -> int:
+        return int(self.lib.dppo_dp_slot(dp, C.c_int64(seq)))
 
-    def dp_zero_slot(self, dp, step):
-        self._check(self.lib.dppo_dp_zero_slot(self.h, dp, C.c_int64(step), _stream()), "dppo_dp_zero_slot")
+    def dp_zero_slot(self, dp, seq):
+        self._check(self.lib.dppo_dp_zero_slot(self.h, dp, C.c_int64(seq), _stream()), "dppo_dp_zero_slot")
 
     def dp_workspace_bytes(self, n):
         return int(self.lib.dppo_dp_workspace_bytes(C.c_int64(n)))
 
-    def dp_allreduce_clip_adam(self, dp, params, grads_out, exp_avg, exp_avg_sq, hyper, losses_out, ws, grad_norm_out=None):
-        self._check(self.lib.dppo_dp_allreduce_clip_adam(self.h, dp, _ptr(params), _ptr(grads_out), _ptr(exp_avg), _ptr(exp_avg_sq),
+    def dp_status(self, dp) -> int:
+        """0: fine; 1 + q: an exchange kernel gave up waiting for rank q (crashed / desynchronised peer).  No synchronisation."""
+        return int(self.lib.dppo_dp_status(dp))
+
+    def dp_allreduce_clip_adam(self, dp, seq, params, grads_out, exp_avg, exp_avg_sq, hyper, losses_out, ws, grad_norm_out=None):
+        self._check(self.lib.dppo_dp_allreduce_clip_adam(self.h, dp, C.c_int64(seq), _ptr(params), _ptr(grads_out), _ptr(exp_avg), _ptr(exp_avg_sq),
                                                          C.byref(hyper), _ptr(losses_out), _ptr(grad_norm_out), _ptr(ws),
                                                          C.c_int64(ws.numel() * ws.element_size()), _stream()),
                     "dppo_dp_allreduce_clip_adam")
+        self.launches += 2
 
     def dp_destroy(self, dp):
         self.lib.dppo_dp_destroy(dp)

@@ -220,7 +220,7 @@ class _Dist:
     exchange: "fused" (default on CUDA/NCCL groups) -- dppo_dp_allreduce_clip_adam over NVLink peer memory;
     "nccl" -- torch.distributed all_reduce followed by dppo_clip_adam_step."""
 
-    def __init__(self, group=None, enabled=False, permutation="local", exchange="fused"):
+    def __init__(self, group=None, enabled=False, permutation="local", exchange="fused", perm_mode="numpy"):
         import torch.distributed as dist
         self.dist = dist
         self.enabled = bool(enabled or group is not None) and dist.is_available() and dist.is_initialized()
@@ -229,10 +229,27 @@ class _Dist:
         self.rank = dist.get_rank(group) if self.enabled else 0
         if self.world == 1:
             self.enabled = False
-        if permutation not in ("local", "global") or exchange not in ("fused", "nccl"):
-            raise ValueError("dp_permutation must be 'local' or 'global', dp_exchange 'fused' or 'nccl'")
-        self.permutation, self.exchange = permutation, exchange
+        if permutation not in ("local", "global") or exchange not in ("fused", "nccl") or perm_mode not in ("numpy", "device"):
+            raise ValueError("dp_permutation must be 'local' or 'global', dp_exchange 'fused' or 'nccl', "
+                             "minibatch_permutation 'numpy' or 'device'")
+        self.permutation, self.exchange, self.perm_mode = permutation, exchange, perm_mode
         self.global_perm = self.enabled and permutation == "global"
+
+    def sync_numpy_stream(self, device=None):
+        """dp_permutation='global' draws the SAME permutation on every rank from each rank's own numpy global stream: put all
+        ranks on rank 0's MT19937 state (a rank whose np.random was consumed differently would otherwise disagree silently on
+        minibatch membership; learn() additionally carries a state hash through its all-reduce, FusedMlpEngine.check_health)."""
+        if not self.global_perm:
+            return
+        st = np.random.get_state(legacy=True)
+        packed = np.concatenate([np.asarray(st[1], dtype=np.float64), np.array([st[2], st[3], st[4]], dtype=np.float64)])  # exact
+        t = torch.as_tensor(packed)
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.to(device if device is not None else "cuda")
+        src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        self.dist.broadcast(t, src=src, group=self.group)
+        packed = t.cpu().numpy()
+        np.random.set_state(("MT19937", packed[:624].astype(np.uint32), int(packed[624]), int(packed[625]), float(packed[626])))
 
     def all_reduce_sum(self, t: torch.Tensor):
         if self.enabled:
@@ -254,40 +271,25 @@ class _Dist:
 class _PermWorker(threading.Thread):
     """Generates the E minibatch permutations of one learn() (ppo.py:252-255) on a host thread while
     the GPU runs the pre-update pass / previous epoch.  Bit-exact continuation of numpy's global
-    legacy stream (dppo_permutation_mt19937); under data parallelism each global permutation is
-    also filtered down to this rank's env shard and re-indexed to local flat indices."""
+    legacy stream (dppo_permutation_mt19937).  Under data parallelism with the global permutation every rank
+    generates the same permutations; the shard filter runs on the device (dppo_perm_shard_filter)."""
 
-    def __init__(self, B_global, E, MB, outs, shard=None):
+    def __init__(self, B_perm, E, MB, outs):
         super().__init__(daemon=True)
         st = np.random.get_state(legacy=True)
         self.state_tail = (st[3], st[4])
         self.key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
         self.pos = int(st[2])
-        self.B, self.E, self.MB, self.outs, self.shard = B_global, E, MB, outs, shard
+        # 24-bit hash of the stream state (data-parallel lockstep check: h and h^2 are summed over the ranks in fp64, exactly)
+        self.state_hash = float((int(self.key[::7].astype(np.uint64).sum()) * 2654435761 + self.pos * 40503) % (1 << 24))
+        self.B, self.E, self.MB, self.outs = B_perm, E, MB, outs
         self.ready = [threading.Event() for _ in range(E)]
-        self.counts = [None] * E
         self.error = None
-        self.scratch = np.empty(B_global, np.int32) if shard is not None else None
 
     def run(self):
         try:
-            M = self.B // self.MB
             for e in range(self.E):
-                if self.shard is None:
-                    _, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.outs[e])
-                else:
-                    n_global, lo, n_local = self.shard
-                    perm, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.scratch)
-                    t, env = np.divmod(perm, n_global)
-                    mine = (env >= lo) & (env < lo + n_local)
-                    local = (t * n_local + (env - lo)).astype(np.int32)
-                    counts, o = [], 0
-                    for k in range(self.MB):
-                        sel = local[k * M:(k + 1) * M][mine[k * M:(k + 1) * M]]
-                        self.outs[e][o:o + sel.size] = sel
-                        counts.append((o, int(sel.size)))
-                        o += sel.size
-                    self.counts[e] = counts
+                _, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.outs[e])
                 self.ready[e].set()
         except BaseException as ex:      # surfaced by wait()
             self.error = ex
@@ -304,6 +306,21 @@ class _PermWorker(threading.Thread):
         if self.error is not None:
             raise self.error
         np.random.set_state(("MT19937", self.key, self.pos) + self.state_tail)
+
+
+def permutation_plan(B: int, world: int, MB: int, global_perm: bool) -> dict:
+    """Index space of the minibatch permutation and rows per optimiser step of one rank holding B samples.
+    single GPU / DP "local": permutation of this rank's B samples, B/MB rows per step.
+    DP "global": ONE permutation of the concatenated buffer on every rank (the reference's, ppo.py:252-255); a rank's share of
+    a global minibatch is binomial(M_global, 1/G), so every step runs rows = mean + 6 sigma (rounded up to 128), the index list
+    padded with -1: fixed shapes (CUDA-graph replay), padding rows contribute nothing (dppo_perm_shard_filter)."""
+    if global_perm and world > 1:
+        B_global = B * world
+        M_global = B_global // MB
+        want = M_global / world + 6.0 * sqrt(M_global * (1.0 / world) * (1.0 - 1.0 / world)) + 16
+        rows = min(B, M_global, (int(want) + 127) // 128 * 128)
+        return dict(B_perm=B_global, rows=rows, filter=True)
+    return dict(B_perm=B, rows=B // MB, filter=False)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -399,6 +416,11 @@ class FusedMlpEngine(_EngineBase):
         self._seen_key = None
         self._idx_consumed = None       # event after the last async copy out of the pinned per-epoch index buffers
         self.reuse_rollout_values = True   # learn() takes log-probs / values recorded at sampling time when they are still valid
+        self.dp_seq = 0                    # data-parallel exchanges issued so far (monotonic; independent of the Adam step)
+        self.perm_mode = dist.perm_mode    # "numpy": bit-exact np.random stream on a host thread; "device": keyed-bijection generator
+        self.perm_seed = (self.seed * 0x9E3779B97F4A7C15 + (0 if dist.global_perm or not dist.enabled else dist.rank + 1)) % (1 << 64)
+        self.perm_counter = 0
+        self._pending_check = None
 
     # ---- rollout side: fused forward + sampling (ppo.py:73-82) -----------------------------------
     def sample_actions(self, observations: np.ndarray) -> np.ndarray:
@@ -456,39 +478,91 @@ class FusedMlpEngine(_EngineBase):
         return (self.adam_step, self.P._version, self.P.data_ptr(), sum(p._version for _, p, *_ in self.param_list))
 
     # ---- learn (ppo.py:224-287) ---------------------------------------------------------------------
+    def _plan(self, T, N_, MB):
+        return permutation_plan(T * N_, self.dist.world if self.dist.enabled else 1, MB, self.dist.global_perm)
+
     def _alloc(self, T, N_, E, MB):
-        key = (T, N_, E, MB)
+        key = (T, N_, E, MB, self.dist.global_perm)
         if key in self._bufs:
             return self._bufs[key]
         dev, B = self.device, T * N_
-        B_global = B * self.dist.world
-        B_perm = B_global if (self.dist.global_perm or not self.dist.enabled) else B    # indices generated per epoch
+        plan = self._plan(T, N_, MB)
         f = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
         b = dict(head=torch.empty(B, self.A, **f), values=torch.empty(T, N_, **f), next_values=torch.empty(T, N_, **f),
                  old_logp=torch.empty(T, N_, **f), adv=torch.empty(T, N_, **f), ret=torch.empty(T, N_, **f),
-                 stats=torch.zeros(2, dtype=torch.float64, device=dev), losses=torch.zeros(E * MB, 4, **f),
-                 idx=torch.empty(E, B if self.dist.enabled else B_perm, dtype=torch.int32, device=dev),
-                 h_idx=[torch.empty(B if self.dist.enabled else B_perm, dtype=torch.int32).pin_memory() for _ in range(E)])
-        m_max = B_perm // MB
-        if self.dist.global_perm:
-            m_max = min(B, B_global // MB)                          # a rank may own a whole global minibatch in the worst case
-        b["train_ws"] = torch.empty(self.ctx.mlp_workspace_bytes(self.fm.desc, m_max, True) // 4 + 256, **f)
-        b["m_max"] = m_max
+                 stats=torch.zeros(4, dtype=torch.float64, device=dev), losses=torch.zeros(E * MB, 4, **f),
+                 # per-epoch staging, double-buffered by epoch parity: the step indices [MB * rows] and, when they are derived on
+                 # the device (shard filter), the permutation they are derived from
+                 idx=[torch.empty(MB * plan["rows"], **i32) for _ in range(2)],
+                 perm=[torch.empty(plan["B_perm"], **i32) for _ in range(2)] if plan["filter"] else None,
+                 counts=[torch.zeros(MB, **i32) for _ in range(2)], overflow=torch.zeros(1, **i32),
+                 h_idx=[torch.empty(plan["B_perm"], dtype=torch.int32).pin_memory() for _ in range(E)],
+                 copy_stream=torch.cuda.Stream(), copied=[torch.cuda.Event() for _ in range(2)],
+                 done=[torch.cuda.Event() for _ in range(2)], plan=plan)
+        for ev in b["done"]:
+            ev.record()
+        b["train_ws"] = torch.empty(self.ctx.mlp_workspace_bytes(self.fm.desc, plan["rows"], True) // 4 + 256, **f)
+        b["m_max"] = plan["rows"]
         self._bufs[key] = b
         return b
 
-    def _learn_epochs_graphed(self, b, worker, hyper, desc, obs_flat, actions, old_logp, adv, ret, losses, E, MB, M, key):
+    def _stage_epoch(self, b, worker, e, T, N_, MB):
+        """Makes b["idx"][e & 1] hold the MB index lists of epoch e on the current stream: bit-exact numpy stream (host worker ->
+        pinned buffer -> async copy on a side stream) or the device generator; under DP "global" followed by the shard filter."""
+        p = e & 1
+        plan, ctx, dist = b["plan"], self.ctx, self.dist
+        target = b["perm"][p] if plan["filter"] else b["idx"][p]
+        main = torch.cuda.current_stream()
+        if worker is not None:
+            worker.wait(e)
+            cs = b["copy_stream"]
+            cs.wait_event(b["done"][p])                                  # the steps that last read idx[p] / perm[p] have finished
+            with torch.cuda.stream(cs):
+                target.copy_(b["h_idx"][e], non_blocking=True)
+                b["copied"][p].record()
+            self._idx_consumed = b["copied"][p]
+            main.wait_event(b["copied"][p])
+        else:
+            ctx.permutation_device(self.perm_seed, self.perm_counter, plan["B_perm"], target)
+            self.perm_counter += 1
+        if plan["filter"]:
+            ctx.perm_shard_filter(b["perm"][p], plan["B_perm"], N_ * dist.world, dist.rank * N_, N_, MB, plan["rows"], b["idx"][p],
+                                  b["counts"][p], b["overflow"])
+        return b["idx"][p]
+
+    def _step(self, b, hyper, desc, tensors, idx_k, rows, losses_k, seq):
+        """One optimiser step on the current stream: minibatch gradient, [exchange,] clip + Adam."""
+        ctx = self.ctx
+        obs_flat, actions, old_logp, adv, ret = tensors
+        if self.dpx is not None:
+            # env-sharded DP, fused exchange: the local gradient and loss sums go straight into this exchange's slot of the
+            # exchange buffer; one kernel per rank then sums all ranks' slots over NVLink and starts the optimiser step
+            slot = ctx.dp_slot(self.dpx, seq)
+            ctx.mlp_grad_minibatch(desc, self.P, slot, obs_flat, actions, old_logp, adv, ret, b["stats"], idx_k, rows, hyper,
+                                   slot + 4 * self.total, b["train_ws"])
+            ctx.dp_allreduce_clip_adam(self.dpx, seq, self.P, self.G, self.M, self.V, hyper, losses_k, self.adam_ws, self.grad_norm)
+            return
+        ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"], idx_k, rows, hyper, losses_k,
+                               b["train_ws"])
+        if self.dist.enabled:
+            self.dist.all_reduce_sum(self.G)              # env-sharded DP over NCCL: sum of per-shard gradients
+            self.dist.all_reduce_sum(losses_k)
+        ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+
+    def _learn_epochs_graphed(self, b, worker, hyper, desc, tensors, losses, E, MB, T, N_, key):
+        """The MB optimiser steps of an epoch replayed as ONE CUDA graph.  Everything that changes between replays is
+        device-resident: the step indices (b["idx"][parity], refilled per epoch), Adam's two step-dependent constants and, under
+        data parallelism, the exchange sequence number."""
         ctx, dev = self.ctx, self.device
+        rows = b["plan"]["rows"]
         gs = b.get("graph")
         if gs is None or gs["key"] != key:
-            B = M * MB
             gs = dict(key=key, graphs=[], launches=0,
-                      idx=[torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)],
                       consts=[torch.zeros(MB, 4, dtype=torch.float32, device=dev) for _ in range(2)],
                       h_consts=[torch.zeros(MB, 4, dtype=torch.float32).pin_memory() for _ in range(2)],
                       losses=[torch.zeros(MB, 4, dtype=torch.float32, device=dev) for _ in range(2)],
-                      copy_stream=torch.cuda.Stream(), copied=[torch.cuda.Event() for _ in range(2)],
-                      done=[torch.cuda.Event() for _ in range(2)])
+                      consts_copied=[torch.cuda.Event() for _ in range(2)])
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
             for p in range(2):
@@ -496,52 +570,36 @@ class FusedMlpEngine(_EngineBase):
                 l0 = ctx.launches
                 with torch.cuda.graph(g, stream=cap):
                     for k in range(MB):
-                        # only the parity of `step` is baked in (exchange slot); the kernels read consts[p][k]
-                        hyper.step = 2 + ((self.adam_step + k + 1) & 1)
+                        # Adam's constants and the exchange sequence number are read from consts[p][k]; only the PARITY of the
+                        # sequence number is baked in (exchange slot): replays start on an odd sequence number (dp_seq even)
+                        hyper.step = 1
                         hyper.step_consts = gs["consts"][p][k].data_ptr()
-                        if self.dpx is not None:
-                            slot = ctx.dp_slot(self.dpx, hyper.step)
-                            ctx.mlp_grad_minibatch(desc, self.P, slot, obs_flat, actions, old_logp, adv, ret, b["stats"],
-                                                   gs["idx"][p][k * M:(k + 1) * M], M, hyper, slot + 4 * self.total, b["train_ws"])
-                            ctx.dp_allreduce_clip_adam(self.dpx, self.P, self.G, self.M, self.V, hyper, gs["losses"][p][k],
-                                                       self.adam_ws, self.grad_norm)
-                        else:
-                            ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"],
-                                                   gs["idx"][p][k * M:(k + 1) * M], M, hyper, gs["losses"][p][k], b["train_ws"])
-                            ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+                        self._step(b, hyper, desc, tensors, b["idx"][p][k * rows:(k + 1) * rows], rows, gs["losses"][p][k], k + 1)
                 gs["launches"] = ctx.launches - l0
                 gs["graphs"].append(g)
             hyper.step_consts = None
             torch.cuda.current_stream().wait_stream(cap)
-            for p in range(2):
-                gs["done"][p].record()
             b["graph"] = gs
         main = torch.cuda.current_stream()
         b1, b2 = hyper.beta1, hyper.beta2
         for e in range(E):
             p = e & 1
-            worker.wait(e)
-            gs["copied"][p].synchronize()                                # the previous copy out of h_consts[p] has been issued and is done
+            gs["consts_copied"][p].synchronize()                         # the previous copy out of h_consts[p] is done
             hc = gs["h_consts"][p].numpy()
-            hc_step = hc.view(np.uint64)                                 # [MB, 2]: column 1 aliases floats 2..3
+            hc_seq = hc.view(np.uint64)                                  # [MB, 2]: column 1 aliases floats 2..3
             for k in range(MB):
                 step = self.adam_step + k + 1                            # torch/optim/adam.py:531-547, python-float bias corrections
                 hc[k, 0] = np.float32(np.sqrt(1.0 - b2 ** step))
                 hc[k, 1] = np.float32(-(hyper.lr / (1.0 - b1 ** step)))
-                hc_step[k, 1] = step
-            cs = gs["copy_stream"]
-            cs.wait_event(gs["done"][p])                                 # the graph that last read idx[p] / consts[p] has finished
-            with torch.cuda.stream(cs):
-                gs["idx"][p].copy_(b["h_idx"][e], non_blocking=True)
-                gs["consts"][p].copy_(gs["h_consts"][p], non_blocking=True)
-                gs["copied"][p].record()
-                if e == E - 1:
-                    self._idx_consumed = gs["copied"][p]
-            main.wait_event(gs["copied"][p])
+                hc_seq[k, 1] = self.dp_seq + k + 1
+            self._stage_epoch(b, worker, e, T, N_, MB)
+            gs["consts"][p].copy_(gs["h_consts"][p], non_blocking=True)  # stream-ordered after the graph that last read consts[p]
+            gs["consts_copied"][p].record()
             gs["graphs"][p].replay()
             losses[e * MB:(e + 1) * MB].copy_(gs["losses"][p])
-            gs["done"][p].record()
+            b["done"][p].record()
             self.adam_step += MB
+            self.dp_seq += MB
             ctx.count_launches(gs["launches"])
 
     def prepass(self, buf: RolloutBuffer, b):
@@ -589,6 +647,25 @@ class FusedMlpEngine(_EngineBase):
         self.ctx.mlp_forward(self.fm.desc, self.P, buf.next_obs.view(B, self.D), n, 2, None, tmp, self.fwd_ws, idx=idx.to(torch.int32))
         nv.view(B).index_copy_(0, idx, tmp)
 
+    def check_health(self):
+        """Raises if an earlier learn() detected (asynchronously) a data-parallel fault: ranks whose numpy permutation streams
+        disagree, a shard-filter overflow, or an exchange kernel that timed out waiting for a peer.  Called at the start of every
+        learn() and by train() at its end; costs no device synchronisation."""
+        if self.dpx is not None:
+            st = self.ctx.dp_status(self.dpx)
+            if st != 0:
+                raise N.NativeError(f"data-parallel exchange timed out waiting for rank {st - 1} (crashed or desynchronised peer)")
+        chk = self._pending_check
+        if chk is not None and chk["event"].query():
+            self._pending_check = None
+            s1, s2, over = (float(x) for x in chk["host"])
+            if over != 0:
+                raise RuntimeError("dp_permutation='global': a rank's share of a global minibatch exceeded the padded step size "
+                                   "(6-sigma bound); the update of that learn() dropped samples")
+            if abs(s2 * self.dist.world - s1 * s1) > 0.5:
+                raise RuntimeError("dp_permutation='global': the ranks' numpy permutation streams disagree (np.random was consumed "
+                                   "differently per rank); minibatch membership is inconsistent")
+
     def learn(self, buf: RolloutBuffer, events=None):
         cfg, ctx, dist = self.cfg, self.ctx, self.dist
         T, N_ = buf.T, buf.N
@@ -598,16 +675,20 @@ class FusedMlpEngine(_EngineBase):
         if B_global % MB != 0:              # the reference's reshape raises here (ppo.py:255)
             raise ValueError(f"cannot reshape array of size {E * B_global} into shape ({E},{MB},{B_global // MB})")
         M_global = B_global // MB
+        self.check_health()
         self._resync_optimizer()
         b = self._alloc(T, N_, E, MB)
-        shard = (N_ * dist.world, dist.rank * N_, N_) if dist.global_perm else None
-        B_perm = B_global if (dist.global_perm or not dist.enabled) else B
-        if B_perm % MB != 0:
-            raise ValueError(f"cannot reshape array of size {E * B_perm} into shape ({E},{MB},{B_perm // MB})")
-        if self._idx_consumed is not None:
-            self._idx_consumed.synchronize()   # the previous learn()'s async H2D copies out of the pinned index buffers are done
-        worker = _PermWorker(B_perm, E, MB, [h.numpy() for h in b["h_idx"]], shard)
-        worker.start()                      # host permutation overlaps the pre-update pass on the GPU
+        plan = b["plan"]
+        if plan["B_perm"] % MB != 0:
+            raise ValueError(f"cannot reshape array of size {E * plan['B_perm']} into shape ({E},{MB},{plan['B_perm'] // MB})")
+        worker = None
+        lock_hash = 0.0
+        if self.perm_mode == "numpy":
+            if self._idx_consumed is not None:
+                self._idx_consumed.synchronize()   # the previous learn()'s async H2D copies out of the pinned index buffers are done
+            worker = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_idx"]])
+            lock_hash = worker.state_hash
+            worker.start()                      # host permutation overlaps the pre-update pass on the GPU
 
         def mark(name):
             if events is not None:
@@ -621,7 +702,9 @@ class FusedMlpEngine(_EngineBase):
             self.prepass(buf, b)
         mark("prepass_end")
         b["stats"].zero_()
-        # the kernel right before the GAE launch is the 16-byte fill above, not the pre-update pass: inputs are settled
+        if dist.global_perm:                # ranks must hold the same numpy stream: 24-bit state hash h and h^2 ride in the all-reduce
+            b["stats"][2:4].copy_(torch.tensor([lock_hash, lock_hash * lock_hash], dtype=torch.float64), non_blocking=True)
+        # the kernel right before the GAE launch is a 32-byte fill, not the pre-update pass: inputs are settled
         ctx.gae(buf.rewards, buf.terminations, buf.truncations, b["values"], b["next_values"], cfg.gamma, cfg.gae_lambda,
                 advantages=b["adv"], returns=b["ret"], stats=b["stats"], inputs_settled=True)
         dist.all_reduce_sum(b["stats"])     # global mean/std of the advantages (ppo.py:243)
@@ -629,67 +712,41 @@ class FusedMlpEngine(_EngineBase):
 
         hyper = self._hyper(cfg, M_global, B_global)
         desc = self.fm.desc
-        obs_flat = buf.obs.view(B, self.D)
-        actions = buf.actions.view(B, self.A) if self.continuous else buf.actions.view(B)
-        old_logp, adv, ret = b["old_logp"].view(B), b["adv"].view(B), b["ret"].view(B)
+        tensors = (buf.obs.view(B, self.D), buf.actions.view(B, self.A) if self.continuous else buf.actions.view(B),
+                   b["old_logp"].view(B), b["adv"].view(B), b["ret"].view(B))
         losses = b["losses"]
-        # Single-GPU steady state: the MB optimiser steps of an epoch are replayed as one CUDA graph (kernel-to-kernel launch
-        # gaps are 6 % of the step otherwise).  Everything that changes between replays is device-resident: the minibatch
-        # indices (copied per epoch on a side stream, double-buffered) and Adam's two step-dependent constants.  The graph is
-        # keyed on the data pointers it bakes in and only used from the second consecutive learn() on the same buffers.
+        rows = plan["rows"]
+        # Steady state: the MB optimiser steps of an epoch are replayed as one CUDA graph (kernel-to-kernel launch gaps are 6 % of
+        # the step otherwise, far more at data-parallel step sizes).  The graph is keyed on the data pointers it bakes in and
+        # only used from the second consecutive learn() on the same buffers.
         ptr_key = (buf.obs.data_ptr(), buf.actions.data_ptr(), buf.T, buf.N, E, MB, cfg.ppo_clip, cfg.value_loss_weight,
-                   cfg.entropy_beta, cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm))
-        # under DP: rank-local permutations + fused exchange only, and an even MB so that the baked slot parity repeats
-        dp_ok = not dist.enabled or (self.dpx is not None and not dist.global_perm and MB % 2 == 0 and self.adam_step % 2 == 0)
-        use_graph = self.use_graphs and dp_ok and self._seen_key == ptr_key and B % MB == 0
+                   cfg.entropy_beta, cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm), dist.global_perm)
+        # under DP: fused exchange only, and an even MB so that the baked slot parity repeats
+        dp_ok = not dist.enabled or (self.dpx is not None and MB % 2 == 0 and self.dp_seq % 2 == 0)
+        use_graph = self.use_graphs and dp_ok and self._seen_key == ptr_key
         self._seen_key = ptr_key
         if not dist.enabled:
             hyper.grad_sumsq = self.grad_sumsq.data_ptr()    # gradient assembly leaves the norm partials for the Adam kernel
         if use_graph:
-            self._learn_epochs_graphed(b, worker, hyper, desc, obs_flat, actions, old_logp, adv, ret, losses, E, MB, B // MB, ptr_key)
-            mark("update_end")
-            worker.finish()
-            self._publish_steps()
-            self.last_losses = losses
-            return
-        for e in range(E):
-            worker.wait(e)
-            b["idx"][e].copy_(b["h_idx"][e], non_blocking=True)
-            if e == E - 1:
-                self._idx_consumed = torch.cuda.Event()
-                self._idx_consumed.record()
-            for k in range(MB):
-                if dist.global_perm:
-                    off, m = worker.counts[e][k]
-                else:
-                    m = B_perm // MB
-                    off = k * m
-                self.adam_step += 1
-                hyper.step = self.adam_step
-                if self.dpx is not None:
-                    # env-sharded DP, fused exchange: the local gradient and loss sums go straight into this step's slot of
-                    # the exchange buffer; one kernel per rank then sums all ranks' slots over NVLink and starts the optimiser step
-                    slot = ctx.dp_slot(self.dpx, self.adam_step)
-                    if m > 0:
-                        ctx.mlp_grad_minibatch(desc, self.P, slot, obs_flat, actions, old_logp, adv, ret, b["stats"],
-                                               b["idx"][e][off:off + m], m, hyper, slot + 4 * self.total, b["train_ws"])
-                    else:
-                        ctx.dp_zero_slot(self.dpx, self.adam_step)
-                    ctx.dp_allreduce_clip_adam(self.dpx, self.P, self.G, self.M, self.V, hyper, losses[e * MB + k], self.adam_ws,
-                                               self.grad_norm)
-                    continue
-                if m > 0:
-                    ctx.mlp_grad_minibatch(desc, self.P, self.G, obs_flat, actions, old_logp, adv, ret, b["stats"],
-                                           b["idx"][e][off:off + m], m, hyper, losses[e * MB + k], b["train_ws"])
-                else:
-                    self.G.zero_()
-                    losses[e * MB + k].zero_()
-                if dist.enabled:
-                    dist.all_reduce_sum(self.G)              # env-sharded DP: sum of per-shard gradients
-                    dist.all_reduce_sum(losses[e * MB + k])
-                ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+            self._learn_epochs_graphed(b, worker, hyper, desc, tensors, losses, E, MB, T, N_, ptr_key)
+        else:
+            for e in range(E):
+                idx = self._stage_epoch(b, worker, e, T, N_, MB)
+                for k in range(MB):
+                    self.adam_step += 1
+                    self.dp_seq += 1
+                    hyper.step = self.adam_step
+                    self._step(b, hyper, desc, tensors, idx[k * rows:(k + 1) * rows], rows, losses[e * MB + k], self.dp_seq)
+                b["done"][e & 1].record()
         mark("update_end")
-        worker.finish()
+        if dist.global_perm:                 # verified lazily by check_health(): no synchronisation here
+            host = torch.empty(3, dtype=torch.float64).pin_memory()
+            host.copy_(torch.cat([b["stats"][2:4], b["overflow"].double()]), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending_check = dict(host=host, event=ev)
+        if worker is not None:
+            worker.finish()
         self._publish_steps()
         self.last_losses = losses
 
@@ -793,13 +850,16 @@ class _PPOBase:
     _continuous = False
     _default_network: Any = None
 
-    def _setup(self, env_fn, cfg, network_cls, process_group=None, dp=False, dp_permutation="local", dp_exchange="fused"):
+    def _setup(self, env_fn, cfg, network_cls, process_group=None, dp=False, dp_permutation="local", dp_exchange="fused",
+               minibatch_permutation="numpy"):
         self.device = _require_cuda()
         self.ctx = N.get_context(self.device.index)
         if cfg.seed is not None:
             np.random.seed(cfg.seed)                                   # ppo.py:120-122
             torch.manual_seed(cfg.seed)
-        self._dist = _Dist(process_group, dp, dp_permutation, dp_exchange)
+        self._dist = _Dist(process_group, dp, dp_permutation, dp_exchange, minibatch_permutation)
+        if self._dist.perm_mode == "numpy":
+            self._dist.sync_numpy_stream(self.device)
 
         if getattr(env_fn, "vectorized", False):                       # additive: env_fn(num_envs) -> batched vector env
             self.envs = env_fn(cfg.num_envs)
@@ -952,8 +1012,9 @@ class PPO(_PPOBase):
     _default_network = ActorCriticNetwork
 
     def __init__(self, env_fn: Callable[[], Any], cfg: PPOConfig = PPOConfig(), network_cls: Any = ActorCriticNetwork,
-                 *, process_group=None, dp: bool = False, dp_permutation: str = "local", dp_exchange: str = "fused") -> None:
-        self._setup(env_fn, cfg, network_cls, process_group, dp, dp_permutation, dp_exchange)
+                 *, process_group=None, dp: bool = False, dp_permutation: str = "local", dp_exchange: str = "fused",
+                 minibatch_permutation: str = "numpy") -> None:
+        self._setup(env_fn, cfg, network_cls, process_group, dp, dp_permutation, dp_exchange, minibatch_permutation)
         self.current_step = 0
 
 
@@ -964,5 +1025,5 @@ class ContinuousPPO(_PPOBase):
 
     def __init__(self, env_fn: Callable[[], Any], cfg: ContinuousPPOConfig = ContinuousPPOConfig(),
                  network_cls: Any = ContinuousActorCriticNetwork, *, process_group=None, dp: bool = False,
-                 dp_permutation: str = "local", dp_exchange: str = "fused") -> None:
-        self._setup(env_fn, cfg, network_cls, process_group, dp, dp_permutation, dp_exchange)
+                 dp_permutation: str = "local", dp_exchange: str = "fused", minibatch_permutation: str = "numpy") -> None:
+        self._setup(env_fn, cfg, network_cls, process_group, dp, dp_permutation, dp_exchange, minibatch_permutation)

@@ -68,11 +68,10 @@ typedef struct dppo_hyper {
     int32_t pad1;
     int64_t adv_count;        /* number of samples behind adv_stats (global batch T*N) */
     int64_t loss_denominator; /* rows the loss means divide by (global minibatch size) */
-    const float* step_consts; /* optional DEVICE pointer to 16 bytes {f32 sqrt(1 - beta2^step), f32 -lr / (1 - beta1^step), u64 step}:
+    const float* step_consts; /* optional DEVICE pointer to 16 bytes {f32 sqrt(1 - beta2^step), f32 -lr / (1 - beta1^step), u64 seq}:
                                  when set, the Adam kernel reads its two step-dependent constants (and the data-parallel exchange
-                                 kernel the step number it publishes / waits for) from device memory instead of from lr / step,
-                                 so a captured CUDA graph of an optimiser step can be replayed.  `step` must still carry the
-                                 parity (step & 1) of the launch: it selects the exchange slot */
+                                 kernel the sequence number it publishes / waits for) from device memory instead of from lr / step,
+                                 so a captured CUDA graph of an optimiser step can be replayed */
     double* grad_sumsq;       /* optional DEVICE buffer of dppo_grad_sumsq_bytes(): dppo_mlp_grad_minibatch leaves the fp64 partial
                                  sums of squares of the gradient it assembled there and dppo_clip_adam_step reads them instead of
                                  launching its own norm kernel (single-GPU path; under DP the norm is taken after the exchange) */
@@ -138,7 +137,20 @@ int dppo_adv_normalize_f32(dppo_ctx* ctx, const float* adv, float* out, const do
  * out: int32 [n].  Meant to run on a worker thread while the GPU processes the previous epoch. */
 int dppo_permutation_mt19937(uint32_t* key, int32_t* pos, int64_t n, int32_t* out);
 int dppo_mt19937_seed(uint32_t* key, int32_t* pos, uint32_t seed);      /* np.random.seed(int) */
-/* dst[i, :] = src[idx[i], :]  (row_floats floats per row); the fused update gathers on the fly,
+/* FAST (non-parity) generator, SURVEY.md 2.2 K4a: out[0..n) = a pseudo-random permutation of [0, n) that is a pure function of
+ * (seed, counter) -- a keyed Feistel bijection over the next power of two with cycle walking, evaluated per element on the
+ * device (no sort, no host work; every data-parallel rank computes the same permutation without communication).  It replaces
+ * the reference's np.random.permutation draw (ppo.py:254) when the caller opts out of the bit-exact numpy stream. */
+int dppo_permutation_device(dppo_ctx* ctx, uint64_t seed, uint64_t counter, int64_t n, int32_t* out, void* stream);
+/* Env-sharded data parallelism: perm is ONE global permutation of the concatenated buffer (flat index
+ * t*n_global_envs + env, B_global entries, identical on every rank), cut into num_minibatches consecutive global minibatches
+ * (ppo.py:255).  For every minibatch k the members whose env lies in [env_lo, env_lo + n_local) are kept in permutation order,
+ * re-indexed to the rank-local buffer (t*n_local + env - env_lo) and written to idx_out[k*M_pad ..], padded with -1 up to M_pad
+ * (rows with a negative index contribute nothing to dppo_mlp_grad_minibatch); counts[k] = members kept; *overflow |= 1 if a
+ * minibatch had more than M_pad members (the surplus is dropped: the caller must treat that as an error). */
+int dppo_perm_shard_filter(dppo_ctx* ctx, const int32_t* perm, int64_t B_global, int n_global_envs, int env_lo, int n_local,
+                           int num_minibatches, int64_t M_pad, int32_t* idx_out, int32_t* counts, int32_t* overflow, void* stream);
+/* dst[i, :] = src[idx[i], :]  (row_floats floats per row; a negative index reads row 0); the fused update gathers on the fly,
  * this standalone form serves the custom-network path. */
 int dppo_gather_rows_f32(dppo_ctx* ctx, const float* src, const int32_t* idx, float* dst, int64_t rows,
                          int row_floats, void* stream);
@@ -161,6 +173,7 @@ int dppo_logprob_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std
 /* One minibatch of ppo.py:258-283: gather rows idx[0..M) of the flat rollout tensors, forward,
  * clipped-surrogate + value + entropy loss, full backward.  Writes the flat gradient (layout of
  * dppo_mlp_layout) to grads and (policy, value, entropy, total) to losses[0..3].
+ * idx[i] < 0 marks a padding row: it enters no loss term and no gradient (fixed-shape steps under data parallelism).
  * actions: int32 [B] (discrete) or f32 [B, A] (continuous).  adv is the UN-normalised advantage
  * when hyper->advantage_norm is set (normalised on the fly from adv_stats), else used as is. */
 int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* desc, const float* params, float* grads,
@@ -182,7 +195,9 @@ int64_t dppo_grad_sumsq_bytes(dppo_ctx* ctx, int64_t n);
  * replicas obtain the bit-identical gradient) together with the partial sums of the global gradient norm, followed by the
  * clip + Adam kernel of dppo_clip_adam_step.  Set-up: dppo_dp_create (allocates the exchange buffer -- the one device
  * allocation libdppo makes, CUDA IPC needs a base allocation), all-gather the dppo_dp_handle bytes of every rank
- * (torch.distributed), dppo_dp_connect.  All ranks must call dppo_dp_allreduce_clip_adam with the same step sequence. */
+ * (torch.distributed), dppo_dp_connect.  Exchanges are numbered by their own monotonic sequence `seq` = 1, 2, 3, ... (never
+ * the Adam step, which a restored checkpoint may move backwards); all ranks must call dppo_dp_allreduce_clip_adam with the
+ * same sequence.  A kernel that waits ~10 s for a peer in vain gives up and raises the flag dppo_dp_status() reports. */
 #define DPPO_MAX_RANKS 16
 typedef struct dppo_dp dppo_dp;
 int dppo_dp_create(dppo_ctx* ctx, int world, int rank, int64_t n_floats, dppo_dp** out);
@@ -190,10 +205,13 @@ int dppo_dp_handle_bytes(void);
 int dppo_dp_handle(dppo_dp* dp, void* handle_out);
 int dppo_dp_connect(dppo_ctx* ctx, dppo_dp* dp, const void* all_handles);
 int dppo_dp_destroy(dppo_dp* dp);
-float* dppo_dp_slot(dppo_dp* dp, int64_t step);      /* [n_floats gradient | 4 loss sums] of optimiser step `step` */
-int dppo_dp_zero_slot(dppo_ctx* ctx, dppo_dp* dp, int64_t step, void* stream);   /* a rank with no rows contributes zeros */
+int dppo_dp_status(dppo_dp* dp);                     /* 0 ok; 1 + q: timed out waiting for rank q (host-mapped flag, no sync) */
+float* dppo_dp_slot(dppo_dp* dp, int64_t seq);       /* [n_floats gradient | 4 loss sums] of exchange number `seq` */
+int dppo_dp_zero_slot(dppo_ctx* ctx, dppo_dp* dp, int64_t seq, void* stream);   /* a rank with no rows contributes zeros */
 int64_t dppo_dp_workspace_bytes(int64_t n_floats);
-int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, float* params, float* grads_out, float* exp_avg,
+/* hyper->step_consts (optional): the exchange kernel then reads the sequence number it publishes / waits for from the u64 at
+ * step_consts + 2 floats (CUDA-graph replay); `seq` must still carry its parity (it selects the slot). */
+int dppo_dp_allreduce_clip_adam(dppo_ctx* ctx, dppo_dp* dp, int64_t seq, float* params, float* grads_out, float* exp_avg,
                                 float* exp_avg_sq, const dppo_hyper* hyper, float* losses_out, float* grad_norm_out,
                                 void* ws, int64_t ws_bytes, void* stream);
 

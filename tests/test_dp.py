@@ -13,39 +13,73 @@ GLOO_WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(ROOT, "diamond-ppo_b200")); sys.path.insert(0, ROOT)
-from diamond.agents import _PermWorker, _Dist
+from diamond.agents import _PermWorker, _Dist, permutation_plan
+from oracle.dp_oracle import shard_filter
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-d = _Dist(None, True)
-assert d.enabled and d.world == world and d.rank == rank
+d = _Dist(None, True, "global")
+assert d.enabled and d.world == world and d.rank == rank and d.global_perm
+# ranks start from different numpy streams; sync_numpy_stream puts everyone on rank 0's
+np.random.seed(5 + 17 * rank)
+np.random.normal()                                         # leaves a cached gaussian on every rank (part of the legacy state)
+d.sync_numpy_stream()
 T, NL, MB, E = 8, 6, 4, 3
 NG, B = NL * world, T * NL * world
 M = B // MB
-np.random.seed(5)
-outs = [np.empty(T * NL, np.int32) for _ in range(E)]
-w = _PermWorker(B, E, MB, outs, (NG, rank * NL, NL)); w.start()
+plan = permutation_plan(T * NL, world, MB, True)
+assert plan["B_perm"] == B and plan["filter"] and plan["rows"] <= T * NL
+outs = [np.empty(B, np.int32) for _ in range(E)]
+w = _PermWorker(B, E, MB, outs); w.start()
 for e in range(E): w.wait(e)
 w.finish()
-np.random.seed(5)
-ref = [np.random.permutation(B) for _ in range(E)]
-after = np.random.randint(0, 2**31, 2)
+h = torch.tensor([w.state_hash, w.state_hash ** 2], dtype=torch.float64); d.all_reduce_sum(h)
+assert abs(float(h[1]) * world - float(h[0]) ** 2) < 0.5    # the lockstep check learn() carries through its all-reduce
+after = torch.tensor(np.random.randint(0, 2**31, 2)); ref_after = after.clone(); dist.broadcast(ref_after, src=0)
+assert torch.equal(after, ref_after)                        # streams still agree after the permutations
 for e in range(E):
+    everyone = [None] * world
+    dist.all_gather_object(everyone, outs[e].tolist())
+    assert all(x == everyone[0] for x in everyone)          # the same global permutation on every rank
+    idx, counts, overflow = shard_filter(outs[e], NG, rank * NL, NL, MB, plan["rows"])
+    assert overflow == 0
     seen = []
-    for k, (off, m) in enumerate(w.counts[e]):
-        loc = outs[e][off:off + m]
+    for k in range(MB):
+        loc = idx[k, :counts[k]]
+        assert (idx[k, counts[k]:] == -1).all()
         t, env = np.divmod(loc, NL)
         glob = t * NG + env + rank * NL                     # local flat index -> global flat index
-        seg = ref[e][k * M:(k + 1) * M]
+        seg = outs[e][k * M:(k + 1) * M]
         mine = seg[(seg % NG >= rank * NL) & (seg % NG < (rank + 1) * NL)]
         assert np.array_equal(glob, mine), (e, k)           # same members, same order as the global minibatch
         seen.append(loc)
-        cnt = torch.tensor([m]); dist.all_reduce(cnt); assert int(cnt) == M     # shards partition every minibatch
+        cnt = torch.tensor([int(counts[k])]); dist.all_reduce(cnt); assert int(cnt) == M     # shards partition every minibatch
     assert sorted(np.concatenate(seen).tolist()) == list(range(T * NL))
+# a rank whose stream was consumed differently is caught by the hash check
+if rank == 1: np.random.random()
+w2 = _PermWorker(B, 1, MB, [np.empty(B, np.int32)])
+h = torch.tensor([w2.state_hash, w2.state_hash ** 2], dtype=torch.float64); d.all_reduce_sum(h)
+assert abs(float(h[1]) * world - float(h[0]) ** 2) > 0.5
 x = torch.full((5,), float(rank + 1), dtype=torch.float64); d.all_reduce_sum(x)
 assert torch.equal(x, torch.full((5,), float(sum(range(1, world + 1))), dtype=torch.float64))
 dist.destroy_process_group()
 print("ok", rank)
 '''
+
+
+def test_permutation_plan_bounds():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "diamond-ppo_b200"))
+    from diamond.agents import permutation_plan
+    assert permutation_plan(524288, 1, 8, False) == dict(B_perm=524288, rows=65536, filter=False)
+    assert permutation_plan(65536, 8, 8, False) == dict(B_perm=65536, rows=8192, filter=False)        # rank-local permutation
+    for world in (2, 4, 8):
+        p = permutation_plan(524288 // world, world, 8, True)
+        mean = 65536 / world
+        sigma = (65536 * (1 / world) * (1 - 1 / world)) ** 0.5
+        assert p["B_perm"] == 524288 and p["filter"] and p["rows"] % 128 == 0
+        assert mean + 6 * sigma <= p["rows"] <= mean + 6 * sigma + 16 + 128
+    # tiny shards: a rank can never own more rows than it has
+    assert permutation_plan(32, 2, 4, True)["rows"] <= 16
 
 
 def test_dp_host_logic_gloo_world2(tmp_path):

@@ -569,3 +569,87 @@ def test_tc_wgrad_vs_fp64(ctx, M, N1, N2):
     assert ((dW.double() - ref).abs().max() / ref.abs().max()).item() <= TC_TOL
     # bit-reproducible (fixed summation order)
     assert torch.equal(dW, ctx.tc_wgrad(Dm, Hm))
+
+
+# ---------------------------------------------------------------- device permutation + shard filter ----
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 4096, 65537, 524288])
+def test_permutation_device_is_a_keyed_permutation(ctx, n):
+    """Fast-mode generator: a bijection of [0, n) for every (seed, counter), deterministic, key-sensitive."""
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    a = ctx.permutation_device(7, 0, n, out).cpu().numpy().copy()
+    assert np.array_equal(np.sort(a), np.arange(n))
+    assert np.array_equal(a, ctx.permutation_device(7, 0, n, out).cpu().numpy())              # pure function of (seed, counter)
+    if n >= 1000:
+        b = ctx.permutation_device(7, 1, n, out).cpu().numpy().copy()
+        c = ctx.permutation_device(8, 0, n, out).cpu().numpy().copy()
+        assert np.array_equal(np.sort(b), np.arange(n)) and np.array_equal(np.sort(c), np.arange(n))
+        for other in (b, c):
+            assert (a == other).mean() < 0.01                                                 # different keys: unrelated permutations
+        assert (a == np.arange(n)).mean() < 0.01                                              # few fixed points
+        # positions look uniform: the first tenth of the outputs covers all ten value deciles evenly (chi^2, 9 dof, p ~ 1e-6 at 45)
+        head = a[:n // 10]
+        obs_counts = np.bincount((head.astype(np.int64) * 10 // n).clip(0, 9), minlength=10)
+        chi2 = ((obs_counts - head.size / 10) ** 2 / (head.size / 10)).sum()
+        assert chi2 < 45, chi2
+        # neighbours are not kept together: correlation of consecutive outputs is ~ 0
+        assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 0.05
+
+
+@pytest.mark.parametrize("T,NL,world,MB", [(8, 6, 2, 4), (32, 40, 4, 8), (128, 512, 8, 8), (16, 3, 3, 2)])
+def test_perm_shard_filter_matches_oracle(ctx, T, NL, world, MB):
+    from diamond.agents import permutation_plan
+    from oracle.dp_oracle import shard_filter
+    NG, B = NL * world, T * NL * world
+    if B % MB:
+        pytest.skip("shape does not divide")
+    rng = np.random.default_rng(T + NL)
+    perm = rng.permutation(B).astype(np.int32)
+    rows = permutation_plan(T * NL, world, MB, True)["rows"]
+    for rank in range(world):
+        idx = torch.full((MB * rows,), 12345, dtype=torch.int32, device="cuda")
+        counts = torch.zeros(MB, dtype=torch.int32, device="cuda"); over = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ctx.perm_shard_filter(dev(perm, torch.int32), B, NG, rank * NL, NL, MB, rows, idx, counts, over)
+        ref_idx, ref_counts, ref_over = shard_filter(perm, NG, rank * NL, NL, MB, rows)
+        assert np.array_equal(idx.cpu().numpy().reshape(MB, rows), ref_idx)                    # bit-exact, order preserved, -1 padding
+        assert np.array_equal(counts.cpu().numpy(), ref_counts) and int(over) == ref_over == 0
+    # too small a pad: surplus dropped, flag raised (the caller treats it as an error)
+    tiny = max(1, (B // MB) // world // 2)
+    idx = torch.empty(MB * tiny, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(MB, dtype=torch.int32, device="cuda"); over = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx.perm_shard_filter(dev(perm, torch.int32), B, NG, 0, NL, MB, tiny, idx, counts, over)
+    ref_idx, ref_counts, ref_over = shard_filter(perm, NG, 0, NL, MB, tiny)
+    assert int(over) == ref_over == 1 and np.array_equal(idx.cpu().numpy().reshape(MB, tiny), ref_idx)
+
+
+@pytest.mark.parametrize("D,H,A,cont,B,M,pad", [(8, 64, 4, False, 600, 200, 56), (64, 256, 4, False, 8192, 3000, 1096),
+                                                (5, 64, 3, True, 512, 100, 28), (32, 128, 3, False, 4096, 2000, 48)])
+def test_padding_rows_contribute_nothing(ctx, D, H, A, cont, B, M, pad):
+    """idx < 0 marks a padding row (fixed-shape steps under data parallelism): losses and the flat gradient of M real rows
+    followed by `pad` padding rows equal those of the M rows alone (same loss denominator)."""
+    from diamond import _native as N
+    from diamond.flat import FlatMlp
+    rng = np.random.default_rng(B + M)
+    names = O.CONTINUOUS_PARAM_NAMES if cont else O.DISCRETE_PARAM_NAMES
+    p = rand_params(rng, names, D, H, A, cont)
+    fm = FlatMlp(D, H, A, cont)
+    flat = fm.pack(p, device="cuda")
+    obs = dev(rng.standard_normal((B, D)).astype(np.float32))
+    act = dev(rng.standard_normal((B, A)).astype(np.float32)) if cont else dev(rng.integers(0, A, B), torch.int32)
+    old_lp = dev((rng.standard_normal(B) * 0.3 - 1.0).astype(np.float32))
+    adv = dev(rng.standard_normal(B).astype(np.float32)); ret = dev(rng.standard_normal(B).astype(np.float32))
+    real = rng.permutation(B)[:M].astype(np.int32)
+    # padding interleaved and at the end
+    padded = np.concatenate([real[:M // 2], np.full(pad // 2, -1, np.int32), real[M // 2:], np.full(pad - pad // 2, -1, np.int32)])
+    hyper, _ = make_hyper(N, M)
+    outs = []
+    for idx in (real, padded):
+        rows = idx.size
+        ws = torch.empty(ctx.mlp_workspace_bytes(fm.desc, rows, True) // 4 + 512, device="cuda")
+        grads = torch.full((fm.total,), 7.0, device="cuda"); losses = torch.zeros(4, device="cuda")
+        ctx.mlp_grad_minibatch(fm.desc, flat, grads, obs, act, old_lp, adv, ret, None, dev(idx, torch.int32), rows, hyper, losses, ws)
+        torch.cuda.synchronize()
+        outs.append((grads.cpu().numpy(), losses.cpu().numpy()))
+    np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=2e-6, atol=1e-7)
+    gv0, gv1 = fm.views(torch.as_tensor(outs[0][0])), fm.views(torch.as_tensor(outs[1][0]))
+    for n in names:
+        assert nerr(gv1[n].numpy(), gv0[n].numpy()) <= 5e-6, n
