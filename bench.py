@@ -3,10 +3,12 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[4], "synthetic scale"): 4096 envs x 128 steps per GPU, obs_dim 64,
-default actor-critic MLP at hidden 256, 4 actions, 4 epochs x 8 minibatches.  A "step" is one
-PPO.learn() over that buffer: pre-update pass, GAE, advantage statistics, 32 optimiser steps.
-Prints ONE JSON line (rank 0).
+Workload (BASELINE.json configs[4], "synthetic scale"): ONE 4096-env x 128-step buffer, obs_dim 64, default actor-critic
+MLP at hidden 256, 4 actions, 4 epochs x 8 minibatches.  A "step" is one PPO.learn() over that buffer: pre-update pass,
+GAE, advantage statistics, 32 optimiser steps.  With --gpus N the buffer is env-sharded over the N ranks (rank r owns envs
+[r*4096/N, (r+1)*4096/N), STRONG scaling) and every rank holds the reference's global permutation, so the N-GPU update
+is the single-GPU update up to fp32 summation order; the round-1 weak-scaling measurement (4096 envs per GPU) is kept
+as the extra key `weak_scaling`.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -84,8 +86,8 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(r for r in self.reasons if r not in ("GpuIdle", "ApplicationsClocksSetting"))}
 
 
-def synth_host_rollout(seed):
-    """Synthetic rollout of config S in the buffer's dtypes, in pinned host memory."""
+def synth_host_rollout(seed, envs=None, pin=True):
+    """Synthetic rollout of config S in the buffer's dtypes; envs = (lo, hi) keeps that env range of the 4096."""
     g = torch.Generator().manual_seed(seed)
     obs = torch.randn(T, N_ENVS, D, generator=g)
     next_obs = torch.randn(T, N_ENVS, D, generator=g)
@@ -93,18 +95,28 @@ def synth_host_rollout(seed):
     rewards = torch.randn(T, N_ENVS, generator=g)
     term = (torch.rand(T, N_ENVS, generator=g) < 0.01).float()
     trunc = ((torch.rand(T, N_ENVS, generator=g) < 0.01) & (term == 0)).float()
-    pin = torch.cuda.is_available()                       # the reference arm also runs on hosts without a GPU
-    return [x.pin_memory() if pin else x for x in (obs, next_obs, actions, rewards, term, trunc)]
+    out = [obs, next_obs, actions, rewards, term, trunc]
+    if envs is not None:
+        out = [x[:, envs[0]:envs[1]].contiguous() for x in out]
+    pin = pin and torch.cuda.is_available()               # the reference arm also runs on hosts without a GPU
+    return [x.pin_memory() if pin else x for x in out]
 
 
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference's learn() on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, minibatches_per_step=2):
+CPU_SAMPLE_ENVS = 512
+
+
+def cpu_reference(steps, warmup, sample_envs=CPU_SAMPLE_ENVS):
+    """Each step = ONE WHOLE learn() of the oracle port (oracle/ppo_oracle.py: tensorisation, pre-update pass, GAE, returns +
+    normalisation, np.random permutations, 4 epochs x 8 minibatches of forward / loss / backward / clip / Adam; ppo.py:224-287)
+    on a bounded sample of the workload: the first `sample_envs` of the 4096 envs (all 128 steps), i.e. minibatches of
+    sample_envs*128/8 rows at the same network size.  Throughput is per sample-update, the same unit as the GPU arm."""
     from oracle import ppo_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    host = synth_host_rollout(1)
+    host = synth_host_rollout(1, envs=(0, sample_envs), pin=False)
     obs, nobs, act, rew, term, trunc = (x.numpy() for x in host)
     from diamond.networks import ActorCriticNetwork, network_parameter_init_
     from diamond.config import PPOConfig
@@ -116,39 +128,32 @@ def cpu_reference(steps, warmup, minibatches_per_step=2):
     p = {n: q.detach().clone() for n, q in net.named_parameters()}
     names = O.DISCRETE_PARAM_NAMES
     state = O.new_adam_state(p, names)
-    ocfg = O.default_cfg()
-    B = T * N_ENVS
-    M = B // MB
-    t0 = time.perf_counter()
-    flat_obs = torch.as_tensor(obs).reshape(B, D)
-    logp, values, next_values = O.prepass(p, flat_obs, torch.as_tensor(nobs).reshape(B, D), torch.as_tensor(act).reshape(B).long())
-    t_prepass = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    adv = O.gae(rew, term, trunc, values.reshape(T, N_ENVS).numpy(), next_values.reshape(T, N_ENVS).numpy())
-    t_gae = time.perf_counter() - t0
-    ret, adv_n = O.returns_and_normalise(values.reshape(T, N_ENVS).numpy(), adv, True)
-    adv_f, ret_f, act_f = torch.as_tensor(adv_n).reshape(B), torch.as_tensor(ret).reshape(B), torch.as_tensor(act).reshape(B).long()
+    ocfg = O.default_cfg(num_epochs=E, num_minibatches=MB)
+    B = T * sample_envs
     np.random.seed(123)
-    perm = np.random.permutation(B)
+    t_gae = []
 
-    def step(i):
-        for k in range(minibatches_per_step):
-            kk = (i * minibatches_per_step + k) % MB
-            idx = torch.as_tensor(perm[kk * M:(kk + 1) * M].astype(np.int64))
-            _, grads = O.loss_and_grads(p, flat_obs[idx], act_f[idx], logp[idx], adv_f[idx], ret_f[idx], ocfg, False)
-            O.clip_grad_norm_(grads, names, ocfg["grad_norm_clip"])
-            O.adam_step_(p, grads, state, names, ocfg["lr"], ocfg["adam_eps"])
-    for i in range(warmup):
-        step(i)
+    def step():
+        perms = np.stack([np.random.permutation(B) for _ in range(E)])              # ppo.py:252-255
+        O.learn(p, state, obs, nobs, act.astype(np.int64), rew.astype(np.float64), term != 0, trunc != 0, ocfg, perms)
+    for _ in range(warmup):
+        step()
     t0 = time.perf_counter()
-    for i in range(steps):
-        step(warmup + i)
+    for _ in range(steps):
+        step()
     dt = time.perf_counter() - t0
-    samples = steps * minibatches_per_step * M
-    return dict(value=samples / dt, ms_per_step=dt / steps * 1e3, cores=cores, t_prepass_s=t_prepass, t_gae_s=t_gae,
-                gae_gbps=B * GAE_BYTES_PER_ELEM / t_gae / 1e9,
-                sample=f"{minibatches_per_step} optimiser steps of {M}-row minibatches per step on the {N_ENVS}x{T} buffer "
-                       f"(pre-update pass {t_prepass:.2f}s and GAE {t_gae * 1e3:.1f}ms timed once, outside)")
+    # GAE alone (the reference's reverse time loop, ppo.py:188-222) on the full 4096 x 128 shape, for the GB/s line
+    full = synth_host_rollout(1, pin=False)
+    v, nv = np.random.standard_normal((2, T, N_ENVS)).astype(np.float32)
+    t1 = time.perf_counter()
+    O.gae(full[3].numpy(), full[4].numpy(), full[5].numpy(), v, nv)
+    t_gae = time.perf_counter() - t1
+    samples = steps * E * B
+    return dict(value=samples / dt, ms_per_step=dt / steps * 1e3, cores=cores, t_gae_s=t_gae,
+                gae_gbps=T * N_ENVS * GAE_BYTES_PER_ELEM / t_gae / 1e9,
+                sample=f"each step = one whole learn() (pre-update pass, GAE, normalisation, {E} numpy permutations, {E} x {MB} optimiser "
+                       f"steps) of the oracle port on the first {sample_envs} of the {N_ENVS} envs x {T} steps ({B // MB}-row minibatches, "
+                       f"same network); ms_per_step is for that {sample_envs}/{N_ENVS} sample")
 
 
 def run_reference(args, rank, world):
@@ -157,7 +162,7 @@ def run_reference(args, rank, world):
     r = cpu_reference(args.steps, args.warmup)
     line = {"impl": "reference", "metric": "ppo_update_samples_per_s", "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(1),
             "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                              "gae_gbps": r["gae_gbps"]},
@@ -166,15 +171,16 @@ def run_reference(args, rank, world):
 
 
 def workload_config(world):
-    return {"workload": f"synthetic scale (BASELINE.json configs[4]): {N_ENVS} envs x {T} steps per GPU, obs_dim {D}, "
+    return {"workload": f"synthetic scale (BASELINE.json configs[4]): {N_ENVS} envs x {T} steps, obs_dim {D}, "
                         f"2x{H} trunk + {H}-wide heads, {A} actions, {E} epochs x {MB} minibatches",
-            "envs_per_gpu": N_ENVS, "rollout_steps": T, "global_batch": T * N_ENVS * world, "minibatch": T * N_ENVS * world // MB,
-            "parallelism": f"env-sharded dp{world}" if world > 1 else "single GPU",
+            "envs_total": N_ENVS, "envs_per_gpu": N_ENVS // world, "rollout_steps": T, "global_batch": T * N_ENVS,
+            "minibatch": T * N_ENVS // MB, "parallelism": f"env-sharded dp{world} (strong scaling of the one buffer)" if world > 1 else "single GPU",
             "permutation": ("bit-exact numpy MT19937 stream (host thread, overlapped)" if world == 1 else
-                            "rank-local bit-exact numpy MT19937 stream per shard (host thread, overlapped); equal 1/MB slices per rank"),
+                            "the reference's GLOBAL permutation on every rank (bit-exact numpy MT19937 stream, host thread); a device "
+                            "kernel keeps each rank's members per minibatch, padded to fixed step shapes"),
             "exchange": None if world == 1 else "per optimiser step: one fused kernel per rank sums all ranks' gradients over NVLink peer "
                                                 "memory (rank order) + global-norm partials, then clip + Adam",
-            "l2": "inputs (2 x 134 MB observations) exceed the 126 MB L2; GAE sub-benchmark cycles 20 buffer sets (294 MB)"}
+            "l2": "inputs (2 x 134 MB observations at 1 GPU) exceed the 126 MB L2; GAE sub-benchmark cycles 20 buffer sets (294 MB)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -298,42 +304,23 @@ def bench_train_iteration(reps=3):
             "sample_updates_per_s": E * T * N_ENVS / (ms_iter * 1e-3)}
 
 
-def run_ours(args, rank, world, local_rank):
-    import torch.distributed as dist
-    from diamond import PPO, PPOConfig, envs, _native
-    from diamond.agents import RolloutBuffer
-    torch.cuda.set_device(local_rank)
-    ctx = _native.get_context(local_rank)
-    hbm_peak, bf16_peak, peak_src = measured_peaks()
-
-    def env_fn(n):
-        return envs.BatchedSyntheticVectorEnv(n, D, A)
-    env_fn.vectorized = True
-    cfg = PPOConfig(num_envs=N_ENVS, rollout_steps=T, network_hidden_dim=H, num_epochs=E, num_minibatches=MB, verbose=False,
-                    total_steps=T * N_ENVS * 1000)
-    agent = PPO(env_fn, cfg, dp=world > 1, dp_exchange=args.dp_exchange)
-    host = synth_host_rollout(1 + rank)
-    buf = RolloutBuffer(ctx, T, N_ENVS, D, 1, False, agent.device)
-    buf.load_host(*host)
-    torch.cuda.synchronize()
-    np.random.seed(123)
-
+def time_learn(agent, buf, host, steps, warmup, world, dist, ctx):
+    """(ms per learn() device-resident, per-phase ms, launches, clocks, ms per learn() end to end, h2d bytes, losses)."""
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: `value` ----
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         agent.learn(buf)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
     launches0 = ctx.launches
     ev_all = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ev = {}
         agent.learn(buf, events=ev)
         ev_all.append(ev)
@@ -344,21 +331,19 @@ def run_ours(args, rank, world, local_rank):
     ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms_total) / args.steps
-    t_pre = np.mean([ev["start"].elapsed_time(ev["prepass_end"]) for ev in ev_all])
-    t_gae = np.mean([ev["prepass_end"].elapsed_time(ev["gae_end"]) for ev in ev_all])
-    t_upd = np.mean([ev["gae_end"].elapsed_time(ev["update_end"]) for ev in ev_all])
-    sample_updates = E * T * N_ENVS * world
-    value = sample_updates / (ms_per_step * 1e-3)
-
-    # ---- end to end through the public API with host buffers: `e2e` ----
+    phases = {"prepass": float(np.mean([ev["start"].elapsed_time(ev["prepass_end"]) for ev in ev_all])),
+              "gae_and_stats": float(np.mean([ev["prepass_end"].elapsed_time(ev["gae_end"]) for ev in ev_all])),
+              "update_loop": float(np.mean([ev["gae_end"].elapsed_time(ev["update_end"]) for ev in ev_all]))}
+    out = dict(ms=float(ms_total) / steps, phases=phases, launches=launches, clocks=clocks)
+    if host is None:
+        return out
+    # ---- end to end through the public API with host buffers ----
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h_losses = torch.empty(E * MB, 4).pin_memory()
-    t_wall0 = time.perf_counter()
     e0.record()
     h2d = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         h2d = buf.load_host(*host)                    # this step's inputs: pinned host -> device
         agent.learn(buf)
         h_losses.copy_(agent.last_losses, non_blocking=True)     # result read back
@@ -368,8 +353,78 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = sample_updates / (float(ms_e2e) / args.steps * 1e-3)
     assert torch.isfinite(h_losses).all()
+    out.update(ms_e2e=float(ms_e2e) / steps, h2d=int(h2d), d2h=int(h_losses.numel() * 4))
+    return out
+
+
+def replicas_identical(agent, dist):
+    flat = agent.engine.P.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    ok = torch.tensor([int(torch.equal(flat, ref) and bool(torch.isfinite(flat).all()))], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return bool(int(ok))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from diamond import PPO, PPOConfig, envs, _native
+    from diamond.agents import RolloutBuffer
+    torch.cuda.set_device(local_rank)
+    ctx = _native.get_context(local_rank)
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
+    if N_ENVS % world != 0:
+        raise SystemExit(f"--gpus {world} does not divide the {N_ENVS} environments of the workload")
+    n_local = N_ENVS // world
+
+    def env_fn(n):
+        return envs.BatchedSyntheticVectorEnv(n, D, A)
+    env_fn.vectorized = True
+
+    def make(n_envs, **kw):
+        cfg = PPOConfig(num_envs=n_envs, rollout_steps=T, network_hidden_dim=H, num_epochs=E, num_minibatches=MB, verbose=False,
+                        total_steps=T * n_envs * 1000, seed=7)
+        return PPO(env_fn, cfg, dp=world > 1, dp_exchange=args.dp_exchange, **kw)
+
+    # ---- headline: the ONE 4096 x 128 buffer, env-sharded over the ranks, the reference's global permutation (bit-exact numpy stream) ----
+    agent = make(n_local, dp_permutation="global")
+    host = synth_host_rollout(1, envs=(rank * n_local, (rank + 1) * n_local))      # this rank's env range of the same global rollout
+    buf = RolloutBuffer(ctx, T, n_local, D, 1, False, agent.device)
+    buf.load_host(*host)
+    torch.cuda.synchronize()
+    np.random.seed(123)
+    main = time_learn(agent, buf, host, args.steps, args.warmup, world, dist, ctx)
+    agent.engine.check_health()
+    ms_per_step, clocks, launches = main["ms"], main["clocks"], main["launches"]
+    t_pre, t_gae, t_upd = (main["phases"][k] for k in ("prepass", "gae_and_stats", "update_loop"))
+    sample_updates = E * T * N_ENVS
+    value = sample_updates / (ms_per_step * 1e-3)
+    e2e_value = sample_updates / (main["ms_e2e"] * 1e-3)
+    extra = {}
+    if world > 1:
+        extra["dp_replicas_identical"] = replicas_identical(agent, dist)
+        assert extra["dp_replicas_identical"], "data-parallel replicas diverged"
+        # the same strong-scaling run with the device permutation generator (no host permutation work; not numpy's numbers)
+        ag = make(n_local, dp_permutation="global", minibatch_permutation="device")
+        r = time_learn(ag, buf, None, args.steps, args.warmup, world, dist, ctx)
+        ag.engine.check_health()
+        extra["device_permutation"] = {"value": sample_updates / (r["ms"] * 1e-3), "ms_per_step": r["ms"], "phases_ms": r["phases"],
+                                       "replicas_identical": replicas_identical(ag, dist),
+                                       "note": "same run with minibatch_permutation='device' (keyed-bijection generator on the GPU)"}
+        del ag
+        # round 1's measurement: weak scaling, 4096 envs per GPU, rank-local permutations
+        if not args.no_weak:
+            agw = make(N_ENVS)
+            hostw = synth_host_rollout(1 + rank)
+            bufw = RolloutBuffer(ctx, T, N_ENVS, D, 1, False, agw.device)
+            bufw.load_host(*hostw)
+            torch.cuda.synchronize()
+            r = time_learn(agw, bufw, None, args.steps, args.warmup, world, dist, ctx)
+            extra["weak_scaling"] = {"value": E * T * N_ENVS * world / (r["ms"] * 1e-3), "ms_per_step": r["ms"], "phases_ms": r["phases"],
+                                     "envs_per_gpu": N_ENVS, "permutation": "rank-local", "replicas_identical": replicas_identical(agw, dist)}
+            del agw, bufw, hostw
+            torch.cuda.empty_cache()
 
     if rank != 0:
         return
@@ -379,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
     gae_cons = bench_gae(ctx, hbm_peak, settled=False)
     # a shape where launch latency amortises: 65 536 envs x 128 steps = 235 MB per launch, two buffer sets (470 MB > L2)
     gae_large = bench_gae(ctx, hbm_peak, sets=2, launches=10, settled=False, n_envs=65536)
-    upd_tflops = E * T * N_ENVS * FLOP_PER_SAMPLE_UPDATE / (t_upd * 1e-3) / 1e12
+    upd_tflops = E * T * n_local * FLOP_PER_SAMPLE_UPDATE / (t_upd * 1e-3) / 1e12        # per GPU
     # fp32-accurate products cost three TF32 tensor passes; TF32 runs at half the bf16 rate (same cycles per instruction
     # at half the K, confirmed by the in-run probe), so the algorithmic peak is bf16 / 2 / 3
     tensor_peak = bf16_peak / 6.0
@@ -391,10 +446,10 @@ def run_ours(args, rank, world, local_rank):
                  "%.1f clk per 256x256x8 tf32 MMA = %.0f TF/s tf32 at %d MHz" % (bf16_peak, peak_src, clk_per_mma, probe_tf32, sm_mhz))
     line = {
         "metric": "ppo_update_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "phases_ms": {"prepass": t_pre, "gae_and_stats": t_gae, "update_loop": t_upd},
-        "update_loop_samples_per_s": E * T * N_ENVS * world / (t_upd * 1e-3),
+        "update_loop_samples_per_s": E * T * N_ENVS / (t_upd * 1e-3),
         # dominant kernel (52 % of the step in profiles/): algorithmic flops per launch / CUDA-event time of the kernel alone
         "roofline": dict(gemm, peak_source=peak_note, traffic=GEMM_DRAM_TRAFFIC),
         # the whole update loop (32 optimiser steps: gather, forward, loss, backward, reduce, clip + Adam)
@@ -408,13 +463,14 @@ def run_ours(args, rank, world, local_rank):
                              large_shape_65536x128={"us_per_launch": gae_large["us_per_launch"], "achieved": gae_large["achieved"],
                                                     "frac": gae_large["frac"], "bytes_per_launch": gae_large["bytes_per_launch"],
                                                     "inputs_settled": False}),
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_losses.numel() * 4)},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    line.update(extra)
     if world == 1:
         line["train_iteration"] = bench_train_iteration()
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(4, 1)
+        r = cpu_reference(3, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                                 "gae_gbps": r["gae_gbps"]}
     print(json.dumps(line), flush=True)
@@ -428,6 +484,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dp-exchange", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement at --gpus > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

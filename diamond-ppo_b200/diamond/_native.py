@@ -57,7 +57,7 @@ class Hyper(C.Structure):
 EXPORTS = [
     "dppo_create", "dppo_destroy", "dppo_last_error", "dppo_version", "dppo_device_info", "dppo_set_option", "dppo_launch_count", "dppo_count_launches",
     "dppo_buffer_store_step", "dppo_step_record_bytes", "dppo_sample_categorical", "dppo_sample_gaussian",
-    "dppo_gae_f32", "dppo_adv_normalize_f32", "dppo_permutation_mt19937", "dppo_mt19937_seed",
+    "dppo_gae_f32", "dppo_adv_normalize_f32", "dppo_permutation_mt19937", "dppo_permutation_mt19937_skip", "dppo_mt19937_seed",
     "dppo_gather_rows_f32", "dppo_mlp_layout_compute", "dppo_mlp_workspace_bytes", "dppo_mlp_forward",
     "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_clip_adam_step",
     "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
@@ -143,6 +143,15 @@ def permutation_mt19937(key: np.ndarray, pos: int, n: int, out: np.ndarray | Non
     if rc:
         raise NativeError("dppo_permutation_mt19937: bad arguments")
     return out, p.value
+
+
+def permutation_mt19937_skip(key: np.ndarray, pos: int, n: int) -> int:
+    """Advances (key, pos) exactly as permutation_mt19937(key, pos, n) would, without building the permutation; returns the new pos."""
+    assert key.dtype == np.uint32 and key.size == 624 and key.flags["C_CONTIGUOUS"]
+    p = C.c_int32(pos)
+    if load_library().dppo_permutation_mt19937_skip(_ptr(key), C.byref(p), C.c_int64(n)):
+        raise NativeError("dppo_permutation_mt19937_skip: bad arguments")
+    return p.value
 
 
 def numpy_global_permutations(n: int, count: int, outs=None):

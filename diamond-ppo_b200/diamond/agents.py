@@ -251,6 +251,19 @@ class _Dist:
         packed = t.cpu().numpy()
         np.random.set_state(("MT19937", packed[:624].astype(np.uint32), int(packed[624]), int(packed[625]), float(packed[626])))
 
+    def shared_seed(self, seed, device=None) -> int:
+        """The run's base seed for the counter-based generators (action sampling keyed by global env id, device permutation):
+        cfg.seed, or a random one when it is None -- in which case rank 0's choice is broadcast so that all ranks agree."""
+        if seed is not None:
+            return int(seed)
+        t = torch.tensor([int.from_bytes(__import__("os").urandom(4), "little") & 0x7FFFFFFF], dtype=torch.int64)
+        if self.enabled:
+            if self.dist.get_backend(self.group) == "nccl":
+                t = t.to(device if device is not None else "cuda")
+            src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            self.dist.broadcast(t, src=src, group=self.group)
+        return int(t.item())
+
     def all_reduce_sum(self, t: torch.Tensor):
         if self.enabled:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -408,7 +421,7 @@ class FusedMlpEngine(_EngineBase):
         self._train_ws = None
         self._bufs = {}
         self.draws = 0
-        self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        self.seed = dist.shared_seed(cfg.seed, device)
         self._act_stage = {}
         self.last_losses = None
         self.timing = {}
@@ -777,7 +790,7 @@ class AutogradEngine(_EngineBase):
         self._resync_optimizer()
         dev = self.device
         h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
-        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
+        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx])
         worker.start()
         buf.wait_all()
         obs, nobs = buf.obs, buf.next_obs
@@ -863,6 +876,10 @@ class _PPOBase:
 
         if getattr(env_fn, "vectorized", False):                       # additive: env_fn(num_envs) -> batched vector env
             self.envs = env_fn(cfg.num_envs)
+            # env-sharded data parallelism: this rank simulates global envs [rank*N, (rank+1)*N) -- distinct reset / dynamics
+            # draws per shard unless the factory already placed the shard itself
+            if self._dist.enabled and getattr(self.envs, "device_resident", False) and self.envs.desc.env_offset == 0:
+                self.envs.desc.env_offset = self._dist.rank * cfg.num_envs
         else:
             self.envs = gym.vector.SyncVectorEnv([env_fn for _ in range(cfg.num_envs)], copy=True, autoreset_mode="Disabled")
         obs_space, act_space = self.envs.single_observation_space, self.envs.single_action_space
@@ -990,7 +1007,12 @@ class _PPOBase:
     # ---- train (ppo.py:289-312) ----------------------------------------------------------------------
     def train(self) -> None:
         cfg = self.cfg
-        self.current_observations, _ = self.envs.reset(seed=cfg.seed)
+        # under data parallelism the shards are different environments of one global run: host vector envs seed sub-env i with
+        # seed + i (Gymnasium), so rank r starts at seed + r*N; device envs key their draws by global env id (env_offset)
+        seed = cfg.seed
+        if seed is not None and self._dist.enabled and not getattr(self.envs, "device_resident", False):
+            seed = cfg.seed + self._dist.rank * cfg.num_envs
+        self.current_observations, _ = self.envs.reset(seed=seed)
         last_checkpoint_time = time.time()
         total_rollouts = cfg.total_steps // (cfg.rollout_steps * cfg.num_envs)
         env_steps = 0
@@ -998,11 +1020,14 @@ class _PPOBase:
             experience = self.rollout()
             self.learn(experience)
             env_steps = (rollout_idx + 1) * cfg.rollout_steps * cfg.num_envs
-            if cfg.checkpoint and time.time() - last_checkpoint_time >= cfg.save_interval:
-                self.checkpointer.save(env_steps, self.network, self.optimizer)
+            if cfg.checkpoint and self._dist.rank == 0 and time.time() - last_checkpoint_time >= cfg.save_interval:
+                self.checkpointer.save(env_steps, self.network, self.optimizer)      # replicas are identical: rank 0 writes
                 last_checkpoint_time = time.time()
-        if cfg.checkpoint and total_rollouts > 0:
+        if cfg.checkpoint and total_rollouts > 0 and self._dist.rank == 0:
             self.checkpointer.save(env_steps, self.network, self.optimizer)
+        if hasattr(self.engine, "check_health"):
+            torch.cuda.current_stream().synchronize()
+            self.engine.check_health()
         self.envs.close()
 
 

@@ -26,7 +26,10 @@ import torch
 import torch.nn as nn
 
 from . import _native as N
-from . import envs as gym
+try:                                    # the real package when present, else the in-repo shim (same rule as agents.py)
+    import gymnasium as gym             # noqa: F401
+except ImportError:                     # pragma: no cover - the GPU image has no gymnasium
+    from . import envs as gym
 from .agents import _Dist, _EngineBase, _PermWorker, _require_cuda
 from .config import RecurrentPPOConfig
 from .networks import _obs_dim, network_parameter_init_
@@ -157,7 +160,7 @@ class RecurrentEngine(_EngineBase):
         M = B // MB
         self._resync_optimizer()
         h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
-        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
+        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx])
         worker.start()
         # GAE with the values stored at rollout time, returns, advantage normalisation (recurrent_ppo.py:315-318)
         stats = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -260,7 +263,7 @@ class FusedRecurrentEngine(_EngineBase):
         M = B // MB
         self._resync_optimizer()
         h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
-        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx], None)
+        worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx])
         worker.start()
         # GAE with the values stored at rollout time + returns + advantage sums (recurrent_ppo.py:315-318); the normalisation
         # itself is applied while the head kernel gathers the advantages

@@ -137,6 +137,8 @@ int dppo_adv_normalize_f32(dppo_ctx* ctx, const float* adv, float* out, const do
  * out: int32 [n].  Meant to run on a worker thread while the GPU processes the previous epoch. */
 int dppo_permutation_mt19937(uint32_t* key, int32_t* pos, int64_t n, int32_t* out);
 int dppo_mt19937_seed(uint32_t* key, int32_t* pos, uint32_t seed);      /* np.random.seed(int) */
+/* Advances the stream exactly as dppo_permutation_mt19937(key, pos, n, .) would, without building the permutation. */
+int dppo_permutation_mt19937_skip(uint32_t* key, int32_t* pos, int64_t n);
 /* FAST (non-parity) generator, SURVEY.md 2.2 K4a: out[0..n) = a pseudo-random permutation of [0, n) that is a pure function of
  * (seed, counter) -- a keyed Feistel bijection over the next power of two with cycle walking, evaluated per element on the
  * device (no sort, no host work; every data-parallel rank computes the same permutation without communication).  It replaces

@@ -109,7 +109,7 @@ def test_learn_config_S_tensor_core_path_matches_reference(name, epochs):
     check(agent, g, f"e{epochs}", ptol=tol, ltol=tol)
     # the advantages feeding the update (thin slice kept in the fixture), 1e-5 normalised
     if epochs == 1:
-        adv = agent.engine._bufs[(T, N_, epochs, MB)]["adv"][:, :16].cpu().numpy()
+        adv = agent.engine._bufs[(T, N_, epochs, MB, False)]["adv"][:, :16].cpu().numpy()
         ref = g["gae.advantages16"]
         assert np.abs(adv - ref).max() / np.abs(ref).max() <= 1e-5
     assert agent.ctx.launches > l0

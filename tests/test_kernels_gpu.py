@@ -584,15 +584,15 @@ def test_permutation_device_is_a_keyed_permutation(ctx, n):
         c = ctx.permutation_device(8, 0, n, out).cpu().numpy().copy()
         assert np.array_equal(np.sort(b), np.arange(n)) and np.array_equal(np.sort(c), np.arange(n))
         for other in (b, c):
-            assert (a == other).mean() < 0.01                                                 # different keys: unrelated permutations
-        assert (a == np.arange(n)).mean() < 0.01                                              # few fixed points
+            assert (a == other).mean() < max(0.01, 10.0 / n)                                                 # different keys: unrelated permutations
+        assert (a == np.arange(n)).mean() < max(0.01, 10.0 / n)                                              # few fixed points
         # positions look uniform: the first tenth of the outputs covers all ten value deciles evenly (chi^2, 9 dof, p ~ 1e-6 at 45)
         head = a[:n // 10]
         obs_counts = np.bincount((head.astype(np.int64) * 10 // n).clip(0, 9), minlength=10)
         chi2 = ((obs_counts - head.size / 10) ** 2 / (head.size / 10)).sum()
         assert chi2 < 45, chi2
         # neighbours are not kept together: correlation of consecutive outputs is ~ 0
-        assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 0.05
+        assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < max(0.02, 5.0 / np.sqrt(n))
 
 
 @pytest.mark.parametrize("T,NL,world,MB", [(8, 6, 2, 4), (32, 40, 4, 8), (128, 512, 8, 8), (16, 3, 3, 2)])
