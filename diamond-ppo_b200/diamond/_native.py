@@ -64,7 +64,7 @@ EXPORTS = [
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
     "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy", "dppo_dp_status",
     "dppo_permutation_device", "dppo_perm_shard_filter", "dppo_dp_slot", "dppo_dp_zero_slot", "dppo_dp_workspace_bytes", "dppo_dp_allreduce_clip_adam",
-    "dppo_env_reset", "dppo_env_step", "dppo_set_draw_counter_base",
+    "dppo_env_reset", "dppo_env_step", "dppo_set_draw_counter_base", "dppo_episode_stats", "dppo_episode_stats_workspace_bytes",
     "dppo_rnn_layout_compute", "dppo_rnn_workspace_bytes", "dppo_rnn_forward", "dppo_rnn_grad_minibatch",
 ]
 
@@ -85,7 +85,7 @@ def load_library() -> C.CDLL:
             lib.dppo_last_error.argtypes = [C.c_void_p]
             for name in ("dppo_step_record_bytes", "dppo_mlp_workspace_bytes", "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes",
                          "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes", "dppo_grad_sumsq_bytes",
-                         "dppo_rnn_workspace_bytes"):
+                         "dppo_rnn_workspace_bytes", "dppo_episode_stats_workspace_bytes"):
                 getattr(lib, name).restype = C.c_int64
             lib.dppo_dp_slot.restype = C.c_void_p
             _lib = lib
@@ -311,6 +311,18 @@ class Context:
         self._check(self.lib.dppo_env_step(self.h, C.byref(desc), C.byref(state), _ptr(actions), C.c_int(t), C.c_int(int(auto_reset)),
                                            _ptr(obs), _ptr(next_obs), _ptr(buf_actions), _ptr(rewards), _ptr(terminations),
                                            _ptr(truncations), _ptr(done_return), _stream()), "dppo_env_step")
+
+    def episode_stats(self, rewards, terminations, truncations, ep_return, ep_len, window, out_returns, out_lengths, out_n, finished, ws):
+        """Device-side Ticker bookkeeping of one rollout (dppo_episode_stats)."""
+        T, N = rewards.shape
+        self._check(self.lib.dppo_episode_stats(self.h, _ptr(rewards), _ptr(terminations), _ptr(truncations), C.c_int(T), C.c_int(N),
+                                                _ptr(ep_return), _ptr(ep_len), C.c_int(window), _ptr(out_returns), _ptr(out_lengths),
+                                                _ptr(out_n), _ptr(finished), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()),
+                                                _stream()), "dppo_episode_stats")
+        self.launches += 2
+
+    def episode_stats_workspace_bytes(self, T, N):
+        return int(self.lib.dppo_episode_stats_workspace_bytes(C.c_int(T), C.c_int(N)))
 
     # ---- recurrent actor-critic (recurrent_ppo.py) -----------------------------------------------
     def rnn_workspace_bytes(self, desc, T, N, M, training):

@@ -264,6 +264,11 @@ class _Dist:
             self.dist.broadcast(t, src=src, group=self.group)
         return int(t.item())
 
+    def broadcast(self, t: torch.Tensor, src_rank: int):
+        if self.enabled:
+            src = self.dist.get_global_rank(self.group, src_rank) if self.group is not None else src_rank
+            self.dist.broadcast(t, src=src, group=self.group)
+
     def all_reduce_sum(self, t: torch.Tensor):
         if self.enabled:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -287,7 +292,11 @@ class _PermWorker(threading.Thread):
     legacy stream (dppo_permutation_mt19937).  Under data parallelism with the global permutation every rank
     generates the same permutations; the shard filter runs on the device (dppo_perm_shard_filter)."""
 
-    def __init__(self, B_perm, E, MB, outs):
+    def __init__(self, B_perm, E, MB, outs, owner=None):
+        """owner(e) -> bool (optional): under data parallelism with the global permutation the E permutations of a learn() are
+        divided among the ranks (epoch e belongs to rank e % world, which broadcasts it over NVLink); a rank only ADVANCES the
+        stream over the permutations it does not own (dppo_permutation_mt19937_skip: the draws without the shuffle, ~2.5x
+        cheaper), so every rank's stream stays identical while the sequential host work per rank shrinks."""
         super().__init__(daemon=True)
         st = np.random.get_state(legacy=True)
         self.state_tail = (st[3], st[4])
@@ -295,14 +304,17 @@ class _PermWorker(threading.Thread):
         self.pos = int(st[2])
         # 24-bit hash of the stream state (data-parallel lockstep check: h and h^2 are summed over the ranks in fp64, exactly)
         self.state_hash = float((int(self.key[::7].astype(np.uint64).sum()) * 2654435761 + self.pos * 40503) % (1 << 24))
-        self.B, self.E, self.MB, self.outs = B_perm, E, MB, outs
+        self.B, self.E, self.MB, self.outs, self.owner = B_perm, E, MB, outs, owner
         self.ready = [threading.Event() for _ in range(E)]
         self.error = None
 
     def run(self):
         try:
             for e in range(self.E):
-                _, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.outs[e])
+                if self.owner is None or self.owner(e):
+                    _, self.pos = N.permutation_mt19937(self.key, self.pos, self.B, self.outs[e])
+                else:
+                    self.pos = N.permutation_mt19937_skip(self.key, self.pos, self.B)
                 self.ready[e].set()
         except BaseException as ex:      # surfaced by wait()
             self.error = ex
@@ -528,14 +540,18 @@ class FusedMlpEngine(_EngineBase):
         target = b["perm"][p] if plan["filter"] else b["idx"][p]
         main = torch.cuda.current_stream()
         if worker is not None:
-            worker.wait(e)
-            cs = b["copy_stream"]
-            cs.wait_event(b["done"][p])                                  # the steps that last read idx[p] / perm[p] have finished
-            with torch.cuda.stream(cs):
-                target.copy_(b["h_idx"][e], non_blocking=True)
-                b["copied"][p].record()
-            self._idx_consumed = b["copied"][p]
-            main.wait_event(b["copied"][p])
+            owner = (e % dist.world) if plan["filter"] else dist.rank          # global permutation: epoch e is generated by one rank
+            if owner == dist.rank:
+                worker.wait(e)
+                cs = b["copy_stream"]
+                cs.wait_event(b["done"][p])                              # the steps that last read idx[p] / perm[p] have finished
+                with torch.cuda.stream(cs):
+                    target.copy_(b["h_idx"][e], non_blocking=True)
+                    b["copied"][p].record()
+                self._idx_consumed = b["copied"][p]
+                main.wait_event(b["copied"][p])
+            if plan["filter"]:
+                dist.broadcast(target, owner)                            # 4 bytes per index over NVLink instead of a shuffle per rank
         else:
             ctx.permutation_device(self.perm_seed, self.perm_counter, plan["B_perm"], target)
             self.perm_counter += 1
@@ -699,7 +715,8 @@ class FusedMlpEngine(_EngineBase):
         if self.perm_mode == "numpy":
             if self._idx_consumed is not None:
                 self._idx_consumed.synchronize()   # the previous learn()'s async H2D copies out of the pinned index buffers are done
-            worker = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_idx"]])
+            owner = (lambda e: e % dist.world == dist.rank) if plan["filter"] else None
+            worker = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_idx"]], owner)
             lock_hash = worker.state_hash
             worker.start()                      # host permutation overlaps the pre-update pass on the GPU
 
@@ -910,6 +927,7 @@ class _PPOBase:
         self.cfg = cfg
         self._buffer = None
         self._rollout_graph, self._rollout_seen = None, None
+        self._epstats = None
 
     # ---- rollout (ppo.py:153-186) -------------------------------------------------------------------
     def rollout(self) -> RolloutBuffer:
@@ -960,11 +978,8 @@ class _PPOBase:
                     envs.step_into(buf, step_idx, self.engine.sample_actions_device(envs.cur_obs, buf.values[step_idx], buf.logp[step_idx]))
             if self.engine.policy_stamp() == stamp:
                 buf.policy_stamp = stamp                               # V(obs), log_prob(action) of exactly these parameters
-            if self.ticker is not None:                                # episode statistics: one read-back per rollout
-                rew = buf.rewards.double().cpu().numpy()
-                dones = ((buf.terminations + buf.truncations) > 0).cpu().numpy()
-                for step_idx in range(cfg.rollout_steps):
-                    self.ticker.tick(rew[step_idx], dones[step_idx])
+            if self.ticker is not None:                                # episode statistics on the device, read lazily (no sync here)
+                self._device_episode_stats(buf)
             self.current_observations = envs.cur_obs
             return buf
         observations = self.current_observations
@@ -981,6 +996,44 @@ class _PPOBase:
                 self.ticker.tick(rewards, dones)
         self.current_observations = observations
         return buf
+
+    # ---- episode statistics of device-resident rollouts (utils.py:99-123 without the per-step host loop) ------------
+    def _device_episode_stats(self, buf):
+        """Ticker bookkeeping of this rollout in two kernels (dppo_episode_stats); the ~100 numbers the Ticker needs are copied to
+        pinned memory asynchronously and consumed at the next rollout / when `ticker.logs` is read -- the host never waits for
+        the rollout between rollout() and learn()."""
+        st = self._epstats
+        W, dev = self.ticker.window_size, self.device
+        if st is None or st["N"] != buf.N or st["T"] != buf.T or st["W"] != W:
+            st = self._epstats = dict(N=buf.N, T=buf.T, W=W, pending=None,
+                                      ep_return=torch.zeros(buf.N, dtype=torch.float64, device=dev),
+                                      ep_len=torch.zeros(buf.N, dtype=torch.int32, device=dev),
+                                      out=torch.zeros(W + 2, dtype=torch.float64, device=dev),        # [returns W | finished | kept]
+                                      out_len=torch.zeros(W, dtype=torch.int32, device=dev), out_n=torch.zeros(1, dtype=torch.int32, device=dev),
+                                      finished=torch.zeros(1, dtype=torch.int64, device=dev),
+                                      ws=torch.empty(self.ctx.episode_stats_workspace_bytes(buf.T, buf.N) + 8, dtype=torch.uint8, device=dev),
+                                      h_out=torch.zeros(W + 2, dtype=torch.float64).pin_memory(), h_len=torch.zeros(W, dtype=torch.int32).pin_memory())
+            self.ticker._flush_pending = self._flush_episode_stats
+        self._flush_episode_stats()                                    # the previous rollout's numbers (long since copied)
+        self.ctx.episode_stats(buf.rewards, buf.terminations, buf.truncations, st["ep_return"], st["ep_len"], W, st["out"][:W],
+                               st["out_len"], st["out_n"], st["finished"], st["ws"])
+        st["out"][W:W + 1].copy_(st["finished"])
+        st["out"][W + 1:W + 2].copy_(st["out_n"])
+        st["h_out"].copy_(st["out"], non_blocking=True)
+        st["h_len"].copy_(st["out_len"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["pending"] = dict(event=ev, steps=buf.T)
+
+    def _flush_episode_stats(self):
+        st = self._epstats
+        if st is None or st["pending"] is None:
+            return
+        pend, st["pending"] = st["pending"], None
+        pend["event"].synchronize()
+        W = st["W"]
+        finished, kept = int(st["h_out"][W]), int(st["h_out"][W + 1])
+        self.ticker.tick_rollout(pend["steps"], finished, st["h_out"][:kept].tolist(), st["h_len"][:kept].tolist())
 
     # ---- GAE (ppo.py:188-222) -----------------------------------------------------------------------
     def calculate_advantage(self, rewards, terminations, truncations, values, next_values) -> torch.Tensor:
@@ -1013,6 +1066,10 @@ class _PPOBase:
         if seed is not None and self._dist.enabled and not getattr(self.envs, "device_resident", False):
             seed = cfg.seed + self._dist.rank * cfg.num_envs
         self.current_observations, _ = self.envs.reset(seed=seed)
+        if self._epstats is not None:                                  # fresh environments: running returns / lengths restart
+            self._flush_episode_stats()
+            self._epstats["ep_return"].zero_()
+            self._epstats["ep_len"].zero_()
         last_checkpoint_time = time.time()
         total_rollouts = cfg.total_steps // (cfg.rollout_steps * cfg.num_envs)
         env_steps = 0
@@ -1025,6 +1082,7 @@ class _PPOBase:
                 last_checkpoint_time = time.time()
         if cfg.checkpoint and total_rollouts > 0 and self._dist.rank == 0:
             self.checkpointer.save(env_steps, self.network, self.optimizer)
+        self._flush_episode_stats()
         if hasattr(self.engine, "check_health"):
             torch.cuda.current_stream().synchronize()
             self.engine.check_health()

@@ -52,9 +52,22 @@ class Ticker:
         if self.verbose:
             self.print_logs()
 
-    def print_logs(self) -> None:
+    def tick_rollout(self, num_steps: int, finished: int, returns, lengths, **custom_logs: Any) -> None:
+        """`num_steps` vector steps at once, for rollouts whose bookkeeping ran on the device (dppo_episode_stats): `finished`
+        episodes ended, `returns` / `lengths` are the last min(window, finished) of them in tick() order.  Leaves the same window,
+        step and episode counters as `num_steps` tick() calls (the per-environment running sums stay on the device)."""
+        self.current_step += self.num_envs * num_steps
+        self.current_episode += int(finished)
+        for r, l in zip(returns, lengths):
+            self.recent_returns.append(float(r))
+            self.recent_lengths.append(int(l))
+        self.custom_logs.update(custom_logs)
+        if self.verbose:
+            self.print_logs(force=True)
+
+    def print_logs(self, force: bool = False) -> None:
         at_checkpoint = self.current_step in self.checkpoints
-        due = self.current_step % (self.num_envs * self.print_every) == 0 and len(self.recent_returns) > 0
+        due = (force or self.current_step % (self.num_envs * self.print_every) == 0) and len(self.recent_returns) > 0
         if not (due or at_checkpoint) or not self.recent_returns:
             return
         if not self._header:
@@ -70,6 +83,9 @@ class Ticker:
 
     @property
     def logs(self) -> dict[str, Any]:
+        flush = getattr(self, "_flush_pending", None)          # device-side statistics of the last rollout still in flight
+        if flush is not None:
+            flush()
         elapsed = time.time() - self.start_time
         return dict(total_steps=self.current_step, total_episodes=self.current_episode - 1,
                     episode_returns=list(self.recent_returns), episode_lengths=list(self.recent_lengths),

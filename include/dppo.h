@@ -302,6 +302,17 @@ int dppo_env_step(dppo_ctx* ctx, const dppo_env_desc* desc, const dppo_env_state
                   float* obs, float* next_obs, void* buf_actions, float* rewards, float* terminations, float* truncations,
                   float* done_return, void* stream);
 
+/* ---- device-side episode statistics ------------------------------------------- */
+/* Replaces the per-step host Ticker.tick(rewards, dones) (diamond/utils.py:99-123, call site ppo.py:181-182) for rollouts that
+ * live on the device: one pass over the [T, N] rewards / terminations / truncations of a rollout updates the per-environment
+ * running return (fp64) and length in ep_return / ep_len (carried across rollouts; caller zeroes them when the environments
+ * are reset), writes the number of episodes that finished to *finished and the last min(window, *finished) of them, in the
+ * Ticker's order (step by step, environments in index order), to out_returns / out_lengths[0 .. *out_n). */
+int64_t dppo_episode_stats_workspace_bytes(int T, int N);
+int dppo_episode_stats(dppo_ctx* ctx, const float* rewards, const float* terminations, const float* truncations, int T, int N,
+                       double* ep_return, int32_t* ep_len, int window, double* out_returns, int32_t* out_lengths, int32_t* out_n,
+                       unsigned long long* finished, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- tensor-core building blocks of the fused update (unit tests, A/B measurements) ---------- */
 /* C[M,N] = epi(A[M,K] * op(W)) as an error-compensated 3xTF32 tcgen05 GEMM (fp32-accurate) on CTA pairs
  * (tcgen05 cta_group::2, 256-row tiles shared by the two SMs of a TPC; persistent, TMA-fed, warp-specialised).

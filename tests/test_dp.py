@@ -54,6 +54,18 @@ for e in range(E):
         seen.append(loc)
         cnt = torch.tensor([int(counts[k])]); dist.all_reduce(cnt); assert int(cnt) == M     # shards partition every minibatch
     assert sorted(np.concatenate(seen).tolist()) == list(range(T * NL))
+# epoch ownership: rank e % world shuffles epoch e, the others only advance the stream (skip) -- same stream on every rank afterwards,
+# and the owned permutations are the ones the plain generator produces
+np.random.seed(21)
+plain = [np.random.permutation(B) for _ in range(E)]
+tail_ref = np.random.randint(0, 2**31, 2)
+np.random.seed(21)
+outs2 = [np.full(B, -7, np.int32) for _ in range(E)]
+w3 = _PermWorker(B, E, MB, outs2, lambda e: e % world == rank); w3.start(); w3.finish()
+assert np.array_equal(np.random.randint(0, 2**31, 2), tail_ref)
+for e in range(E):
+    if e % world == rank: assert np.array_equal(outs2[e], plain[e])
+    else: assert (outs2[e] == -7).all()
 # a rank whose stream was consumed differently is caught by the hash check
 if rank == 1: np.random.random()
 w2 = _PermWorker(B, 1, MB, [np.empty(B, np.int32)])

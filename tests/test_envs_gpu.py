@@ -191,3 +191,36 @@ def test_rollout_graph_replay_is_bit_identical_to_eager(env_id):
     for it, (xa, xb) in enumerate(zip(a, b)):
         for k, (u, v) in enumerate(zip(xa, xb)):
             assert torch.equal(u, v), (it, k)
+
+
+@pytest.mark.parametrize("env_id,N_,T,rollouts", [("CartPole-v1", 64, 128, 4), ("CartPole-v1", 2500, 32, 3), ("Pendulum-v1", 16, 250, 3),
+                                                  ("Synthetic", 4096, 16, 2)])
+def test_device_episode_statistics_equal_host_ticker(env_id, N_, T, rollouts):
+    """the device-side episode statistics (dppo_episode_stats, consumed lazily once per rollout) leave the Ticker in
+    the state the reference's per-step `ticker.tick(rewards, dones)` (utils.py:99-123, ppo.py:181-182) leaves it in: same step and
+    episode counters, same window of the last 100 (return, length) pairs in the same order -- returns bit-equal (same fp64 sums)."""
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig
+    from diamond.envs import DeviceVectorEnv
+    from diamond.utils import Ticker
+    cont = env_id == "Pendulum-v1"
+    Agent, Cfg = (ContinuousPPO, ContinuousPPOConfig) if cont else (PPO, PPOConfig)
+    kw = dict(obs_dim=8, n_actions=4, p_term=0.002, p_trunc=0.001) if env_id == "Synthetic" else {}
+    cfg = Cfg(num_envs=N_, rollout_steps=T, verbose=False, seed=3, total_steps=T * N_ * 100)
+    agent = Agent(DeviceVectorEnv.factory(env_id, seed=3, **kw), cfg)
+    agent.current_observations, _ = agent.envs.reset(seed=3)
+    host = Ticker(cfg.total_steps, N_, T, verbose=False)
+    for _ in range(rollouts):
+        buf = agent.rollout()
+        rew = buf.rewards.double().cpu().numpy()
+        dones = ((buf.terminations + buf.truncations) > 0).cpu().numpy()
+        for t in range(T):
+            host.tick(rew[t], dones[t])                     # the reference's per-step bookkeeping, replayed on the host
+    got, ref = agent.ticker.logs, host.logs
+    assert got["total_steps"] == ref["total_steps"] and got["total_episodes"] == ref["total_episodes"]
+    assert got["episode_lengths"] == ref["episode_lengths"]
+    assert got["episode_returns"] == ref["episode_returns"]
+    if env_id != "Pendulum-v1" or T * rollouts >= 200:
+        assert ref["total_episodes"] > 0
+    # running sums of unfinished episodes carried across rollouts on the device
+    np.testing.assert_array_equal(agent._epstats["ep_len"].cpu().numpy(), host.current_lengths)
+    np.testing.assert_array_equal(agent._epstats["ep_return"].cpu().numpy(), host.current_returns)
