@@ -49,6 +49,7 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->gae_inputs_settled = 0;
     c->tc_debug = 0;
     c->draw_base = nullptr;
+    c->rows_dev = nullptr;
     c->launch_count = 0;
     c->tm_cache = nullptr;
     c->tm_cache_free = nullptr;
@@ -422,6 +423,125 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     tab.nseg = n;
     return launch_grad_reduce(ctx, tab, grads, L.total, w.hp + off_loss, w.head_blocks, w.head_stride, hy->value_loss_weight,
                               hy->entropy_beta, inv_m, losses, hy->grad_sumsq, st);
+}
+
+// ---- V(final observation) only where it is needed, shapes decided on the device --------------------
+namespace {
+
+// next_values[t] = values[t+1] wherever the environment did not finish at step t (then next_obs[t] IS obs[t+1] and the rollout
+// already recorded its value); the flat indices of all other (t, env) -- finished steps and the last row -- are appended to idx
+// (order irrelevant: every entry is scattered back to its own index) and counted in *count.
+__global__ void __launch_bounds__(256)
+next_value_plan_kernel(const float* __restrict__ terms, const float* __restrict__ truncs, const float* __restrict__ values, int T, int N,
+                       float* __restrict__ next_values, int32_t* __restrict__ idx, int* __restrict__ count)
+{
+    const int64_t B = (int64_t)T * N;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < B; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        bool need = false;
+        if (i < B) {
+            need = i >= B - N || terms[i] != 0.0f || truncs[i] != 0.0f;
+            if (!need) next_values[i] = values[i + N];
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, need);
+        int start = 0;
+        if (lane == 0 && ballot) start = atomicAdd(count, __popc(ballot));
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (need) idx[start + __popc(ballot & ((1u << lane) - 1u))] = (int32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_values_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, const int* __restrict__ count, float* __restrict__ dst)
+{
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[idx[i]] = src[i];
+}
+
+struct NextWs { int* count; int32_t* idx; float *xg, *h1, *h2, *h3, *tmp; int64_t img_off, bytes; };
+
+NextWs carve_next(const dppo_mlp_desc* d, int64_t B, char* base)
+{
+    NextWs w;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { char* p = base + o; o += align_up(bytes, 256); return p; };
+    w.count = reinterpret_cast<int*>(take(256));
+    w.idx = reinterpret_cast<int32_t*>(take(B * 4));
+    w.xg = reinterpret_cast<float*>(take(B * d->obs_dim * 4));
+    w.h1 = reinterpret_cast<float*>(take(B * d->hidden * 4));
+    w.h2 = reinterpret_cast<float*>(take(B * d->hidden * 4));
+    w.h3 = reinterpret_cast<float*>(take(B * d->hidden * 4));
+    w.tmp = reinterpret_cast<float*>(take(B * 4));
+    o = align_up(o, 1024);
+    w.img_off = o;
+    o += carve_images(d, nullptr).bytes + 1024;
+    w.bytes = o;
+    return w;
+}
+
+}  // namespace
+
+extern "C" int64_t dppo_mlp_next_values_workspace_bytes(const dppo_mlp_desc* d, int T, int N)
+{
+    if (!d || T < 1 || N < 1) return 0;
+    return carve_next(d, (int64_t)T * N, nullptr).bytes + 256;
+}
+
+extern "C" int dppo_mlp_next_values(dppo_ctx* ctx, const dppo_mlp_desc* d, const float* params, const float* next_obs,
+                                    const float* terminations, const float* truncations, const float* values, int T, int N,
+                                    float* next_values, void* ws, int64_t ws_bytes, void* stream)
+{
+    if (!ctx) return 1;
+    if (!d || !params || !next_obs || !terminations || !truncations || !values || !next_values || !ws || T < 1 || N < 1)
+        DPPO_FAIL(ctx, "mlp_next_values: bad arguments");
+    dppo_mlp_layout L;
+    if (dppo_mlp_layout_compute(d, &L)) DPPO_FAIL(ctx, "mlp_next_values: bad descriptor");
+    const int D = d->obs_dim, H = d->hidden;
+    const int64_t B = (int64_t)T * N;
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    NextWs w = carve_next(d, B, base);
+    if ((base - (char*)ws) + w.bytes > ws_bytes) DPPO_FAIL(ctx, "mlp_next_values: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(w.count, 0, sizeof(int), st) != cudaSuccess) DPPO_FAIL(ctx, "mlp_next_values: memset failed");
+    int blocks = (int)((B + 255) / 256);
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    next_value_plan_kernel<<<blocks, 256, 0, st>>>(terminations, truncations, values, T, N, next_values, w.idx, w.count);
+    DPPO_CHECK_LAUNCH(ctx, "next_value_plan_kernel");
+
+    // critic of the listed rows: every launch below has the fixed shape of B rows and reads the true row count on the device
+    char* img_base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base + w.img_off) + 1023) & ~(uintptr_t)1023);
+    WImages img = carve_images(d, img_base);
+    const bool tc_on = ctx->use_tensor_cores != 0;
+    const bool tc1 = tc_on && dppo_tc3_gemm_supported(B, H, D), tc2 = tc_on && dppo_tc3_gemm_supported(B, H, H);
+    {
+        PrepJobs jobs;
+        jobs.n = 0;
+        jobs.gather = GatherJob{nullptr, nullptr, nullptr, 0, 0};
+        auto job = [&](bool on, const float* W, int rows_w, int cols_w, unsigned char* im) {
+            if (on) { jobs.job[jobs.n].W = W; jobs.job[jobs.n].rows_w = rows_w; jobs.job[jobs.n].cols_w = cols_w;
+                      jobs.job[jobs.n].transpose = 0; jobs.job[jobs.n].n_tile = 0; jobs.job[jobs.n].img = im; ++jobs.n; }
+        };
+        job(tc1, params + L.w1, H, D, img.w1f);
+        job(tc2, params + L.w2, H, H, img.w2f);
+        job(tc2, params + L.w3 + (int64_t)H * H, H, H, img.w3f);          // critic_head.0
+        if (dppo_tc_prep_weights_multi(ctx, jobs, st)) return 1;
+    }
+    ctx->rows_dev = w.count;
+    int rc = dppo_gather_rows_f32(ctx, next_obs, w.idx, w.xg, B, D, stream);
+    if (!rc) rc = tc1 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.xg, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, B, H, D, st)
+                      : dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.xg, D, nullptr, params + L.w1, D, params + L.b1, w.h1, H, B, H, D, st);
+    if (!rc) rc = tc2 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, B, H, H, st)
+                      : dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, B, H, H, st);
+    if (!rc) rc = tc2 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3 + H, nullptr, 0, w.h3, H, nullptr, B, H, H, st)
+                      : dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3 + (int64_t)H * H, H, params + L.b3 + H, w.h3, H, B, H, H, st);
+    if (!rc) rc = launch_head_eval(ctx, nullptr, w.h3, H, params + L.wa, params + L.ba, params + L.wc, params + L.bc, nullptr, w.tmp, B, H,
+                                   d->act_dim, st);
+    ctx->rows_dev = nullptr;
+    if (rc) return 1;
+    scatter_values_kernel<<<blocks, 256, 0, st>>>(w.tmp, w.idx, w.count, next_values);
+    DPPO_CHECK_LAUNCH(ctx, "scatter_values_kernel");
+    return 0;
 }
 
 // ---- tensor-core building blocks exposed for unit tests and A/B measurements ----------------------

@@ -18,6 +18,8 @@ struct dppo_ctx {
     long long launch_count;               // kernels launched through this context (bench.py's gpu_launches)
     int tc_debug;                         // timing-experiment switches; only honoured by builds with -DDPPO_TIMING_SWITCHES (see DPPO_DBG)
     const unsigned long long* draw_base;  // optional device counter added to every sampling draw counter (CUDA-graph replay of rollouts)
+    const int* rows_dev;                  // optional DEVICE row count: while set, the forward kernels (gather, GEMMs, head evaluation) process
+                                          // min(rows, *rows_dev) rows -- shapes decided on the device, launches of fixed size, no host sync
     void* tm_cache;                       // tensor-map cache owned by gae.cu
     void (*tm_cache_free)(void*);
 };

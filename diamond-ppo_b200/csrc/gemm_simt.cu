@@ -74,8 +74,13 @@ template <int BM, int BN, int BK, int TM, int TN, int MODE, int EPI>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2)
 gemm_kernel(const float* __restrict__ A, int lda, const int32_t* __restrict__ a_rows, const float* __restrict__ B, int ldb,
             const float* __restrict__ bias, const float* __restrict__ Hact, int ldh, float* __restrict__ C, int ldc,
-            float* __restrict__ colsum, int64_t M, int N, int K, int vecA, int vecB, int vecC)
+            float* __restrict__ colsum, int64_t M, int N, int K, int vecA, int vecB, int vecC, const int* __restrict__ m_dev)
 {
+    if (m_dev != nullptr) {                           // row count decided on the device: tiles past it exit at once
+        const int64_t md = *m_dev;
+        if (md < M) M = md;
+        if ((int64_t)blockIdx.x * BM >= M) return;
+    }
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int TXN = BN / TN;                      // threads along n
     __shared__ Smem<BM, BN, BK> sm;
@@ -351,11 +356,11 @@ int launch_gemm(dppo_ctx* ctx, const float* A, int lda, const int32_t* a_rows, c
     if (use_large(M, N)) {
         dim3 grid((unsigned)((M + LBM - 1) / LBM), (unsigned)((N + LBN - 1) / LBN));
         gemm_kernel<LBM, LBN, LBK, LT, LT, MODE, EPI><<<grid, 256, 0, st>>>(A, lda, a_rows, B, ldb, bias, Hact, ldh, C, ldc,
-                                                                           colsum, M, N, K, vecA, vecB, vecC);
+                                                                           colsum, M, N, K, vecA, vecB, vecC, ctx->rows_dev);
     } else {
         dim3 grid((unsigned)((M + SBM - 1) / SBM), (unsigned)((N + SBN - 1) / SBN));
         gemm_kernel<SBM, SBN, SBK, ST, ST, MODE, EPI><<<grid, 256, 0, st>>>(A, lda, a_rows, B, ldb, bias, Hact, ldh, C, ldc,
-                                                                           colsum, M, N, K, vecA, vecB, vecC);
+                                                                           colsum, M, N, K, vecA, vecB, vecC, ctx->rows_dev);
     }
     DPPO_CHECK_LAUNCH(ctx, "gemm_kernel");
     return 0;

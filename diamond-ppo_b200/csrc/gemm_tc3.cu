@@ -36,8 +36,14 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, const unsigned char* __restrict__ Wimg,
                 const float* __restrict__ bias, const float* __restrict__ Hact, int ldh, float* __restrict__ colsum, int64_t M,
-                int N, int K, int n_tile, int pair_tiles, int tail_halves, int dbg)
+                int N, int K, int n_tile, int pair_tiles, int tail_halves, int dbg, const int* __restrict__ m_dev)
 {
+    if (m_dev != nullptr) {                              // row count decided on the device (tiles past it are never touched)
+        const int64_t md = *m_dev;
+        if (md < M) M = md < 0 ? 0 : md;
+        pair_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
+        tail_halves = 0;
+    }
     extern __shared__ unsigned char dyn_raw[];
     __shared__ __align__(8) uint64_t full[STAGES], ready[STAGES], empty[STAGES], tfull[2], tempty[2];
     __shared__ uint32_t s_tmem;
@@ -339,11 +345,11 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     if (epi == DPPO_EPI_BIAS_TANH) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, Wimg, bias, Hact, ldh, colsum, M,
-                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug);
+                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug, ctx->rows_dev);
     } else if (epi == DPPO_EPI_TANH_BWD) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, Wimg, bias, Hact, ldh, colsum, M,
-                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug);
+                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug, ctx->rows_dev);
     } else {
         DPPO_FAIL(ctx, "tc3_gemm: unknown epilogue %d", epi);
     }

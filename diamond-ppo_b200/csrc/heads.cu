@@ -560,9 +560,10 @@ template <int KPL>
 __global__ void __launch_bounds__(256)
 head_eval_kernel(const float* __restrict__ ha_base, const float* __restrict__ hc_base, int ld, const float* __restrict__ wa,
                  const float* __restrict__ ba, const float* __restrict__ wc, const float* __restrict__ bc,
-                 float* __restrict__ head_out, float* __restrict__ values, int64_t rows, int H, int A)
+                 float* __restrict__ head_out, float* __restrict__ values, int64_t rows, int H, int A, const int* __restrict__ rows_dev)
 {
     extern __shared__ float smem[];
+    if (rows_dev != nullptr && *rows_dev < rows) rows = *rows_dev;
     float* s_wa = smem;
     float* s_wc = smem + A * H;
     if (ha_base) for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = wa[i];
@@ -760,7 +761,7 @@ int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, co
 #define HE(KPL)                                                                                                   \
     do {                                                                                                          \
         cudaFuncSetAttribute(head_eval_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        head_eval_kernel<KPL><<<blocks, 256, smem, st>>>(ha, hc, ld, wa, ba, wc, bc, head_out, values, rows, H, A); \
+        head_eval_kernel<KPL><<<blocks, 256, smem, st>>>(ha, hc, ld, wa, ba, wc, bc, head_out, values, rows, H, A, ctx->rows_dev); \
     } while (0)
     if (H <= 64) HE(2); else if (H <= 128) HE(4); else if (H <= 256) HE(8); else HE(16);
 #undef HE

@@ -174,8 +174,9 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
-                                   int64_t rows, int row_floats)
+                                   int64_t rows, int row_floats, const int* __restrict__ rows_dev)
 {
+    if (rows_dev != nullptr && *rows_dev < rows) rows = *rows_dev;
     const int64_t total = rows * row_floats;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / row_floats;
@@ -186,8 +187,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
 
 // row_floats % 4 == 0 and 16-byte aligned bases: one float4 per thread, a row is read by row_floats/4 consecutive threads
 __global__ void gather_rows4_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx, float4* __restrict__ dst,
-                                    int64_t rows, int row_vec)
+                                    int64_t rows, int row_vec, const int* __restrict__ rows_dev)
 {
+    if (rows_dev != nullptr && *rows_dev < rows) rows = *rows_dev;
     const int64_t total = rows * row_vec;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / row_vec;
@@ -300,14 +302,14 @@ extern "C" int dppo_gather_rows_f32(dppo_ctx* ctx, const float* src, const int32
         int blocks4 = (int)((total4 + 255) / 256);
         if (blocks4 > 16 * ctx->sm_count) blocks4 = 16 * ctx->sm_count;
         gather_rows4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), idx,
-                                                                      reinterpret_cast<float4*>(dst), rows, row_floats / 4);
+                                                                      reinterpret_cast<float4*>(dst), rows, row_floats / 4, ctx->rows_dev);
         DPPO_CHECK_LAUNCH(ctx, "gather_rows4_kernel");
         return 0;
     }
     const int64_t total = rows * row_floats;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
-    gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, dst, rows, row_floats);
+    gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, dst, rows, row_floats, ctx->rows_dev);
     DPPO_CHECK_LAUNCH(ctx, "gather_rows_kernel");
     return 0;
 }

@@ -58,7 +58,7 @@ EXPORTS = [
     "dppo_create", "dppo_destroy", "dppo_last_error", "dppo_version", "dppo_device_info", "dppo_set_option", "dppo_launch_count", "dppo_count_launches",
     "dppo_buffer_store_step", "dppo_step_record_bytes", "dppo_sample_categorical", "dppo_sample_gaussian",
     "dppo_gae_f32", "dppo_adv_normalize_f32", "dppo_permutation_mt19937", "dppo_permutation_mt19937_skip", "dppo_mt19937_seed",
-    "dppo_gather_rows_f32", "dppo_mlp_layout_compute", "dppo_mlp_workspace_bytes", "dppo_mlp_forward",
+    "dppo_gather_rows_f32", "dppo_mlp_layout_compute", "dppo_mlp_workspace_bytes", "dppo_mlp_forward", "dppo_mlp_next_values", "dppo_mlp_next_values_workspace_bytes",
     "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_clip_adam_step",
     "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
@@ -85,7 +85,7 @@ def load_library() -> C.CDLL:
             lib.dppo_last_error.argtypes = [C.c_void_p]
             for name in ("dppo_step_record_bytes", "dppo_mlp_workspace_bytes", "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes",
                          "dppo_ppo_loss_workspace_bytes", "dppo_tc_linear_workspace_bytes", "dppo_tc_wgrad_workspace_bytes", "dppo_launch_count", "dppo_dp_workspace_bytes", "dppo_grad_sumsq_bytes",
-                         "dppo_rnn_workspace_bytes", "dppo_episode_stats_workspace_bytes"):
+                         "dppo_rnn_workspace_bytes", "dppo_episode_stats_workspace_bytes", "dppo_mlp_next_values_workspace_bytes"):
                 getattr(lib, name).restype = C.c_int64
             lib.dppo_dp_slot.restype = C.c_void_p
             _lib = lib
@@ -286,6 +286,17 @@ class Context:
         self._check(self.lib.dppo_logprob_categorical(self.h, _ptr(logits), _ptr(actions_i32), _ptr(out), C.c_int64(rows),
                                                       C.c_int(A), _stream()), "dppo_logprob_categorical")
         self.launches += 1
+
+    def mlp_next_values_workspace_bytes(self, desc, T, N):
+        return int(self.lib.dppo_mlp_next_values_workspace_bytes(C.byref(desc), C.c_int(T), C.c_int(N)))
+
+    def mlp_next_values(self, desc, params, next_obs, terminations, truncations, values, next_values, ws):
+        """next_values from recorded rollout values + the critic on final observations only; row selection on the device, no sync."""
+        T, N = values.shape
+        self._check(self.lib.dppo_mlp_next_values(self.h, C.byref(desc), _ptr(params), _ptr(next_obs), _ptr(terminations), _ptr(truncations),
+                                                  _ptr(values), C.c_int(T), C.c_int(N), _ptr(next_values), _ptr(ws),
+                                                  C.c_int64(ws.numel() * ws.element_size()), _stream()), "dppo_mlp_next_values")
+        self.launches += 8
 
     def logprob_gaussian(self, mean, log_std, actions, out):
         rows, A = mean.shape

@@ -662,19 +662,14 @@ class FusedMlpEngine(_EngineBase):
         there, and the critic is evaluated only on the final observations of finished steps and on the last row --
         ~3 % of the 2 B rows the full pass touches."""
         T, N_ = buf.T, buf.N
-        B = T * N_
         b["values"].copy_(buf.values)
         b["old_logp"].copy_(buf.logp)
-        nv = b["next_values"]
-        if T > 1:
-            nv[:-1].copy_(buf.values[1:])
-        need = (buf.terminations + buf.truncations) > 0
-        need[-1] = True
-        idx = need.view(B).nonzero().squeeze(1)
-        n = int(idx.numel())
-        tmp = torch.empty(n, dtype=torch.float32, device=self.device)
-        self.ctx.mlp_forward(self.fm.desc, self.P, buf.next_obs.view(B, self.D), n, 2, None, tmp, self.fwd_ws, idx=idx.to(torch.int32))
-        nv.view(B).index_copy_(0, idx, tmp)
+        ws = b.get("next_ws")
+        if ws is None:
+            ws = b["next_ws"] = torch.empty(self.ctx.mlp_next_values_workspace_bytes(self.fm.desc, T, N_), dtype=torch.uint8, device=self.device)
+        # row selection, gather, critic and scatter all take their row count from device memory: no host synchronisation
+        self.ctx.mlp_next_values(self.fm.desc, self.P, buf.next_obs.view(T * N_, self.D), buf.terminations, buf.truncations, buf.values,
+                                 b["next_values"], ws)
 
     def check_health(self):
         """Raises if an earlier learn() detected (asynchronously) a data-parallel fault: ranks whose numpy permutation streams
@@ -1014,6 +1009,10 @@ class _PPOBase:
                                       ws=torch.empty(self.ctx.episode_stats_workspace_bytes(buf.T, buf.N) + 8, dtype=torch.uint8, device=dev),
                                       h_out=torch.zeros(W + 2, dtype=torch.float64).pin_memory(), h_len=torch.zeros(W, dtype=torch.int32).pin_memory())
             self.ticker._flush_pending = self._flush_episode_stats
+            pend = getattr(self, "_pending_epstats", None)             # resumed run: running returns / lengths of open episodes
+            if pend is not None and pend["ep_len"].numel() == buf.N:
+                st["ep_return"].copy_(pend["ep_return"]); st["ep_len"].copy_(pend["ep_len"])
+            self._pending_epstats = None
         self._flush_episode_stats()                                    # the previous rollout's numbers (long since copied)
         self.ctx.episode_stats(buf.rewards, buf.terminations, buf.truncations, st["ep_return"], st["ep_len"], W, st["out"][:W],
                                st["out_len"], st["out_n"], st["finished"], st["ws"])
@@ -1058,35 +1057,119 @@ class _PPOBase:
         return self.engine.last_losses
 
     # ---- train (ppo.py:289-312) ----------------------------------------------------------------------
-    def train(self) -> None:
+    # ---- train-level checkpoint state (the resume path the reference lacks) ---------------------------
+    def _train_state(self, rollouts_done: int) -> dict:
+        """Everything beyond {"model_state", "opt_state"} that a bit-identical continuation of train() needs: position in the
+        run, LR schedule, the numpy global stream (minibatch permutations) and torch CPU stream, the engine's counter-based
+        generators, the environments and the Ticker."""
+        eng, envs = self.engine, self.envs
+        st = dict(version=1, rollouts_done=int(rollouts_done), lr_scheduler=self.lr_scheduler.state_dict(),
+                  numpy_state=np.random.get_state(legacy=True), torch_rng=torch.get_rng_state(),
+                  engine={k: getattr(eng, k) for k in ("draws", "seed", "perm_counter", "perm_seed") if hasattr(eng, k)})
+        self._flush_episode_stats()
+        tk = self.ticker
+        if tk is not None:
+            st["ticker"] = dict(current_step=tk.current_step, current_episode=tk.current_episode, returns=list(tk.recent_returns),
+                                lengths=list(tk.recent_lengths), current_returns=tk.current_returns.copy(),
+                                current_lengths=tk.current_lengths.copy(), elapsed=time.time() - tk.start_time)
+        if self._epstats is not None:
+            st["epstats"] = dict(ep_return=self._epstats["ep_return"].cpu(), ep_len=self._epstats["ep_len"].cpu())
+        if getattr(envs, "device_resident", False):
+            st["envs"] = dict(kind="device", seed=int(envs.desc.seed), env_offset=int(envs.desc.env_offset),
+                              **{k: getattr(envs, k).cpu() for k in ("state", "steps", "episode", "ep_return", "cur_obs")})
+        else:
+            import pickle
+            try:                                                       # host environments: whatever pickles (the in-repo shim does)
+                st["envs"] = dict(kind="pickle", blob=pickle.dumps(envs), obs=np.asarray(self.current_observations).copy())
+            except Exception:
+                st["envs"] = dict(kind="none")
+        return st
+
+    def _restore_train_state(self, st: dict) -> int:
+        if st.get("version") != 1:
+            raise ValueError("unknown train_state version in checkpoint")
+        self.lr_scheduler.load_state_dict(st["lr_scheduler"])
+        lr = self.lr_scheduler.get_last_lr()[0]
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr
+        np.random.set_state(st["numpy_state"])
+        torch.set_rng_state(st["torch_rng"])
+        for k, v in st["engine"].items():
+            setattr(self.engine, k, v)
+        tk, ts = self.ticker, st.get("ticker")
+        if tk is not None and ts is not None:
+            tk.current_step, tk.current_episode = ts["current_step"], ts["current_episode"]
+            tk.recent_returns.clear(); tk.recent_returns.extend(ts["returns"])
+            tk.recent_lengths.clear(); tk.recent_lengths.extend(ts["lengths"])
+            tk.current_returns[:] = ts["current_returns"]; tk.current_lengths[:] = ts["current_lengths"]
+            tk.start_time = time.time() - ts["elapsed"]
+        self._pending_epstats = st.get("epstats")                      # adopted when the device accumulators are created
+        es = st["envs"]
+        if es["kind"] == "device":
+            envs = self.envs
+            envs.desc.seed, envs.desc.env_offset = es["seed"], es["env_offset"]
+            for k in ("state", "steps", "episode", "ep_return", "cur_obs"):
+                getattr(envs, k).copy_(es[k])
+            self.current_observations = envs.cur_obs
+        elif es["kind"] == "pickle":
+            import pickle
+            self.envs = pickle.loads(es["blob"])
+            self.current_observations = es["obs"]
+        else:
+            raise RuntimeError("the checkpoint holds no environment state (the environments could not be pickled): cannot resume")
+        return int(st["rollouts_done"])
+
+    def save_checkpoint(self, rollouts_done: int):
+        """Reference payload keys (utils.py:584-600: step, model_state, opt_state) + "train_state" for resume."""
+        env_steps = rollouts_done * self.cfg.rollout_steps * self.cfg.num_envs
+        return self.checkpointer.save(env_steps, self.network, self.optimizer, extra={"train_state": self._train_state(rollouts_done)})
+
+    # ---- train (ppo.py:289-312) ----------------------------------------------------------------------
+    def train(self, *, resume_from=None, max_rollouts: int | None = None) -> None:
+        """The reference's training loop.  Additive: `resume_from=<checkpoint path>` continues an interrupted run (model, Adam
+        moments and step, LR schedule, RNG streams, environments, Ticker) so that it ends bit-identical to an uninterrupted
+        one; `max_rollouts` stops after that many rollouts of THIS call, saving a checkpoint (interruption point for tests)."""
         cfg = self.cfg
-        # under data parallelism the shards are different environments of one global run: host vector envs seed sub-env i with
-        # seed + i (Gymnasium), so rank r starts at seed + r*N; device envs key their draws by global env id (env_offset)
-        seed = cfg.seed
-        if seed is not None and self._dist.enabled and not getattr(self.envs, "device_resident", False):
-            seed = cfg.seed + self._dist.rank * cfg.num_envs
-        self.current_observations, _ = self.envs.reset(seed=seed)
-        if self._epstats is not None:                                  # fresh environments: running returns / lengths restart
-            self._flush_episode_stats()
-            self._epstats["ep_return"].zero_()
-            self._epstats["ep_len"].zero_()
+        first = 0
+        if resume_from is not None:
+            chk = torch.load(resume_from, map_location="cpu", weights_only=False)
+            if "train_state" not in chk:
+                raise ValueError(f"{resume_from} has no train_state: it was not written by train() of this package")
+            self.network.load_state_dict(chk["model_state"])
+            self.optimizer.load_state_dict(chk["opt_state"])
+            if hasattr(self.engine, "_resync_optimizer"):
+                self.engine._resync_optimizer()
+            first = self._restore_train_state(chk["train_state"])
+        else:
+            # under data parallelism the shards are different environments of one global run: host vector envs seed sub-env i
+            # with seed + i (Gymnasium), so rank r starts at seed + r*N; device envs key their draws by global env id (env_offset)
+            seed = cfg.seed
+            if seed is not None and self._dist.enabled and not getattr(self.envs, "device_resident", False):
+                seed = cfg.seed + self._dist.rank * cfg.num_envs
+            self.current_observations, _ = self.envs.reset(seed=seed)
+            if self._epstats is not None:                              # fresh environments: running returns / lengths restart
+                self._flush_episode_stats()
+                self._epstats["ep_return"].zero_()
+                self._epstats["ep_len"].zero_()
         last_checkpoint_time = time.time()
         total_rollouts = cfg.total_steps // (cfg.rollout_steps * cfg.num_envs)
-        env_steps = 0
-        for rollout_idx in range(total_rollouts):
+        stop = total_rollouts if max_rollouts is None else min(total_rollouts, first + max_rollouts)
+        done = first
+        for rollout_idx in range(first, stop):
             experience = self.rollout()
             self.learn(experience)
-            env_steps = (rollout_idx + 1) * cfg.rollout_steps * cfg.num_envs
+            done = rollout_idx + 1
             if cfg.checkpoint and self._dist.rank == 0 and time.time() - last_checkpoint_time >= cfg.save_interval:
-                self.checkpointer.save(env_steps, self.network, self.optimizer)      # replicas are identical: rank 0 writes
+                self.save_checkpoint(done)                             # replicas are identical: rank 0 writes
                 last_checkpoint_time = time.time()
-        if cfg.checkpoint and total_rollouts > 0 and self._dist.rank == 0:
-            self.checkpointer.save(env_steps, self.network, self.optimizer)
+        if (cfg.checkpoint or max_rollouts is not None) and done > first and self._dist.rank == 0:
+            self.last_checkpoint = self.save_checkpoint(done)
         self._flush_episode_stats()
         if hasattr(self.engine, "check_health"):
             torch.cuda.current_stream().synchronize()
             self.engine.check_health()
-        self.envs.close()
+        if stop == total_rollouts:
+            self.envs.close()
 
 
 class PPO(_PPOBase):

@@ -142,12 +142,17 @@ class Checkpointer:
     def __init__(self, folder: str | Path = "models", run_name: str = "run", *, keep_last: int | None = None) -> None:
         self.folder, self.run_name, self.keep_last = Path(folder), run_name, keep_last
 
-    def save(self, step: int, model: torch.nn.Module, optimizer: torch.optim.Optimizer | None = None) -> Path:
+    def save(self, step: int, model: torch.nn.Module, optimizer: torch.optim.Optimizer | None = None, *,
+             extra: dict | None = None) -> Path:
         self.folder.mkdir(parents=True, exist_ok=True)
         path = self.folder / f"{self.run_name}-step{step:06d}.pt"
         payload = {"step": step, "model_state": {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}}
         if optimizer is not None:
-            payload["opt_state"] = optimizer.state_dict()
+            osd = optimizer.state_dict()                   # moments are views of the device buffers: detach them from the live run
+            payload["opt_state"] = {"state": {i: {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                                              for i, st in osd["state"].items()}, "param_groups": osd["param_groups"]}
+        if extra:
+            payload.update(extra)                          # e.g. "train_state" (resume); readers of the reference's keys ignore it
         torch.save(payload, path)
         if self.keep_last is not None:
             for old in sorted(self.folder.glob(f"{self.run_name}-step*.pt"))[:-self.keep_last]:
@@ -155,7 +160,7 @@ class Checkpointer:
         return path
 
     def load(self, path: str | Path, model: torch.nn.Module, optimizer: torch.optim.Optimizer | None = None) -> int:
-        chk = torch.load(path, map_location="cpu")
+        chk = torch.load(path, map_location="cpu", weights_only=False)
         model.load_state_dict(chk["model_state"])          # copies into the flat device buffers in place
         if optimizer is not None and "opt_state" in chk:
             optimizer.load_state_dict(chk["opt_state"])

@@ -167,6 +167,16 @@ int64_t dppo_mlp_workspace_bytes(const dppo_mlp_desc* desc, int64_t rows, int tr
 int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* desc, const float* params, const float* obs,
                      const int32_t* idx, int64_t rows, int heads, float* head_out, float* values,
                      void* ws, int64_t ws_bytes, void* stream);
+/* next_values for GAE when the rollout already recorded values[t] = V(obs[t]) with the current parameters
+ * (replaces the critic half of the pre-update pass, ppo.py:238).  Wherever the environment did not finish at step t,
+ * next_obs[t] is obs[t+1] and next_values[t] = values[t+1]; the critic is evaluated only on the final observations of finished
+ * steps and on the last row.  Which rows those are is decided ON THE DEVICE: every launch has a fixed shape and reads the row
+ * count from device memory, so the call needs no host synchronisation between rollout and learn().  next_obs [T*N, D],
+ * terminations / truncations / values / next_values [T, N]. */
+int64_t dppo_mlp_next_values_workspace_bytes(const dppo_mlp_desc* desc, int T, int N);
+int dppo_mlp_next_values(dppo_ctx* ctx, const dppo_mlp_desc* desc, const float* params, const float* next_obs,
+                         const float* terminations, const float* truncations, const float* values, int T, int N,
+                         float* next_values, void* ws, int64_t ws_bytes, void* stream);
 int dppo_logprob_categorical(dppo_ctx* ctx, const float* logits, const int32_t* actions, float* log_probs,
                              int64_t rows, int A, void* stream);
 int dppo_logprob_gaussian(dppo_ctx* ctx, const float* mean, const float* log_std, const float* actions,

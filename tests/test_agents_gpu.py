@@ -430,3 +430,41 @@ def test_graph_replay_of_update_loop_is_bit_identical_to_eager():
     assert torch.equal(a0.engine.P, a1.engine.P) and torch.equal(a0.engine.M, a1.engine.M) and torch.equal(a0.engine.V, a1.engine.V)
     assert a0.engine.adam_step == a1.engine.adam_step == 3 * 3 * 4
     np.testing.assert_array_equal(r0, r1)
+
+
+@pytest.mark.parametrize("kind", ["device", "host"])
+def test_train_resume_is_bit_identical_to_uninterrupted_run(tmp_path, kind):
+    """train(resume_from=checkpoint) restores model, Adam moments + step, LinearLR, the numpy / counter-based RNG streams,
+    the environments and the Ticker; an interrupted + resumed run ends with bit-identical parameters, optimiser state and episode
+    statistics.  (The reference saves checkpoints, ppo.py:303-310 / utils.py:584-600, but never loads them.)"""
+    from diamond import PPO, PPOConfig, envs
+    from diamond.envs import DeviceVectorEnv
+    from diamond.utils import Checkpointer
+    N_, T, R = (64, 32, 7) if kind == "device" else (4, 16, 6)
+
+    def make(tag):
+        cfg = PPOConfig(num_envs=N_, rollout_steps=T, verbose=False, seed=5, total_steps=N_ * T * R, decay_lr=True, num_minibatches=4)
+        env_fn = DeviceVectorEnv.factory("CartPole-v1", seed=5) if kind == "device" else (lambda: envs.CartPoleEnv())
+        agent = PPO(env_fn, cfg)
+        agent.checkpointer = Checkpointer(tmp_path / tag, "run")
+        return agent
+
+    full = make("full")
+    full.train()
+    part = make("part")
+    part.train(max_rollouts=3)
+    path = part.last_checkpoint
+    chk = torch.load(path, map_location="cpu", weights_only=False)
+    assert {"step", "model_state", "opt_state", "train_state"} <= set(chk) and chk["step"] == 3 * N_ * T     # reference payload keys kept
+    resumed = make("resumed")
+    resumed.train(resume_from=path)
+    torch.cuda.synchronize()
+    assert torch.equal(resumed.engine.P, full.engine.P)
+    assert torch.equal(resumed.engine.M, full.engine.M) and torch.equal(resumed.engine.V, full.engine.V)
+    assert resumed.engine.adam_step == full.engine.adam_step == R * 4 * 4
+    assert resumed.optimizer.param_groups[0]["lr"] == full.optimizer.param_groups[0]["lr"]
+    a, b = resumed.ticker.logs, full.ticker.logs
+    for k in ("total_steps", "total_episodes", "episode_returns", "episode_lengths"):
+        assert a[k] == b[k], k
+    # and the interrupted agent itself was not at the end
+    assert not torch.equal(part.engine.P, full.engine.P)
