@@ -220,7 +220,7 @@ def bench_gae(ctx, hbm_peak, sets=20, launches=200, settled=True, n_envs=None):
     bytes_ = T * N_ENVS * GAE_BYTES_PER_ELEM
     gbps = bytes_ / (us * 1e-6) / 1e9
     return {"us_per_launch": us, "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak, "bound": "hbm",
-            "bytes_per_launch": bytes_, "launches": launches, "buffer_sets": sets, "inputs_settled": bool(settled)}
+            "bytes_per_launch": bytes_, "launches": launches, "buffer_sets": sets, "inputs_settled": settled}
 
 
 def bench_dominant_gemm(ctx, tensor_peak, sets=4, reps=12):
@@ -431,9 +431,10 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline evidence (rank 0) ----
     fma_peak = bench_fma_peak(ctx)
     gae = bench_gae(ctx, hbm_peak)
-    gae_cons = bench_gae(ctx, hbm_peak, settled=False)
+    gae_cons = bench_gae(ctx, hbm_peak, settled="rollout")       # only the rollout tensors are promised settled
+    gae_plain = bench_gae(ctx, hbm_peak, settled=False)          # no promise, no programmatic dependent launch (the public API's default)
     # a shape where launch latency amortises: 65 536 envs x 128 steps = 235 MB per launch, two buffer sets (470 MB > L2)
-    gae_large = bench_gae(ctx, hbm_peak, sets=2, launches=10, settled=False, n_envs=65536)
+    gae_large = bench_gae(ctx, hbm_peak, sets=2, launches=10, settled="rollout", n_envs=65536)
     upd_tflops = E * T * n_local * FLOP_PER_SAMPLE_UPDATE / (t_upd * 1e-3) / 1e12        # per GPU
     # fp32-accurate products cost three TF32 tensor passes; TF32 runs at half the bf16 rate (same cycles per instruction
     # at half the K, confirmed by the in-run probe), so the algorithmic peak is bf16 / 2 / 3
@@ -459,7 +460,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline_gae": dict(gae, kernel="gae_pipe_kernel (chunked TMA loads, programmatic dependent launch)",
                              peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", traffic=GAE_DRAM_TRAFFIC,
                              without_settled_promise={"us_per_launch": gae_cons["us_per_launch"], "achieved": gae_cons["achieved"],
-                                                      "frac": gae_cons["frac"]},
+                                                      "frac": gae_cons["frac"], "note": "values / next_values wait for the predecessor grid"},
+                             plain_launch_no_promise={"us_per_launch": gae_plain["us_per_launch"], "achieved": gae_plain["achieved"],
+                                                      "frac": gae_plain["frac"], "note": "no programmatic dependent launch (calculate_advantage API)"},
                              large_shape_65536x128={"us_per_launch": gae_large["us_per_launch"], "achieved": gae_large["achieved"],
                                                     "frac": gae_large["frac"], "bytes_per_launch": gae_large["bytes_per_launch"],
                                                     "inputs_settled": False}),

@@ -77,7 +77,7 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
         DPPO_FAIL(ctx, "dppo_set_option: 'tc_debug' needs a library built with -DDPPO_TIMING_SWITCHES (timing experiments only)");
 #endif
     }
-    if (!strcmp(name, "gae_inputs_settled")) { ctx->gae_inputs_settled = value != 0; return 0; }
+    if (!strcmp(name, "gae_inputs_settled")) { ctx->gae_inputs_settled = value < 0 ? 0 : value > 2 ? 2 : value; return 0; }
     DPPO_FAIL(ctx, "dppo_set_option: unknown option '%s'", name);
 }
 

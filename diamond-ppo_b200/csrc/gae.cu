@@ -510,10 +510,12 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
-                lc.attrs = attr; lc.numAttrs = 1;
+                // level 0 (public API default): no programmatic dependent launch -- the kernel starts after its predecessor has
+                // completed and nothing is loaded early; 1: rollout tensors early; 2: all five inputs early (dppo.h)
+                lc.attrs = attr; lc.numAttrs = ctx->gae_inputs_settled >= 1 ? 1 : 0;
                 cudaFuncSetAttribute(gae_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 cudaLaunchKernelEx(&lc, gae_pipe_kernel, m[0], m[1], m[2], m[3], m[4], advantages, returns, stats, T, N, epc, chunk_bytes,
-                                   g, gl, ctx->gae_inputs_settled);
+                                   g, gl, ctx->gae_inputs_settled >= 2 ? 1 : 0);
                 DPPO_CHECK_LAUNCH(ctx, "gae_pipe_kernel");
                 return 0;
             }
@@ -534,7 +536,7 @@ extern "C" int dppo_gae_f32(dppo_ctx* ctx, const float* rewards, const float* te
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = attr; lc.numAttrs = 1;
+            lc.attrs = attr; lc.numAttrs = ctx->gae_inputs_settled >= 1 ? 1 : 0;
 #define GAE_TMA_LAUNCH(LL)                                                                                              \
             do {                                                                                                        \
                 cudaFuncSetAttribute(gae_tma_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \

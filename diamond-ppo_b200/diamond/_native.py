@@ -222,8 +222,10 @@ class Context:
         T, N = rewards.shape
         if advantages is None:
             advantages = torch.empty_like(rewards)
-        # inputs_settled: none of the five inputs is written by the kernel launched just before this call (include/dppo.h)
-        self.lib.dppo_set_option(self.h, b"gae_inputs_settled", C.c_int(int(bool(inputs_settled))))
+        # inputs_settled (include/dppo.h): False -- plain launch, nothing requested early (any caller); "rollout" -- the kernel
+        # launched just before this call writes none of rewards / terminations / truncations; True -- none of the five inputs
+        level = 1 if inputs_settled == "rollout" else (2 if inputs_settled else 0)
+        self.lib.dppo_set_option(self.h, b"gae_inputs_settled", C.c_int(level))
         self._check(self.lib.dppo_gae_f32(self.h, _ptr(rewards), _ptr(terminations), _ptr(truncations), _ptr(values),
                                           _ptr(next_values), _ptr(advantages), _ptr(returns), _ptr(stats), C.c_int(T),
                                           C.c_int(N), C.c_double(gamma), C.c_double(gae_lambda), _stream()), "dppo_gae_f32")

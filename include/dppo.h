@@ -90,11 +90,13 @@ int dppo_count_launches(dppo_ctx* ctx, int64_t n);   /* add n: launches replayed
  *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128); 0: FP32 FFMA GEMMs everywhere
  *   "gae_variant"  0 (default): pipelined TMA-staged GAE kernel (T >= 128; chunked loads, stores overlap them) or the
  *                  single-barrier TMA kernel when the layout allows, 1: register-staged, 2: single-barrier TMA
- *   "gae_inputs_settled" 0 (default) / 1: promise that none of the five GAE input tensors is written by the kernel launched
- *                  immediately before dppo_gae_f32 on the stream.  The GAE kernels are launched with programmatic stream
- *                  serialization; with the promise they request all input tiles before griddepcontrol.wait (which then only
- *                  guards their global writes), so consecutive launches overlap.  Without it only rewards/terminations/
- *                  truncations (rollout data) are requested early. */
+ *   "gae_inputs_settled" 0 (default): plain launch -- the GAE kernel starts after its stream predecessor has completed and
+ *                  requests nothing early (safe for any caller, e.g. a cast kernel writing a mask right before it);
+ *                  1: promise that the kernel launched immediately before dppo_gae_f32 on the stream writes none of
+ *                  rewards / terminations / truncations (rollout data): the launch uses programmatic stream serialization and
+ *                  requests those three tiles before griddepcontrol.wait; 2: promise that it writes none of the five inputs:
+ *                  all tiles are requested early and the wait only guards the kernel's global writes, so consecutive
+ *                  launches overlap (PPO.learn(): the predecessor is the 32-byte statistics fill). */
 int dppo_set_option(dppo_ctx* ctx, const char* name, int value);
 
 /* ---- rollout buffer + batched action sampling (diamond/ppo.py:153-186, 73-82) ---------- */
