@@ -42,7 +42,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int64_t md = *m_dev;
         if (md < M) M = md < 0 ? 0 : md;
         pair_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
-        tail_halves = 0;
+        if (tail_halves == 1) tail_halves = 0;           // the tail split was planned for the host's row count
     }
     extern __shared__ unsigned char dyn_raw[];
     __shared__ __align__(8) uint64_t full[STAGES], ready[STAGES], empty[STAGES], tfull[2], tempty[2];
@@ -62,11 +62,16 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // Tile schedule of this cluster: `base` full 256 x n_tile tiles (round robin), then the remainder.  When the remainder
     // R satisfies 2R <= clusters (tail_halves), each leftover tile is split into two half-width (n_tile/2 columns) tiles
     // that go to different clusters: the makespan drops from base + 1 to base + ~0.63 tiles.
-    const int base_tiles = total / n_clusters, rem_tiles = total - base_tiles * n_clusters;
-    const int extra = tail_halves ? (cluster_id < 2 * rem_tiles ? 1 : 0) : (cluster_id < rem_tiles ? 1 : 0);
+    // tail_halves == 2 (small problems: fewer full tiles than half of the clusters): EVERY tile is split into its two half-width
+    // tiles, so twice as many SM pairs work and each runs the cheaper N = n_tile/2 instruction.
+    const bool all_halves = tail_halves == 2;
+    const int units = all_halves ? 2 * total : total;
+    const int base_tiles = units / n_clusters, rem_tiles = units - base_tiles * n_clusters;
+    const int extra = tail_halves == 1 ? (cluster_id < 2 * rem_tiles ? 1 : 0) : (cluster_id < rem_tiles ? 1 : 0);
     const int n_my = base_tiles + extra;
     auto tile_of = [&](int i, int& tile, int& half) {
-        if (i < base_tiles) { tile = i * n_clusters + cluster_id; half = -1; }
+        if (all_halves) { const int u = i * n_clusters + cluster_id; tile = u >> 1; half = u & 1; }
+        else if (i < base_tiles) { tile = i * n_clusters + cluster_id; half = -1; }
         else if (tail_halves) { tile = base_tiles * n_clusters + (cluster_id >> 1); half = cluster_id & 1; }
         else { tile = base_tiles * n_clusters + cluster_id; half = -1; }
     };
@@ -304,13 +309,35 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 }  // namespace
 
 namespace {
-int tc3_grid(dppo_ctx* ctx, int64_t M, int N)
+// Tile schedule of a launch: grid (2 CTAs per cluster) and how the tiles are cut.  mode 0: full 256 x n_tile tiles round robin;
+// 1: the remainder tiles are split into half-width tiles (one per cluster); 2: every tile is split (small problems).
+// Makespans are compared in full-tile units; a half-width tile costs ~0.63 of a full one (the N = 128 instruction is paced by
+// operand fetch, dppo_tc_mma_probe).
+void tc3_plan(dppo_ctx* ctx, int64_t M, int N, int* grid_out, int* mode_out)
 {
     const int n_tile = dppo_tc_n_tile(N);
     const int64_t total = ((M + 2 * BM - 1) / (2 * BM)) * (N / n_tile);
-    int64_t clusters = ctx->sm_count / 2;
-    if (clusters > total) clusters = total;
-    return (int)(2 * clusters);
+    const int64_t max_clusters = ctx->sm_count / 2;
+    if (total < 1 || max_clusters < 1) { *grid_out = 2; *mode_out = 0; return; }      // unsupported shape (sizing calls only)
+    int64_t clusters = max_clusters < total ? max_clusters : total;
+    const int64_t base = total / clusters, rem = total - base * clusters;
+    int mode = (!DPPO_DBG(ctx->tc_debug, 128) && n_tile == 256 && base >= 1 && rem > 0 && 2 * rem <= clusters) ? 1 : 0;
+    if (n_tile == 256 && !DPPO_DBG(ctx->tc_debug, 128) && ctx->rows_dev == nullptr) {
+        const double full_span = (double)base + (rem > 0 ? (mode == 1 ? 0.63 : 1.0) : 0.0);
+        const double half_span = 0.63 * (double)((2 * total + max_clusters - 1) / max_clusters);
+        if (half_span < full_span - 0.05) {
+            mode = 2;
+            clusters = max_clusters < 2 * total ? max_clusters : 2 * total;
+        }
+    }
+    *grid_out = (int)(2 * clusters);
+    *mode_out = mode;
+}
+int tc3_grid(dppo_ctx* ctx, int64_t M, int N)
+{
+    int grid, mode;
+    tc3_plan(ctx, M, N, &grid, &mode);
+    return grid;
 }
 }  // namespace
 
@@ -333,13 +360,10 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
         DPPO_FAIL(ctx, "tc3_gemm: cuTensorMapEncodeTiled failed");
     const int n_tile = dppo_tc_n_tile(N);
     const int pair_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
-    const int total = pair_tiles * (N / n_tile);
     const size_t smem = (size_t)STAGES * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK + 1024;
-    const int grid = tc3_grid(ctx, M, N);
-    const int clusters = grid / 2, base_tiles = total / clusters, rem = total - base_tiles * clusters;
-    // half-width tail tiles: only when every cluster still starts with a full tile and the halves fit one per cluster
-    const int tail_halves = (!DPPO_DBG(ctx->tc_debug, 128) && n_tile == 256 && base_tiles >= 1 && rem > 0 && 2 * rem <= clusters) ? 1 : 0;
-    if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && N / n_tile > 1 &&
+    int grid, tail_halves;
+    tc3_plan(ctx, M, N, &grid, &tail_halves);
+    if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && (N / n_tile > 1 || tail_halves == 2) &&
         cudaMemsetAsync(colsum + (size_t)grid * N, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {

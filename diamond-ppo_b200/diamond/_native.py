@@ -59,7 +59,7 @@ EXPORTS = [
     "dppo_buffer_store_step", "dppo_step_record_bytes", "dppo_sample_categorical", "dppo_sample_gaussian",
     "dppo_gae_f32", "dppo_adv_normalize_f32", "dppo_permutation_mt19937", "dppo_permutation_mt19937_skip", "dppo_mt19937_seed",
     "dppo_gather_rows_f32", "dppo_mlp_layout_compute", "dppo_mlp_workspace_bytes", "dppo_mlp_forward", "dppo_mlp_next_values", "dppo_mlp_next_values_workspace_bytes",
-    "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_clip_adam_step",
+    "dppo_logprob_categorical", "dppo_logprob_gaussian", "dppo_mlp_grad_minibatch", "dppo_small_update", "dppo_small_update_supported", "dppo_clip_adam_step",
     "dppo_clip_adam_workspace_bytes", "dppo_grad_sumsq_bytes", "dppo_ppo_loss_discrete", "dppo_ppo_loss_gaussian",
     "dppo_ppo_loss_workspace_bytes", "dppo_fma_peak_kernel", "dppo_tc_linear_f32", "dppo_tc_linear_workspace_bytes",
     "dppo_tc_colsum_parts", "dppo_tc_wgrad_f32", "dppo_tc_wgrad_workspace_bytes", "dppo_tc_mma_probe", "dppo_dp_create", "dppo_dp_handle_bytes", "dppo_dp_handle", "dppo_dp_connect", "dppo_dp_destroy", "dppo_dp_status",
@@ -314,6 +314,18 @@ class Context:
                                                      _ptr(losses), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()),
                                                      _stream()), "dppo_mlp_grad_minibatch")
         self.launches += 10
+
+    def small_update_supported(self, desc) -> bool:
+        return bool(self.lib.dppo_small_update_supported(C.byref(desc)))
+
+    def small_update(self, desc, params, grads, exp_avg, exp_avg_sq, obs, actions, old_logp, adv, returns, adv_stats, idx, rows, steps,
+                     hyper, step_consts, losses, grad_norm_out=None):
+        """All `steps` optimiser steps of a learn() in one cluster launch (default 64-wide network; dppo_small_update)."""
+        self._check(self.lib.dppo_small_update(self.h, C.byref(desc), _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                               _ptr(obs), _ptr(actions), _ptr(old_logp), _ptr(adv), _ptr(returns), _ptr(adv_stats),
+                                               _ptr(idx), C.c_int64(rows), C.c_int(steps), C.byref(hyper), _ptr(step_consts),
+                                               _ptr(losses), _ptr(grad_norm_out), _stream()), "dppo_small_update")
+        self.launches += 1
 
     # ---- device-resident vector environments -----------------------------------------------------
     def env_reset(self, desc, state, mask=None):

@@ -69,6 +69,7 @@ class RolloutBuffer:
         self.h2d_bytes = 0
         self._copy_stream = None        # side stream of load_host
         self._h2d = None                # pending sliced load: {"bounds", "events"}
+        self._consumed = None           # event after the last learn() that read this buffer
         self.filled = 0
 
     def _carve(self, raw: np.ndarray):
@@ -120,7 +121,7 @@ class RolloutBuffer:
         A = int(np.prod(act.shape[2:])) if continuous else 1
         buf = cls.__new__(cls)
         buf.ctx, buf.T, buf.N, buf.D, buf.A, buf.continuous, buf.device = ctx, T, N_, D, A, continuous, device
-        buf._copy_stream, buf._h2d = None, None
+        buf._copy_stream, buf._h2d, buf._consumed = None, None, None
 
         def up(x, dtype):
             t = torch.as_tensor(np.ascontiguousarray(x)).to(dtype)
@@ -144,7 +145,13 @@ class RolloutBuffer:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
         cs = self._copy_stream
-        cs.wait_stream(torch.cuda.current_stream())            # everything enqueued so far may still read the old contents
+        # the old contents may still be read by work already enqueued: wait for the last learn() that consumed THIS buffer when it
+        # left a mark (a caller alternating two buffers then overlaps this copy with the other buffer's update loop), else for
+        # everything enqueued so far
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)
+        else:
+            cs.wait_stream(torch.cuda.current_stream())
         n = 0
         T, nch = self.T, min(self.H2D_CHUNKS, self.T)
         bounds = [T * c // nch for c in range(nch + 1)]
@@ -438,9 +445,10 @@ class FusedMlpEngine(_EngineBase):
         self.last_losses = None
         self.timing = {}
         self.use_graphs = True          # replay the optimiser steps of an epoch as a CUDA graph (single GPU, steady state)
-        self._seen_key = None
+        self._seen_keys = []
         self._idx_consumed = None       # event after the last async copy out of the pinned per-epoch index buffers
         self.reuse_rollout_values = True   # learn() takes log-probs / values recorded at sampling time when they are still valid
+        self.use_small_kernel = True       # default 64-wide nets: the whole update loop of a learn() as one cluster launch
         self.dp_seq = 0                    # data-parallel exchanges issued so far (monotonic; independent of the Adam step)
         self.perm_mode = dist.perm_mode    # "numpy": bit-exact np.random stream on a host thread; "device": keyed-bijection generator
         self.perm_seed = (self.seed * 0x9E3779B97F4A7C15 + (0 if dist.global_perm or not dist.enabled else dist.rank + 1)) % (1 << 64)
@@ -560,6 +568,43 @@ class FusedMlpEngine(_EngineBase):
                                   b["counts"][p], b["overflow"])
         return b["idx"][p]
 
+    SMALL_ROWS = 1024      # minibatch rows up to which the one-launch cluster kernel beats the per-layer kernels
+
+    def _learn_small(self, b, worker, hyper, desc, tensors, losses, E, MB, rows):
+        """Default 64-wide networks: all E x MB optimiser steps in ONE launch (dppo_small_update) -- parameters, gradient partials
+        and sharded Adam state live in the distributed shared memory of an 8-CTA cluster for the whole update loop."""
+        ctx, dev = self.ctx, self.device
+        S, B = E * MB, MB * rows
+        sm = b.get("small")
+        if sm is None:
+            sm = b["small"] = dict(idx=torch.empty(E * B, dtype=torch.int32, device=dev), consts=torch.empty(S, 2, dtype=torch.float32, device=dev),
+                                   h_consts=torch.empty(S, 2, dtype=torch.float32).pin_memory(), copied=None)
+        if sm["copied"] is not None:
+            sm["copied"].synchronize()                                   # the previous copy out of h_consts has completed
+        hc = sm["h_consts"].numpy()
+        b1, b2 = hyper.beta1, hyper.beta2
+        for k in range(S):
+            step = self.adam_step + k + 1                                # torch/optim/adam.py:531-547, python-float bias corrections
+            hc[k, 0] = np.float32(np.sqrt(1.0 - b2 ** step))
+            hc[k, 1] = np.float32(-(hyper.lr / (1.0 - b1 ** step)))
+        sm["consts"].copy_(sm["h_consts"], non_blocking=True)
+        sm["copied"] = torch.cuda.Event()
+        sm["copied"].record()
+        for e in range(E):
+            if worker is not None:
+                worker.wait(e)
+                sm["idx"][e * B:(e + 1) * B].copy_(b["h_idx"][e], non_blocking=True)
+                self._idx_consumed = torch.cuda.Event()
+                self._idx_consumed.record()
+            else:
+                ctx.permutation_device(self.perm_seed, self.perm_counter, B, sm["idx"][e * B:(e + 1) * B])
+                self.perm_counter += 1
+        hyper.step = self.adam_step + 1
+        obs_flat, actions, old_logp, adv, ret = tensors
+        ctx.small_update(desc, self.P, self.G, self.M, self.V, obs_flat, actions, old_logp, adv, ret, b["stats"], sm["idx"], rows, S, hyper,
+                         sm["consts"], losses, self.grad_norm)
+        self.adam_step += S
+
     def _step(self, b, hyper, desc, tensors, idx_k, rows, losses_k, seq):
         """One optimiser step on the current stream: minibatch gradient, [exchange,] clip + Adam."""
         ctx = self.ctx
@@ -585,8 +630,11 @@ class FusedMlpEngine(_EngineBase):
         data parallelism, the exchange sequence number."""
         ctx, dev = self.ctx, self.device
         rows = b["plan"]["rows"]
-        gs = b.get("graph")
-        if gs is None or gs["key"] != key:
+        graphs = b.setdefault("graph", {})                               # one captured pair per set of baked-in pointers
+        gs = graphs.get(key)
+        if gs is None:
+            if len(graphs) >= 4:                                         # bounded: callers cycling through many buffers re-capture
+                graphs.pop(next(iter(graphs)))
             gs = dict(key=key, graphs=[], launches=0,
                       consts=[torch.zeros(MB, 4, dtype=torch.float32, device=dev) for _ in range(2)],
                       h_consts=[torch.zeros(MB, 4, dtype=torch.float32).pin_memory() for _ in range(2)],
@@ -608,7 +656,7 @@ class FusedMlpEngine(_EngineBase):
                 gs["graphs"].append(g)
             hyper.step_consts = None
             torch.cuda.current_stream().wait_stream(cap)
-            b["graph"] = gs
+            graphs[key] = gs
         main = torch.cuda.current_stream()
         b1, b2 = hyper.beta1, hyper.beta2
         for e in range(E):
@@ -748,11 +796,14 @@ class FusedMlpEngine(_EngineBase):
                    cfg.entropy_beta, cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm), dist.global_perm)
         # under DP: fused exchange only, and an even MB so that the baked slot parity repeats
         dp_ok = not dist.enabled or (self.dpx is not None and MB % 2 == 0 and self.dp_seq % 2 == 0)
-        use_graph = self.use_graphs and dp_ok and self._seen_key == ptr_key
-        self._seen_key = ptr_key
+        # (double-buffered callers alternate between two rollout buffers: both keys are remembered)
+        use_graph = self.use_graphs and dp_ok and ptr_key in self._seen_keys
+        self._seen_keys = (self._seen_keys + [ptr_key])[-4:] if ptr_key not in self._seen_keys else self._seen_keys
         if not dist.enabled:
             hyper.grad_sumsq = self.grad_sumsq.data_ptr()    # gradient assembly leaves the norm partials for the Adam kernel
-        if use_graph:
+        if self.use_small_kernel and not dist.enabled and rows <= self.SMALL_ROWS and ctx.small_update_supported(desc):
+            self._learn_small(b, worker, hyper, desc, tensors, losses, E, MB, rows)
+        elif use_graph:
             self._learn_epochs_graphed(b, worker, hyper, desc, tensors, losses, E, MB, T, N_, ptr_key)
         else:
             for e in range(E):
@@ -774,6 +825,8 @@ class FusedMlpEngine(_EngineBase):
             worker.finish()
         self._publish_steps()
         self.last_losses = losses
+        buf._consumed = torch.cuda.Event()
+        buf._consumed.record()
 
 
 class AutogradEngine(_EngineBase):

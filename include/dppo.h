@@ -195,6 +195,20 @@ int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* desc, const floa
                             const float* returns, const double* adv_stats, const int32_t* idx, int64_t M,
                             const dppo_hyper* hyper, float* losses, void* ws, int64_t ws_bytes, void* stream);
 
+/* The whole update loop of a learn() for the DEFAULT 64-wide network (ppo.py:258-285; BASELINE north_star item 4) in ONE launch:
+ * `steps` consecutive optimiser steps (all epochs x minibatches), each on `rows` samples idx[step*rows .. +rows) (idx < 0: padding
+ * row), run by one thread-block cluster of 8 CTAs with the parameters, the gradient partials and the sharded Adam state resident
+ * in (distributed) shared memory -- gather, forward, loss, backward, gradient reduce-scatter, global-norm clip, Adam and parameter
+ * all-gather never leave the SMs.  step_consts: DEVICE float [steps][2] = {sqrt(1 - beta2^t), -lr / (1 - beta1^t)} of each step
+ * (torch/optim/adam.py:531-547, computed by the caller in double).  params / exp_avg / exp_avg_sq are updated in place, grads
+ * receives the clipped gradient of the last step, losses [steps][4] = policy, value, entropy, total per step.  Supported:
+ * hidden == 64, obs_dim <= 64, act_dim <= 8 (dppo_small_update_supported); meant for minibatches of up to ~1024 rows. */
+int dppo_small_update_supported(const dppo_mlp_desc* desc);
+int dppo_small_update(dppo_ctx* ctx, const dppo_mlp_desc* desc, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                      const float* obs, const void* actions, const float* old_log_probs, const float* adv, const float* returns,
+                      const double* adv_stats, const int32_t* idx, int64_t rows, int steps, const dppo_hyper* hyper,
+                      const float* step_consts, float* losses, float* grad_norm_out, void* stream);
+
 /* clip_grad_norm_ (ppo.py:284) + Adam (ppo.py:285) over flat buffers of n floats.
  * grad_norm_out (optional, device float) receives the pre-clip global norm. */
 int dppo_clip_adam_step(dppo_ctx* ctx, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -95,7 +95,7 @@ def main():
             ag.engine.check_health()
             finals.append(ag.engine.P.clone())
             if use_graphs:
-                assert any("graph" in b_ for b_ in ag.engine._bufs.values()), "graph path was not taken under DP"
+                assert any(b_.get("graph") for b_ in ag.engine._bufs.values()), "graph path was not taken under DP"
         graph_ok = bool(torch.equal(finals[0], finals[1]))
         if rank == 0:
             print(f"dp{world} [{mode} permutation, graph replay vs eager]: bit-identical -> {'OK' if graph_ok else 'FAIL'}", flush=True)

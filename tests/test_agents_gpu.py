@@ -425,7 +425,7 @@ def test_graph_replay_of_update_loop_is_bit_identical_to_eager():
 
     a0, l0, r0 = run(False)
     a1, l1, r1 = run(True)
-    assert a1.engine._bufs and any("graph" in b for b in a1.engine._bufs.values()), "graph path was not taken"
+    assert a1.engine._bufs and any(b.get("graph") for b in a1.engine._bufs.values()), "graph path was not taken"
     assert torch.equal(l0, l1)
     assert torch.equal(a0.engine.P, a1.engine.P) and torch.equal(a0.engine.M, a1.engine.M) and torch.equal(a0.engine.V, a1.engine.V)
     assert a0.engine.adam_step == a1.engine.adam_step == 3 * 3 * 4
@@ -468,3 +468,33 @@ def test_train_resume_is_bit_identical_to_uninterrupted_run(tmp_path, kind):
         assert a[k] == b[k], k
     # and the interrupted agent itself was not at the end
     assert not torch.equal(part.engine.P, full.engine.P)
+
+
+@pytest.mark.parametrize("cont,D,A,N_,T,MB", [(False, 4, 2, 8, 128, 8), (False, 8, 4, 5, 20, 1), (True, 3, 1, 64, 64, 8), (True, 5, 3, 7, 33, 3),
+                                              (False, 64, 8, 16, 64, 2), (False, 17, 5, 4, 100, 4)])
+def test_small_net_cluster_kernel_matches_per_layer_kernels(cont, D, A, N_, T, MB):
+    """Default 64-wide networks: the one-launch cluster kernel (dppo_small_update: whole update loop in distributed shared memory)
+    against the per-layer kernel path on the same learn(): losses and parameters agree to fp32 summation order, Adam moments too.
+    Ragged shapes: rows per minibatch that are not multiples of the 16-row tile or of the 8 CTAs."""
+    from diamond import PPO, PPOConfig, ContinuousPPO, ContinuousPPOConfig, envs
+    Agent, Cfg = (ContinuousPPO, ContinuousPPOConfig) if cont else (PPO, PPOConfig)
+    rng = np.random.default_rng(D * 7 + A)
+    exp = [[rng.standard_normal((N_, D)).astype(np.float32), rng.standard_normal((N_, D)).astype(np.float32),
+            rng.standard_normal((N_, A)).astype(np.float32) if cont else rng.integers(0, A, N_), rng.standard_normal(N_),
+            rng.random(N_) < 0.05, rng.random(N_) < 0.05] for _ in range(T)]
+    outs = []
+    for small in (True, False):
+        cfg = Cfg(num_envs=N_, rollout_steps=T, num_epochs=3, num_minibatches=MB, verbose=False, seed=11)
+        agent = Agent(lambda: envs.SyntheticEnv(D, A, continuous=cont), cfg)
+        agent.engine.use_small_kernel = small
+        np.random.seed(5)
+        agent.learn(exp)
+        agent.learn(exp)                                   # Adam moments / step carried into a second launch
+        torch.cuda.synchronize()
+        outs.append((agent.engine.P.clone(), agent.engine.M.clone(), agent.engine.V.clone(), agent.last_losses.clone(), agent.engine.adam_step))
+    (p1, m1, v1, l1, s1), (p0, m0, v0, l0, s0) = outs
+    assert s1 == s0 == 2 * 3 * MB
+    np.testing.assert_allclose(l1.cpu().numpy(), l0.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    assert float((p1 - p0).abs().max() / p0.abs().max()) <= 2e-5
+    assert float((m1 - m0).abs().max()) <= 1e-5 * max(1.0, float(m0.abs().max()))
+    assert float((v1 - v0).abs().max()) <= 1e-5 * max(1e-3, float(v0.abs().max()))
