@@ -23,11 +23,16 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int SK_CL = 8;            // CTAs per cluster
 constexpr int SK_THREADS = 256;
-constexpr int RT = 16;              // rows per tile
+constexpr int SK_WARPS = SK_THREADS / 32;
+// RT = rows per tile (template parameter): 32 (lane <-> row) or 16 for the smallest minibatches (two column groups per warp), so that
+// a CTA holding only 16 rows of the minibatch still uses every lane.
+template <int RT> struct RowStride { static constexpr int v = RT + 4; };   // row stride of the k-major activation tiles (floats):
+                                    // 16-byte aligned rows, and consecutive rows start 4 banks apart, so a warp reading 32 different
+                                    // rows with float4 loads is conflict-free
 constexpr int HN = 64;              // hidden width this kernel is specialised for
 constexpr int AMAX = 8;             // actions / action dims
+constexpr int ROWS_MAX = 128;       // minibatch rows per CTA
 
 struct SmallArgs {
     dppo_mlp_layout L;
@@ -45,19 +50,22 @@ struct SmallArgs {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// out[n][r] = tanh(b[n] + sum_k in[k][r] * W[n][k]) for the 16 rows of a tile; thread = (row r, column group cg)
-template <int N>
+// out[n][r] = tanh(b[n] + sum_k in[k][r] * W[n][k]) for the 32 rows of a tile; lane = row, warp = group of N/8 output columns
+// (the weight reads are warp-wide broadcasts, the activation reads conflict-free)
+template <int N, int RT>
 __device__ __forceinline__ void fwd_layer(const float* __restrict__ in, int K, const float* __restrict__ W, const float* __restrict__ b,
                                           float* __restrict__ out)
 {
-    constexpr int NC = N / 16;
-    const int r = threadIdx.x & 15, c0 = (threadIdx.x >> 4) * NC;
+    constexpr int RS = RowStride<RT>::v;
+    constexpr int NC = N * RT / SK_THREADS;           // columns per thread: thread = (row r, column group)
+    const int r = threadIdx.x % RT, c0 = (threadIdx.x / RT) * NC;
     float acc[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = b[c0 + j];
     if ((K & 3) == 0) {
+#pragma unroll 2
         for (int k = 0; k < K; k += 4) {
-            const float a0 = in[k * RT + r], a1 = in[(k + 1) * RT + r], a2 = in[(k + 2) * RT + r], a3 = in[(k + 3) * RT + r];
+            const float a0 = in[k * RS + r], a1 = in[(k + 1) * RS + r], a2 = in[(k + 2) * RS + r], a3 = in[(k + 3) * RS + r];
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 const float4 w = ld4(W + (c0 + j) * K + k);
@@ -66,46 +74,56 @@ __device__ __forceinline__ void fwd_layer(const float* __restrict__ in, int K, c
         }
     } else {
         for (int k = 0; k < K; ++k) {
-            const float a = in[k * RT + r];
+            const float a = in[k * RS + r];
 #pragma unroll
             for (int j = 0; j < NC; ++j) acc[j] = fmaf(a, W[(c0 + j) * K + k], acc[j]);
         }
     }
 #pragma unroll
-    for (int j = 0; j < NC; ++j) out[(c0 + j) * RT + r] = tanhf(acc[j]);
+    for (int j = 0; j < NC; ++j) out[(c0 + j) * RS + r] = tanhf(acc[j]);
 }
 
-// din[k][r] = (sum_n dout[n][r] * W[n][k]) * (1 - hin[k][r]^2), K = 64 outputs (4 per thread), W row-major [N][64]
-template <int N>
+// din[k][r] = (sum_n dout[n][r] * W[n][k]) * (1 - hin[k][r]^2); lane = row, warp = 8 consecutive k; W row-major [N][64]
+template <int N, int RT>
 __device__ __forceinline__ void dgrad_layer(const float* __restrict__ dout, const float* __restrict__ W, const float* __restrict__ hin,
                                             float* __restrict__ din)
 {
-    const int r = threadIdx.x & 15, k0 = (threadIdx.x >> 4) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int RS = RowStride<RT>::v;
+    constexpr int KC = HN * RT / SK_THREADS;          // outputs per thread: 8 (RT = 32) or 4 (RT = 16)
+    const int r = threadIdx.x % RT, k0 = (threadIdx.x / RT) * KC;
+    float acc[KC];
+#pragma unroll
+    for (int q = 0; q < KC; ++q) acc[q] = 0.f;
 #pragma unroll 4
     for (int n = 0; n < N; ++n) {
-        const float d = dout[n * RT + r];
-        const float4 w = ld4(W + n * HN + k0);
-        acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+        const float d = dout[n * RS + r];
+#pragma unroll
+        for (int q = 0; q < KC; q += 4) {
+            const float4 w = ld4(W + n * HN + k0 + q);
+            acc[q] = fmaf(d, w.x, acc[q]); acc[q + 1] = fmaf(d, w.y, acc[q + 1]); acc[q + 2] = fmaf(d, w.z, acc[q + 2]); acc[q + 3] = fmaf(d, w.w, acc[q + 3]);
+        }
     }
-    const float h0 = hin[k0 * RT + r], h1 = hin[(k0 + 1) * RT + r], h2 = hin[(k0 + 2) * RT + r], h3 = hin[(k0 + 3) * RT + r];
-    din[k0 * RT + r] = acc.x * (1.0f - h0 * h0);
-    din[(k0 + 1) * RT + r] = acc.y * (1.0f - h1 * h1);
-    din[(k0 + 2) * RT + r] = acc.z * (1.0f - h2 * h2);
-    din[(k0 + 3) * RT + r] = acc.w * (1.0f - h3 * h3);
+#pragma unroll
+    for (int q = 0; q < KC; ++q) {
+        const float h = hin[(k0 + q) * RS + r];
+        din[(k0 + q) * RS + r] = acc[q] * (1.0f - h * h);
+    }
 }
 
-__device__ __forceinline__ float dot16(const float* __restrict__ a, const float* __restrict__ b)
+template <int RT>
+__device__ __forceinline__ float dotR(const float* __restrict__ a, const float* __restrict__ b)
 {
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int q = 0; q < RT; q += 4) {
-        const float4 x = ld4(a + q), y = ld4(b + q);
-        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    for (int q = 0; q < RT; q += 8) {
+        const float4 x = ld4(a + q), y = ld4(b + q), x2 = ld4(a + q + 4), y2 = ld4(b + q + 4);
+        s0 = fmaf(x.x, y.x, s0); s0 = fmaf(x.y, y.y, s0); s0 = fmaf(x.z, y.z, s0); s0 = fmaf(x.w, y.w, s0);
+        s1 = fmaf(x2.x, y2.x, s1); s1 = fmaf(x2.y, y2.y, s1); s1 = fmaf(x2.z, y2.z, s1); s1 = fmaf(x2.w, y2.w, s1);
     }
-    return s;
+    return s0 + s1;
 }
-__device__ __forceinline__ float sum16(const float* __restrict__ a)
+template <int RT>
+__device__ __forceinline__ float sumR(const float* __restrict__ a)
 {
     float s = 0.f;
 #pragma unroll
@@ -113,36 +131,51 @@ __device__ __forceinline__ float sum16(const float* __restrict__ a)
     return s;
 }
 
-// g[n][k] += sum_r dout[n][r] * hin[k][r] for a [N][64] weight: thread owns N*64/256 consecutive k of one n
-template <int N>
+// g[n][k] += sum_r dout[n][r] * hin[k][r] for a [N][64] weight: thread = (k = tid % 64, quarter of the n range); the thread keeps
+// its activation row hin[k][0..31] in registers, the gradient rows are warp-wide broadcasts, g is written with consecutive k
+template <int N, int RT>
 __device__ __forceinline__ void wgrad_layer(const float* __restrict__ dout, const float* __restrict__ hin, float* __restrict__ g)
 {
-    constexpr int PER = N * HN / SK_THREADS;            // 32 (N = 128) or 16 (N = 64)
-    constexpr int TPN = HN / PER;                       // threads per output row
-    const int n = threadIdx.x / TPN, k0 = (threadIdx.x % TPN) * PER;
-    const float* d = dout + n * RT;
-    const float4 d0 = ld4(d), d1 = ld4(d + 4), d2 = ld4(d + 8), d3 = ld4(d + 12);
-#pragma unroll 8
-    for (int k = 0; k < PER; ++k) {
-        const float* h = hin + (k0 + k) * RT;
-        const float4 h0 = ld4(h), h1 = ld4(h + 4), h2 = ld4(h + 8), h3 = ld4(h + 12);
-        float s = d0.x * h0.x;
-        s = fmaf(d0.y, h0.y, s); s = fmaf(d0.z, h0.z, s); s = fmaf(d0.w, h0.w, s);
-        s = fmaf(d1.x, h1.x, s); s = fmaf(d1.y, h1.y, s); s = fmaf(d1.z, h1.z, s); s = fmaf(d1.w, h1.w, s);
-        s = fmaf(d2.x, h2.x, s); s = fmaf(d2.y, h2.y, s); s = fmaf(d2.z, h2.z, s); s = fmaf(d2.w, h2.w, s);
-        s = fmaf(d3.x, h3.x, s); s = fmaf(d3.y, h3.y, s); s = fmaf(d3.z, h3.z, s); s = fmaf(d3.w, h3.w, s);
-        g[n * HN + k0 + k] += s;
+    constexpr int RS = RowStride<RT>::v;
+    const int k = threadIdx.x & 63, n0 = (threadIdx.x >> 6) * (N / 4);
+    float4 h[RT / 4];
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) h[q] = ld4(hin + k * RS + 4 * q);
+#pragma unroll 2
+    for (int n = n0; n < n0 + N / 4; ++n) {
+        const float* d = dout + n * RS;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < RT / 4; q += 2) {
+            const float4 x = ld4(d + 4 * q), y = ld4(d + 4 * q + 4);
+            s0 = fmaf(x.x, h[q].x, s0); s0 = fmaf(x.y, h[q].y, s0); s0 = fmaf(x.z, h[q].z, s0); s0 = fmaf(x.w, h[q].w, s0);
+            s1 = fmaf(y.x, h[q + 1].x, s1); s1 = fmaf(y.y, h[q + 1].y, s1); s1 = fmaf(y.z, h[q + 1].z, s1); s1 = fmaf(y.w, h[q + 1].w, s1);
+        }
+        g[n * HN + k] += s0 + s1;
     }
 }
 
-template <bool CONT>
-__global__ void __cluster_dims__(SK_CL, 1, 1) __launch_bounds__(SK_THREADS, 1)
+__device__ __forceinline__ float group8_sum(float v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 4, 8); v += __shfl_xor_sync(0xffffffffu, v, 2, 8); v += __shfl_xor_sync(0xffffffffu, v, 1, 8);
+    return v;
+}
+__device__ __forceinline__ float group8_max(float v)
+{
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4, 8)); v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2, 8));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1, 8));
+    return v;
+}
+
+template <bool CONT, int RT, int SK_CL>
+__global__ void __launch_bounds__(SK_THREADS, 1)
 small_update_kernel(const SmallArgs a)
 {
+    constexpr int RS = RowStride<RT>::v;
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const dppo_mlp_layout& L = a.L;
     const int total = (int)L.total, D = a.D, A = a.A;
     const int SL = ((total + SK_CL - 1) / SK_CL + 3) & ~3;              // slice of the flat buffers owned by one CTA
@@ -153,24 +186,25 @@ small_update_kernel(const SmallArgs a)
     float* sGs = sG + total;                   // [SL] reduced gradient slice
     float* sMs = sGs + SL;                     // [SL] exp_avg slice
     float* sVs = sMs + SL;                     // [SL] exp_avg_sq slice
-    float* sX = sVs + SL;                      // [D][RT]
-    float* sH1 = sX + ((D * RT + 3) & ~3);     // [64][RT]
-    float* sH2 = sH1 + HN * RT;
-    float* sH3 = sH2 + HN * RT;                // [128][RT]
-    float* sD3 = sH3 + 2 * HN * RT;
-    float* sD2 = sD3 + 2 * HN * RT;
-    float* sD1 = sD2 + HN * RT;
-    float* sZ = sD1 + HN * RT;                 // [RT][AMAX] head outputs, then d(loss)/dz
-    float* sVal = sZ + RT * AMAX;              // [RT] values, then d(loss)/dv
-    float* sDls = sVal + RT;                   // [RT][AMAX] per-row d(loss)/d(log_std) (continuous)
-    float* sRed = sDls + RT * AMAX;            // [16] block reductions: [0..2] loss sums, [4..5] norm partial (double)
-    __shared__ int s_src[RT];
-    __shared__ float s_oldlp[RT], s_adv[RT], s_ret[RT], s_actf[RT * AMAX];
-    __shared__ int s_acti[RT];
+    float* sX = sVs + SL;                      // [D][RS]
+    float* sH1 = sX + D * RS;                  // [64][RS]
+    float* sH2 = sH1 + HN * RS;
+    float* sH3 = sH2 + HN * RS;                // [128][RS]
+    float* sD3 = sH3 + 2 * HN * RS;
+    float* sD2 = sD3 + 2 * HN * RS;
+    float* sD1 = sD2 + HN * RS;
+    float* sZ = sD1 + HN * RS;                 // [RT][AMAX] head outputs
+    float* sVal = sZ + RT * AMAX;              // [RT] values
+    float* sDz = sVal + RT;                    // [AMAX + 1][RS]: d(loss)/dz per action (rows 0..A-1), d(loss)/dv (row AMAX)
+    float* sDls = sDz + (AMAX + 1) * RS;       // [AMAX][RS] per-row d(loss)/d(log_std) (continuous)
+    float* sRed = sDls + AMAX * RS;            // [8]: [0..2] loss sums, [4..5] norm partial (double)
+    __shared__ int s_src[ROWS_MAX], s_acti[ROWS_MAX];
+    __shared__ float s_oldlp[ROWS_MAX], s_adv[ROWS_MAX], s_ret[ROWS_MAX], s_actf[ROWS_MAX * AMAX];
     __shared__ float s_coef;
-    __shared__ double s_wsum[SK_THREADS / 32];
+    __shared__ float s_loss[3][SK_WARPS];
+    __shared__ double s_wsum[SK_WARPS];
 
-    for (int i = tid; i < total; i += SK_THREADS) sP[i] = a.P[i];
+    for (int i = tid; i < total; i += SK_THREADS) { sP[i] = a.P[i]; sG[i] = 0.f; }
     for (int i = s0 + tid; i < s1; i += SK_THREADS) { sMs[i - s0] = a.M[i]; sVs[i - s0] = a.V[i]; }
     float adv_mean = 0.f, adv_denom = 1.f;
     if (a.advantage_norm) {
@@ -182,142 +216,120 @@ small_update_kernel(const SmallArgs a)
     }
     const int rows_per = (a.rows + SK_CL - 1) / SK_CL;
     const int row_lo = min(a.rows, rank * rows_per), row_hi = min(a.rows, row_lo + rows_per);
+    const int my_rows = row_hi - row_lo;
     cluster.sync();
 
     for (int step = 0; step < a.steps; ++step) {
-        const int32_t* idx = a.idx + (int64_t)step * a.rows;
-        for (int i = tid; i < total; i += SK_THREADS) sG[i] = 0.f;
-        float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;                      // thread tid < RT: sums over its rows
+        const int32_t* idx = a.idx + (int64_t)step * a.rows + row_lo;
+        // ---- per-row scalars of all my rows of this step (ppo.py:265-272): one round of dependent global loads per step ----
+        for (int m = tid; m < my_rows; m += SK_THREADS) {
+            const int src = idx[m];
+            const bool live = src >= 0;
+            s_src[m] = src;
+            s_oldlp[m] = live ? a.old_logp[src] : 0.f;
+            s_adv[m] = live ? (a.adv[src] - adv_mean) / adv_denom : 0.f;
+            s_ret[m] = live ? a.ret[src] : 0.f;
+            if (!CONT) s_acti[m] = live ? reinterpret_cast<const int32_t*>(a.actions)[src] : 0;
+            else
+                for (int j = 0; j < A; ++j) s_actf[m * AMAX + j] = live ? reinterpret_cast<const float*>(a.actions)[(int64_t)src * A + j] : 0.f;
+        }
+        float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;                      // threads with (tid & 7) == 0: sums over their rows
         __syncthreads();
 
-        for (int t0 = row_lo; t0 < row_hi; t0 += RT) {
-            // ---- gather (ppo.py:261-272) ----
-            if (tid < RT) {
-                const int m = t0 + tid;
-                const int src = m < row_hi ? idx[m] : -1;
-                s_src[tid] = src;
-                const bool live = src >= 0;
-                s_oldlp[tid] = live ? a.old_logp[src] : 0.f;
-                s_adv[tid] = live ? (a.adv[src] - adv_mean) / adv_denom : 0.f;
-                s_ret[tid] = live ? a.ret[src] : 0.f;
-                if (!CONT) s_acti[tid] = live ? reinterpret_cast<const int32_t*>(a.actions)[src] : 0;
-            }
-            __syncthreads();
+        for (int t0 = 0; t0 < my_rows; t0 += RT) {
+            // ---- gather the observations of the tile (ppo.py:261) ----
             for (int i = tid; i < D * RT; i += SK_THREADS) {
                 const int r = i / D, k = i - r * D;                      // consecutive threads read consecutive floats of a row
-                const int src = s_src[r];
-                sX[k * RT + r] = src >= 0 ? a.obs[(int64_t)src * D + k] : 0.f;
-            }
-            if (CONT) {
-                for (int i = tid; i < RT * A; i += SK_THREADS) {
-                    const int r = i / A, j = i - r * A;
-                    const int src = s_src[r];
-                    s_actf[r * AMAX + j] = src >= 0 ? reinterpret_cast<const float*>(a.actions)[(int64_t)src * A + j] : 0.f;
-                }
+                const int src = t0 + r < my_rows ? s_src[t0 + r] : -1;
+                sX[k * RS + r] = src >= 0 ? a.obs[(int64_t)src * D + k] : 0.f;
             }
             __syncthreads();
             // ---- forward (ppo.py:91-96) ----
-            fwd_layer<HN>(sX, D, sP + L.w1, sP + L.b1, sH1);
+            fwd_layer<HN, RT>(sX, D, sP + L.w1, sP + L.b1, sH1);
             __syncthreads();
-            fwd_layer<HN>(sH1, HN, sP + L.w2, sP + L.b2, sH2);
+            fwd_layer<HN, RT>(sH1, HN, sP + L.w2, sP + L.b2, sH2);
             __syncthreads();
-            fwd_layer<2 * HN>(sH2, HN, sP + L.w3, sP + L.b3, sH3);
+            fwd_layer<2 * HN, RT>(sH2, HN, sP + L.w3, sP + L.b3, sH3);
             __syncthreads();
-            {   // output heads: thread = (row, output o): o < A actor, o == A critic
-                const int r = tid & 15, o = tid >> 4;
-                if (o <= A) {
+            {   // output heads: thread = (row r, output o): o < A actor, o == A critic
+                const int r = tid % RT;
+                for (int o = tid / RT; o <= A; o += SK_THREADS / RT) {
                     const float* w = o < A ? sP + L.wa + o * HN : sP + L.wc;
-                    const float* h = o < A ? sH3 : sH3 + HN * RT;
+                    const float* h = o < A ? sH3 : sH3 + HN * RS;
                     float s = o < A ? sP[L.ba + o] : sP[L.bc];
+#pragma unroll 4
                     for (int k = 0; k < HN; k += 4) {
                         const float4 w4 = ld4(w + k);
-                        s = fmaf(h[k * RT + r], w4.x, s); s = fmaf(h[(k + 1) * RT + r], w4.y, s);
-                        s = fmaf(h[(k + 2) * RT + r], w4.z, s); s = fmaf(h[(k + 3) * RT + r], w4.w, s);
+                        s = fmaf(h[k * RS + r], w4.x, s); s = fmaf(h[(k + 1) * RS + r], w4.y, s);
+                        s = fmaf(h[(k + 2) * RS + r], w4.z, s); s = fmaf(h[(k + 3) * RS + r], w4.w, s);
                     }
                     if (o < A) sZ[r * AMAX + o] = s; else sVal[r] = s;
                 }
             }
             __syncthreads();
-            // ---- distribution, loss terms, d(loss)/d(head outputs) (ppo.py:264-280) ----
-            if (tid < RT) {
-                const int r = tid;
-                const bool live = s_src[r] >= 0;
-                float z[AMAX], dz[AMAX];
-#pragma unroll
-                for (int j = 0; j < AMAX; ++j) { z[j] = j < A ? sZ[r * AMAX + j] : 0.f; dz[j] = 0.f; }
-                float new_lp, entropy;
-                float aux1[AMAX], aux2[AMAX];                             // discrete: p, lsm; gaussian: diff, var
+            // ---- distribution, loss terms, d(loss)/d(head outputs) (ppo.py:264-280): 8 lanes per row, lane j <-> action j ----
+            {
+                const int r = tid >> 3, j = tid & 7, m = t0 + r;           // (RT = 16: the upper half of the block idles here)
+                const bool in_tile = r < RT;
+                const bool live = in_tile && m < my_rows && s_src[m] >= 0;
+                const bool on = j < A;
+                const float z = (on && in_tile) ? sZ[r * AMAX + j] : 0.f;
+                float new_lp, entropy, dz = 0.f, dls = 0.f;
+                float p = 0.f, lsm = 0.f, diff = 0.f, var = 1.f;
+                const int act = (!CONT && live) ? s_acti[m] : 0;
                 if (!CONT) {
-                    float mx = -CUDART_INF_F;
-#pragma unroll
-                    for (int j = 0; j < AMAX; ++j) if (j < A) mx = fmaxf(mx, z[j]);
-                    float s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < AMAX; ++j) if (j < A) s += expf(z[j] - mx);
+                    // torch/distributions/categorical.py:78 (logits - logsumexp), :151-163 (log_prob, entropy)
+                    const float mx = group8_max(on ? z : -CUDART_INF_F);
+                    const float s = group8_sum(on ? expf(z - mx) : 0.f);
                     const float lse = mx + logf(s);
-                    entropy = 0.f; new_lp = 0.f;
-                    const int act = s_acti[r];
-#pragma unroll
-                    for (int j = 0; j < AMAX; ++j) {
-                        if (j < A) {
-                            aux2[j] = z[j] - lse; aux1[j] = expf(aux2[j]);
-                            entropy -= aux1[j] * aux2[j];
-                            if (j == act) new_lp = aux2[j];
-                        }
-                    }
+                    lsm = on ? z - lse : 0.f;
+                    p = on ? expf(lsm) : 0.f;
+                    entropy = -group8_sum(p * lsm);
+                    new_lp = __shfl_sync(0xffffffffu, lsm, act, 8);
                 } else {
-                    new_lp = 0.f; entropy = 0.f;
-#pragma unroll
-                    for (int j = 0; j < AMAX; ++j) {
-                        if (j < A) {
-                            const float ls = sP[L.log_std + j];
-                            const float sigma = expf(ls), log_scale = logf(sigma);
-                            aux2[j] = sigma * sigma; aux1[j] = s_actf[r * AMAX + j] - z[j];
-                            new_lp += -(aux1[j] * aux1[j]) / (2.0f * aux2[j]) - log_scale - 0.91893853320467274178f;
-                            entropy += 0.5f + 0.91893853320467274178f + log_scale;
-                        }
-                    }
+                    // torch/distributions/normal.py:87-102, :114-115, summed over dims (continuous_ppo.py:40-47)
+                    const float sigma = on ? expf(sP[L.log_std + j]) : 1.f;
+                    const float log_scale = logf(sigma);
+                    var = sigma * sigma;
+                    diff = (on && live ? s_actf[m * AMAX + j] : 0.f) - z;
+                    new_lp = group8_sum(on ? (-(diff * diff) / (2.0f * var) - log_scale - 0.91893853320467274178f) : 0.f);
+                    entropy = group8_sum(on ? (0.5f + 0.91893853320467274178f + log_scale) : 0.f);
                 }
                 // clipped surrogate (ppo.py:266-270) and the gradient autograd assigns
-                const float adv = s_adv[r];
-                const float ratio = expf(new_lp - s_oldlp[r]);
+                const float adv = live ? s_adv[m] : 0.f;
+                const float ratio = expf(new_lp - (live ? s_oldlp[m] : 0.f));
                 const float lo = 1.0f - a.clip, hi = 1.0f + a.clip;
                 const float u1 = -adv * ratio, u2 = -adv * fminf(fmaxf(ratio, lo), hi);
                 const bool in_range = ratio >= lo && ratio <= hi;
                 const float wsel = in_range ? 1.0f : (u1 > u2 ? 1.0f : (u1 == u2 ? 0.5f : 0.0f));
                 const float dlogp = (-adv * wsel * a.inv_m) * ratio;
-                const float verr = sVal[r] - s_ret[r];
-                float dv = 0.f;
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < AMAX; ++j) {
-                        if (j < A) {
-                            if (!CONT) dz[j] = dlogp * ((j == s_acti[r] ? 1.0f : 0.0f) - aux1[j]) + (a.beta * a.inv_m) * aux1[j] * (aux2[j] + entropy);
-                            else dz[j] = dlogp * aux1[j] / aux2[j];
-                        }
-                    }
-                    dv = a.vw * verr * a.inv_m;
-                    l_pol += fmaxf(u1, u2); l_val += verr * verr; l_ent += entropy;
+                const float verr = (in_tile ? sVal[r] : 0.f) - (live ? s_ret[m] : 0.f);
+                if (live && on) {
+                    if (!CONT) dz = dlogp * ((j == act ? 1.0f : 0.0f) - p) + (a.beta * a.inv_m) * p * (lsm + entropy);
+                    else { dz = dlogp * diff / var; dls = dlogp * (diff * diff / var - 1.0f) - a.beta * a.inv_m; }
                 }
-#pragma unroll
-                for (int j = 0; j < AMAX; ++j) {
-                    sZ[r * AMAX + j] = dz[j];
-                    if (CONT) sDls[r * AMAX + j] = (live && j < A) ? dlogp * (aux1[j] * aux1[j] / aux2[j] - 1.0f) - a.beta * a.inv_m : 0.f;
+                if (in_tile) {
+                    sDz[j * RS + r] = dz;
+                    if (CONT) sDls[j * RS + r] = dls;
                 }
-                sVal[r] = dv;
+                if (j == 0 && in_tile) {
+                    sDz[AMAX * RS + r] = live ? a.vw * verr * a.inv_m : 0.f;
+                    if (live) { l_pol += fmaxf(u1, u2); l_val += verr * verr; l_ent += entropy; }
+                }
             }
             __syncthreads();
-            // ---- backward into the first head layers: d3[n][r] ----
+            // ---- backward into the first head layers: d3[n][r]; thread = (row r, group of 128 * RT / 256 columns) ----
             {
-                const int r = tid & 15, c0 = (tid >> 4) * 8;
+                constexpr int NC3 = 2 * HN * RT / SK_THREADS;
+                const int r = tid % RT, c0 = (tid / RT) * NC3;
                 float dzr[AMAX];
 #pragma unroll
-                for (int j = 0; j < AMAX; ++j) dzr[j] = sZ[r * AMAX + j];
-                const float dv = sVal[r];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int j = 0; j < AMAX; ++j) dzr[j] = sDz[j * RS + r];
+                const float dv = sDz[AMAX * RS + r];
+#pragma unroll 4
+                for (int q = 0; q < NC3; ++q) {
                     const int n = c0 + q;
-                    const float h = sH3[n * RT + r];
+                    const float h = sH3[n * RS + r];
                     float g;
                     if (n < HN) {
                         g = 0.f;
@@ -326,76 +338,81 @@ small_update_kernel(const SmallArgs a)
                     } else {
                         g = dv * sP[L.wc + (n - HN)];
                     }
-                    sD3[n * RT + r] = g * (1.0f - h * h);
+                    sD3[n * RS + r] = g * (1.0f - h * h);
                 }
             }
             // head weight gradients (from dz / dv and h3): each output owned by one thread
             for (int o = tid; o < (A + 1) * HN; o += SK_THREADS) {
                 const int j = o / HN, k = o - j * HN;
-                float s = 0.f;
-                if (j < A) {
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) s = fmaf(sZ[r * AMAX + j], sH3[k * RT + r], s);
-                    sG[L.wa + j * HN + k] += s;
-                } else {
-                    s = dot16(sVal, sH3 + (HN + k) * RT);
-                    sG[L.wc + k] += s;
-                }
+                if (j < A) sG[L.wa + j * HN + k] += dotR<RT>(sDz + j * RS, sH3 + k * RS);
+                else sG[L.wc + k] += dotR<RT>(sDz + AMAX * RS, sH3 + (HN + k) * RS);
             }
             if (tid < A) {
-                float s = 0.f, sl = 0.f;
-#pragma unroll
-                for (int r = 0; r < RT; ++r) { s += sZ[r * AMAX + tid]; if (CONT) sl += sDls[r * AMAX + tid]; }
-                sG[L.ba + tid] += s;
-                if (CONT) sG[L.log_std + tid] += sl;
+                sG[L.ba + tid] += sumR<RT>(sDz + tid * RS);
+                if (CONT) sG[L.log_std + tid] += sumR<RT>(sDls + tid * RS);
             } else if (tid == AMAX) {
-                sG[L.bc] += sum16(sVal);
+                sG[L.bc] += sumR<RT>(sDz + AMAX * RS);
             }
             __syncthreads();
             // ---- backward (ppo.py:283) ----
-            if (tid < 2 * HN) sG[L.b3 + tid] += sum16(sD3 + tid * RT);
-            dgrad_layer<2 * HN>(sD3, sP + L.w3, sH2, sD2);
-            wgrad_layer<2 * HN>(sD3, sH2, sG + L.w3);
+            if (tid < 2 * HN) sG[L.b3 + tid] += sumR<RT>(sD3 + tid * RS);
+            dgrad_layer<2 * HN, RT>(sD3, sP + L.w3, sH2, sD2);
+            wgrad_layer<2 * HN, RT>(sD3, sH2, sG + L.w3);
             __syncthreads();
-            if (tid < HN) sG[L.b2 + tid] += sum16(sD2 + tid * RT);
-            dgrad_layer<HN>(sD2, sP + L.w2, sH1, sD1);
-            wgrad_layer<HN>(sD2, sH1, sG + L.w2);
+            if (tid < HN) sG[L.b2 + tid] += sumR<RT>(sD2 + tid * RS);
+            dgrad_layer<HN, RT>(sD2, sP + L.w2, sH1, sD1);
+            wgrad_layer<HN, RT>(sD2, sH1, sG + L.w2);
             __syncthreads();
-            if (tid < HN) sG[L.b1 + tid] += sum16(sD1 + tid * RT);
+            if (tid < HN) sG[L.b1 + tid] += sumR<RT>(sD1 + tid * RS);
             for (int o = tid; o < HN * D; o += SK_THREADS) {
                 const int n = o / D, k = o - n * D;
-                sG[L.w1 + o] += dot16(sD1 + n * RT, sX + k * RT);
+                sG[L.w1 + o] += dotR<RT>(sD1 + n * RS, sX + k * RS);
             }
             __syncthreads();
         }
 
         // ---- loss sums of this CTA ----
-        if (tid < 32) {
-            float p = tid < RT ? l_pol : 0.f, v = tid < RT ? l_val : 0.f, e = tid < RT ? l_ent : 0.f;
-            p = warp_sum(p); v = warp_sum(v); e = warp_sum(e);
-            if (tid == 0) { sRed[0] = p; sRed[1] = v; sRed[2] = e; }
+        {
+            const float p = warp_sum(l_pol), v = warp_sum(l_val), e = warp_sum(l_ent);
+            if (lane == 0) { s_loss[0][warp] = p; s_loss[1][warp] = v; s_loss[2][warp] = e; }
+            __syncthreads();
+            if (tid < 3) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < SK_WARPS; ++w) s += s_loss[tid][w];
+                sRed[tid] = s;
+            }
         }
         cluster.sync();                                                    // (1) all eight partial gradients are complete
 
         // ---- reduce-scatter over distributed shared memory: my slice of the summed gradient + its sum of squares ----
         double sq = 0.0;
-        for (int i = s0 + tid; i < s1; i += SK_THREADS) {
-            float g = 0.f;
+        {
+            const float* rg[SK_CL];
 #pragma unroll
-            for (int q = 0; q < SK_CL; ++q) g += cluster.map_shared_rank(sG, q)[i];          // fixed rank order
-            sGs[i - s0] = g;
-            sq += (double)g * (double)g;
+            for (int q = 0; q < SK_CL; ++q) rg[q] = cluster.map_shared_rank(sG, q);
+            for (int i = s0 + tid; i < s1; i += SK_THREADS) {
+                float v[SK_CL];
+#pragma unroll
+                for (int q = 0; q < SK_CL; ++q) v[q] = rg[q][i];
+                float g = v[0];
+#pragma unroll
+                for (int q = 1; q < SK_CL; ++q) g += v[q];                // fixed rank order
+                sGs[i - s0] = g;
+                sq += (double)g * (double)g;
+            }
         }
         sq = warp_sum_d(sq);
-        if ((tid & 31) == 0) s_wsum[tid >> 5] = sq;
+        if (lane == 0) s_wsum[warp] = sq;
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < SK_THREADS / 32; ++w) s += s_wsum[w];
+            for (int w = 0; w < SK_WARPS; ++w) s += s_wsum[w];
             *reinterpret_cast<double*>(sRed + 4) = s;
         }
-        cluster.sync();                                                    // (2) every slice's partial norm is published
+        cluster.sync();                                                    // (2) every slice's partial norm is published; partials consumed
+        for (int i = tid; i < total; i += SK_THREADS) sG[i] = 0.f;         // ready for the next step (peers finished reading it)
         if (tid == 0) {
             double s = 0.0;
             float lp = 0.f, lv = 0.f, le = 0.f;
@@ -420,28 +437,60 @@ small_update_kernel(const SmallArgs a)
         const float coef = s_coef;
         const float bc2_sqrt = a.step_consts[2 * step], neg_step = a.step_consts[2 * step + 1];
         const bool last = step == a.steps - 1;
-        for (int i = s0 + tid; i < s1; i += SK_THREADS) {
-            const float gi = __fmul_rn(sGs[i - s0], coef);
-            float mi = sMs[i - s0], vi = sVs[i - s0];
-            mi = fmaf(a.w1, gi - mi, mi);
-            vi = __fadd_rn(__fmul_rn(vi, a.beta2), __fmul_rn(__fmul_rn(a.w2, gi), gi));
-            const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), a.eps);
-            const float pn = __fadd_rn(sP[i], __fmul_rn(neg_step, __fdiv_rn(mi, denom)));
-            sMs[i - s0] = mi; sVs[i - s0] = vi;
+        {
+            float* rp[SK_CL];
 #pragma unroll
-            for (int q = 0; q < SK_CL; ++q) cluster.map_shared_rank(sP, q)[i] = pn;
-            if (last) { a.P[i] = pn; a.M[i] = mi; a.V[i] = vi; a.G[i] = gi; }
+            for (int q = 0; q < SK_CL; ++q) rp[q] = cluster.map_shared_rank(sP, q);
+            for (int i = s0 + tid; i < s1; i += SK_THREADS) {
+                const float gi = __fmul_rn(sGs[i - s0], coef);
+                float mi = sMs[i - s0], vi = sVs[i - s0];
+                mi = fmaf(a.w1, gi - mi, mi);
+                vi = __fadd_rn(__fmul_rn(vi, a.beta2), __fmul_rn(__fmul_rn(a.w2, gi), gi));
+                const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), a.eps);
+                const float pn = __fadd_rn(sP[i], __fmul_rn(neg_step, __fdiv_rn(mi, denom)));
+                sMs[i - s0] = mi; sVs[i - s0] = vi;
+#pragma unroll
+                for (int q = 0; q < SK_CL; ++q) rp[q][i] = pn;
+                if (last) { a.P[i] = pn; a.M[i] = mi; a.V[i] = vi; a.G[i] = gi; }
+            }
         }
-        cluster.sync();                                                    // (3) all parameter copies updated; partials may be zeroed
+        cluster.sync();                                                    // (3) all parameter copies updated
     }
 }
 
-size_t small_smem_bytes(const dppo_mlp_layout& L, int D)
+size_t small_smem_bytes(const dppo_mlp_layout& L, int D, int RT, int CL)
 {
-    const int total = (int)L.total;
-    const int SL = ((total + SK_CL - 1) / SK_CL + 3) & ~3;
-    size_t fl = (size_t)2 * total + 3 * SL + ((D * RT + 3) & ~3) + (size_t)(HN * 3 + 2 * HN * 2 + HN) * RT + RT * AMAX + RT + RT * AMAX + 16;
+    const int total = (int)L.total, RS = RT + 4;
+    const int SL = ((total + CL - 1) / CL + 3) & ~3;
+    const size_t fl = (size_t)2 * total + 3 * SL + (size_t)(D + 4 * HN + 2 * 2 * HN) * RS + RT * AMAX + RT + (size_t)(2 * AMAX + 1) * RS + 8;
     return fl * sizeof(float) + 64;
+}
+
+// shape of the launch for a minibatch of `rows`: 16-row tiles when a CTA of the 8-CTA cluster gets at most 16 rows, else 32-row
+// tiles; 16 CTAs (non-portable cluster size, allowed on B200) once the 8-CTA split would give a CTA more than one 32-row tile
+void small_plan(int64_t rows, int* RT, int* CL)
+{
+    *CL = rows > 8 * 32 ? 16 : 8;
+    *RT = (rows + *CL - 1) / *CL <= 16 ? 16 : 32;
+}
+
+template <bool CONT, int RT, int CL>
+int small_launch(dppo_ctx* ctx, const SmallArgs& a, cudaStream_t st)
+{
+    const size_t smem = small_smem_bytes(a.L, a.D, RT, CL);
+    auto kern = small_update_kernel<CONT, RT, CL>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        (CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess))
+        DPPO_FAIL(ctx, "small_update: cudaFuncSetAttribute failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(CL); lc.blockDim = dim3(SK_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, kern, a);
+    DPPO_CHECK_LAUNCH(ctx, "small_update_kernel");
+    return 0;
 }
 
 }  // namespace
@@ -452,7 +501,7 @@ extern "C" int dppo_small_update_supported(const dppo_mlp_desc* d)
     dppo_mlp_layout L;
     if (dppo_mlp_layout_compute(d, &L)) return 0;
     return d->hidden == HN && d->obs_dim >= 1 && d->obs_dim <= 64 && d->act_dim >= 1 && d->act_dim <= AMAX && L.total % 4 == 0 &&
-           small_smem_bytes(L, d->obs_dim) <= 220 * 1024;
+           small_smem_bytes(L, d->obs_dim, 32, 8) <= 220 * 1024;
 }
 
 extern "C" int dppo_small_update(dppo_ctx* ctx, const dppo_mlp_desc* d, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
@@ -465,7 +514,9 @@ extern "C" int dppo_small_update(dppo_ctx* ctx, const dppo_mlp_desc* d, float* p
         !step_consts || !losses)
         DPPO_FAIL(ctx, "small_update: null argument");
     if (!dppo_small_update_supported(d)) DPPO_FAIL(ctx, "small_update: unsupported network (hidden must be %d, obs_dim <= 64, actions <= %d)", HN, AMAX);
-    if (rows < 1 || rows > (1 << 24) || steps < 1) DPPO_FAIL(ctx, "small_update: bad shape rows=%lld steps=%d", (long long)rows, steps);
+    int RT, CL;
+    small_plan(rows, &RT, &CL);
+    if (rows < 1 || rows > (int64_t)CL * ROWS_MAX || steps < 1) DPPO_FAIL(ctx, "small_update: bad shape rows=%lld steps=%d", (long long)rows, steps);
     if (hy->advantage_norm && (!adv_stats || hy->adv_count < 2)) DPPO_FAIL(ctx, "small_update: advantage_norm needs adv_stats and adv_count >= 2");
     SmallArgs a;
     dppo_mlp_layout_compute(d, &a.L);
@@ -479,15 +530,14 @@ extern "C" int dppo_small_update(dppo_ctx* ctx, const dppo_mlp_desc* d, float* p
     a.max_norm = hy->grad_norm_clip; a.w1 = (float)(1.0 - hy->beta1); a.beta2 = (float)hy->beta2; a.w2 = (float)(1.0 - hy->beta2);
     a.eps = hy->adam_eps;
     a.losses = losses; a.grad_norm_out = grad_norm_out;
-    const size_t smem = small_smem_bytes(a.L, a.D);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->continuous) {
-        cudaFuncSetAttribute(small_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        small_update_kernel<true><<<SK_CL, SK_THREADS, smem, st>>>(a);
-    } else {
-        cudaFuncSetAttribute(small_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        small_update_kernel<false><<<SK_CL, SK_THREADS, smem, st>>>(a);
-    }
-    DPPO_CHECK_LAUNCH(ctx, "small_update_kernel");
-    return 0;
+#define SMALL_GO(CONT)                                                          \
+    do {                                                                        \
+        if (CL == 8 && RT == 16) return small_launch<CONT, 16, 8>(ctx, a, st);  \
+        if (CL == 8) return small_launch<CONT, 32, 8>(ctx, a, st);              \
+        return small_launch<CONT, 32, 16>(ctx, a, st);                          \
+    } while (0)
+    if (d->continuous) SMALL_GO(true);
+    SMALL_GO(false);
+#undef SMALL_GO
 }
