@@ -29,13 +29,17 @@ constexpr int SPLIT_THREADS = N_SPLIT * 32;
 constexpr int KC = 16;                     // k per chunk (one SWIZZLE_64B atom width)
 constexpr int BM = 128;                    // rows per CTA (the pair computes 256)
 constexpr int A_IMG = BM * KC * 4;         // 8 KB: one image (hi or lo) of this CTA's activation chunk
-constexpr int STAGES = 6;
+constexpr int MAX_STAGES = 6;
+// Ring depth: six 32 KB stages for the forward GEMM; the dgrad variant gives one stage to the epilogue warps, which receive their
+// 32 x 32 tiles of the layer's activations (tanh' factors) by TMA instead of thread-per-row global loads (32 different 128-byte
+// lines per load instruction: 1.27x the algorithmic DRAM traffic and 12 us per launch, profiles/r1f_kernels.csv).
+template <int EPI> struct RingDepth { static constexpr int v = EPI == DPPO_EPI_TANH_BWD ? 5 : 6; };
 constexpr int STG_BLK = 32 * 128;          // one 32-row x 32-column fp32 staging block (SWIZZLE_128B layout)
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, const unsigned char* __restrict__ Wimg,
-                const float* __restrict__ bias, const float* __restrict__ Hact, int ldh, float* __restrict__ colsum, int64_t M,
+tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmH,
+                const unsigned char* __restrict__ Wimg, const float* __restrict__ bias, float* __restrict__ colsum, int64_t M,
                 int N, int K, int n_tile, int pair_tiles, int tail_halves, int dbg, const int* __restrict__ m_dev)
 {
     if (m_dev != nullptr) {                              // row count decided on the device (tiles past it are never touched)
@@ -45,7 +49,8 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (tail_halves == 1) tail_halves = 0;           // the tail split was planned for the host's row count
     }
     extern __shared__ unsigned char dyn_raw[];
-    __shared__ __align__(8) uint64_t full[STAGES], ready[STAGES], empty[STAGES], tfull[2], tempty[2];
+    constexpr int STAGES = RingDepth<EPI>::v;
+    __shared__ __align__(8) uint64_t full[MAX_STAGES], ready[MAX_STAGES], empty[MAX_STAGES], tfull[2], tempty[2], hbar[N_EPI];
     __shared__ uint32_t s_tmem;
 
     unsigned char* dyn = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn_raw) + 1023) & ~(uintptr_t)1023);
@@ -81,6 +86,8 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 2 * N_SPLIT); mbar_init(&empty[s], 1); }
 #pragma unroll
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * N_EPI); }
+#pragma unroll
+        for (int w = 0; w < N_EPI; ++w) mbar_init(&hbar[w], 1);
         fence_mbar_init();
     }
     if (warp == W_MMA) tmem_alloc2(&s_tmem, 512);
@@ -196,8 +203,12 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ew = warp - W_EPI0;
         const int q = warp & 3, grp = ew >> 2;
         const uint32_t stg = smem_u32(dyn + STAGES * stage_bytes) + (uint32_t)ew * STG_BLK;
+        // dgrad: this warp's landing block for the 32 x 32 activation tiles (SWIZZLE_128B, as delivered by TMA) + its barrier
+        unsigned char* hblk = dyn + STAGES * stage_bytes + N_EPI * STG_BLK + ew * STG_BLK;
+        const uint32_t hst = smem_u32(hblk);
+        uint32_t hph = 0;
         const uint32_t row_off = (uint32_t)lane * 128, sw = (uint32_t)(lane & 7);
-        if (lane == 0) tma_prefetch_desc(&tmC);
+        if (lane == 0) { tma_prefetch_desc(&tmC); if (EPI == DPPO_EPI_TANH_BWD) tma_prefetch_desc(&tmH); }
         for (uint32_t it = 0; it < (uint32_t)n_my; ++it) {
             int tile, half;
             tile_of((int)it, tile, half);
@@ -208,8 +219,12 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int nblk = ncols / 32;
             const int n0 = n_blk * n_tile + (half < 0 ? 0 : half * (n_tile / 2)) + col0;
             const int m0 = m_pair * 2 * BM + (int)rank * BM + q * 32;
-            const int64_t m = (int64_t)m0 + lane;
             const uint32_t set = it & 1;
+            if (EPI == DPPO_EPI_TANH_BWD && lane == 0 && !DPPO_DBG(dbg, 8)) {
+                // the first activation tile of this output tile travels while the MMAs of the tile are still running
+                mbar_expect_tx(&hbar[ew], (uint32_t)STG_BLK);
+                tma_load_2d(hblk, &tmH, n0, m0, &hbar[ew]);
+            }
             mbar_wait(&tfull[set], (it >> 1) & 1);
             fence_after();
             for (int k = 0; k < (DPPO_DBG(dbg, 8) ? 0 : nblk); ++k) {
@@ -221,9 +236,16 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 8; ++j) aux[j] = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
                 } else {
+                    mbar_wait(&hbar[ew], hph);
+                    hph ^= 1u;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        aux[j] = (m < M && !DPPO_DBG(dbg, 8192)) ? __ldg(reinterpret_cast<const float4*>(Hact + m * (int64_t)ldh + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < 8; ++j) aux[j] = lds128(hst + row_off + ((((uint32_t)j) ^ sw) << 4));    // rows >= M: zero-filled
+                    __syncwarp();
+                    if (lane == 0 && k + 1 < nblk) {                    // next tile of activations: overlaps this block's epilogue work
+                        fence_proxy_async();
+                        mbar_expect_tx(&hbar[ew], (uint32_t)STG_BLK);
+                        tma_load_2d(hblk, &tmH, n + 32, m0, &hbar[ew]);
+                    }
                 }
                 tmem_ld32_wait(r);
                 float v[32];
@@ -355,12 +377,16 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     if (!dppo_tc3_gemm_supported(M, N, K)) DPPO_FAIL(ctx, "tc3_gemm: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
     if (lda % 4 != 0 || ldc % 4 != 0 || !al16(A) || !al16(C) || !al16(Wimg) || (Hact && (!al16(Hact) || ldh % 4 != 0)) || (bias && !al16(bias)))
         DPPO_FAIL(ctx, "tc3_gemm: operands must be 16-byte aligned with row pitches multiple of 4 floats");
-    CUtensorMap tmA, tmC;
+    CUtensorMap tmA, tmC, tmH;
     if (!dppo_make_tensor_map_2d(&tmA, A, M, K, lda, KC, BM, 2) || !dppo_make_tensor_map_2d(&tmC, C, M, N, ldc, 32, 32, 3))
         DPPO_FAIL(ctx, "tc3_gemm: cuTensorMapEncodeTiled failed");
+    tmH = tmC;
+    if (epi == DPPO_EPI_TANH_BWD && !dppo_make_tensor_map_2d(&tmH, Hact, M, N, ldh, 32, 32, 3))      // activation tiles of the epilogue
+        DPPO_FAIL(ctx, "tc3_gemm: cuTensorMapEncodeTiled(Hact) failed");
     const int n_tile = dppo_tc_n_tile(N);
     const int pair_tiles = (int)((M + 2 * BM - 1) / (2 * BM));
-    const size_t smem = (size_t)STAGES * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK + 1024;
+    const int stages = epi == DPPO_EPI_TANH_BWD ? RingDepth<DPPO_EPI_TANH_BWD>::v : RingDepth<DPPO_EPI_BIAS_TANH>::v;
+    const size_t smem = (size_t)stages * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK * (epi == DPPO_EPI_TANH_BWD ? 2 : 1) + 1024;
     int grid, tail_halves;
     tc3_plan(ctx, M, N, &grid, &tail_halves);
     if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && (N / n_tile > 1 || tail_halves == 2) &&
@@ -368,11 +394,11 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");
     if (epi == DPPO_EPI_BIAS_TANH) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, Wimg, bias, Hact, ldh, colsum, M,
+        dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, tmH, Wimg, bias, colsum, M,
                         N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug, ctx->rows_dev);
     } else if (epi == DPPO_EPI_TANH_BWD) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, Wimg, bias, Hact, ldh, colsum, M,
+        dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, tmH, Wimg, bias, colsum, M,
                         N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug, ctx->rows_dev);
     } else {
         DPPO_FAIL(ctx, "tc3_gemm: unknown epilogue %d", epi);
