@@ -340,7 +340,8 @@ def time_learn(agent, buf, host, steps, warmup, world, dist, ctx):
     # ---- end to end through the public API with host buffers ----
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h_losses = torch.empty(E * MB, 4).pin_memory()
+    h_losses = [torch.empty(E * MB, 4).pin_memory() for _ in range(2)]
+    read_done = [None, None]
     # Two device buffers: the host -> device copy of step k+1's inputs is issued as soon as learn(k) has been enqueued and runs on
     # the copy stream under step k's update loop (every step's inputs are copied and every step's losses are read inside the
     # timed region; only the first copy is exposed).
@@ -357,15 +358,20 @@ def time_learn(agent, buf, host, steps, warmup, world, dist, ctx):
         agent.learn(cur)
         if k + 1 < steps:
             bufs[(k + 1) & 1].load_host(*host)        # next step's inputs, overlapped with this step's update loop
-        h_losses.copy_(agent.last_losses, non_blocking=True)     # result read back
-        torch.cuda.current_stream().synchronize()
+        h_losses[k & 1].copy_(agent.last_losses, non_blocking=True)      # this step's result read back (asynchronously) ...
+        read_done[k & 1] = torch.cuda.Event()
+        read_done[k & 1].record()
+        if k > 0:
+            read_done[(k - 1) & 1].synchronize()                          # ... and consumed one step later: the host never idles the GPU
+            assert torch.isfinite(h_losses[(k - 1) & 1]).all()
+    read_done[(steps - 1) & 1].synchronize()
     e1.record()
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    assert torch.isfinite(h_losses).all()
-    out.update(ms_e2e=float(ms_e2e) / steps, h2d=int(h2d), d2h=int(h_losses.numel() * 4))
+    assert torch.isfinite(h_losses[(steps - 1) & 1]).all()
+    out.update(ms_e2e=float(ms_e2e) / steps, h2d=int(h2d), d2h=int(h_losses[0].numel() * 4))
     return out
 
 

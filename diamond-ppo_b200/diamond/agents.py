@@ -446,7 +446,6 @@ class FusedMlpEngine(_EngineBase):
         self.timing = {}
         self.use_graphs = True          # replay the optimiser steps of an epoch as a CUDA graph (single GPU, steady state)
         self._seen_keys = []
-        self._idx_consumed = None       # event after the last async copy out of the pinned per-epoch index buffers
         self.reuse_rollout_values = True   # learn() takes log-probs / values recorded at sampling time when they are still valid
         self.use_small_kernel = True       # default 64-wide nets: the whole update loop of a learn() as one cluster launch
         self.dp_seq = 0                    # data-parallel exchanges issued so far (monotonic; independent of the Adam step)
@@ -530,7 +529,10 @@ class FusedMlpEngine(_EngineBase):
                  idx=[torch.empty(MB * plan["rows"], **i32) for _ in range(2)],
                  perm=[torch.empty(plan["B_perm"], **i32) for _ in range(2)] if plan["filter"] else None,
                  counts=[torch.zeros(MB, **i32) for _ in range(2)], overflow=torch.zeros(1, **i32),
-                 h_idx=[torch.empty(plan["B_perm"], dtype=torch.int32).pin_memory() for _ in range(E)],
+                 # pinned staging of the host permutations: two sets, alternating between consecutive learn() calls, so that the host
+                 # worker of learn k+1 never waits for the last asynchronous copy of learn k
+                 h_sets=[[torch.empty(plan["B_perm"], dtype=torch.int32).pin_memory() for _ in range(E)] for _ in range(2)],
+                 h_set=0, h_consumed=[None, None],
                  copy_stream=torch.cuda.Stream(), copied=[torch.cuda.Event() for _ in range(2)],
                  done=[torch.cuda.Event() for _ in range(2)], plan=plan)
         for ev in b["done"]:
@@ -556,7 +558,8 @@ class FusedMlpEngine(_EngineBase):
                 with torch.cuda.stream(cs):
                     target.copy_(b["h_idx"][e], non_blocking=True)
                     b["copied"][p].record()
-                self._idx_consumed = b["copied"][p]
+                    b["h_consumed"][b["h_set"]] = torch.cuda.Event()
+                    b["h_consumed"][b["h_set"]].record()
                 main.wait_event(b["copied"][p])
             if plan["filter"]:
                 dist.broadcast(target, owner)                            # 4 bytes per index over NVLink instead of a shuffle per rank
@@ -594,8 +597,8 @@ class FusedMlpEngine(_EngineBase):
             if worker is not None:
                 worker.wait(e)
                 sm["idx"][e * B:(e + 1) * B].copy_(b["h_idx"][e], non_blocking=True)
-                self._idx_consumed = torch.cuda.Event()
-                self._idx_consumed.record()
+                b["h_consumed"][b["h_set"]] = torch.cuda.Event()
+                b["h_consumed"][b["h_set"]].record()
             else:
                 ctx.permutation_device(self.perm_seed, self.perm_counter, B, sm["idx"][e * B:(e + 1) * B])
                 self.perm_counter += 1
@@ -756,8 +759,10 @@ class FusedMlpEngine(_EngineBase):
         worker = None
         lock_hash = 0.0
         if self.perm_mode == "numpy":
-            if self._idx_consumed is not None:
-                self._idx_consumed.synchronize()   # the previous learn()'s async H2D copies out of the pinned index buffers are done
+            b["h_set"] ^= 1
+            b["h_idx"] = b["h_sets"][b["h_set"]]
+            if b["h_consumed"][b["h_set"]] is not None:
+                b["h_consumed"][b["h_set"]].synchronize()   # the async copies out of this pinned set (two learn() calls ago) are done
             owner = (lambda e: e % dist.world == dist.rank) if plan["filter"] else None
             worker = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_idx"]], owner)
             lock_hash = worker.state_hash
