@@ -69,7 +69,7 @@ dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long s
         const unsigned long long* f = pp.flags[rank] + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < step) {
-            __nanosleep(64);
+            __nanosleep(20);
             if (clock64() - t0 > DP_WAIT_CYCLES) {             // peer never published: report instead of hanging the GPU
                 if (blockIdx.x == 0) *status = 1 + (int)threadIdx.x;
                 break;
@@ -79,11 +79,16 @@ dp_allreduce_sumsq_kernel(PeerPtrs pp, int world, int rank, unsigned long long s
     __syncthreads();
     double s = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n4; i += (int64_t)gridDim.x * blockDim.x) {
+        // every rank's element is requested before the first one is used: ONE NVLink round trip per thread instead of `world`
+        // dependent ones (the loop over a run-time rank count serialised load -> add -> load: 8 x ~2.5 us at 8 GPUs)
+        float4 v[DPPO_MAX_RANKS];
+#pragma unroll
+        for (int q = 0; q < DPPO_MAX_RANKS; ++q)
+            if (q < world) v[q] = __ldcv(reinterpret_cast<const float4*>(pp.slot[q]) + i);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < world; ++q) {                                   // fixed rank order: identical sums on every rank
-            const float4 v = __ldcv(reinterpret_cast<const float4*>(pp.slot[q]) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+#pragma unroll
+        for (int q = 0; q < DPPO_MAX_RANKS; ++q)                             // fixed rank order: identical sums on every rank
+            if (q < world) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
         if (i < n4) {
             reinterpret_cast<float4*>(grads_out)[i] = acc;
             s += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
