@@ -30,7 +30,7 @@ try:                                    # the real package when present, else th
     import gymnasium as gym             # noqa: F401
 except ImportError:                     # pragma: no cover - the GPU image has no gymnasium
     from . import envs as gym
-from .agents import _Dist, _EngineBase, _PermWorker, _require_cuda
+from .agents import _Dist, _EngineBase, _PermWorker, _PPOBase, _require_cuda
 from .config import RecurrentPPOConfig
 from .networks import _obs_dim, network_parameter_init_
 from .utils import Checkpointer, Logger, Ticker, Timer
@@ -234,6 +234,9 @@ class FusedRecurrentEngine(_EngineBase):
         self.draws = 0
         self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
         self._ws = {}
+        self._bufs = {}
+        self._seen_keys = []
+        self.use_graphs = True
 
     def _workspace(self, T, N_, M, training):
         key = (T, N_, M, bool(training))
@@ -253,6 +256,24 @@ class FusedRecurrentEngine(_EngineBase):
                              logits, values, hx_out, self._workspace(T, N_, T * N_, False))
         return logits, values, hx_out
 
+    def _buffers(self, T, N_, E, MB):
+        key = (T, N_, E, MB)
+        b = self._bufs.get(key)
+        if b is None:
+            dev, B = self.device, T * N_
+            b = self._bufs[key] = dict(
+                stats=torch.zeros(2, dtype=torch.float64, device=dev), adv=torch.empty(T, N_, device=dev), ret=torch.empty(T, N_, device=dev),
+                losses=torch.zeros(E * MB, 4, device=dev), idx=[torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)],
+                h_sets=[[torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)] for _ in range(2)], h_set=0, h_consumed=[None, None],
+                old_logp=torch.empty(B, device=dev), actions=torch.empty(B, dtype=torch.int32, device=dev),
+                pd=torch.empty(T, N_, dtype=torch.uint8, device=dev), hx0=torch.empty(N_, self.desc.gru_hidden, device=dev),
+                values=torch.empty(T, N_, device=dev), next_values=torch.empty(T, N_, device=dev),
+                consts=[torch.zeros(MB, 4, dtype=torch.float32, device=dev) for _ in range(2)],
+                h_consts=[torch.zeros(MB, 4, dtype=torch.float32).pin_memory() for _ in range(2)],
+                consts_copied=[torch.cuda.Event() for _ in range(2)], g_losses=[torch.zeros(MB, 4, device=dev) for _ in range(2)],
+                graphs={})
+        return b
+
     def learn(self, ro: RecurrentRollout):
         cfg, ctx, dev = self.cfg, self.ctx, self.device
         T, N_ = ro.T, ro.N
@@ -262,34 +283,83 @@ class FusedRecurrentEngine(_EngineBase):
             raise ValueError(f"cannot reshape array of size {E * B} into shape ({E},{MB},{B // MB})")
         M = B // MB
         self._resync_optimizer()
-        h_idx = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(E)]
+        b = self._buffers(T, N_, E, MB)
+        b["h_set"] ^= 1
+        h_idx = b["h_sets"][b["h_set"]]
+        if b["h_consumed"][b["h_set"]] is not None:
+            b["h_consumed"][b["h_set"]].synchronize()                    # the async copies out of this pinned set are done
         worker = _PermWorker(B, E, MB, [h.numpy() for h in h_idx])
         worker.start()
+        # learn()-persistent copies in the kernels' dtypes (stable addresses: the optimiser steps are replayed as a CUDA graph)
+        b["old_logp"].copy_(ro.log_probs.reshape(B)); b["actions"].copy_(ro.actions.reshape(B))
+        b["pd"].copy_(ro.prev_dones); b["hx0"].copy_(ro.hx0.reshape(N_, -1))
+        b["values"].copy_(ro.values); b["next_values"].copy_(ro.next_values)
         # GAE with the values stored at rollout time + returns + advantage sums (recurrent_ppo.py:315-318); the normalisation
         # itself is applied while the head kernel gathers the advantages
-        stats = torch.zeros(2, dtype=torch.float64, device=dev)
-        adv = torch.empty(T, N_, device=dev)
-        ret = torch.empty(T, N_, device=dev)
-        ctx.gae(ro.rewards, ro.terminations, ro.truncations, ro.values.contiguous(), ro.next_values.contiguous(), cfg.gamma,
-                cfg.gae_lambda, advantages=adv, returns=ret, stats=stats)
+        stats, adv, ret = b["stats"], b["adv"], b["ret"]
+        stats.zero_()
+        ctx.gae(ro.rewards, ro.terminations, ro.truncations, b["values"], b["next_values"], cfg.gamma, cfg.gae_lambda, advantages=adv,
+                returns=ret, stats=stats)
         hyper = self._hyper(cfg, M, B)
         hyper.grad_sumsq = self.grad_sumsq.data_ptr()
-        old_logp = ro.log_probs.reshape(B).contiguous()
-        actions = ro.actions.reshape(B).to(torch.int32)
-        pd = ro.prev_dones.to(torch.uint8).contiguous()
-        hx0 = ro.hx0.reshape(N_, -1).contiguous()
-        losses = torch.zeros(E * MB, 4, device=dev)
+        losses = b["losses"]
         ws = self._workspace(T, N_, M, True)
-        idx = torch.empty(E, B, dtype=torch.int32, device=dev)
+
+        def step(idx_k, losses_k):
+            ctx.rnn_grad_minibatch(self.desc, self.P, self.G, ro.obs, b["pd"], b["hx0"], T, N_, b["actions"], b["old_logp"], adv.view(B),
+                                   ret.view(B), stats, idx_k, M, hyper, losses_k, ws)
+            ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+
+        # From the second learn() on the same rollout buffers the MB optimiser steps of an epoch (15 launches each) are replayed as
+        # one CUDA graph; the minibatch indices and Adam's two step-dependent constants are device-resident (like the MLP engine).
+        key = (ro.obs.data_ptr(), ro.rewards.data_ptr(), T, N_, E, MB, cfg.ppo_clip, cfg.value_loss_weight, cfg.entropy_beta,
+               cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm))
+        use_graph = self.use_graphs and key in self._seen_keys
+        if key not in self._seen_keys:
+            self._seen_keys = (self._seen_keys + [key])[-4:]
+        gs = None
+        if use_graph:
+            gs = b["graphs"].get(key)
+            if gs is None:
+                if len(b["graphs"]) >= 4:
+                    b["graphs"].pop(next(iter(b["graphs"])))
+                gs = b["graphs"][key] = []
+                cap = torch.cuda.Stream()
+                cap.wait_stream(torch.cuda.current_stream())
+                for p in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cap):
+                        for k in range(MB):
+                            hyper.step = 1
+                            hyper.step_consts = b["consts"][p][k].data_ptr()
+                            step(b["idx"][p][k * M:(k + 1) * M], b["g_losses"][p][k])
+                    gs.append(g)
+                hyper.step_consts = None
+                torch.cuda.current_stream().wait_stream(cap)
+        b1, b2 = hyper.beta1, hyper.beta2
         for e in range(E):
+            p = e & 1
             worker.wait(e)
-            idx[e].copy_(h_idx[e], non_blocking=True)
+            b["idx"][p].copy_(h_idx[e], non_blocking=True)               # stream-ordered after the steps that last read idx[p]
+            b["h_consumed"][b["h_set"]] = torch.cuda.Event()
+            b["h_consumed"][b["h_set"]].record()
+            if gs is not None:
+                b["consts_copied"][p].synchronize()
+                hc = b["h_consts"][p].numpy()
+                for k in range(MB):
+                    st = self.adam_step + k + 1                          # torch/optim/adam.py:531-547, python-float bias corrections
+                    hc[k, 0] = np.float32(np.sqrt(1.0 - b2 ** st))
+                    hc[k, 1] = np.float32(-(hyper.lr / (1.0 - b1 ** st)))
+                b["consts"][p].copy_(b["h_consts"][p], non_blocking=True)
+                b["consts_copied"][p].record()
+                gs[p].replay()
+                losses[e * MB:(e + 1) * MB].copy_(b["g_losses"][p])
+                self.adam_step += MB
+                continue
             for k in range(MB):
                 self.adam_step += 1
                 hyper.step = self.adam_step
-                ctx.rnn_grad_minibatch(self.desc, self.P, self.G, ro.obs, pd, hx0, T, N_, actions, old_logp, adv.view(B), ret.view(B),
-                                       stats, idx[e][k * M:(k + 1) * M], M, hyper, losses[e * MB + k], ws)
-                ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
+                step(b["idx"][p][k * M:(k + 1) * M], losses[e * MB + k])
         worker.finish()
         self._publish_steps()
         self.last_losses = losses
@@ -327,11 +397,18 @@ class RecurrentPPO:
         self.checkpointer = Checkpointer(folder="models", run_name="default")
         self.ticker = Ticker(cfg.total_steps, cfg.num_envs, cfg.rollout_steps, verbose=cfg.verbose)
         self.cfg = cfg
+        self._device_ro, self._epstats = None, None
+
+    # device-side episode statistics (shared with the MLP agents)
+    _device_episode_stats = _PPOBase._device_episode_stats
+    _flush_episode_stats = _PPOBase._flush_episode_stats
 
     # ---- rollout (recurrent_ppo.py:205-263) ----------------------------------------------------------
     def rollout(self) -> RecurrentRollout:
         cfg, dev = self.cfg, self.device
         T, N_ = cfg.rollout_steps, cfg.num_envs
+        if getattr(self.envs, "device_resident", False) and getattr(self.engine, "fused", False):
+            return self._rollout_device()
         ro = RecurrentRollout(T, N_, self.obs_dim, cfg.gru_hidden_dim, dev)
         observations, hx, prev_dones = self.current_observations, self.current_hx, self.prev_dones
         ro.hx0.copy_(hx)
@@ -372,6 +449,46 @@ class RecurrentPPO:
         self.current_observations, self.current_hx, self.prev_dones = observations, hx, prev_dones
         return ro
 
+    def _rollout_device(self) -> RecurrentRollout:
+        """Device-resident environments (diamond.envs.DeviceVectorEnv): the whole rollout loop of recurrent_ppo.py:214-263 stays on
+        the GPU -- GRU step, sampling kernel, environment kernel (which writes row t of the rollout tensors and resets finished
+        environments), V(final observation | h_{t+1}) -- with no PCIe crossing and no host synchronisation; the rollout tensors are
+        persistent, so learn() replays its optimiser steps as CUDA graphs.  Episode statistics: dppo_episode_stats, read lazily."""
+        cfg, dev, envs = self.cfg, self.device, self.envs
+        T, N_ = cfg.rollout_steps, cfg.num_envs
+        ro = self._device_ro
+        if ro is None:
+            ro = self._device_ro = RecurrentRollout(T, N_, self.obs_dim, cfg.gru_hidden_dim, dev)
+            ro.next_obs = torch.empty(T, N_, self.obs_dim, device=dev)
+            ro.pd_u8 = torch.zeros(N_, dtype=torch.uint8, device=dev)
+            ro.actions_dev = torch.empty(N_, dtype=torch.int64, device=dev)
+            ro.pd_f32 = torch.empty(N_, device=dev)
+        hx = self.current_hx
+        if not torch.is_tensor(self.prev_dones):
+            ro.pd_u8.copy_(torch.as_tensor(np.asarray(self.prev_dones, dtype=np.uint8)))
+        ro.hx0.copy_(hx)
+        for t in range(T):
+            ro.prev_dones[t].copy_(ro.pd_u8)
+            logits, values, new_hx = self.engine.forward(envs.cur_obs.unsqueeze(0), hx, ro.pd_u8.unsqueeze(0))
+            self.ctx.sample_categorical(logits.squeeze(0), self.engine.seed, self.engine.draws, 0, ro.actions_dev, ro.log_probs[t])
+            self.engine.draws += 1
+            ro.actions[t].copy_(ro.actions_dev)
+            ro.values[t].copy_(values.squeeze(0))
+            # environment kernel: writes obs[t] (the observation acted on), next_obs[t] (true final observation), rewards, masks;
+            # finished environments are reset in the same kernel
+            self.ctx.env_step(envs.desc, envs._st, ro.actions_dev, t, True, ro.obs, ro.next_obs, None, ro.rewards, ro.terminations,
+                              ro.truncations)
+            _, next_values, _ = self.engine.forward(ro.next_obs[t].unsqueeze(0), new_hx, None, heads=2)   # no reset (:226-232)
+            ro.next_values[t].copy_(next_values.squeeze(0))
+            torch.add(ro.terminations[t], ro.truncations[t], out=ro.pd_f32)
+            ro.pd_u8.copy_(ro.pd_f32 > 0)                                # dones of step t = prev_dones of step t + 1 (:259-261)
+            hx = new_hx
+        ro.filled = T
+        if self.ticker is not None:
+            self._device_episode_stats(ro)
+        self.current_observations, self.current_hx, self.prev_dones = envs.cur_obs, hx, ro.pd_u8
+        return ro
+
     # ---- GAE (recurrent_ppo.py:265-299) ----------------------------------------------------------------
     def calculate_advantage(self, rewards, terminations, truncations, values, next_values) -> torch.Tensor:
         args = [torch.as_tensor(x).to(self.device, torch.float32).contiguous() for x in
@@ -395,6 +512,10 @@ class RecurrentPPO:
         self.current_observations, _ = self.envs.reset(seed=cfg.seed)
         self.prev_dones = np.zeros(cfg.num_envs, dtype=bool)
         self.current_hx = torch.zeros(1, cfg.num_envs, cfg.gru_hidden_dim, device=self.device)
+        if self._epstats is not None:                                  # fresh environments: running returns / lengths restart
+            self._flush_episode_stats()
+            self._epstats["ep_return"].zero_()
+            self._epstats["ep_len"].zero_()
         last_checkpoint_time = time.time()
         total_rollouts = cfg.total_steps // (cfg.rollout_steps * cfg.num_envs)
         env_steps = 0
@@ -407,4 +528,5 @@ class RecurrentPPO:
                 last_checkpoint_time = time.time()
         if cfg.checkpoint and total_rollouts > 0:
             self.checkpointer.save(env_steps, self.network, self.optimizer)
+        self._flush_episode_stats()
         self.envs.close()

@@ -498,3 +498,60 @@ def test_small_net_cluster_kernel_matches_per_layer_kernels(cont, D, A, N_, T, M
     assert float((p1 - p0).abs().max() / p0.abs().max()) <= 2e-5
     assert float((m1 - m0).abs().max()) <= 1e-5 * max(1.0, float(m0.abs().max()))
     assert float((v1 - v0).abs().max()) <= 1e-5 * max(1e-3, float(v0.abs().max()))
+
+
+def test_recurrent_graph_replay_is_bit_identical_to_eager():
+    """RecurrentPPO.learn(): from the second call on the same rollout tensors the optimiser steps (15 launches each) are replayed as a
+    CUDA graph with device-resident step constants; parameters and losses equal the eager launches bit for bit."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig, envs
+    from diamond.recurrent import RecurrentRollout
+    g = np.load(os.path.join(GOLDEN, "learn_R4.npz"))
+    D, A, H, Hg, N_, T, E, MB = (int(x) for x in g["meta"])
+    outs = []
+    for use_graphs in (True, False):
+        cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, num_epochs=E, num_minibatches=MB, verbose=False, network_hidden_dim=H,
+                                 gru_hidden_dim=Hg, seed=2)
+        agent = RecurrentPPO(lambda: envs.SyntheticEnv(D, A), cfg)
+        agent.network.load_state_dict({k[len("init."):]: torch.as_tensor(g[k]) for k in g.files if k.startswith("init.")})
+        agent.engine.use_graphs = use_graphs
+        ro = RecurrentRollout(T, N_, D, Hg, agent.device)
+        for name in ("obs", "actions", "rewards", "terminations", "truncations", "prev_dones", "log_probs", "values", "next_values"):
+            getattr(ro, name).copy_(torch.as_tensor(g[name]).to(getattr(ro, name).dtype))
+        ro.hx0.copy_(torch.as_tensor(g["hx0"]).reshape(ro.hx0.shape))
+        ro.filled = T
+        np.random.seed(123)
+        for _ in range(3):
+            agent.learn(ro)
+        torch.cuda.synchronize()
+        outs.append((agent.engine.P.clone(), agent.last_losses.clone()))
+        if use_graphs:
+            assert any(b["graphs"] for b in agent.engine._bufs.values()), "graph path was not taken"
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_recurrent_device_rollout_matches_module_and_learns():
+    """RecurrentPPO on device-resident CartPole: the rollout recorded on the device (GRU step, sampling, environment kernel, V(final
+    obs | h_{t+1})) is what the torch module computes from the same observations / hidden states / resets (recurrent_ppo.py:214-263),
+    prev_dones chain the environment's done flags, and train() improves the policy."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig
+    from diamond.envs import DeviceVectorEnv
+    N_, T = 32, 32
+    cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, verbose=False, seed=4, total_steps=N_ * T * 60)
+    agent = RecurrentPPO(DeviceVectorEnv.factory("CartPole-v1", seed=4), cfg)
+    agent.current_observations, _ = agent.envs.reset(seed=4)
+    agent.prev_dones = np.zeros(N_, dtype=bool)
+    agent.current_hx = torch.zeros(1, N_, cfg.gru_hidden_dim, device=agent.device)
+    ro = agent.rollout()
+    torch.cuda.synchronize()
+    dones = (ro.terminations + ro.truncations) > 0
+    assert torch.equal(ro.prev_dones[1:], dones[:-1]) and not ro.prev_dones[0].any()
+    assert torch.all(ro.rewards == 1.0) and dones.any()
+    # the torch module on the recorded sequence reproduces the recorded values and log-probs
+    with torch.inference_mode():
+        logits, values, _ = agent.network.get_logits_values_and_hx(ro.obs, ro.hx0.clone(), ro.prev_dones)
+    lp = torch.distributions.Categorical(logits=logits).log_prob(ro.actions)
+    assert float((values - ro.values).abs().max()) <= 1e-5 and float((lp - ro.log_probs).abs().max()) <= 1e-5
+    assert bool(torch.isfinite(ro.next_values).all())
+    agent.train()
+    lengths = agent.ticker.logs["episode_lengths"]
+    assert len(lengths) > 10 and np.mean(lengths) > 40.0, np.mean(lengths)
