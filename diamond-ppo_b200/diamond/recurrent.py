@@ -454,39 +454,73 @@ class RecurrentPPO:
         the GPU -- GRU step, sampling kernel, environment kernel (which writes row t of the rollout tensors and resets finished
         environments), V(final observation | h_{t+1}) -- with no PCIe crossing and no host synchronisation; the rollout tensors are
         persistent, so learn() replays its optimiser steps as CUDA graphs.  Episode statistics: dppo_episode_stats, read lazily."""
-        cfg, dev, envs = self.cfg, self.device, self.envs
+        cfg, dev, envs, eng, ctx = self.cfg, self.device, self.envs, self.engine, self.ctx
         T, N_ = cfg.rollout_steps, cfg.num_envs
+        A, Hg = eng.desc.act_dim, eng.desc.gru_hidden
         ro = self._device_ro
         if ro is None:
             ro = self._device_ro = RecurrentRollout(T, N_, self.obs_dim, cfg.gru_hidden_dim, dev)
             ro.next_obs = torch.empty(T, N_, self.obs_dim, device=dev)
             ro.pd_u8 = torch.zeros(N_, dtype=torch.uint8, device=dev)
             ro.actions_dev = torch.empty(N_, dtype=torch.int64, device=dev)
-            ro.pd_f32 = torch.empty(N_, device=dev)
-        hx = self.current_hx
+            ro.pd_f32, ro.pd_bool = torch.empty(N_, device=dev), torch.zeros(N_, dtype=torch.bool, device=dev)
+            ro.logits, ro.val1, ro.nv1 = torch.empty(N_, A, device=dev), torch.empty(N_, device=dev), torch.empty(N_, device=dev)
+            ro.hx_buf = [torch.zeros(N_, Hg, device=dev) for _ in range(3)]      # [0], [1]: ping-pong state; [2]: discarded output
+            ro.ws1 = eng._workspace(1, N_, N_, False)
+            self._ro_graph, self._ro_seen = None, 0
         if not torch.is_tensor(self.prev_dones):
             ro.pd_u8.copy_(torch.as_tensor(np.asarray(self.prev_dones, dtype=np.uint8)))
-        ro.hx0.copy_(hx)
-        for t in range(T):
-            ro.prev_dones[t].copy_(ro.pd_u8)
-            logits, values, new_hx = self.engine.forward(envs.cur_obs.unsqueeze(0), hx, ro.pd_u8.unsqueeze(0))
-            self.ctx.sample_categorical(logits.squeeze(0), self.engine.seed, self.engine.draws, 0, ro.actions_dev, ro.log_probs[t])
-            self.engine.draws += 1
-            ro.actions[t].copy_(ro.actions_dev)
-            ro.values[t].copy_(values.squeeze(0))
-            # environment kernel: writes obs[t] (the observation acted on), next_obs[t] (true final observation), rewards, masks;
-            # finished environments are reset in the same kernel
-            self.ctx.env_step(envs.desc, envs._st, ro.actions_dev, t, True, ro.obs, ro.next_obs, None, ro.rewards, ro.terminations,
-                              ro.truncations)
-            _, next_values, _ = self.engine.forward(ro.next_obs[t].unsqueeze(0), new_hx, None, heads=2)   # no reset (:226-232)
-            ro.next_values[t].copy_(next_values.squeeze(0))
-            torch.add(ro.terminations[t], ro.truncations[t], out=ro.pd_f32)
-            ro.pd_u8.copy_(ro.pd_f32 > 0)                                # dones of step t = prev_dones of step t + 1 (:259-261)
-            hx = new_hx
+        if self.current_hx.data_ptr() != ro.hx_buf[0].data_ptr():
+            ro.hx_buf[0].copy_(self.current_hx.reshape(N_, Hg))
+        ro.hx0.copy_(ro.hx_buf[0].reshape(ro.hx0.shape))
+
+        def steps(counter_of):
+            for t in range(T):
+                hx, new_hx = ro.hx_buf[t & 1], ro.hx_buf[(t + 1) & 1]
+                ro.prev_dones[t].copy_(ro.pd_u8)
+                ctx.rnn_forward(eng.desc, eng.P, envs.cur_obs, ro.pd_u8, hx, 1, N_, 3, ro.logits, ro.val1, new_hx, ro.ws1)
+                ctx.sample_categorical(ro.logits, eng.seed, counter_of(t), 0, ro.actions_dev, ro.log_probs[t])
+                ro.actions[t].copy_(ro.actions_dev)
+                ro.values[t].copy_(ro.val1)
+                # environment kernel: writes obs[t] (the observation acted on), next_obs[t] (true final observation), rewards, masks;
+                # finished environments are reset in the same kernel
+                ctx.env_step(envs.desc, envs._st, ro.actions_dev, t, True, ro.obs, ro.next_obs, None, ro.rewards, ro.terminations,
+                             ro.truncations)
+                # V(final observation | h_{t+1}): one more GRU step from the post-step state, no reset (recurrent_ppo.py:226-232)
+                ctx.rnn_forward(eng.desc, eng.P, ro.next_obs[t], None, new_hx, 1, N_, 2, None, ro.nv1, ro.hx_buf[2], ro.ws1)
+                ro.next_values[t].copy_(ro.nv1)
+                torch.add(ro.terminations[t], ro.truncations[t], out=ro.pd_f32)
+                torch.gt(ro.pd_f32, 0, out=ro.pd_bool)
+                ro.pd_u8.copy_(ro.pd_bool)                               # dones of step t = prev_dones of step t + 1 (:259-261)
+            if T & 1:                                                    # the state always ends in hx_buf[0]
+                ro.hx_buf[0].copy_(ro.hx_buf[1])
+
+        # From the third rollout the T x 14 launches are replayed as ONE CUDA graph; the sampling draw counters baked into it are
+        # relative to a device-resident base (dppo_set_draw_counter_base), so every replay draws fresh numbers.
+        if self._ro_graph is not None:
+            self._ro_graph["base"].fill_(eng.draws)
+            self._ro_graph["graph"].replay()
+        elif eng.use_graphs and self._ro_seen >= 2:
+            base = torch.zeros(1, dtype=torch.int64, device=dev)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            ctx.set_draw_counter_base(base)
+            try:
+                with torch.cuda.graph(graph):
+                    steps(lambda t: t)
+            finally:
+                ctx.set_draw_counter_base(None)
+            self._ro_graph = dict(graph=graph, base=base)
+            base.fill_(eng.draws)
+            graph.replay()
+        else:
+            self._ro_seen += 1
+            steps(lambda t: eng.draws + t)
+        eng.draws += T
         ro.filled = T
         if self.ticker is not None:
             self._device_episode_stats(ro)
-        self.current_observations, self.current_hx, self.prev_dones = envs.cur_obs, hx, ro.pd_u8
+        self.current_observations, self.current_hx, self.prev_dones = envs.cur_obs, ro.hx_buf[0].reshape(1, N_, Hg), ro.pd_u8
         return ro
 
     # ---- GAE (recurrent_ppo.py:265-299) ----------------------------------------------------------------

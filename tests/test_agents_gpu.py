@@ -555,3 +555,32 @@ def test_recurrent_device_rollout_matches_module_and_learns():
     agent.train()
     lengths = agent.ticker.logs["episode_lengths"]
     assert len(lengths) > 10 and np.mean(lengths) > 40.0, np.mean(lengths)
+
+
+def test_recurrent_rollout_graph_replay_is_bit_identical_to_eager():
+    """The recurrent device rollout replayed as one CUDA graph (from the third rollout; draw counters relative to a device-resident
+    base) records exactly what the eager launches record."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig
+    from diamond.envs import DeviceVectorEnv
+    N_, T = 48, 17                                           # odd T: the hidden-state ping-pong ends in the other buffer
+    recs = []
+    for use_graphs in (True, False):
+        cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, verbose=False, seed=6, total_steps=N_ * T * 100)
+        agent = RecurrentPPO(DeviceVectorEnv.factory("CartPole-v1", seed=6), cfg)
+        agent.engine.use_graphs = use_graphs
+        agent.ticker = None
+        agent.current_observations, _ = agent.envs.reset(seed=6)
+        agent.prev_dones = np.zeros(N_, dtype=bool)
+        agent.current_hx = torch.zeros(1, N_, cfg.gru_hidden_dim, device=agent.device)
+        out = []
+        for _ in range(5):
+            ro = agent.rollout()
+            out.append([getattr(ro, k).clone() for k in ("obs", "actions", "rewards", "terminations", "truncations", "prev_dones", "log_probs",
+                                                         "values", "next_values", "hx0")])
+        torch.cuda.synchronize()
+        if use_graphs:
+            assert agent._ro_graph is not None, "graph path was not taken"
+        recs.append(out)
+    for a, b in zip(*recs):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
