@@ -849,8 +849,9 @@ class AutogradEngine(_EngineBase):
 
     def learn(self, buf: RolloutBuffer, events=None):
         cfg, ctx, dist, net = self.cfg, self.ctx, self.dist, self.network
-        if dist.enabled:
-            raise NotImplementedError("data parallelism is implemented for the default networks only")
+        # Env-sharded data parallelism for a user module: rank-local permutations (equal 1/MB slices of every shard), loss means over the
+        # GLOBAL minibatch, gradients and loss sums summed over the ranks with NCCL before the clip (ppo.py:284); the advantage
+        # statistics are global too.  (The fused NVLink exchange needs the flat-gradient kernels of the default networks.)
         T, N_ = buf.T, buf.N
         E, MB = cfg.num_epochs, cfg.num_minibatches
         B = T * N_
@@ -885,9 +886,10 @@ class AutogradEngine(_EngineBase):
         ret = torch.empty(T, N_, device=dev)
         ctx.gae(buf.rewards, buf.terminations, buf.truncations, values, next_values, cfg.gamma, cfg.gae_lambda,
                 advantages=adv, returns=ret, stats=stats)
+        dist.all_reduce_sum(stats)                     # global mean / std of the advantages (ppo.py:243)
         if cfg.advantage_norm:
-            adv = ctx.adv_normalize(adv, stats, B)
-        hyper = self._hyper(cfg, M, B)
+            adv = ctx.adv_normalize(adv, stats, B * dist.world)
+        hyper = self._hyper(cfg, M * dist.world, B * dist.world)
         hyper.advantage_norm = 0                       # already normalised above
         obs_flat, adv_f, ret_f = obs.view(B, -1), adv.view(B), ret.view(B)
         act_bits = buf.actions.view(B, A) if self.continuous else buf.actions.view(B).view(torch.float32)
@@ -920,6 +922,9 @@ class AutogradEngine(_EngineBase):
                     ctx.ppo_loss_discrete(logits_c.detach(), val_c.detach(), a_mb.view(torch.int32), lp_mb, adv_mb, ret_mb, hyper,
                                           losses[e * MB + k], dlogits, dval, loss_ws)
                     torch.autograd.backward([logits_c, val_c], [dlogits, dval])
+                if dist.enabled:
+                    dist.all_reduce_sum(self.G)
+                    dist.all_reduce_sum(losses[e * MB + k])
                 ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
         worker.finish()
         self._publish_steps()

@@ -120,6 +120,49 @@ def main():
         dev_ok = dev_ok and worst <= 2e-5
         print(f"dp{world} [device permutation] vs single: max param err {worst:.2e} -> {'OK' if dev_ok else 'FAIL'}", flush=True)
     same = same and dev_ok
+    # a user network_cls under DP (autograd module, NCCL gradient sum): replicas identical, and -- with every rank holding the SAME data
+    # and the same permutation -- equal to the single-GPU update on one copy (sums of G identical shard gradients / G x the rows)
+    import torch.nn as nn
+
+    class TinyNet(nn.Module):
+        def __init__(self, observation_space, action_space, cfg):
+            super().__init__()
+            d = int(np.prod(observation_space.shape))
+            self.actor = nn.Sequential(nn.Linear(d, 32), nn.ReLU(), nn.Linear(32, action_space.n))
+            self.critic = nn.Sequential(nn.Linear(d, 32), nn.ReLU(), nn.Linear(32, 1))
+            self.actor_out_layer = self.actor[-1]
+
+        def get_actions(self, observations, device):
+            with torch.inference_mode():
+                return torch.distributions.Categorical(logits=self.actor(torch.as_tensor(observations, dtype=torch.float32, device=device))).sample().cpu().numpy()
+
+        def get_values(self, observations):
+            with torch.inference_mode():
+                return self.critic(observations).squeeze(-1)
+
+        def get_logits_and_values(self, x):
+            return self.actor(x), self.critic(x).squeeze(-1)
+
+    cfg_c = PPOConfig(num_envs=NL, rollout_steps=T, num_epochs=2, num_minibatches=4, verbose=False, seed=3)
+    shard0 = [[x[0:NL] for x in step] for step in full]                 # every rank learns from shard 0
+    ag = PPO(env_fn, cfg_c, network_cls=TinyNet, dp=True)
+    init = {k: v.detach().clone() for k, v in ag.network.state_dict().items()}
+    np.random.seed(31)
+    ag.learn(shard0)
+    torch.cuda.synchronize()
+    flat = ag.engine.P.clone(); ref = flat.clone(); dist.broadcast(ref, src=0)
+    cust_ok = bool(torch.equal(flat, ref)) and bool(torch.isfinite(flat).all())
+    if rank == 0:
+        single = PPO(env_fn, cfg_c, network_cls=TinyNet, dp=False)
+        single.network.load_state_dict(init)
+        np.random.seed(31)
+        single.learn(shard0)
+        torch.cuda.synchronize()
+        worst = max(float((p_ - q_).abs().max() / q_.abs().max().clamp_min(1e-12))
+                    for (_, p_), (_, q_) in zip(ag.network.named_parameters(), single.network.named_parameters()))
+        cust_ok = cust_ok and worst <= 2e-5
+        print(f"dp{world} [custom network_cls, NCCL gradient sum] vs single on replicated data: max param err {worst:.2e} -> {'OK' if cust_ok else 'FAIL'}", flush=True)
+    same = same and cust_ok
     # a rank whose numpy stream drifted is detected (asynchronously) instead of silently mis-assigning minibatch members
     ag = PPO(env_fn, cfg, dp=True, dp_permutation="global")
     if rank == world - 1:
