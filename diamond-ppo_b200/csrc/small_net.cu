@@ -21,6 +21,11 @@
 
 namespace cg = cooperative_groups;
 
+#ifdef DPPO_SMALL_PROFILE
+long long* g_small_prof = nullptr;
+extern "C" long long* dppo_small_prof(void) { return g_small_prof; }
+#endif
+
 namespace {
 
 constexpr int SK_THREADS = 256;
@@ -46,6 +51,7 @@ struct SmallArgs {
     float clip, vw, beta, inv_m, max_norm, w1, beta2, w2, eps;
     float* losses;                                          // [steps][4]
     float* grad_norm_out;                                   // optional: pre-clip norm of the last step
+    long long* prof;                                        // DPPO_SMALL_PROFILE builds: per-phase cycle counts of CTA 0
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -167,6 +173,12 @@ __device__ __forceinline__ float group8_max(float v)
     return v;
 }
 
+#ifdef DPPO_SMALL_PROFILE
+#define SK_MARK(i) do { if (prof_on) { __syncthreads(); if (tid == 0) { const long long now = clock64(); a.prof[i] += now - prof_t; prof_t = now; } } } while (0)
+#else
+#define SK_MARK(i) do { } while (0)
+#endif
+
 template <bool CONT, int RT, int SK_CL>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 small_update_kernel(const SmallArgs a)
@@ -217,24 +229,52 @@ small_update_kernel(const SmallArgs a)
     const int rows_per = (a.rows + SK_CL - 1) / SK_CL;
     const int row_lo = min(a.rows, rank * rows_per), row_hi = min(a.rows, row_lo + rows_per);
     const int my_rows = row_hi - row_lo;
+    int src_next = -1;                                                   // my row's index for the NEXT step (loaded one step ahead)
     cluster.sync();
 
+#ifdef DPPO_SMALL_PROFILE
+    const bool prof_on = a.prof != nullptr && rank == 0;
+    long long prof_t = clock64();
+#endif
     for (int step = 0; step < a.steps; ++step) {
+        SK_MARK(15);
         const int32_t* idx = a.idx + (int64_t)step * a.rows + row_lo;
-        // ---- per-row scalars of all my rows of this step (ppo.py:265-272): one round of dependent global loads per step ----
-        for (int m = tid; m < my_rows; m += SK_THREADS) {
-            const int src = idx[m];
-            const bool live = src >= 0;
-            s_src[m] = src;
-            s_oldlp[m] = live ? a.old_logp[src] : 0.f;
-            s_adv[m] = live ? (a.adv[src] - adv_mean) / adv_denom : 0.f;
-            s_ret[m] = live ? a.ret[src] : 0.f;
-            if (!CONT) s_acti[m] = live ? reinterpret_cast<const int32_t*>(a.actions)[src] : 0;
-            else
-                for (int j = 0; j < A; ++j) s_actf[m * AMAX + j] = live ? reinterpret_cast<const float*>(a.actions)[(int64_t)src * A + j] : 0.f;
+        // ---- per-row scalars of all my rows of this step (ppo.py:265-272) ----
+        // index -> data is a chain of two global-memory latencies (~4 us per step when exposed); every step's lists are known up
+        // front, so thread m keeps the pipeline two steps deep in registers: its index for step + 1 was loaded a step ago, the data
+        // loads for step + 1 are issued now and land in shared memory at the end of this step.
+        if (step == 0) {
+            if (tid < my_rows) {
+                const int src = idx[tid];
+                const bool live = src >= 0;
+                s_src[tid] = src;
+                s_oldlp[tid] = live ? a.old_logp[src] : 0.f;
+                s_adv[tid] = live ? (a.adv[src] - adv_mean) / adv_denom : 0.f;
+                s_ret[tid] = live ? a.ret[src] : 0.f;
+                if (!CONT) s_acti[tid] = live ? reinterpret_cast<const int32_t*>(a.actions)[src] : 0;
+                else
+                    for (int j = 0; j < A; ++j) s_actf[tid * AMAX + j] = live ? reinterpret_cast<const float*>(a.actions)[(int64_t)src * A + j] : 0.f;
+                src_next = a.steps > 1 ? idx[a.rows + tid] : -1;
+            }
+        }
+        float n_oldlp = 0.f, n_adv = 0.f, n_ret = 0.f, n_actf[AMAX];
+        int n_acti = 0, n_src = -1, src_next2 = -1;
+        if (tid < my_rows && step + 1 < a.steps) {
+            n_src = src_next;
+            const bool live = n_src >= 0;
+            n_oldlp = live ? a.old_logp[n_src] : 0.f;
+            n_adv = live ? a.adv[n_src] : adv_mean;
+            n_ret = live ? a.ret[n_src] : 0.f;
+            if (!CONT) n_acti = live ? reinterpret_cast<const int32_t*>(a.actions)[n_src] : 0;
+            else {
+#pragma unroll
+                for (int j = 0; j < AMAX; ++j) n_actf[j] = (live && j < A) ? reinterpret_cast<const float*>(a.actions)[(int64_t)n_src * A + j] : 0.f;
+            }
+            if (step + 2 < a.steps) src_next2 = idx[2 * (int64_t)a.rows + tid];
         }
         float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;                      // threads with (tid & 7) == 0: sums over their rows
         __syncthreads();
+        SK_MARK(0);
 
         for (int t0 = 0; t0 < my_rows; t0 += RT) {
             // ---- gather the observations of the tile (ppo.py:261) ----
@@ -244,13 +284,17 @@ small_update_kernel(const SmallArgs a)
                 sX[k * RS + r] = src >= 0 ? a.obs[(int64_t)src * D + k] : 0.f;
             }
             __syncthreads();
+            SK_MARK(1);
             // ---- forward (ppo.py:91-96) ----
             fwd_layer<HN, RT>(sX, D, sP + L.w1, sP + L.b1, sH1);
             __syncthreads();
+            SK_MARK(2);
             fwd_layer<HN, RT>(sH1, HN, sP + L.w2, sP + L.b2, sH2);
             __syncthreads();
+            SK_MARK(3);
             fwd_layer<2 * HN, RT>(sH2, HN, sP + L.w3, sP + L.b3, sH3);
             __syncthreads();
+            SK_MARK(4);
             {   // output heads: thread = (row r, output o): o < A actor, o == A critic
                 const int r = tid % RT;
                 for (int o = tid / RT; o <= A; o += SK_THREADS / RT) {
@@ -267,6 +311,7 @@ small_update_kernel(const SmallArgs a)
                 }
             }
             __syncthreads();
+            SK_MARK(5);
             // ---- distribution, loss terms, d(loss)/d(head outputs) (ppo.py:264-280): 8 lanes per row, lane j <-> action j ----
             {
                 const int r = tid >> 3, j = tid & 7, m = t0 + r;           // (RT = 16: the upper half of the block idles here)
@@ -318,6 +363,7 @@ small_update_kernel(const SmallArgs a)
                 }
             }
             __syncthreads();
+            SK_MARK(6);
             // ---- backward into the first head layers: d3[n][r]; thread = (row r, group of 128 * RT / 256 columns) ----
             {
                 constexpr int NC3 = 2 * HN * RT / SK_THREADS;
@@ -354,15 +400,18 @@ small_update_kernel(const SmallArgs a)
                 sG[L.bc] += sumR<RT>(sDz + AMAX * RS);
             }
             __syncthreads();
+            SK_MARK(7);
             // ---- backward (ppo.py:283) ----
             if (tid < 2 * HN) sG[L.b3 + tid] += sumR<RT>(sD3 + tid * RS);
             dgrad_layer<2 * HN, RT>(sD3, sP + L.w3, sH2, sD2);
             wgrad_layer<2 * HN, RT>(sD3, sH2, sG + L.w3);
             __syncthreads();
+            SK_MARK(8);
             if (tid < HN) sG[L.b2 + tid] += sumR<RT>(sD2 + tid * RS);
             dgrad_layer<HN, RT>(sD2, sP + L.w2, sH1, sD1);
             wgrad_layer<HN, RT>(sD2, sH1, sG + L.w2);
             __syncthreads();
+            SK_MARK(9);
             if (tid < HN) sG[L.b1 + tid] += sumR<RT>(sD1 + tid * RS);
             for (int o = tid; o < HN * D; o += SK_THREADS) {
                 const int n = o / D, k = o - n * D;
@@ -371,6 +420,20 @@ small_update_kernel(const SmallArgs a)
             __syncthreads();
         }
 
+        SK_MARK(10);
+        // next step's per-row scalars -> shared memory (their loads were issued at the top of this step)
+        if (tid < my_rows && step + 1 < a.steps) {
+            s_src[tid] = n_src;
+            s_oldlp[tid] = n_oldlp;
+            s_adv[tid] = n_src >= 0 ? (n_adv - adv_mean) / adv_denom : 0.f;
+            s_ret[tid] = n_ret;
+            if (!CONT) s_acti[tid] = n_acti;
+            else {
+#pragma unroll
+                for (int j = 0; j < AMAX; ++j) if (j < A) s_actf[tid * AMAX + j] = n_actf[j];
+            }
+            src_next = src_next2;
+        }
         // ---- loss sums of this CTA ----
         {
             const float p = warp_sum(l_pol), v = warp_sum(l_val), e = warp_sum(l_ent);
@@ -384,6 +447,7 @@ small_update_kernel(const SmallArgs a)
             }
         }
         cluster.sync();                                                    // (1) all eight partial gradients are complete
+        SK_MARK(11);
 
         // ---- reduce-scatter over distributed shared memory: my slice of the summed gradient + its sum of squares ----
         double sq = 0.0;
@@ -391,15 +455,15 @@ small_update_kernel(const SmallArgs a)
             const float* rg[SK_CL];
 #pragma unroll
             for (int q = 0; q < SK_CL; ++q) rg[q] = cluster.map_shared_rank(sG, q);
-            for (int i = s0 + tid; i < s1; i += SK_THREADS) {
-                float v[SK_CL];
+            for (int i = s0 + 4 * tid; i < s1; i += 4 * SK_THREADS) {       // slices are multiples of 4 floats
+                float4 v[SK_CL];
 #pragma unroll
-                for (int q = 0; q < SK_CL; ++q) v[q] = rg[q][i];
-                float g = v[0];
+                for (int q = 0; q < SK_CL; ++q) v[q] = ld4(rg[q] + i);
+                float4 g = v[0];
 #pragma unroll
-                for (int q = 1; q < SK_CL; ++q) g += v[q];                // fixed rank order
-                sGs[i - s0] = g;
-                sq += (double)g * (double)g;
+                for (int q = 1; q < SK_CL; ++q) { g.x += v[q].x; g.y += v[q].y; g.z += v[q].z; g.w += v[q].w; }    // fixed rank order
+                *reinterpret_cast<float4*>(sGs + (i - s0)) = g;
+                sq += (double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z + (double)g.w * g.w;
             }
         }
         sq = warp_sum_d(sq);
@@ -411,8 +475,11 @@ small_update_kernel(const SmallArgs a)
             for (int w = 0; w < SK_WARPS; ++w) s += s_wsum[w];
             *reinterpret_cast<double*>(sRed + 4) = s;
         }
+        SK_MARK(12);
         cluster.sync();                                                    // (2) every slice's partial norm is published; partials consumed
-        for (int i = tid; i < total; i += SK_THREADS) sG[i] = 0.f;         // ready for the next step (peers finished reading it)
+        SK_MARK(13);
+        for (int i = 4 * tid; i < total; i += 4 * SK_THREADS)              // ready for the next step (peers finished reading it)
+            *reinterpret_cast<float4*>(sG + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid == 0) {
             double s = 0.0;
             float lp = 0.f, lv = 0.f, le = 0.f;
@@ -441,19 +508,35 @@ small_update_kernel(const SmallArgs a)
             float* rp[SK_CL];
 #pragma unroll
             for (int q = 0; q < SK_CL; ++q) rp[q] = cluster.map_shared_rank(sP, q);
-            for (int i = s0 + tid; i < s1; i += SK_THREADS) {
-                const float gi = __fmul_rn(sGs[i - s0], coef);
-                float mi = sMs[i - s0], vi = sVs[i - s0];
-                mi = fmaf(a.w1, gi - mi, mi);
-                vi = __fadd_rn(__fmul_rn(vi, a.beta2), __fmul_rn(__fmul_rn(a.w2, gi), gi));
-                const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), a.eps);
-                const float pn = __fadd_rn(sP[i], __fmul_rn(neg_step, __fdiv_rn(mi, denom)));
-                sMs[i - s0] = mi; sVs[i - s0] = vi;
+            for (int i = s0 + 4 * tid; i < s1; i += 4 * SK_THREADS) {
+                const float4 g4 = ld4(sGs + (i - s0)), m4 = ld4(sMs + (i - s0)), v4 = ld4(sVs + (i - s0)), p4 = ld4(sP + i);
+                const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w},
+                            ps[4] = {p4.x, p4.y, p4.z, p4.w};
+                float go[4], mo[4], vo[4], po[4];
 #pragma unroll
-                for (int q = 0; q < SK_CL; ++q) rp[q][i] = pn;
-                if (last) { a.P[i] = pn; a.M[i] = mi; a.V[i] = vi; a.G[i] = gi; }
+                for (int c = 0; c < 4; ++c) {
+                    const float gi = __fmul_rn(gs[c], coef);
+                    float mi = ms[c], vi = vs[c];
+                    mi = fmaf(a.w1, gi - mi, mi);
+                    vi = __fadd_rn(__fmul_rn(vi, a.beta2), __fmul_rn(__fmul_rn(a.w2, gi), gi));
+                    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), a.eps);
+                    po[c] = __fadd_rn(ps[c], __fmul_rn(neg_step, __fdiv_rn(mi, denom)));
+                    go[c] = gi; mo[c] = mi; vo[c] = vi;
+                }
+                const float4 pn = make_float4(po[0], po[1], po[2], po[3]);
+                *reinterpret_cast<float4*>(sMs + (i - s0)) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+                *reinterpret_cast<float4*>(sVs + (i - s0)) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+#pragma unroll
+                for (int q = 0; q < SK_CL; ++q) *reinterpret_cast<float4*>(rp[q] + i) = pn;
+                if (last) {
+                    *reinterpret_cast<float4*>(a.P + i) = pn;
+                    *reinterpret_cast<float4*>(a.M + i) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+                    *reinterpret_cast<float4*>(a.V + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+                    *reinterpret_cast<float4*>(a.G + i) = make_float4(go[0], go[1], go[2], go[3]);
+                }
             }
         }
+        SK_MARK(14);
         cluster.sync();                                                    // (3) all parameter copies updated
     }
 }
@@ -530,6 +613,10 @@ extern "C" int dppo_small_update(dppo_ctx* ctx, const dppo_mlp_desc* d, float* p
     a.max_norm = hy->grad_norm_clip; a.w1 = (float)(1.0 - hy->beta1); a.beta2 = (float)hy->beta2; a.w2 = (float)(1.0 - hy->beta2);
     a.eps = hy->adam_eps;
     a.losses = losses; a.grad_norm_out = grad_norm_out;
+    a.prof = nullptr;
+#ifdef DPPO_SMALL_PROFILE
+    { static long long* p = nullptr; if (!p) { cudaMallocManaged(&p, 16 * sizeof(long long)); memset(p, 0, 128); } a.prof = p; g_small_prof = p; }
+#endif
     cudaStream_t st = (cudaStream_t)stream;
 #define SMALL_GO(CONT)                                                          \
     do {                                                                        \
