@@ -555,33 +555,38 @@ class FusedMlpEngine(_EngineBase):
         return b
 
     def _stage_epoch(self, b, worker, e, T, N_, MB):
-        """Makes b["idx"][e & 1] hold the MB index lists of epoch e on the current stream: bit-exact numpy stream (host worker ->
-        pinned buffer -> async copy on a side stream) or the device generator; under DP "global" followed by the shard filter."""
+        """Fills b["idx"][e & 1] with the MB index lists of epoch e ON THE SIDE STREAM and records b["copied"][e & 1]: bit-exact numpy
+        stream (host worker -> pinned buffer -> async copy; under the DP global permutation generated by rank e mod G only and broadcast
+        over NVLink) or the device generator, then -- DP "global" -- the shard filter.  Callers stage epoch e + 1 right after they have
+        enqueued epoch e, so host shuffle, copy, broadcast and filter all run under the previous epoch's optimiser steps; the
+        consumer waits for the event with `_await_epoch`."""
         p = e & 1
         plan, ctx, dist = b["plan"], self.ctx, self.dist
         target = b["perm"][p] if plan["filter"] else b["idx"][p]
-        main = torch.cuda.current_stream()
-        if worker is not None:
-            owner = (e % dist.world) if plan["filter"] else dist.rank          # global permutation: epoch e is generated by one rank
-            if owner == dist.rank:
-                worker.wait(e)
-                cs = b["copy_stream"]
-                cs.wait_event(b["done"][p])                              # the steps that last read idx[p] / perm[p] have finished
-                with torch.cuda.stream(cs):
+        cs = b["copy_stream"]
+        owner = (e % dist.world) if plan["filter"] else dist.rank              # global permutation: epoch e is generated by one rank
+        if worker is not None and owner == dist.rank:
+            worker.wait(e)
+        cs.wait_event(b["done"][p])                                      # the steps that last read idx[p] / perm[p] have finished
+        with torch.cuda.stream(cs):
+            if worker is not None:
+                if owner == dist.rank:
                     target.copy_(b["h_idx"][e], non_blocking=True)
-                    b["copied"][p].record()
                     b["h_consumed"][b["h_set"]] = torch.cuda.Event()
                     b["h_consumed"][b["h_set"]].record()
-                main.wait_event(b["copied"][p])
+                if plan["filter"]:
+                    dist.broadcast(target, owner)                        # 4 bytes per index over NVLink instead of a shuffle per rank
+            else:
+                ctx.permutation_device(self.perm_seed, self.perm_counter, plan["B_perm"], target)
+                self.perm_counter += 1
             if plan["filter"]:
-                dist.broadcast(target, owner)                            # 4 bytes per index over NVLink instead of a shuffle per rank
-        else:
-            ctx.permutation_device(self.perm_seed, self.perm_counter, plan["B_perm"], target)
-            self.perm_counter += 1
-        if plan["filter"]:
-            ctx.perm_shard_filter(b["perm"][p], plan["B_perm"], N_ * dist.world, dist.rank * N_, N_, MB, plan["rows"], b["idx"][p],
-                                  b["counts"][p], b["overflow"])
-        return b["idx"][p]
+                ctx.perm_shard_filter(b["perm"][p], plan["B_perm"], N_ * dist.world, dist.rank * N_, N_, MB, plan["rows"], b["idx"][p],
+                                      b["counts"][p], b["overflow"])
+            b["copied"][p].record()
+
+    def _await_epoch(self, b, e):
+        torch.cuda.current_stream().wait_event(b["copied"][e & 1])
+        return b["idx"][e & 1]
 
     SMALL_ROWS = 1024      # minibatch rows up to which the one-launch cluster kernel beats the per-layer kernels
 
@@ -674,6 +679,7 @@ class FusedMlpEngine(_EngineBase):
             graphs[key] = gs
         main = torch.cuda.current_stream()
         b1, b2 = hyper.beta1, hyper.beta2
+        self._stage_epoch(b, worker, 0, T, N_, MB)
         for e in range(E):
             p = e & 1
             gs["consts_copied"][p].synchronize()                         # the previous copy out of h_consts[p] is done
@@ -684,12 +690,14 @@ class FusedMlpEngine(_EngineBase):
                 hc[k, 0] = np.float32(np.sqrt(1.0 - b2 ** step))
                 hc[k, 1] = np.float32(-(hyper.lr / (1.0 - b1 ** step)))
                 hc_seq[k, 1] = self.dp_seq + k + 1
-            self._stage_epoch(b, worker, e, T, N_, MB)
+            self._await_epoch(b, e)
             gs["consts"][p].copy_(gs["h_consts"][p], non_blocking=True)  # stream-ordered after the graph that last read consts[p]
             gs["consts_copied"][p].record()
             gs["graphs"][p].replay()
             losses[e * MB:(e + 1) * MB].copy_(gs["losses"][p])
             b["done"][p].record()
+            if e + 1 < E:
+                self._stage_epoch(b, worker, e + 1, T, N_, MB)            # under this epoch's optimiser steps
             self.adam_step += MB
             self.dp_seq += MB
             ctx.count_launches(gs["launches"])
@@ -823,14 +831,17 @@ class FusedMlpEngine(_EngineBase):
         elif use_graph:
             self._learn_epochs_graphed(b, worker, hyper, desc, tensors, losses, E, MB, T, N_, ptr_key)
         else:
+            self._stage_epoch(b, worker, 0, T, N_, MB)
             for e in range(E):
-                idx = self._stage_epoch(b, worker, e, T, N_, MB)
+                idx = self._await_epoch(b, e)
                 for k in range(MB):
                     self.adam_step += 1
                     self.dp_seq += 1
                     hyper.step = self.adam_step
                     self._step(b, hyper, desc, tensors, idx[k * rows:(k + 1) * rows], rows, losses[e * MB + k], self.dp_seq)
                 b["done"][e & 1].record()
+                if e + 1 < E:
+                    self._stage_epoch(b, worker, e + 1, T, N_, MB)        # under this epoch's optimiser steps
         mark("update_end")
         if dist.global_perm:                 # verified lazily by check_health(): no synchronisation here
             host = torch.empty(3, dtype=torch.float64).pin_memory()
