@@ -778,8 +778,8 @@ class FusedMlpEngine(_EngineBase):
             raise ValueError(f"cannot reshape array of size {E * plan['B_perm']} into shape ({E},{MB},{plan['B_perm'] // MB})")
         worker = None
         lock_hash = 0.0
+        b["h_set"] ^= 1                      # host-side staging buffers alternate between consecutive learn() calls
         if self.perm_mode == "numpy":
-            b["h_set"] ^= 1
             b["h_idx"] = b["h_sets"][b["h_set"]]
             if b["h_consumed"][b["h_set"]] is not None:
                 b["h_consumed"][b["h_set"]].synchronize()   # the async copies out of this pinned set (two learn() calls ago) are done
@@ -801,7 +801,9 @@ class FusedMlpEngine(_EngineBase):
         mark("prepass_end")
         b["stats"].zero_()
         if dist.global_perm:                # ranks must hold the same numpy stream: 24-bit state hash h and h^2 ride in the all-reduce
-            b["stats"][2:4].copy_(torch.tensor([lock_hash, lock_hash * lock_hash], dtype=torch.float64), non_blocking=True)
+            lk = b.setdefault("lock_host", [torch.zeros(2, dtype=torch.float64).pin_memory() for _ in range(2)])[b["h_set"]]
+            lk[0], lk[1] = lock_hash, lock_hash * lock_hash            # pinned: the copy below must not block the host on the stream
+            b["stats"][2:4].copy_(lk, non_blocking=True)
         # the kernel right before the GAE launch is a 32-byte fill, not the pre-update pass: inputs are settled
         ctx.gae(buf.rewards, buf.terminations, buf.truncations, b["values"], b["next_values"], cfg.gamma, cfg.gae_lambda,
                 advantages=b["adv"], returns=b["ret"], stats=b["stats"], inputs_settled=True)
@@ -844,7 +846,7 @@ class FusedMlpEngine(_EngineBase):
                     self._stage_epoch(b, worker, e + 1, T, N_, MB)        # under this epoch's optimiser steps
         mark("update_end")
         if dist.global_perm:                 # verified lazily by check_health(): no synchronisation here
-            host = torch.empty(3, dtype=torch.float64).pin_memory()
+            host = b.setdefault("check_host", [torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(2)])[b["h_set"]]
             host.copy_(torch.cat([b["stats"][2:4], b["overflow"].double()]), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
