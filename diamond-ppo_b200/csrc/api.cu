@@ -181,7 +181,7 @@ TrainWs carve_train(const dppo_mlp_desc* d, int64_t M, int sm_count, char* base)
     const int cparts = mx(dppo_tc3_colsum_rows(&fake, M, (int)H), w.tiles2);
     w.c2 = take((int64_t)cparts * H);
     w.c1 = take((int64_t)cparts * H);
-    w.head_blocks = head_train_blocks(&fake, M);
+    w.head_blocks = head_train_blocks(&fake, M, (int)H, (int)A);
     w.head_stride = (int)align_up(head_partial_floats((int)H, (int)A), 4);
     w.hp = take((int64_t)w.head_blocks * w.head_stride);
     o = align_up(o, 1024);

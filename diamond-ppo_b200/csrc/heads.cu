@@ -368,188 +368,307 @@ __device__ __forceinline__ float4 one_minus_sq4(const float4& h)                
 }
 
 // ---------------------------------------------------------------------------------------------
-// Register-accumulator variant of the training kernel (H a multiple of 128, A <= AMAX, float4 columns).
-// The per-warp head weight gradients live in registers (the shared-memory read-modify-write of the generic kernel moved
-// 20 KB through shared memory per row — the kernel ran at half of HBM speed), and the R rows of an iteration share
-// every weight load.  Same per-element arithmetic and the same partial layout as head_train_kernel.
+// Role-split variant (H a multiple of 128, H <= 256, A <= 4).  The actor half of a row (policy loss, entropy, d3[:, :H], dWa)
+// and the critic half (value loss, d3[:, H:], dWc) share nothing but the row index, so they are given to DIFFERENT warps:
+// NA actor warps and HEAD_WARPS - NA critic warps per CTA walk the rows independently.  Neither role carries the other's
+// accumulators (<= 96 registers, three CTAs per SM, nothing spilled), and the warp-wide reductions become multi-value
+// butterflies: the 2 x 4 head products of an actor iteration are reduced with 9 shuffles into the lane layout
+// (row = lane bit 4, action = lane bits 3:2) on which the distribution of BOTH rows is evaluated at once (softmax sums are two
+// xor steps); a critic iteration reduces the values of 4 rows with 6 shuffles (row = lane bits 4:3).  Per-row scalars are
+// loaded by the lanes that use them.  ~300 instructions per row against ~530 for the round-1 kernel that kept both halves of a row in one warp (ncu, config S:
+// 76.6 -> 54.1 us per launch, 268 MB = 76 % of the HBM peak).
+// Same per-element arithmetic; only the order of the reductions differs.
 // ---------------------------------------------------------------------------------------------
-template <bool CONT, int KPL, int R, int AMAX>
-__global__ void __launch_bounds__(HEAD_WARPS * 32, 2)
-head_train_reg_kernel(HeadTrainArgs a)
+constexpr int SPLIT_WARPS = 10;              // warps per CTA (two CTAs per SM at <= 96 registers)
+constexpr int SPLIT_NA = 8;                  // actor warps (an actor row costs ~4x a critic row); the other warps take the critic role
+template <bool CONT, int G>
+__global__ void __launch_bounds__(SPLIT_WARPS * 32, 2)
+head_train_split_kernel(HeadTrainArgs a)
 {
+    constexpr int NA = SPLIT_NA;
     extern __shared__ float smem[];
-    const int H = a.H, A = a.A;
-    constexpr int G = KPL / 4;                  // float4 groups per half row
-    float* s_wa = smem;                         // [A][H]
-    float* s_wc = s_wa + A * H;                 // [H]
-    float* s_acc = s_wc + H;                    // [HEAD_WARPS][(A+1)][H]  flushed once at the end
+    constexpr int AM = 4;                       // action slots (rows of s_wa beyond A are zero)
+    constexpr int H = 128 * G;
+    const int A = a.A;
+    constexpr int NC = SPLIT_WARPS - NA;
+    float* s_wa = smem;                         // [AM][H]
+    float* s_acc = s_wa + AM * H;               // actor warps: [NA][AM][H]; critic warps: [NC][H]; then per-warp tails [SPLIT_WARPS][H + 16]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DPPO_PDL_ENTER();
-    for (int i = threadIdx.x; i < A * H; i += blockDim.x) s_wa[i] = a.wa[i];
-    for (int i = threadIdx.x; i < H; i += blockDim.x) s_wc[i] = a.wc[i];
+    for (int i = threadIdx.x; i < AM * H; i += blockDim.x) s_wa[i] = i < A * H ? a.wa[i] : 0.f;
     __syncthreads();
+    float* tails = s_acc + (NA * AM + NC) * H;
+    float* tail = tails + warp * (H + 16);
 
-    float mean, denom;
-    adv_norm_consts(a.adv_stats, a.adv_count, a.advantage_norm, mean, denom);
-    const float bias_a = lane < A ? a.ba[lane] : 0.f;
-    const float bias_c = a.bc[0];
-    const float log_std = (CONT && lane < A) ? a.log_std[lane] : 0.f;
+    if (warp < NA) {
+        // ------------------------------------------------ actor role: 2 rows per iteration
+        const int rl = lane >> 4, jl = (lane >> 2) & 3;          // this lane's (row, action) in the reduced layout
+        const bool on = jl < A;
+        float mean, denom;
+        adv_norm_consts(a.adv_stats, a.adv_count, a.advantage_norm, mean, denom);
+        const float bias = on ? a.ba[jl] : 0.f;
+        const float log_std = (CONT && on) ? a.log_std[jl] : 0.f;
+        float4 gwa[AM][G];
+#pragma unroll
+        for (int j = 0; j < AM; ++j)
+#pragma unroll
+            for (int g = 0; g < G; ++g) gwa[j][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* accb = reinterpret_cast<float4*>(tail);         // column sums of d3[:, :H] (db3): this lane's columns, in shared memory
+#pragma unroll
+        for (int g = 0; g < G; ++g) accb[g * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float acc_dba = 0.f, acc_dls = 0.f, l_pol = 0.f, l_ent = 0.f;
 
-    float4 gwa[AMAX][G], gwc[G];                // this lane's columns of dWa / dWc
+        const int Mi = (int)a.M;
+        for (int mb = (blockIdx.x * NA + warp) * 2; mb < Mi; mb += gridDim.x * NA * 2) {
+            const bool ok1 = mb + 1 < Mi;
+            float4 ha[2][G];
+            {
+                const float4* h0 = reinterpret_cast<const float4*>(a.h3 + (int64_t)mb * (2 * H));
+                const float4* h1 = reinterpret_cast<const float4*>(a.h3 + (int64_t)(ok1 ? mb + 1 : mb) * (2 * H));
 #pragma unroll
-    for (int j = 0; j < AMAX; ++j)
-#pragma unroll
-        for (int g = 0; g < G; ++g) gwa[j][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int g = 0; g < G; ++g) gwc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float acc_b3[2 * KPL];
-#pragma unroll
-    for (int i = 0; i < 2 * KPL; ++i) acc_b3[i] = 0.f;
-    float acc_dba = 0.f, acc_dbc = 0.f, acc_dls = 0.f;
-    float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
-
-    const int64_t warp_global = (int64_t)blockIdx.x * HEAD_WARPS + warp;
-    const int64_t warp_stride = (int64_t)gridDim.x * HEAD_WARPS;
-    for (int64_t mb = warp_global * R; mb < a.M; mb += warp_stride * R) {
-        float4 ha[R][G], hc[R][G];
-        float old_lp[R], advv[R], ret[R], act_f[R];
-        int act_i[R];
-        bool ok[R], live[R];                        // ok: row exists; live: and is not a padding row (idx < 0 contributes nothing)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int64_t m = mb + r;
-            ok[r] = m < a.M;
-            const int64_t sidx = ok[r] ? (a.idx ? (int64_t)a.idx[m] : m) : 0;
-            live[r] = ok[r] && sidx >= 0;
-            const int64_t src = live[r] ? sidx : 0;
-            const float4* h3 = reinterpret_cast<const float4*>(a.h3 + (ok[r] ? m : 0) * (int64_t)(2 * H));
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                ha[r][g] = __ldg(h3 + g * 32 + lane);
-                hc[r][g] = __ldg(h3 + (H / 4) + g * 32 + lane);
+                for (int g = 0; g < G; ++g) { ha[0][g] = __ldg(h0 + g * 32 + lane); ha[1][g] = __ldg(h1 + g * 32 + lane); }
             }
-            old_lp[r] = __ldg(a.old_logp + src);
-            advv[r] = (__ldg(a.adv + src) - mean) / denom;
-            ret[r] = __ldg(a.ret + src);
-            act_i[r] = 0; act_f[r] = 0.f;
-            if (CONT) act_f[r] = lane < A ? __ldg(a.actions_f + src * A + lane) : 0.f;
-            else act_i[r] = __ldg(a.actions_i + src);
-        }
+            // this lane's row scalars
+            const int m = mb + rl;
+            const bool okl = m < Mi;
+            const int sidx = okl ? (a.idx ? __ldg(a.idx + m) : m) : 0;
+            const bool live = okl && sidx >= 0;
+            const int src = live ? sidx : 0;
+            const float old_lp = __ldg(a.old_logp + src);
+            const float advv = (__ldg(a.adv + src) - mean) / denom;
+            int act_i = 0; float act_f = 0.f;
+            if (CONT) act_f = on ? __ldg(a.actions_f + (int64_t)src * A + jl) : 0.f;
+            else act_i = __ldg(a.actions_i + src);
 
-        // head products: each weight vector is read once for the R rows
-        float z[R], v[R];
+            // head products: even / odd column partial sums (packed FFMA2), every weight vector read once for both rows
+            float p[2][AM];
 #pragma unroll
-        for (int r = 0; r < R; ++r) z[r] = 0.f;
-#pragma unroll
-        for (int j = 0; j < AMAX; ++j) {
-            if (j < A) {
-                float2 part2[R];                                 // even / odd column partial sums (packed FFMA2)
-#pragma unroll
-                for (int r = 0; r < R; ++r) part2[r] = make_float2(0.f, 0.f);
+            for (int j = 0; j < AM; ++j) {
+                float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) dot4(part2[r], ha[r][g], w);
+                    dot4(q0, ha[0][g], w); dot4(q1, ha[1][g], w);
                 }
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float part = warp_sum(part2[r].x + part2[r].y);
-                    if (lane == j) z[r] = part;
-                }
+                p[0][j] = q0.x + q0.y; p[1][j] = q1.x + q1.y;
             }
-        }
-        float4 wcv[G];
+            // butterfly: 8 values -> lane (row = bit 4, action = bits 3:2)
+            float s1[AM];
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
 #pragma unroll
-        for (int g = 0; g < G; ++g) wcv[g] = reinterpret_cast<const float4*>(s_wc + g * 128)[lane];
+            for (int j = 0; j < AM; ++j) {
+                const float keep = b4 ? p[1][j] : p[0][j], send = b4 ? p[0][j] : p[1][j];
+                s1[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            float s2[2];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float2 vp = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int g = 0; g < G; ++g) dot4(vp, hc[r][g], wcv[g]);
-            v[r] = warp_sum(vp.x + vp.y) + bias_c;
-            z[r] += bias_a;
-        }
+            for (int j = 0; j < 2; ++j) {
+                const float keep = b3 ? s1[2 + j] : s1[j], send = b3 ? s1[j] : s1[2 + j];
+                s2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float z;
+            {
+                const float keep = b2 ? s2[1] : s2[0], send = b2 ? s2[0] : s2[1];
+                z = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            z += bias;
 
-        // distribution, loss terms, d(loss)/d(head outputs); rows past the end contribute exact zeros
-        float dz[R], dv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const Dist<CONT> d = eval_dist<CONT>(z[r], lane, A, act_i[r], act_f[r], log_std);
-            const RowTerms t = policy_terms(d.new_lp, old_lp[r], advv[r], a.clip, a.inv_m);
-            dz[r] = 0.f;
-            float dls = 0.f;
-            if (lane < A) {
-                if (!CONT) {
-                    dz[r] = t.dlogp * ((lane == act_i[r] ? 1.0f : 0.0f) - d.p) + (a.beta * a.inv_m) * d.p * (d.lsm + d.entropy);
-                } else {
-                    dz[r] = t.dlogp * d.diff / d.var;
-                    dls = t.dlogp * (d.diff * d.diff / d.var - 1.0f) - a.beta * a.inv_m;
-                }
-            }
-            const float verr = v[r] - ret[r];
-            dv[r] = a.vw * verr * a.inv_m;
-            if (live[r]) {
-                l_pol += t.policy; l_val += verr * verr; l_ent += d.entropy;
-                acc_dba += dz[r]; acc_dbc += dv[r]; acc_dls += dls;
+            // distribution of both rows at once (reductions over the action bits: xor 4, xor 8)
+            float new_lp, entropy, dz = 0.f, dls = 0.f, pj = 0.f, lsm = 0.f, diff = 0.f, var = 1.f;
+            if (!CONT) {
+                // torch/distributions/categorical.py:78 (logits - logsumexp), :151-163 (log_prob, entropy)
+                const float zz = on ? z : -CUDART_INF_F;
+                float mx = fmaxf(zz, __shfl_xor_sync(0xffffffffu, zz, 4));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+                const float e = on ? expf(zz - mx) : 0.f;
+                float s = e + __shfl_xor_sync(0xffffffffu, e, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                const float lse = mx + logf(s);
+                lsm = on ? z - lse : 0.f;
+                pj = on ? expf(lsm) : 0.f;
+                float en = on ? pj * lsm : 0.f;
+                en += __shfl_xor_sync(0xffffffffu, en, 4);
+                en += __shfl_xor_sync(0xffffffffu, en, 8);
+                entropy = -en;
+                new_lp = __shfl_sync(0xffffffffu, lsm, (lane & 16) | ((act_i & 3) << 2));
             } else {
-                dz[r] = 0.f; dv[r] = 0.f;
+                // torch/distributions/normal.py:87-102, :114-115, summed over dims (continuous_ppo.py:40-47)
+                const float sigma = expf(log_std);
+                const float log_scale = logf(sigma);
+                var = sigma * sigma;
+                diff = act_f - z;
+                float lp = on ? (-(diff * diff) / (2.0f * var) - log_scale - 0.91893853320467274178f) : 0.f;
+                lp += __shfl_xor_sync(0xffffffffu, lp, 4);
+                lp += __shfl_xor_sync(0xffffffffu, lp, 8);
+                new_lp = lp;
+                float en = on ? (0.5f + 0.91893853320467274178f + log_scale) : 0.f;
+                en += __shfl_xor_sync(0xffffffffu, en, 4);
+                en += __shfl_xor_sync(0xffffffffu, en, 8);
+                entropy = en;
             }
-        }
+            const RowTerms t = policy_terms(new_lp, old_lp, advv, a.clip, a.inv_m);
+            if (on && live) {
+                if (!CONT) {
+                    dz = t.dlogp * ((jl == act_i ? 1.0f : 0.0f) - pj) + (a.beta * a.inv_m) * pj * (lsm + entropy);
+                } else {
+                    dz = t.dlogp * diff / var;
+                    dls = t.dlogp * (diff * diff / var - 1.0f) - a.beta * a.inv_m;
+                }
+            }
+            if (live) { l_pol += t.policy; l_ent += entropy; }
+            acc_dba += dz; acc_dls += dls;
 
-        // backward into the first head layers + head weight gradients
-        float4 ga[R][G];
+            // backward into actor_head.0 + dWa
+            float4 ga[2][G];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+            for (int g = 0; g < G; ++g) { ga[0][g] = make_float4(0.f, 0.f, 0.f, 0.f); ga[1][g] = make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-            for (int g = 0; g < G; ++g) ga[r][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < AMAX; ++j) {
-            if (j < A) {
-                float dzj[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) dzj[r] = __shfl_sync(0xffffffffu, dz[r], j);
+            for (int j = 0; j < AM; ++j) {
+                const float d0 = __shfl_sync(0xffffffffu, dz, j << 2), d1 = __shfl_sync(0xffffffffu, dz, 16 | (j << 2));
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const float4 w = reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        axpy4(ga[r][g], dzj[r], w);
-                        axpy4(gwa[j][g], dzj[r], ha[r][g]);
-                    }
+                    axpy4(ga[0][g], d0, w); axpy4(ga[1][g], d1, w);
+                    axpy4(gwa[j][g], d0, ha[0][g]); axpy4(gwa[j][g], d1, ha[1][g]);
                 }
             }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float* d3 = a.d3 + (mb + r) * (int64_t)(2 * H);
+            float* d3 = a.d3 + (int64_t)mb * (2 * H);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                // same per-element operations as the scalar form, two columns per instruction
-                const float4 da = mul4(ga[r][g], one_minus_sq4(ha[r][g]));
-                const float4 dc = mul4(scale4(dv[r], wcv[g]), one_minus_sq4(hc[r][g]));
-                acc_b3[4 * g] += da.x; acc_b3[4 * g + 1] += da.y; acc_b3[4 * g + 2] += da.z; acc_b3[4 * g + 3] += da.w;
-                acc_b3[KPL + 4 * g] += dc.x; acc_b3[KPL + 4 * g + 1] += dc.y; acc_b3[KPL + 4 * g + 2] += dc.z; acc_b3[KPL + 4 * g + 3] += dc.w;
-                axpy4(gwc[g], dv[r], hc[r][g]);
-                if (ok[r]) {
-                    __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, da);
-                    __stcs(reinterpret_cast<float4*>(d3 + H + g * 128) + lane, dc);
-                }
+                const float4 da0 = mul4(ga[0][g], one_minus_sq4(ha[0][g]));
+                const float4 da1 = mul4(ga[1][g], one_minus_sq4(ha[1][g]));
+                __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, da0);
+                if (ok1) __stcs(reinterpret_cast<float4*>(d3 + 2 * H + g * 128) + lane, da1);
+                float4 t = accb[g * 32 + lane];
+                const float2 lo = __fadd2_rn(make_float2(t.x, t.y), __fadd2_rn(make_float2(da0.x, da0.y), make_float2(da1.x, da1.y)));
+                const float2 hi = __fadd2_rn(make_float2(t.z, t.w), __fadd2_rn(make_float2(da0.z, da0.w), make_float2(da1.z, da1.w)));
+                accb[g * 32 + lane] = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
         }
-    }
-
-    // hand the register accumulators to the common flush
-    float* acc = s_acc + (size_t)warp * (A + 1) * H;
+        // per-warp accumulators -> shared memory
+        float* acc = s_acc + (size_t)warp * AM * H;
 #pragma unroll
-    for (int j = 0; j < AMAX; ++j)
-        if (j < A) {
+        for (int j = 0; j < AM; ++j)
 #pragma unroll
             for (int g = 0; g < G; ++g) reinterpret_cast<float4*>(acc + j * H + g * 128)[lane] = gwa[j][g];
-        }
+        acc_dba += __shfl_xor_sync(0xffffffffu, acc_dba, 16);
+        acc_dls += __shfl_xor_sync(0xffffffffu, acc_dls, 16);
+        l_pol += __shfl_xor_sync(0xffffffffu, l_pol, 16);
+        l_ent += __shfl_xor_sync(0xffffffffu, l_ent, 16);
+        if (lane < 16 && (lane & 3) == 0) { tail[H + jl] = acc_dba; tail[H + 4 + jl] = acc_dls; }
+        if (lane == 0) { tail[H + 8] = l_pol; tail[H + 9] = l_ent; }
+    } else {
+        // ------------------------------------------------ critic role: 4 rows per iteration
+        const int cw = warp - NA;
+        const int rl = lane >> 3;
+        const float bias_c = a.bc[0];
+        float4 wcv[G], gwc[G];
+        float2 accb[2 * G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) reinterpret_cast<float4*>(acc + A * H + g * 128)[lane] = gwc[g];
-    head_train_flush<KPL, 4>(a, s_acc, acc_b3, acc_dba, acc_dbc, acc_dls, l_pol, l_val, l_ent);
+        for (int g = 0; g < G; ++g) {
+            wcv[g] = __ldg(reinterpret_cast<const float4*>(a.wc + g * 128) + lane);
+            gwc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            accb[2 * g] = make_float2(0.f, 0.f); accb[2 * g + 1] = make_float2(0.f, 0.f);
+        }
+        float acc_dbc = 0.f, l_val = 0.f;
+        const int Mi = (int)a.M;
+        for (int mb = (blockIdx.x * NC + cw) * 4; mb < Mi; mb += gridDim.x * NC * 4) {
+            float4 hc[4][G];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int mr = mb + r < Mi ? mb + r : mb;
+                const float4* h = reinterpret_cast<const float4*>(a.h3 + (int64_t)mr * (2 * H) + H);
+#pragma unroll
+                for (int g = 0; g < G; ++g) hc[r][g] = __ldg(h + g * 32 + lane);
+            }
+            const int m = mb + rl;
+            const bool okl = m < Mi;
+            const int sidx = okl ? (a.idx ? __ldg(a.idx + m) : m) : 0;
+            const bool live = okl && sidx >= 0;
+            const float ret = __ldg(a.ret + (live ? sidx : 0));
+            float p[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float2 q = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < G; ++g) dot4(q, hc[r][g], wcv[g]);
+                p[r] = q.x + q.y;
+            }
+            const bool b4 = lane & 16, b3 = lane & 8;
+            float s1[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float keep = b4 ? p[2 + r] : p[r], send = b4 ? p[r] : p[2 + r];
+                s1[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            float v;
+            {
+                const float keep = b3 ? s1[1] : s1[0], send = b3 ? s1[0] : s1[1];
+                v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += bias_c;
+            const float verr = v - ret;
+            float dv = 0.f;
+            if (live) { dv = a.vw * verr * a.inv_m; l_val += verr * verr; }
+            acc_dbc += dv;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float dvr = __shfl_sync(0xffffffffu, dv, r << 3);
+                float* d3 = a.d3 + (int64_t)(mb + r) * (2 * H) + H;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float4 dc = mul4(scale4(dvr, wcv[g]), one_minus_sq4(hc[r][g]));
+                    accb[2 * g] = __fadd2_rn(accb[2 * g], make_float2(dc.x, dc.y));
+                    accb[2 * g + 1] = __fadd2_rn(accb[2 * g + 1], make_float2(dc.z, dc.w));
+                    axpy4(gwc[g], dvr, hc[r][g]);
+                    if (mb + r < Mi) __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, dc);
+                }
+            }
+        }
+        float* acc = s_acc + (size_t)NA * AM * H + (size_t)cw * H;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            reinterpret_cast<float4*>(acc + g * 128)[lane] = gwc[g];
+            reinterpret_cast<float4*>(tail + g * 128)[lane] = make_float4(accb[2 * g].x, accb[2 * g].y, accb[2 * g + 1].x, accb[2 * g + 1].y);
+        }
+        // one lane per row slot holds that slot's sums (lanes 0, 8, 16, 24)
+        acc_dbc += __shfl_xor_sync(0xffffffffu, acc_dbc, 16); acc_dbc += __shfl_xor_sync(0xffffffffu, acc_dbc, 8);
+        l_val += __shfl_xor_sync(0xffffffffu, l_val, 16); l_val += __shfl_xor_sync(0xffffffffu, l_val, 8);
+        if (lane == 0) { tail[H + 10] = acc_dbc; tail[H + 11] = l_val; }
+    }
+    __syncthreads();
+
+    // one partial per CTA, summed over the warps of a role in fixed order
+    const HeadOffsets ho = head_offsets(H, A);
+    float* out = a.partials + (int64_t)blockIdx.x * a.partial_stride;
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < NA; ++w) s += s_acc[(size_t)w * AM * H + i];
+        out[i] = s;
+    }
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        float s = 0.f, ba = 0.f, bc = 0.f;
+        for (int w = 0; w < NC; ++w) { s += s_acc[(size_t)NA * AM * H + (size_t)w * H + i]; bc += tails[(NA + w) * (H + 16) + i]; }
+        for (int w = 0; w < NA; ++w) ba += tails[w * (H + 16) + i];
+        out[ho.dwc + i] = s; out[ho.b3 + i] = ba; out[ho.b3 + H + i] = bc;
+    }
+    if (threadIdx.x < 12) {
+        const int i = threadIdx.x;                // 0..3 dba, 4..7 dls, 8 pol, 9 ent (actor warps); 10 dbc, 11 val (critic warps)
+        float s = 0.f;
+        if (i < 10) for (int w = 0; w < NA; ++w) s += tails[w * (H + 16) + H + i];
+        else for (int w = 0; w < NC; ++w) s += tails[(NA + w) * (H + 16) + H + i];
+        if (i < 4) { if (i < A) out[ho.dba + i] = s; }
+        else if (i < 8) { if (i - 4 < A) out[ho.dls + (i - 4)] = s; }
+        else if (i == 8) out[ho.loss] = s;
+        else if (i == 9) out[ho.loss + 2] = s;
+        else if (i == 10) out[ho.dbc] = s;
+        else out[ho.loss + 1] = s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -710,8 +829,11 @@ int launch_head_train(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int
 
 int head_partial_floats(int H, int A) { return head_offsets(H, A).total; }
 
-int head_train_blocks(dppo_ctx* ctx, int64_t M)
+static bool head_split_shape(int H, int A) { return (H == 128 || H == 256) && A <= 4; }
+
+int head_train_blocks(dppo_ctx* ctx, int64_t M, int H, int A)
 {
+    (void)H; (void)A;
     int64_t want = (M + HEAD_WARPS - 1) / HEAD_WARPS;
     int64_t cap = 2 * (int64_t)ctx->sm_count;
     return (int)(want < cap ? want : cap);
@@ -728,20 +850,22 @@ int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuo
     const size_t smem = ((size_t)(A + 1) * H + accf) * sizeof(float);
     if (smem > 200 * 1024) DPPO_FAIL(ctx, "head kernel: (A+1)*H = %d too large for shared memory", (A + 1) * H);
     const bool vec = (H % 128 == 0) && ((reinterpret_cast<uintptr_t>(a.h3) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.d3) & 15u) == 0);
-    if (vec && A <= 4 && H <= 256 && !DPPO_DBG(ctx->tc_debug, 256)) {        // register-accumulator kernel (wider rows spill)
-#define HTR(KPL, R)                                                                                                              \
+    if (vec && head_split_shape(H, A)) {
+        if (a.M >= (int64_t)1 << 30) DPPO_FAIL(ctx, "head kernel: %lld rows exceed the 32-bit row counter", (long long)a.M);
+        const size_t sm = ((size_t)4 * H + (size_t)(SPLIT_NA * 4 + SPLIT_WARPS - SPLIT_NA) * H + (size_t)SPLIT_WARPS * (H + 16)) * sizeof(float);
+#define HTS(G)                                                                                                                   \
     do {                                                                                                                         \
         if (continuous) {                                                                                                        \
-            cudaFuncSetAttribute(head_train_reg_kernel<true, KPL, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            dppo_launch_pdl(ctx, head_train_reg_kernel<true, KPL, R, 4>, dim3(blocks), dim3(HEAD_WARPS * 32), smem, st, a);     \
+            cudaFuncSetAttribute(head_train_split_kernel<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);         \
+            dppo_launch_pdl(ctx, head_train_split_kernel<true, G>, dim3(blocks), dim3(SPLIT_WARPS * 32), sm, st, a);             \
         } else {                                                                                                                 \
-            cudaFuncSetAttribute(head_train_reg_kernel<false, KPL, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            dppo_launch_pdl(ctx, head_train_reg_kernel<false, KPL, R, 4>, dim3(blocks), dim3(HEAD_WARPS * 32), smem, st, a);    \
+            cudaFuncSetAttribute(head_train_split_kernel<false, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
+            dppo_launch_pdl(ctx, head_train_split_kernel<false, G>, dim3(blocks), dim3(SPLIT_WARPS * 32), sm, st, a);            \
         }                                                                                                                        \
     } while (0)
-        if (H == 128) HTR(4, 2); else HTR(8, 2);
-#undef HTR
-        DPPO_CHECK_LAUNCH(ctx, "head_train_reg_kernel");
+        if (H == 128) HTS(1); else HTS(2);
+#undef HTS
+        DPPO_CHECK_LAUNCH(ctx, "head_train_split_kernel");
         return 0;
     }
     if (H <= 64) return launch_head_train<2, 1, 2>(ctx, a, continuous, blocks, smem, st);

@@ -39,7 +39,7 @@ __host__ __device__ inline HeadOffsets head_offsets(int H, int A)
     return o;
 }
 int head_partial_floats(int H, int A);
-int head_train_blocks(dppo_ctx* ctx, int64_t M);
+int head_train_blocks(dppo_ctx* ctx, int64_t M, int H, int A);
 int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int blocks, cudaStream_t st);
 int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, const float* wa, const float* ba, const float* wc,
                      const float* bc, float* head_out, float* values, int64_t rows, int H, int A, cudaStream_t st);

@@ -381,7 +381,7 @@ RnnWs carve_rnn(const dppo_rnn_desc* d, int64_t B, int64_t N, int64_t M, int tra
         w.c1 = take((int64_t)w.tiles1 * H);
         w.scan_parts = scan_blocks((int)N, (int)Hg);
         w.bp = take((int64_t)w.scan_parts * 6 * Hg);
-        w.head_blocks = head_train_blocks(&fake, M);
+        w.head_blocks = head_train_blocks(&fake, M, (int)H, (int)A);
         w.head_stride = (int)align_up(head_partial_floats((int)H, (int)A), 4);
         w.hp = take((int64_t)w.head_blocks * w.head_stride);
     }

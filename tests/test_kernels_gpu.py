@@ -149,6 +149,11 @@ CONFIGS = [
     (64, 256, 4, False, 8192, 2048),
     (17, 96, 7, False, 700, 333),
     (64, 256, 6, True, 4096, 1500),
+    # role-split head kernel (H in {128, 256}, A <= 4): ragged row counts (actor warps take 2 rows, critic warps 4), A < 4, Gaussian
+    (64, 256, 3, False, 4096, 1023),
+    (64, 256, 3, True, 4096, 1501),
+    (16, 128, 2, True, 2048, 1023),
+    (16, 128, 1, False, 2048, 7),
 ]
 
 
@@ -622,7 +627,8 @@ def test_perm_shard_filter_matches_oracle(ctx, T, NL, world, MB):
 
 
 @pytest.mark.parametrize("D,H,A,cont,B,M,pad", [(8, 64, 4, False, 600, 200, 56), (64, 256, 4, False, 8192, 3000, 1096),
-                                                (5, 64, 3, True, 512, 100, 28), (32, 128, 3, False, 4096, 2000, 48)])
+                                                (5, 64, 3, True, 512, 100, 28), (32, 128, 3, False, 4096, 2000, 48),
+                                                (64, 256, 2, True, 4096, 1501, 35)])
 def test_padding_rows_contribute_nothing(ctx, D, H, A, cont, B, M, pad):
     """idx < 0 marks a padding row (fixed-shape steps under data parallelism): losses and the flat gradient of M real rows
     followed by `pad` padding rows equal those of the M rows alone (same loss denominator)."""
