@@ -257,8 +257,8 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if (DPPO_DBG(dbg, 32)) {
                             v[4 * j] += aux[j].x; v[4 * j + 1] += aux[j].y; v[4 * j + 2] += aux[j].z; v[4 * j + 3] += aux[j].w;
                         } else {
-                            v[4 * j] = tanhf(v[4 * j] + aux[j].x); v[4 * j + 1] = tanhf(v[4 * j + 1] + aux[j].y);
-                            v[4 * j + 2] = tanhf(v[4 * j + 2] + aux[j].z); v[4 * j + 3] = tanhf(v[4 * j + 3] + aux[j].w);
+                            v[4 * j] = tanh_rational(v[4 * j] + aux[j].x); v[4 * j + 1] = tanh_rational(v[4 * j + 1] + aux[j].y);
+                            v[4 * j + 2] = tanh_rational(v[4 * j + 2] + aux[j].z); v[4 * j + 3] = tanh_rational(v[4 * j + 3] + aux[j].w);
                         }
                     }
                 } else {

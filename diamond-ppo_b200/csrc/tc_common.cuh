@@ -275,3 +275,23 @@ __device__ __forceinline__ float4 lo_of_trunc_x4(const float4& x)
 // encode fails (unaligned base / pitch).
 bool dppo_make_tensor_map_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
                              int swizzle);
+
+// tanh for the GEMM epilogues: odd 13th-degree over even 6th-degree rational minimax (the coefficients Eigen publishes for its float
+// tanh), evaluated as plain FFMA chains with immediate operands + one MUFU.RCP.  |error| <= 2.9e-7 absolute (< 5 ulp, checked over
+// [-10, 10] and around 0 in tests/test_tanh_approx.py); libm's tanhf costs two MUFU operations and two divergent code paths
+// per element, which made the forward epilogues as expensive as their MMAs.
+__device__ __forceinline__ float tanh_rational(float x)
+{
+    x = fminf(fmaxf(x, -7.90531110763549805f), 7.90531110763549805f);
+    const float x2 = x * x;
+    float p = fmaf(x2, -2.76076847742355e-16f, 2.00018790482477e-13f);
+    p = fmaf(x2, p, -8.60467152213735e-11f);
+    p = fmaf(x2, p, 5.12229709037114e-08f);
+    p = fmaf(x2, p, 1.48572235717979e-05f);
+    p = fmaf(x2, p, 6.37261928875436e-04f);
+    p = fmaf(x2, p, 4.89352455891786e-03f);
+    float q = fmaf(x2, 1.19825839466702e-06f, 1.18534705686654e-04f);
+    q = fmaf(x2, q, 2.26843463243900e-03f);
+    q = fmaf(x2, q, 4.89352518554385e-03f);
+    return __fdividef(x * p, q);
+}
