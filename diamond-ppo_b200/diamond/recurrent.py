@@ -137,9 +137,9 @@ class RecurrentRollout:
 class RecurrentEngine(_EngineBase):
     """learn() of the recurrent agent: sequence forward/backward under autograd, everything else on libdppo kernels."""
 
-    def __init__(self, ctx, network, cfg, device):
+    def __init__(self, ctx, network, cfg, device, dist: _Dist | None = None):
         self.ctx, self.cfg, self.device = ctx, cfg, device
-        self.dist = _Dist(None, False)
+        self.dist = dist if dist is not None else _Dist(None, False)
         self.network = network
         offsets, o = {}, 0
         for name, p in network.named_parameters():
@@ -148,10 +148,11 @@ class RecurrentEngine(_EngineBase):
         self._adopt(network, offsets, max(o, 4))
         self.last_losses = None
         self.draws = 0
-        self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        self.seed = self.dist.shared_seed(cfg.seed if cfg.seed is not None else (None if self.dist.enabled else int(np.random.randint(0, 2 ** 31 - 1))), device)
+        self.env_offset = self.dist.rank * cfg.num_envs              # global id of this shard's first environment (sampling keys)
 
     def learn(self, ro: RecurrentRollout):
-        cfg, ctx, net, dev = self.cfg, self.ctx, self.network, self.device
+        cfg, ctx, net, dev, dist = self.cfg, self.ctx, self.network, self.device, self.dist
         T, N_ = ro.T, ro.N
         E, MB = cfg.num_epochs, cfg.num_minibatches
         B = T * N_
@@ -168,9 +169,12 @@ class RecurrentEngine(_EngineBase):
         ret = torch.empty(T, N_, device=dev)
         ctx.gae(ro.rewards, ro.terminations, ro.truncations, ro.values.contiguous(), ro.next_values.contiguous(), cfg.gamma,
                 cfg.gae_lambda, advantages=adv, returns=ret, stats=stats)
+        # env-sharded data parallelism (rank r holds envs [r N, (r+1) N) of the global rollout; the sequences shard with no halo):
+        # global advantage statistics, loss means over the global minibatch, gradients summed over the ranks before the clip
+        dist.all_reduce_sum(stats)
         if cfg.advantage_norm:
-            adv = ctx.adv_normalize(adv, stats, B)
-        hyper = self._hyper(cfg, M, B)
+            adv = ctx.adv_normalize(adv, stats, B * dist.world)
+        hyper = self._hyper(cfg, M * dist.world, B * dist.world)
         hyper.advantage_norm = 0                                         # already normalised above
         old_logp, adv_f, ret_f = ro.log_probs.reshape(B).contiguous(), adv.view(B), ret.view(B)
         act_bits = ro.actions.reshape(B).to(torch.int32).view(torch.float32)
@@ -198,6 +202,9 @@ class RecurrentEngine(_EngineBase):
                 ctx.ppo_loss_discrete(logits_mb.detach(), val_mb.detach(), a_mb.view(torch.int32), lp_mb, adv_mb, ret_mb, hyper,
                                       losses[e * MB + k], dlogits, dval, loss_ws)
                 torch.autograd.backward([logits_mb, val_mb], [dlogits, dval])
+                if dist.enabled:
+                    dist.all_reduce_sum(self.G)
+                    dist.all_reduce_sum(losses[e * MB + k])
                 ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
         worker.finish()
         self._publish_steps()
@@ -223,16 +230,17 @@ class FusedRecurrentEngine(_EngineBase):
 
     fused = True
 
-    def __init__(self, ctx, network, cfg, obs_dim, act_dim, device):
+    def __init__(self, ctx, network, cfg, obs_dim, act_dim, device, dist: _Dist | None = None):
         self.ctx, self.cfg, self.device = ctx, cfg, device
-        self.dist = _Dist(None, False)
+        self.dist = dist if dist is not None else _Dist(None, False)
         self.network = network
         self.desc = N.RnnDesc(int(obs_dim), int(cfg.network_hidden_dim), int(cfg.gru_hidden_dim), int(act_dim))
         self.layout = N.rnn_layout(self.desc)
         self._adopt(network, rnn_param_slices(self.desc, self.layout), int(self.layout.total))
         self.last_losses = None
         self.draws = 0
-        self.seed = int(cfg.seed) if cfg.seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        self.seed = self.dist.shared_seed(cfg.seed if cfg.seed is not None else (None if self.dist.enabled else int(np.random.randint(0, 2 ** 31 - 1))), device)
+        self.env_offset = self.dist.rank * cfg.num_envs              # global id of this shard's first environment (sampling keys)
         self._ws = {}
         self._bufs = {}
         self._seen_keys = []
@@ -275,7 +283,7 @@ class FusedRecurrentEngine(_EngineBase):
         return b
 
     def learn(self, ro: RecurrentRollout):
-        cfg, ctx, dev = self.cfg, self.ctx, self.device
+        cfg, ctx, dev, dist = self.cfg, self.ctx, self.device, self.dist
         T, N_ = ro.T, ro.N
         E, MB = cfg.num_epochs, cfg.num_minibatches
         B = T * N_
@@ -300,21 +308,30 @@ class FusedRecurrentEngine(_EngineBase):
         stats.zero_()
         ctx.gae(ro.rewards, ro.terminations, ro.truncations, b["values"], b["next_values"], cfg.gamma, cfg.gae_lambda, advantages=adv,
                 returns=ret, stats=stats)
-        hyper = self._hyper(cfg, M, B)
-        hyper.grad_sumsq = self.grad_sumsq.data_ptr()
+        # Env-sharded data parallelism: rank r holds envs [r N, (r+1) N) of the global rollout.  The GRU sequences shard by
+        # environment with no halo, so forward / BPTT scans stay rank-local; what is global: the advantage statistics, the loss
+        # means (global minibatch = the ranks' local minibatches side by side, rank-local permutations) and the gradient, summed
+        # over the ranks with NCCL before the global-norm clip (recurrent_ppo.py:362).
+        dist.all_reduce_sum(stats)
+        hyper = self._hyper(cfg, M * dist.world, B * dist.world)
+        if not dist.enabled:
+            hyper.grad_sumsq = self.grad_sumsq.data_ptr()            # gradient assembly leaves the norm partials for the Adam kernel
         losses = b["losses"]
         ws = self._workspace(T, N_, M, True)
 
         def step(idx_k, losses_k):
             ctx.rnn_grad_minibatch(self.desc, self.P, self.G, ro.obs, b["pd"], b["hx0"], T, N_, b["actions"], b["old_logp"], adv.view(B),
                                    ret.view(B), stats, idx_k, M, hyper, losses_k, ws)
+            if dist.enabled:
+                dist.all_reduce_sum(self.G)
+                dist.all_reduce_sum(losses_k)
             ctx.clip_adam_step(self.P, self.G, self.M, self.V, hyper, self.adam_ws, self.grad_norm)
 
         # From the second learn() on the same rollout buffers the MB optimiser steps of an epoch (15 launches each) are replayed as
         # one CUDA graph; the minibatch indices and Adam's two step-dependent constants are device-resident (like the MLP engine).
         key = (ro.obs.data_ptr(), ro.rewards.data_ptr(), T, N_, E, MB, cfg.ppo_clip, cfg.value_loss_weight, cfg.entropy_beta,
                cfg.grad_norm_clip, cfg.adam_eps, bool(cfg.advantage_norm))
-        use_graph = self.use_graphs and key in self._seen_keys
+        use_graph = self.use_graphs and key in self._seen_keys and not dist.enabled     # (NCCL calls are not captured)
         if key not in self._seen_keys:
             self._seen_keys = (self._seen_keys + [key])[-4:]
         gs = None
@@ -369,24 +386,32 @@ class RecurrentPPO:
     """Recurrent (GRU) discrete-action PPO (reference: diamond/recurrent_ppo.py:164-394)."""
 
     def __init__(self, env_fn: Callable[[], Any], cfg: RecurrentPPOConfig = RecurrentPPOConfig(),
-                 network_cls: Any = RecurrentActorCriticNetwork) -> None:
+                 network_cls: Any = RecurrentActorCriticNetwork, *, process_group=None, dp: bool = False) -> None:
+        """process_group / dp (additive): env-sharded data parallelism, one process per GPU -- this rank simulates and learns from
+        cfg.num_envs of the world_size * cfg.num_envs environments (rank-local minibatch permutations, NCCL gradient sum)."""
         self.device = _require_cuda()
         self.ctx = N.get_context(self.device.index)
         if cfg.seed is not None:
             np.random.seed(cfg.seed)                                    # recurrent_ppo.py:173-175
             torch.manual_seed(cfg.seed)
+        self._dist = _Dist(process_group, dp, "local", "nccl", "numpy")
         if getattr(env_fn, "vectorized", False):
             self.envs = env_fn(cfg.num_envs)
+            if self._dist.enabled and getattr(self.envs, "device_resident", False) and self.envs.desc.env_offset == 0:
+                self.envs.desc.env_offset = self._dist.rank * cfg.num_envs      # distinct reset / dynamics draws per shard
         else:
             self.envs = gym.vector.SyncVectorEnv([env_fn for _ in range(cfg.num_envs)], copy=True, autoreset_mode="Disabled")
         obs_space, act_space = self.envs.single_observation_space, self.envs.single_action_space
         self.network = network_cls(obs_space, act_space, cfg=cfg).to(self.device)
         network_parameter_init_(self.network, gain=sqrt(2.0), small_actor_out=True)     # touches nn.Linear only (:152-161)
+        if self._dist.enabled:                                           # replicas start from rank 0's parameters
+            for p in self.network.parameters():
+                self._dist.dist.broadcast(p.data, src=0, group=self._dist.group)
         self.obs_dim = int(np.prod(obs_space.shape))
         if type(self.network) is RecurrentActorCriticNetwork:            # default network: libdppo kernels end to end
-            self.engine = FusedRecurrentEngine(self.ctx, self.network, cfg, self.obs_dim, int(act_space.n), self.device)
+            self.engine = FusedRecurrentEngine(self.ctx, self.network, cfg, self.obs_dim, int(act_space.n), self.device, self._dist)
         else:                                                            # custom network_cls: the module runs under autograd
-            self.engine = RecurrentEngine(self.ctx, self.network, cfg, self.device)
+            self.engine = RecurrentEngine(self.ctx, self.network, cfg, self.device, self._dist)
         self.optimizer = torch.optim.Adam(self.network.parameters(), lr=cfg.lr, eps=cfg.adam_eps)
         self.engine.bind_optimizer(self.optimizer)
         self.lr_scheduler = torch.optim.lr_scheduler.LinearLR(
@@ -422,7 +447,7 @@ class RecurrentPPO:
                     logits, values, new_hx = self.network.get_logits_values_and_hx(obs_t, hx, pd_t)
             # Categorical(logits).sample() + log_prob on the device (counter-based generator, dppo_sample_categorical)
             actions = torch.empty(N_, dtype=torch.int64, device=dev)
-            self.ctx.sample_categorical(logits.squeeze(0).contiguous(), self.engine.seed, self.engine.draws, 0, actions, ro.log_probs[t])
+            self.ctx.sample_categorical(logits.squeeze(0).contiguous(), self.engine.seed, self.engine.draws, self.engine.env_offset, actions, ro.log_probs[t])
             self.engine.draws += 1
             next_observations, rewards, terminations, truncations, infos = self.envs.step(actions.cpu().numpy())
             final_t = torch.as_tensor(np.asarray(next_observations, dtype=np.float32)[None, ...], device=dev)
@@ -479,7 +504,7 @@ class RecurrentPPO:
                 hx, new_hx = ro.hx_buf[t & 1], ro.hx_buf[(t + 1) & 1]
                 ro.prev_dones[t].copy_(ro.pd_u8)
                 ctx.rnn_forward(eng.desc, eng.P, envs.cur_obs, ro.pd_u8, hx, 1, N_, 3, ro.logits, ro.val1, new_hx, ro.ws1)
-                ctx.sample_categorical(ro.logits, eng.seed, counter_of(t), 0, ro.actions_dev, ro.log_probs[t])
+                ctx.sample_categorical(ro.logits, eng.seed, counter_of(t), eng.env_offset, ro.actions_dev, ro.log_probs[t])
                 ro.actions[t].copy_(ro.actions_dev)
                 ro.values[t].copy_(ro.val1)
                 # environment kernel: writes obs[t] (the observation acted on), next_obs[t] (true final observation), rewards, masks;
@@ -543,7 +568,10 @@ class RecurrentPPO:
     # ---- train (recurrent_ppo.py:369-394) ---------------------------------------------------------------
     def train(self) -> None:
         cfg = self.cfg
-        self.current_observations, _ = self.envs.reset(seed=cfg.seed)
+        seed = cfg.seed                                                # shards are different environments of one global run
+        if seed is not None and self._dist.enabled and not getattr(self.envs, "device_resident", False):
+            seed = cfg.seed + self._dist.rank * cfg.num_envs
+        self.current_observations, _ = self.envs.reset(seed=seed)
         self.prev_dones = np.zeros(cfg.num_envs, dtype=bool)
         self.current_hx = torch.zeros(1, cfg.num_envs, cfg.gru_hidden_dim, device=self.device)
         if self._epstats is not None:                                  # fresh environments: running returns / lengths restart
@@ -557,10 +585,10 @@ class RecurrentPPO:
             experience = self.rollout()
             self.learn(experience)
             env_steps = (rollout_idx + 1) * cfg.rollout_steps * cfg.num_envs
-            if cfg.checkpoint and time.time() - last_checkpoint_time >= cfg.save_interval:
-                self.checkpointer.save(env_steps, self.network, self.optimizer)
+            if cfg.checkpoint and self._dist.rank == 0 and time.time() - last_checkpoint_time >= cfg.save_interval:
+                self.checkpointer.save(env_steps, self.network, self.optimizer)      # replicas are identical: rank 0 writes
                 last_checkpoint_time = time.time()
-        if cfg.checkpoint and total_rollouts > 0:
+        if cfg.checkpoint and total_rollouts > 0 and self._dist.rank == 0:
             self.checkpointer.save(env_steps, self.network, self.optimizer)
         self._flush_episode_stats()
         self.envs.close()

@@ -197,6 +197,61 @@ def main():
     if rank == 0:
         print(f"dp{world} [device envs, train()]: replicas identical, shards distinct, finite -> {'OK' if env_ok else 'FAIL'}", flush=True)
     same = same and env_ok
+    # RecurrentPPO under env-sharded DP (rank-local permutations, NCCL gradient sum; the GRU scans shard by environment): with every
+    # rank holding the SAME rollout and permutation the update equals the single-GPU update on one copy, replicas stay identical;
+    # train() end to end with distinct shards keeps the replicas identical
+    from diamond import RecurrentPPO, RecurrentPPOConfig
+    n_r, t_r = 64, 32
+    # (advantage_norm off: duplicating the data changes the unbiased (n - 1) standard deviation by 1 / (4 B), which is all that would
+    # distinguish the two runs)
+    cfg_r = RecurrentPPOConfig(num_envs=n_r, rollout_steps=t_r, num_epochs=2, num_minibatches=4, verbose=False, seed=11,
+                               total_steps=n_r * t_r * 1000, advantage_norm=False)
+
+    def recurrent_agent(dp):
+        a = RecurrentPPO(DeviceVectorEnv.factory("CartPole-v1", seed=11), cfg_r, dp=dp)
+        a.envs.desc.env_offset = 0                                     # replicated data: every rank simulates the same environments
+        a.engine.env_offset = 0
+        a.current_observations, _ = a.envs.reset(seed=11)
+        a.prev_dones = np.zeros(n_r, dtype=bool)
+        a.current_hx = torch.zeros(1, n_r, cfg_r.gru_hidden_dim, device=a.device)
+        return a
+
+    ag = recurrent_agent(True)
+    init = {k: v.detach().clone() for k, v in ag.network.state_dict().items()}
+    ro = ag.rollout()
+    np.random.seed(5)
+    ag.learn(ro)
+    torch.cuda.synchronize()
+    flat = ag.engine.P.clone(); ref = flat.clone(); dist.broadcast(ref, src=0)
+    rec_ok = bool(torch.equal(flat, ref)) and bool(torch.isfinite(flat).all())
+    if rank == 0:
+        single = recurrent_agent(False)
+        single.network.load_state_dict(init)
+        ro1 = single.rollout()
+        assert torch.equal(ro1.obs, ro.obs) and torch.equal(ro1.actions, ro.actions), "replicated rollouts differ"
+        np.random.seed(5)
+        single.learn(ro1)
+        torch.cuda.synchronize()
+        worst = max(float((p_ - q_).abs().max() / q_.abs().max().clamp_min(1e-12))
+                    for (_, p_), (_, q_) in zip(ag.network.named_parameters(), single.network.named_parameters()))
+        lerr = float((ag.last_losses - single.last_losses).abs().max())
+        rec_ok = rec_ok and worst <= 2e-5 and lerr <= 2e-5
+        print(f"dp{world} [RecurrentPPO, NCCL gradient sum] vs single on replicated data: max param err {worst:.2e}, max loss err {lerr:.2e} "
+              f"-> {'OK' if rec_ok else 'FAIL'}", flush=True)
+    same = same and rec_ok
+    cfg_rt = RecurrentPPOConfig(num_envs=n_r, rollout_steps=t_r, verbose=False, seed=13, total_steps=n_r * t_r * 4)
+    ag = RecurrentPPO(DeviceVectorEnv.factory("CartPole-v1", seed=13), cfg_rt, dp=True)
+    ag.train()
+    torch.cuda.synchronize()
+    flat = ag.engine.P.clone(); ref = flat.clone(); dist.broadcast(ref, src=0)
+    st0 = ag.envs.state.clone()
+    gathered = [torch.empty_like(st0) for _ in range(world)]
+    dist.all_gather(gathered, st0)
+    rec_train_ok = (bool(torch.equal(flat, ref)) and bool(torch.isfinite(flat).all()) and bool(torch.isfinite(ag.last_losses).all())
+                    and all(not torch.equal(gathered[0], g_) for g_ in gathered[1:]))
+    if rank == 0:
+        print(f"dp{world} [RecurrentPPO, device envs, train()]: replicas identical, shards distinct, finite -> {'OK' if rec_train_ok else 'FAIL'}", flush=True)
+    same = same and rec_train_ok
     t = torch.tensor([int(ok and same)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
