@@ -383,6 +383,44 @@ def test_rnn_forward_matches_torch_module(Hg):
     assert (v - ref_v).abs().max().item() <= 1e-5 * max(1.0, ref_v.abs().max().item())
 
 
+@pytest.mark.parametrize("Hg,N_,T", [(64, 37, 19), (48, 8, 33), (128, 5, 12), (20, 70, 9), (64, 4099, 4), (64, 1801, 3)])
+def test_recurrent_fused_engine_matches_autograd_engine_at_wide_gru(Hg, N_, T):
+    """GRU widths beyond the warp kernels (tiled scan kernels; 4 / 2 environments per thread at 4099 / 1801 environments, one
+    otherwise; ragged environment counts):
+    one learn() of the fused engine equals the same network run under torch autograd (RecurrentEngine) on the same rollout."""
+    from diamond import RecurrentPPO, RecurrentPPOConfig, envs
+    from diamond.recurrent import RecurrentActorCriticNetwork, RecurrentRollout, FusedRecurrentEngine, RecurrentEngine
+
+    class Same(RecurrentActorCriticNetwork):
+        pass
+
+    D, A, H = 6, 3, 64
+    agents = []
+    for cls in (RecurrentActorCriticNetwork, Same):
+        cfg = RecurrentPPOConfig(num_envs=N_, rollout_steps=T, num_epochs=2, num_minibatches=1, verbose=False, network_hidden_dim=H,
+                                 gru_hidden_dim=Hg, seed=4, total_steps=N_ * T * 100)
+        agents.append(RecurrentPPO(lambda: envs.SyntheticEnv(D, A), cfg, network_cls=cls))
+    fused, auto = agents
+    assert isinstance(fused.engine, FusedRecurrentEngine) and isinstance(auto.engine, RecurrentEngine)
+    auto.network.load_state_dict(fused.network.state_dict())
+    dev = fused.device
+    gen = torch.Generator(device=dev).manual_seed(Hg)
+    ro = RecurrentRollout(T, N_, D, Hg, dev)
+    ro.obs.normal_(generator=gen); ro.actions.random_(0, A, generator=gen); ro.rewards.normal_(generator=gen)
+    ro.terminations.copy_((torch.rand(T, N_, device=dev, generator=gen) < 0.1).float()); ro.truncations.zero_()
+    ro.prev_dones.copy_(torch.rand(T, N_, device=dev, generator=gen) < 0.1)
+    ro.log_probs.fill_(-float(np.log(A))); ro.values.normal_(generator=gen); ro.next_values.normal_(generator=gen)
+    ro.hx0.normal_(generator=gen); ro.filled = T
+    for ag in (fused, auto):
+        np.random.seed(8)
+        ag.learn(ro)
+    torch.cuda.synchronize()
+    for (k, p), (_, q) in zip(fused.network.named_parameters(), auto.network.named_parameters()):
+        err = float((p - q).abs().max() / q.abs().max().clamp_min(1e-12))
+        assert err <= 1e-4, (k, err)
+    assert float((fused.last_losses - auto.last_losses).abs().max()) <= 1e-4
+
+
 def test_recurrent_train_runs_on_cartpole():
     """Plumbing run of config 4 (RecurrentPPO on CartPole-v1): rollout with done-masked hidden resets, learn, LR schedule."""
     from diamond import RecurrentPPO, RecurrentPPOConfig, envs
