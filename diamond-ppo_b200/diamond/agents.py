@@ -312,8 +312,18 @@ class _PermWorker(threading.Thread):
         # 24-bit hash of the stream state (data-parallel lockstep check: h and h^2 are summed over the ranks in fp64, exactly)
         self.state_hash = float((int(self.key[::7].astype(np.uint64).sum()) * 2654435761 + self.pos * 40503) % (1 << 24))
         self.B, self.E, self.MB, self.outs, self.owner = B_perm, E, MB, outs, owner
+        self.start_state = (self.key.copy(), self.pos, self.state_tail)       # what the stream looked like when this worker was created
         self.ready = [threading.Event() for _ in range(E)]
         self.error = None
+
+    def continues(self, B_perm, E, MB) -> bool:
+        """True if numpy's global stream is still exactly where this worker started from and the request is the one it was
+        started for: a worker started speculatively at the end of the previous learn() (permutations depend on nothing but the
+        stream) may then stand in for a fresh one; any np.random use in between invalidates it."""
+        st = np.random.get_state(legacy=True)
+        key0, pos0, tail0 = self.start_state
+        return ((self.B, self.E, self.MB) == (B_perm, E, MB) and st[0] == "MT19937" and int(st[2]) == pos0 and (st[3], st[4]) == tail0
+                and np.array_equal(np.asarray(st[1], dtype=np.uint32), key0))
 
     def run(self):
         try:
@@ -330,8 +340,8 @@ class _PermWorker(threading.Thread):
 
     def start(self):
         """Small batches are permuted inline (a 1024-index permutation takes microseconds; starting and joining a thread ~0.1 ms)."""
-        if self.B <= 16384:
-            self.inline = True
+        self.inline = self.B <= 16384
+        if self.inline:
             self.run()
         else:
             super().start()
@@ -448,6 +458,7 @@ class FusedMlpEngine(_EngineBase):
         self.dpx = dist.connect_exchange(ctx, self.fm.total, device)    # fused NVLink exchange (None: single GPU / NCCL path)
         self.D, self.A = obs_dim, act_dim
         self.fwd_rows = 65536
+        self.speculate_permutations = True      # generate the next learn()'s numpy-stream permutations in the background (validated)
         self.fwd_ws = torch.empty(ctx.mlp_workspace_bytes(self.fm.desc, self.fwd_rows, False) // 4 + 256, device=device)
         self._train_ws = None
         self._bufs = {}
@@ -781,12 +792,18 @@ class FusedMlpEngine(_EngineBase):
         b["h_set"] ^= 1                      # host-side staging buffers alternate between consecutive learn() calls
         if self.perm_mode == "numpy":
             b["h_idx"] = b["h_sets"][b["h_set"]]
-            if b["h_consumed"][b["h_set"]] is not None:
-                b["h_consumed"][b["h_set"]].synchronize()   # the async copies out of this pinned set (two learn() calls ago) are done
             owner = (lambda e: e % dist.world == dist.rank) if plan["filter"] else None
-            worker = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_idx"]], owner)
+            spec = b.pop("spec", None)
+            if spec is not None and spec.continues(plan["B_perm"], E, MB):
+                worker = spec                   # started at the end of the previous learn(): the permutations are (being) generated already
+            else:
+                if spec is not None:
+                    spec.join()                 # the stream moved on (np.random was used in between): its permutations are discarded
+                if b["h_consumed"][b["h_set"]] is not None:
+                    b["h_consumed"][b["h_set"]].synchronize()   # the async copies out of this pinned set (two learn() calls ago) are done
+                worker = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_idx"]], owner)
+                worker.start()                  # host permutation overlaps the pre-update pass on the GPU
             lock_hash = worker.state_hash
-            worker.start()                      # host permutation overlaps the pre-update pass on the GPU
 
         def mark(name):
             if events is not None:
@@ -853,6 +870,17 @@ class FusedMlpEngine(_EngineBase):
             self._pending_check = dict(host=host, event=ev)
         if worker is not None:
             worker.finish()
+            if self.speculate_permutations and not worker.inline:
+                # The next learn()'s permutations depend on nothing but numpy's stream, which now stands where that learn() will find
+                # it: generate them in the background already (into the other pinned set).  At data-parallel step sizes an epoch
+                # of optimiser steps is shorter than one 524 288-index MT19937 shuffle, so a worker started inside learn() leaves the
+                # GPU waiting; a worker started one learn() ahead does not.  Adopted only if the stream is untouched (continues()).
+                nxt = b["h_set"] ^ 1
+                if b["h_consumed"][nxt] is not None:
+                    b["h_consumed"][nxt].synchronize()
+                owner = (lambda e: e % dist.world == dist.rank) if plan["filter"] else None
+                b["spec"] = _PermWorker(plan["B_perm"], E, MB, [h.numpy() for h in b["h_sets"][nxt]], owner)
+                b["spec"].start()
         self._publish_steps()
         self.last_losses = losses
         buf._consumed = torch.cuda.Event()

@@ -94,6 +94,43 @@ def test_permutation_plan_bounds():
     assert permutation_plan(32, 2, 4, True)["rows"] <= 16
 
 
+def test_speculative_permutation_worker_is_adopted_only_while_the_numpy_stream_is_untouched():
+    """learn() starts the NEXT learn()'s permutation worker in the background (the permutations depend on nothing but numpy's
+    global stream).  It may stand in for a fresh worker only if np.random has not moved in between; either way the permutations and
+    the final stream state equal numpy's own (ppo.py:252-255)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "diamond-ppo_b200"))
+    from diamond.agents import _PermWorker
+    B, E, MB = 40000, 3, 4                       # > 16384: generated on a thread, not inline
+
+    def outs():
+        return [np.empty(B, dtype=np.int32) for _ in range(E)]
+
+    np.random.seed(11)
+    ref = [np.random.permutation(B) for _ in range(2 * E)]
+    after = np.random.get_state(legacy=True)
+    np.random.seed(11)
+    o1 = outs()
+    w = _PermWorker(B, E, MB, o1)
+    w.start(); w.finish()                        # "learn() k": the global stream now stands where learn() k + 1 will find it
+    o2 = outs()
+    spec = _PermWorker(B, E, MB, o2)
+    spec.start()                                 # speculative worker of learn() k + 1
+    assert spec.continues(B, E, MB) and not spec.continues(B, E + 1, MB) and not spec.continues(2 * B, E, MB)
+    spec.finish()
+    for e in range(E):
+        assert np.array_equal(o1[e], ref[e]) and np.array_equal(o2[e], ref[E + e])
+    st = np.random.get_state(legacy=True)
+    assert st[2] == after[2] and np.array_equal(st[1], after[1])
+    # the stream moves between two learn() calls: the speculative worker must be refused
+    np.random.seed(11)
+    w = _PermWorker(B, E, MB, outs()); w.start(); w.finish()
+    spec = _PermWorker(B, E, MB, outs()); spec.start()
+    np.random.random()
+    assert not spec.continues(B, E, MB)
+    spec.join()
+
+
 def test_dp_host_logic_gloo_world2(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(f"ROOT = {ROOT!r}\n" + GLOO_WORKER)
