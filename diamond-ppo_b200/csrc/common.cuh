@@ -66,9 +66,9 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
         asm volatile("griddepcontrol.wait;" ::: "memory");                  \
     } while (0)
 
+// on: launch with programmatic stream serialisation (the kernel must start with DPPO_PDL_ENTER())
 template <typename... KArgs, typename... Args>
-static inline cudaError_t dppo_launch_pdl(dppo_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                          Args&&... args)
+static inline cudaError_t dppo_launch_pdl_if(bool on, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
 {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
@@ -76,8 +76,14 @@ static inline cudaError_t dppo_launch_pdl(dppo_ctx* ctx, void (*kern)(KArgs...),
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = DPPO_DBG(ctx->tc_debug, 512) ? 1 : 0;
+    lc.numAttrs = on ? 1 : 0;
     return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dppo_launch_pdl(dppo_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args)
+{
+    return dppo_launch_pdl_if(DPPO_DBG(ctx->tc_debug, 512), kern, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
