@@ -716,6 +716,106 @@ head_eval_kernel(const float* __restrict__ ha_base, const float* __restrict__ hc
     }
 }
 
+// Vector variant of head_eval_kernel (H a multiple of 128, A <= 4, 16-byte aligned rows): four rows per warp iteration, float4 loads,
+// packed FFMA2 dot products, and ONE multi-value butterfly for the 4 x (A + 1) partial sums instead of 5 shuffle trees per row:
+// the 16 actor values end in the lane layout (row = lane bits 4:3, action = lane bits 2:1), the 4 critic values in (row = bits 4:3).
+// The pre-update pass runs this kernel over every row of the rollout twice (ppo.py:235-238).
+template <int G, bool ACTOR, bool CRITIC>
+__global__ void __launch_bounds__(256)
+head_eval_vec_kernel(const float* __restrict__ ha_base, const float* __restrict__ hc_base, int ld, const float* __restrict__ wa,
+                     const float* __restrict__ ba, const float* __restrict__ wc, const float* __restrict__ bc,
+                     float* __restrict__ head_out, float* __restrict__ values, int64_t rows, int A, const int* __restrict__ rows_dev)
+{
+    constexpr int H = 128 * G, AM = 4;
+    __shared__ __align__(16) float s_wa[ACTOR ? AM * H : 4];
+    if (rows_dev != nullptr && *rows_dev < rows) rows = *rows_dev;
+    if (ACTOR) {
+        for (int i = threadIdx.x; i < AM * H; i += blockDim.x) s_wa[i] = i < A * H ? wa[i] : 0.f;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    float4 wcv[G];
+    if (CRITIC) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) wcv[g] = __ldg(reinterpret_cast<const float4*>(wc + g * 128) + lane);
+    }
+    const int rl = lane >> 3, jl = (lane >> 1) & 3;              // this lane's (row, action) after the reduction
+    const float bias_a = (ACTOR && jl < A) ? ba[jl] : 0.f;
+    const float bias_c = CRITIC ? bc[0] : 0.f;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ws = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t mb = w0 * 4; mb < rows; mb += ws * 4) {
+        float pa[4][AM], pc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t m = mb + r < rows ? mb + r : mb;
+            if (ACTOR) {
+                float4 h[G];
+                const float4* hp = reinterpret_cast<const float4*>(ha_base + m * ld);
+#pragma unroll
+                for (int g = 0; g < G; ++g) h[g] = __ldg(hp + g * 32 + lane);
+#pragma unroll
+                for (int j = 0; j < AM; ++j) {
+                    float2 q = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) dot4(q, h[g], reinterpret_cast<const float4*>(s_wa + j * H + g * 128)[lane]);
+                    pa[r][j] = q.x + q.y;
+                }
+            }
+            if (CRITIC) {
+                const float4* hp = reinterpret_cast<const float4*>(hc_base + m * ld);
+                float2 q = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < G; ++g) dot4(q, __ldg(hp + g * 32 + lane), wcv[g]);
+                pc[r] = q.x + q.y;
+            }
+        }
+        const int64_t m = mb + rl;
+        if (ACTOR) {
+            // 16 values: xor 16 keeps rows {0,1} or {2,3}; xor 8 keeps one row; xor 4 keeps two actions; xor 2 keeps one; xor 1 finishes
+            float s1[2][AM];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int j = 0; j < AM; ++j) {
+                    const float keep = b4 ? pa[2 + r][j] : pa[r][j], send = b4 ? pa[r][j] : pa[2 + r][j];
+                    s1[r][j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            float s2[AM];
+#pragma unroll
+            for (int j = 0; j < AM; ++j) {
+                const float keep = b3 ? s1[1][j] : s1[0][j], send = b3 ? s1[0][j] : s1[1][j];
+                s2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float s3[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float keep = b2 ? s2[2 + j] : s2[j], send = b2 ? s2[j] : s2[2 + j];
+                s3[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            const float keep = b1 ? s3[1] : s3[0], send = b1 ? s3[0] : s3[1];
+            float z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            if ((lane & 1) == 0 && jl < A && m < rows) head_out[m * A + jl] = z + bias_a;
+        }
+        if (CRITIC) {
+            float s1[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float keep = b4 ? pc[2 + r] : pc[r], send = b4 ? pc[r] : pc[2 + r];
+                s1[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            const float keep = b3 ? s1[1] : s1[0], send = b3 ? s1[0] : s1[1];
+            float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 7) == 0 && m < rows) values[m] = v + bias_c;
+        }
+    }
+}
+
+
 __global__ void logprob_categorical_kernel(const float* __restrict__ logits, const int32_t* __restrict__ actions,
                                            float* __restrict__ out, int64_t rows, int A)
 {
@@ -882,6 +982,18 @@ int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, co
     const size_t smem = (size_t)(A + 1) * H * sizeof(float);
     int64_t want = (rows + 7) / 8;
     int blocks = (int)(want < 4 * (int64_t)ctx->sm_count ? want : 4 * (int64_t)ctx->sm_count);
+    const bool al = ld % 4 == 0 && (!ha || (reinterpret_cast<uintptr_t>(ha) & 15u) == 0) && (!hc || (reinterpret_cast<uintptr_t>(hc) & 15u) == 0) &&
+                    (reinterpret_cast<uintptr_t>(wc) & 15u) == 0;
+    if ((H == 128 || H == 256) && A <= 4 && al && (ha || hc)) {
+        want = (rows + 31) / 32;                                 // 8 warps x 4 rows per block iteration
+        blocks = (int)(want < 4 * (int64_t)ctx->sm_count ? want : 4 * (int64_t)ctx->sm_count);
+#define HEV(G, AC, CR) head_eval_vec_kernel<G, AC, CR><<<blocks, 256, 0, st>>>(ha, hc, ld, wa, ba, wc, bc, head_out, values, rows, A, ctx->rows_dev)
+        if (H == 128) { if (ha && hc) HEV(1, true, true); else if (ha) HEV(1, true, false); else HEV(1, false, true); }
+        else { if (ha && hc) HEV(2, true, true); else if (ha) HEV(2, true, false); else HEV(2, false, true); }
+#undef HEV
+        DPPO_CHECK_LAUNCH(ctx, "head_eval_vec_kernel");
+        return 0;
+    }
 #define HE(KPL)                                                                                                   \
     do {                                                                                                          \
         cudaFuncSetAttribute(head_eval_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \

@@ -293,6 +293,18 @@ class _Dist:
         return dp
 
 
+_live_workers: "weakref.WeakSet[_PermWorker]" = None
+
+
+def _join_workers_at_exit():
+    """A speculative worker may still be inside libdppo when the interpreter shuts down: let it finish before its buffers go away."""
+    for w in list(_live_workers or ()):
+        try:
+            w.join(timeout=5.0)
+        except RuntimeError:
+            pass
+
+
 class _PermWorker(threading.Thread):
     """Generates the E minibatch permutations of one learn() (ppo.py:252-255) on a host thread while
     the GPU runs the pre-update pass / previous epoch.  Bit-exact continuation of numpy's global
@@ -340,10 +352,17 @@ class _PermWorker(threading.Thread):
 
     def start(self):
         """Small batches are permuted inline (a 1024-index permutation takes microseconds; starting and joining a thread ~0.1 ms)."""
+        global _live_workers
         self.inline = self.B <= 16384
         if self.inline:
             self.run()
         else:
+            if _live_workers is None:
+                import atexit
+                import weakref
+                _live_workers = weakref.WeakSet()
+                atexit.register(_join_workers_at_exit)
+            _live_workers.add(self)
             super().start()
 
     def join(self, timeout=None):
