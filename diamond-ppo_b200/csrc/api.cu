@@ -48,6 +48,8 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->gae_variant = 0;
     c->gae_inputs_settled = 0;
     c->tc_debug = 0;
+    c->row_sweep = 31;
+    c->head_prefetch = 0;
     c->draw_base = nullptr;
     c->rows_dev = nullptr;
     c->launch_count = 0;
@@ -68,6 +70,8 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
 {
     if (!ctx || !name) return 1;
     if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value != 0 ? 3 : 0; return 0; }
+    if (!strcmp(name, "row_sweep")) { ctx->row_sweep = value & 31; return 0; }
+    if (!strcmp(name, "head_prefetch")) { ctx->head_prefetch = value < 0 ? 0 : value > 8 ? 8 : value; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
     if (!strcmp(name, "tc_debug")) {
 #ifdef DPPO_TIMING_SWITCHES
@@ -245,6 +249,8 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
     float* h3 = (float*)(base + 2 * align_up(chunk * H * 4, 256));
     float* xg = (float*)(base + 2 * align_up(chunk * H * 4, 256) + align_up(chunk * 2 * H * 4, 256));
     const bool actor = heads & 1, critic = heads & 2;
+    const int sweep = ctx->row_sweep;                  // alternating row sweeps along the layer chain (dppo_tc3_gemm)
+    const int hint = (sweep & 8) ? 2 : 0;              // inputs read with the L2 evict-first hint
     const int64_t w3off = actor ? 0 : (int64_t)H * H;
     const int b3off = actor ? 0 : H;
     const int n3 = (actor && critic) ? 2 * H : H;
@@ -274,19 +280,19 @@ extern "C" int dppo_mlp_forward(dppo_ctx* ctx, const dppo_mlp_desc* d, const flo
                 if (dppo_gather_rows_f32(ctx, obs, rowsel, xg, n, D, stream)) return 1;
                 x = xg;
             }
-            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, st)) return 1;
+            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, x, D, img.w1f, params + L.b1, nullptr, 0, h1, H, nullptr, n, H, D, hint, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x, D, rowsel, params + L.w1, D, params + L.b1, h1, H, n, H, D, st)) return 1;
         if (tc2 && dppo_tc3_gemm_supported(n, H, H)) {
-            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, st)) return 1;
+            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, h1, H, img.w2f, params + L.b2, nullptr, 0, h2, H, nullptr, n, H, H, (sweep & 1) | hint, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h1, H, nullptr, params + L.w2, H, params + L.b2, h2, H, n, H, H, st)) return 1;
         // first head layers: both (one [2H,H] product) or only the requested half
         if (tc3 && dppo_tc3_gemm_supported(n, n3, H)) {
-            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, st)) return 1;
+            if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, h2, H, img.w3f, params + L.b3 + b3off, nullptr, 0, h3, n3, nullptr, n, n3, H, hint, st)) return 1;
         } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, h2, H, nullptr, params + L.w3 + w3off, H, params + L.b3 + b3off, h3, n3, n, n3, H, st)) return 1;
         const float* ha = actor ? h3 : nullptr;
         const float* hc = critic ? (actor ? h3 + H : h3) : nullptr;
         if (launch_head_eval(ctx, ha, hc, n3, params + L.wa, params + L.ba, params + L.wc, params + L.bc,
-                             head_out ? head_out + r0 * A : nullptr, values ? values + r0 : nullptr, n, H, A, st)) return 1;
+                             head_out ? head_out + r0 * A : nullptr, values ? values + r0 : nullptr, n, H, A, (sweep >> 1) & 1, st)) return 1;
     }
     return 0;
 }
@@ -317,6 +323,11 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     const bool g1 = tc_on && dppo_tc3_gemm_supported(M, H, D), g2 = tc_on && dppo_tc3_gemm_supported(M, H, H),
                g3 = tc_on && dppo_tc3_gemm_supported(M, 2 * H, H), gb3 = tc_on && dppo_tc3_gemm_supported(M, H, 2 * H), gb2 = g2;
     const bool wg3 = tc_on && w.t3 > 0, wg2 = tc_on && w.t2 > 0, wg1 = tc_on && w.t1 > 0;
+    // Row sweeps along the chain (dppo_tc3_gemm): L1 up, L2 down, L3 up, head kernel down, dgrad3 up, dgrad2 down -- every launch
+    // starts with the rows its predecessor wrote last (still in the L2).
+    const int sweep = ctx->row_sweep;
+    const int hint = (sweep & 8) ? 2 : 0;              // inputs read with the L2 evict-first hint (not dgrad2: the weight-gradient launch
+                                                       // right behind it reads the same d2 / h1 again)
     // the TMA-fed kernels read contiguous rows: gather the minibatch observations once (ppo.py:261 observations[mb])
     const float* x1 = obs;
     const int32_t* x1_idx = idx;
@@ -346,13 +357,13 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
 
     // forward (ppo.py:261), activations kept for the backward pass
     if (g1) {
-        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, x1, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, M, H, D, hint, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, x1, D, x1_idx, params + L.w1, D, params + L.b1, w.h1, H, M, H, D, st)) return 1;
     if (g2) {
-        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, M, H, H, (sweep & 1) | hint, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, M, H, H, st)) return 1;
     if (g3) {
-        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3, nullptr, 0, w.h3, 2 * H, nullptr, M, 2 * H, H, hint, st)) return 1;
     } else if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3, H, params + L.b3, w.h3, 2 * H, M, 2 * H, H, st)) return 1;
 
     // heads + loss (ppo.py:264-280) + backward into the first head layers
@@ -368,17 +379,18 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     ha.M = M; ha.H = H; ha.A = A;
     ha.clip = hy->ppo_clip; ha.vw = hy->value_loss_weight; ha.beta = hy->entropy_beta; ha.inv_m = inv_m;
     ha.partials = w.hp; ha.partial_stride = w.head_stride;
+    ha.rev = (sweep >> 1) & 1; ha.keep_d3 = (sweep >> 2) & 1; ha.h3_first = (sweep >> 3) & 1; ha.pfd = ctx->head_prefetch;
     if (launch_head_train_kernel(ctx, ha, d->continuous, w.head_blocks, st)) return 1;
 
     // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused
     int tiles2 = w.tiles2, tiles1 = w.tiles1;
     if (gb3) {
         tiles2 = dppo_tc3_colsum_parts(ctx, M, H);
-        if (dppo_tc3_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_TANH_BWD, w.d3, 2 * H, img.w3b, nullptr, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, hint, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d3, 2 * H, params + L.w3, H, w.h2, H, w.d2, H, w.c2, M, H, 2 * H, st)) return 1;
     if (gb2) {
         tiles1 = dppo_tc3_colsum_parts(ctx, M, H);
-        if (dppo_tc3_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
+        if (dppo_tc3_gemm(ctx, DPPO_EPI_TANH_BWD, w.d2, H, img.w2b, nullptr, w.h1, H, w.d1, H, w.c1, M, H, H, sweep & 1, st)) return 1;
     } else if (dppo_gemm_nn_tanh_bwd(ctx, w.d2, H, params + L.w2, H, w.h1, H, w.d1, H, w.c1, M, H, H, st)) return 1;
     // weight gradients: deterministic split-K partials
     const int n3p = wg3 ? w.t3 : w.s3, n2p = wg2 ? w.t2 : w.s2, n1p = wg1 ? w.t1 : w.s1;
@@ -529,14 +541,14 @@ extern "C" int dppo_mlp_next_values(dppo_ctx* ctx, const dppo_mlp_desc* d, const
     }
     ctx->rows_dev = w.count;
     int rc = dppo_gather_rows_f32(ctx, next_obs, w.idx, w.xg, B, D, stream);
-    if (!rc) rc = tc1 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.xg, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, B, H, D, st)
+    if (!rc) rc = tc1 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.xg, D, img.w1f, params + L.b1, nullptr, 0, w.h1, H, nullptr, B, H, D, 0, st)
                       : dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.xg, D, nullptr, params + L.w1, D, params + L.b1, w.h1, H, B, H, D, st);
-    if (!rc) rc = tc2 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, B, H, H, st)
+    if (!rc) rc = tc2 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, img.w2f, params + L.b2, nullptr, 0, w.h2, H, nullptr, B, H, H, 0, st)
                       : dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h1, H, nullptr, params + L.w2, H, params + L.b2, w.h2, H, B, H, H, st);
-    if (!rc) rc = tc2 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3 + H, nullptr, 0, w.h3, H, nullptr, B, H, H, st)
+    if (!rc) rc = tc2 ? dppo_tc3_gemm(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, img.w3f, params + L.b3 + H, nullptr, 0, w.h3, H, nullptr, B, H, H, 0, st)
                       : dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.h2, H, nullptr, params + L.w3 + (int64_t)H * H, H, params + L.b3 + H, w.h3, H, B, H, H, st);
     if (!rc) rc = launch_head_eval(ctx, nullptr, w.h3, H, params + L.wa, params + L.ba, params + L.wc, params + L.bc, nullptr, w.tmp, B, H,
-                                   d->act_dim, st);
+                                   d->act_dim, 0, st);
     ctx->rows_dev = nullptr;
     if (rc) return 1;
     scatter_values_kernel<<<blocks, 256, 0, st>>>(w.tmp, w.idx, w.count, next_values);
@@ -567,7 +579,7 @@ extern "C" int dppo_tc_linear_f32(dppo_ctx* ctx, int epi, const float* A, int64_
     if (!dppo_tc3_gemm_supported(M, N, K)) DPPO_FAIL(ctx, "tc_linear: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
     // prepared != 0: the images an earlier call with the same weights left in ws are re-used (kernel-only timing)
     if (!prepared && dppo_tc_prep_weights(ctx, W, rows_w, cols_w, transpose, img, st)) return 1;
-    return dppo_tc3_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, st);
+    return dppo_tc3_gemm(ctx, epi, A, K, img, bias, Hact, N, C, N, colsum, M, N, K, 0, st);
 }
 
 extern "C" int64_t dppo_tc_wgrad_workspace_bytes(dppo_ctx* ctx, int64_t M, int N1, int N2)

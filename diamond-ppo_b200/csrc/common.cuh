@@ -16,6 +16,13 @@ struct dppo_ctx {
     int gae_variant;                      // 0: auto (pipelined TMA kernel for T >= 128), 1: register-staged kernel, 2: single-barrier TMA kernel
     int gae_inputs_settled;               // 1: caller guarantees the GAE inputs are not written by the kernel just before the GAE launch
     long long launch_count;               // kernels launched through this context (bench.py's gpu_launches)
+    int row_sweep;                        // L2 reuse between consecutive launches of the layer chain (gemm_tc3.cu dppo_tc3_gemm), default 31.
+                                          // bit 0: consecutive GEMM launches alternate their row-sweep direction, bit 1: the head kernels
+                                          // sweep against the GEMM before them, bit 2: the head kernel's d3 stores stay cacheable, bit 3:
+                                          // GEMM / head-kernel inputs are read with the L2 evict-first hint, bit 4: so are the operands of
+                                          // the weight-gradient launch.  Bits 2-4 do not change any result; bits 0 / 1 re-order the fp32
+                                          // partial sums of the bias gradients / the head kernel's accumulators (forward outputs unchanged)
+    int head_prefetch;                    // role-split head kernel: L2 prefetch distance in warp iterations (0: off)
     int tc_debug;                         // timing-experiment switches; only honoured by builds with -DDPPO_TIMING_SWITCHES (see DPPO_DBG)
     const unsigned long long* draw_base;  // optional device counter added to every sampling draw counter (CUDA-graph replay of rollouts)
     const int* rows_dev;                  // optional DEVICE row count: while set, the forward kernels (gather, GEMMs, head evaluation) process

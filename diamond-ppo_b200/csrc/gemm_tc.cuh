@@ -27,4 +27,4 @@ bool dppo_tc3_gemm_supported(int64_t M, int N, int K);
 int dppo_tc3_colsum_parts(dppo_ctx* ctx, int64_t M, int N);   // partial rows of the TANH_BWD epilogue the reduction reads: one per CTA
 int dppo_tc3_colsum_rows(dppo_ctx* ctx, int64_t M, int N);    // rows the colsum buffer must hold (partials + per-quadrant working rows)
 int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact,
-                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st);
+                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, int rev, cudaStream_t st);

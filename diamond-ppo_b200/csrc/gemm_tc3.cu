@@ -40,7 +40,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmH,
                 const unsigned char* __restrict__ Wimg, const float* __restrict__ bias, float* __restrict__ colsum, int64_t M,
-                int N, int K, int n_tile, int pair_tiles, int tail_halves, int dbg, const int* __restrict__ m_dev)
+                int N, int K, int n_tile, int pair_tiles, int tail_halves, int rev, int dbg, const int* __restrict__ m_dev)
 {
     if (m_dev != nullptr) {                              // row count decided on the device (tiles past it are never touched)
         const int64_t md = *m_dev;
@@ -57,6 +57,8 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const bool in_first = (rev & 2) != 0;                // inputs are read with the L2 evict-first hint (dppo_tc3_gemm)
+    rev &= 1;
     const int half_n = n_tile / 2;                       // weight rows held by each CTA
     const int b_half = half_n * KC * 4;                  // bytes of one image (hi or lo) of this CTA's weight rows
     const int b_img = n_tile * KC * 4;                   // bytes of one full image in the weight-image buffer
@@ -79,6 +81,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         else if (i < base_tiles) { tile = i * n_clusters + cluster_id; half = -1; }
         else if (tail_halves) { tile = base_tiles * n_clusters + (cluster_id >> 1); half = cluster_id & 1; }
         else { tile = base_tiles * n_clusters + cluster_id; half = -1; }
+        if (rev) tile = total - 1 - tile;                // row sweep from the last rows to the first (see dppo_tc3_gemm)
     };
 
     if (tid == 0) {
@@ -100,6 +103,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == W_PROD) {
         if (lane == 0) {
             tma_prefetch_desc(&tmA);
+            const uint64_t pol = l2_policy_evict_first();
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < n_my; ++i) {
@@ -115,12 +119,16 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (i + 1 < n_my) { int nt, nh; tile_of(i + 1, nt, nh); next_m = nt / n_tiles; }
                 for (int c = 0; c < chunks; ++c) {
                     // pull the next tile's activations into L2 while this tile computes
-                    if (next_m >= 0 && next_m != m_pair) tma_prefetch_2d(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM);
+                    if (next_m >= 0 && next_m != m_pair) {
+                        if (in_first) tma_prefetch_2d_hint(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM, pol);
+                        else tma_prefetch_2d(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM);
+                    }
                     mbar_wait(&empty[s], ph ^ 1);
                     const bool skip_b = DPPO_DBG(dbg, 1) && (i != 0 || c >= STAGES);
                     mbar_expect_tx(&full[s], (uint32_t)(A_IMG + (skip_b ? 0 : 2 * hb)));
                     unsigned char* st = dyn + s * stage_bytes;
-                    tma_load_2d(st, &tmA, c * KC, m0, &full[s]);
+                    if (in_first) tma_load_2d_hint(st, &tmA, c * KC, m0, &full[s], pol);
+                    else tma_load_2d(st, &tmA, c * KC, m0, &full[s]);
                     if (!skip_b) {
                         const unsigned char* w = wsrc + (int64_t)c * 2 * b_img;
                         bulk_copy_g2s(st + 2 * A_IMG, w, (uint32_t)hb, &full[s]);                        // hi rows of this CTA
@@ -371,8 +379,12 @@ bool dppo_tc3_gemm_supported(int64_t M, int N, int K)
     return M >= 1024 && M < (int64_t)1 << 31 && K % KC == 0 && (N % 256 == 0 || N == 128);
 }
 
+// rev != 0: the tiles are visited from the last rows to the first.  Consecutive launches of a layer chain alternate their sweep
+// direction (api.cu), so that a launch starts with the rows its predecessor wrote LAST -- the part of the activations that is still
+// in the L2 -- instead of the rows that were evicted first (an ascending sweep over 67-134 MB after an ascending sweep is the
+// worst case of an LRU-like cache: nothing is ever hit).
 int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact,
-                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, cudaStream_t st)
+                  int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, int rev, cudaStream_t st)
 {
     if (!dppo_tc3_gemm_supported(M, N, K)) DPPO_FAIL(ctx, "tc3_gemm: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
     if (lda % 4 != 0 || ldc % 4 != 0 || !al16(A) || !al16(C) || !al16(Wimg) || (Hact && (!al16(Hact) || ldh % 4 != 0)) || (bias && !al16(bias)))
@@ -399,11 +411,11 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
         // layer i (pre-update pass 3.07 -> 2.93 ms at config S; neutral inside the training step).  The kernel touches global
         // memory only after griddepcontrol.wait.
         dppo_launch_pdl_if(true, tc3_gemm_kernel<DPPO_EPI_BIAS_TANH>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, tmH, Wimg, bias, colsum, M,
-                           N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug, ctx->rows_dev);
+                           N, K, n_tile, pair_tiles, tail_halves, rev, ctx->tc_debug, ctx->rows_dev);
     } else if (epi == DPPO_EPI_TANH_BWD) {
         cudaFuncSetAttribute(tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dppo_launch_pdl(ctx, tc3_gemm_kernel<DPPO_EPI_TANH_BWD>, dim3(grid), dim3(THREADS), smem, st, tmA, tmC, tmH, Wimg, bias, colsum, M,
-                        N, K, n_tile, pair_tiles, tail_halves, ctx->tc_debug, ctx->rows_dev);
+                        N, K, n_tile, pair_tiles, tail_halves, rev, ctx->tc_debug, ctx->rows_dev);
     } else {
         DPPO_FAIL(ctx, "tc3_gemm: unknown epilogue %d", epi);
     }

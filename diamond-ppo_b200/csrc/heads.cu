@@ -379,6 +379,18 @@ __device__ __forceinline__ float4 one_minus_sq4(const float4& h)                
 // 76.6 -> 54.1 us per launch, 268 MB = 76 % of the HBM peak).
 // Same per-element arithmetic; only the order of the reductions differs.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_l2_hint(const float4* p, uint64_t policy)
+{
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 constexpr int SPLIT_WARPS = 10;              // warps per CTA (two CTAs per SM at <= 96 registers)
 constexpr int SPLIT_NA = 8;                  // actor warps (an actor row costs ~4x a critic row); the other warps take the critic role
 template <bool CONT, int G>
@@ -399,6 +411,8 @@ head_train_split_kernel(HeadTrainArgs a)
     __syncthreads();
     float* tails = s_acc + (NA * AM + NC) * H;
     float* tail = tails + warp * (H + 16);
+    const uint64_t pol = l2_evict_first_policy();
+    const bool h3_first = a.h3_first != 0;
 
     if (warp < NA) {
         // ------------------------------------------------ actor role: 2 rows per iteration
@@ -419,14 +433,24 @@ head_train_split_kernel(HeadTrainArgs a)
         float acc_dba = 0.f, acc_dls = 0.f, l_pol = 0.f, l_ent = 0.f;
 
         const int Mi = (int)a.M;
-        for (int mb = (blockIdx.x * NA + warp) * 2; mb < Mi; mb += gridDim.x * NA * 2) {
+        const int nb = (Mi + 1) >> 1;                            // row pairs; a.rev: visited from the last to the first (L2 reuse)
+        for (int b = blockIdx.x * NA + warp; b < nb; b += gridDim.x * NA) {
+            const int mb = (a.rev ? nb - 1 - b : b) * 2;
             const bool ok1 = mb + 1 < Mi;
+            if (a.pfd > 0) {    // L2 prefetch of the actor halves of the row pair a.pfd iterations ahead (4 G lanes per row, one 128-byte line each)
+                const int bp = b + a.pfd * (int)gridDim.x * NA;
+                const int pm = (a.rev ? nb - 1 - bp : bp) * 2 + (lane >> 4);
+                if (bp < nb && pm < Mi && (lane & 15) < 4 * G) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h3 + (int64_t)pm * (2 * H) + (lane & 15) * 32));
+            }
             float4 ha[2][G];
             {
                 const float4* h0 = reinterpret_cast<const float4*>(a.h3 + (int64_t)mb * (2 * H));
                 const float4* h1 = reinterpret_cast<const float4*>(a.h3 + (int64_t)(ok1 ? mb + 1 : mb) * (2 * H));
 #pragma unroll
-                for (int g = 0; g < G; ++g) { ha[0][g] = __ldg(h0 + g * 32 + lane); ha[1][g] = __ldg(h1 + g * 32 + lane); }
+                for (int g = 0; g < G; ++g) {
+                    if (h3_first) { ha[0][g] = ldg_l2_hint(h0 + g * 32 + lane, pol); ha[1][g] = ldg_l2_hint(h1 + g * 32 + lane, pol); }
+                    else { ha[0][g] = __ldg(h0 + g * 32 + lane); ha[1][g] = __ldg(h1 + g * 32 + lane); }
+                }
             }
             // this lane's row scalars
             const int m = mb + rl;
@@ -539,8 +563,13 @@ head_train_split_kernel(HeadTrainArgs a)
             for (int g = 0; g < G; ++g) {
                 const float4 da0 = mul4(ga[0][g], one_minus_sq4(ha[0][g]));
                 const float4 da1 = mul4(ga[1][g], one_minus_sq4(ha[1][g]));
-                __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, da0);
-                if (ok1) __stcs(reinterpret_cast<float4*>(d3 + 2 * H + g * 128) + lane, da1);
+                if (a.keep_d3) {
+                    reinterpret_cast<float4*>(d3 + g * 128)[lane] = da0;
+                    if (ok1) reinterpret_cast<float4*>(d3 + 2 * H + g * 128)[lane] = da1;
+                } else {
+                    __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, da0);
+                    if (ok1) __stcs(reinterpret_cast<float4*>(d3 + 2 * H + g * 128) + lane, da1);
+                }
                 float4 t = accb[g * 32 + lane];
                 const float2 lo = __fadd2_rn(make_float2(t.x, t.y), __fadd2_rn(make_float2(da0.x, da0.y), make_float2(da1.x, da1.y)));
                 const float2 hi = __fadd2_rn(make_float2(t.z, t.w), __fadd2_rn(make_float2(da0.z, da0.w), make_float2(da1.z, da1.w)));
@@ -574,14 +603,21 @@ head_train_split_kernel(HeadTrainArgs a)
         }
         float acc_dbc = 0.f, l_val = 0.f;
         const int Mi = (int)a.M;
-        for (int mb = (blockIdx.x * NC + cw) * 4; mb < Mi; mb += gridDim.x * NC * 4) {
+        const int nb = (Mi + 3) >> 2;                            // blocks of four rows, same sweep direction as the actor warps
+        for (int b = blockIdx.x * NC + cw; b < nb; b += gridDim.x * NC) {
+            const int mb = (a.rev ? nb - 1 - b : b) * 4;
+            if (a.pfd > 0) {    // L2 prefetch of the critic halves of the four rows a.pfd iterations ahead (8 lanes per row, 128 B each)
+                const int bp = b + a.pfd * (int)gridDim.x * NC;
+                const int pm = (a.rev ? nb - 1 - bp : bp) * 4 + (lane >> 3);
+                if (bp < nb && pm < Mi && (lane & 7) < 4 * G) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h3 + (int64_t)pm * (2 * H) + H + (lane & 7) * 32));
+            }
             float4 hc[4][G];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int mr = mb + r < Mi ? mb + r : mb;
                 const float4* h = reinterpret_cast<const float4*>(a.h3 + (int64_t)mr * (2 * H) + H);
 #pragma unroll
-                for (int g = 0; g < G; ++g) hc[r][g] = __ldg(h + g * 32 + lane);
+                for (int g = 0; g < G; ++g) hc[r][g] = h3_first ? ldg_l2_hint(h + g * 32 + lane, pol) : __ldg(h + g * 32 + lane);
             }
             const int m = mb + rl;
             const bool okl = m < Mi;
@@ -626,7 +662,10 @@ head_train_split_kernel(HeadTrainArgs a)
                     accb[2 * g] = __fadd2_rn(accb[2 * g], make_float2(dc.x, dc.y));
                     accb[2 * g + 1] = __fadd2_rn(accb[2 * g + 1], make_float2(dc.z, dc.w));
                     axpy4(gwc[g], dvr, hc[r][g]);
-                    if (mb + r < Mi) __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, dc);
+                    if (mb + r < Mi) {
+                        if (a.keep_d3) reinterpret_cast<float4*>(d3 + g * 128)[lane] = dc;
+                        else __stcs(reinterpret_cast<float4*>(d3 + g * 128) + lane, dc);
+                    }
                 }
             }
         }
@@ -724,7 +763,7 @@ template <int G, bool ACTOR, bool CRITIC>
 __global__ void __launch_bounds__(256)
 head_eval_vec_kernel(const float* __restrict__ ha_base, const float* __restrict__ hc_base, int ld, const float* __restrict__ wa,
                      const float* __restrict__ ba, const float* __restrict__ wc, const float* __restrict__ bc,
-                     float* __restrict__ head_out, float* __restrict__ values, int64_t rows, int A, const int* __restrict__ rows_dev)
+                     float* __restrict__ head_out, float* __restrict__ values, int64_t rows, int A, int rev, const int* __restrict__ rows_dev)
 {
     constexpr int H = 128 * G, AM = 4;
     __shared__ __align__(16) float s_wa[ACTOR ? AM * H : 4];
@@ -744,7 +783,9 @@ head_eval_vec_kernel(const float* __restrict__ ha_base, const float* __restrict_
     const float bias_c = CRITIC ? bc[0] : 0.f;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ws = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t mb = w0 * 4; mb < rows; mb += ws * 4) {
+    const int64_t nb = (rows + 3) >> 2;                          // blocks of four rows; rev: visited from the last to the first (L2 reuse)
+    for (int64_t b = w0; b < nb; b += ws) {
+        const int64_t mb = (rev ? nb - 1 - b : b) * 4;
         float pa[4][AM], pc[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -975,7 +1016,7 @@ int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuo
 }
 
 int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, const float* wa, const float* ba, const float* wc,
-                     const float* bc, float* head_out, float* values, int64_t rows, int H, int A, cudaStream_t st)
+                     const float* bc, float* head_out, float* values, int64_t rows, int H, int A, int rev, cudaStream_t st)
 {
     if (A < 1 || A > DPPO_MAX_ACT) DPPO_FAIL(ctx, "head kernel supports 1..%d actions/action dims, got %d", DPPO_MAX_ACT, A);
     if (H < 1 || H > 512) DPPO_FAIL(ctx, "head kernel supports hidden <= 512, got %d", H);
@@ -987,7 +1028,7 @@ int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, co
     if ((H == 128 || H == 256) && A <= 4 && al && (ha || hc)) {
         want = (rows + 31) / 32;                                 // 8 warps x 4 rows per block iteration
         blocks = (int)(want < 4 * (int64_t)ctx->sm_count ? want : 4 * (int64_t)ctx->sm_count);
-#define HEV(G, AC, CR) head_eval_vec_kernel<G, AC, CR><<<blocks, 256, 0, st>>>(ha, hc, ld, wa, ba, wc, bc, head_out, values, rows, A, ctx->rows_dev)
+#define HEV(G, AC, CR) head_eval_vec_kernel<G, AC, CR><<<blocks, 256, 0, st>>>(ha, hc, ld, wa, ba, wc, bc, head_out, values, rows, A, rev, ctx->rows_dev)
         if (H == 128) { if (ha && hc) HEV(1, true, true); else if (ha) HEV(1, true, false); else HEV(1, false, true); }
         else { if (ha && hc) HEV(2, true, true); else if (ha) HEV(2, true, false); else HEV(2, false, true); }
 #undef HEV

@@ -19,6 +19,10 @@ struct HeadTrainArgs {
     float clip, vw, beta, inv_m;
     float* partials;          // [blocks, partial_stride]
     int partial_stride;
+    int rev;                  // role-split kernel: rows are visited from the last to the first (L2 reuse, gemm_tc3.cu dppo_tc3_gemm)
+    int h3_first;             // role-split kernel: h3 (never read again) is loaded with the L2 evict-first hint
+    int pfd;                  // role-split kernel: L2 prefetch of h3 this many warp iterations ahead (0: off)
+    int keep_d3;              // role-split kernel: plain instead of streaming (evict-first) stores of d3, which the next launch reads
 };
 
 // Layout of one head-kernel partial: [dWa A*H | dba A | dWc H | dbc 1 | dlog_std A | db3 2H | losses 4], every block starting on a
@@ -42,4 +46,4 @@ int head_partial_floats(int H, int A);
 int head_train_blocks(dppo_ctx* ctx, int64_t M, int H, int A);
 int launch_head_train_kernel(dppo_ctx* ctx, const HeadTrainArgs& a, int continuous, int blocks, cudaStream_t st);
 int launch_head_eval(dppo_ctx* ctx, const float* ha, const float* hc, int ld, const float* wa, const float* ba, const float* wc,
-                     const float* bc, float* head_out, float* values, int64_t rows, int H, int A, cudaStream_t st);
+                     const float* bc, float* head_out, float* values, int64_t rows, int H, int A, int rev, cudaStream_t st);

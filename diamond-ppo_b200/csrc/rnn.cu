@@ -670,7 +670,7 @@ extern "C" int dppo_rnn_forward(dppo_ctx* ctx, const dppo_rnn_desc* d, const flo
     if (dppo_gemm_nt(ctx, DPPO_EPI_BIAS_TANH, w.hs, Hg, nullptr, params + L.w3 + w3off, Hg, params + L.b3 + b3off, w.h3, n3, B, n3, Hg, st)) return 1;
     const float* ha = actor ? w.h3 : nullptr;
     const float* hc = critic ? (actor ? w.h3 + H : w.h3) : nullptr;
-    return launch_head_eval(ctx, ha, hc, n3, params + L.wa, params + L.ba, params + L.wc, params + L.bc, logits, values, B, H, A, st);
+    return launch_head_eval(ctx, ha, hc, n3, params + L.wa, params + L.ba, params + L.wc, params + L.bc, logits, values, B, H, A, 0, st);
 }
 
 extern "C" int dppo_rnn_grad_minibatch(dppo_ctx* ctx, const dppo_rnn_desc* d, const float* params, float* grads, const float* obs,
@@ -712,6 +712,7 @@ extern "C" int dppo_rnn_grad_minibatch(dppo_ctx* ctx, const dppo_rnn_desc* d, co
     ha.M = M; ha.H = H; ha.A = A;
     ha.clip = hy->ppo_clip; ha.vw = hy->value_loss_weight; ha.beta = hy->entropy_beta; ha.inv_m = inv_m;
     ha.partials = w.hp; ha.partial_stride = w.head_stride;
+    ha.rev = 0; ha.keep_d3 = 0; ha.h3_first = 0; ha.pfd = 0;
     if (launch_head_train_kernel(ctx, ha, 0, w.head_blocks, st)) return 1;
 
     // d(loss)/d(h_t): rows of the minibatch, zero for every other (t, env)

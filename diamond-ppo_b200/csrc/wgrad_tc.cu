@@ -47,6 +47,7 @@ struct WgradJobs {
     int smem_bytes;            // dynamic shared memory of the launch (each job derives its own stage count from it)
     int64_t M;
     int rn_hi;                 // A/B: store a round-to-nearest hi image instead of using the raw chunk as hi
+    int in_first;              // operands are read with the L2 evict-first hint (row_sweep bit 4): every row is read once per n1 block
 };
 
 template <int NACC>
@@ -101,24 +102,42 @@ tc2_wgrad_kernel(const __grid_constant__ WgradJobs jobs)
             int s = 0;
             uint32_t ph = 0;
             constexpr int PF = 8;                                       // chunks of L2 prefetch distance
+            const bool inf = jobs.in_first != 0;
+            const uint64_t pol = l2_policy_evict_first();
             for (int c = 0; c < PF && c < chunks; ++c) {
                 const int row = (int)(r0 + (int64_t)c * WKC);
-                for (int g = 0; g < gA; ++g) tma_prefetch_2d(&tmD, n1_0 + g * 32, row);
-                for (int g = 0; g < gB; ++g) tma_prefetch_2d(&tmH, g * 32, row);
+                if (inf) {
+                    for (int g = 0; g < gA; ++g) tma_prefetch_2d_hint(&tmD, n1_0 + g * 32, row, pol);
+                    for (int g = 0; g < gB; ++g) tma_prefetch_2d_hint(&tmH, g * 32, row, pol);
+                } else {
+                    for (int g = 0; g < gA; ++g) tma_prefetch_2d(&tmD, n1_0 + g * 32, row);
+                    for (int g = 0; g < gB; ++g) tma_prefetch_2d(&tmH, g * 32, row);
+                }
             }
             for (int c = 0; c < chunks; ++c) {
                 if (c + PF < chunks) {
                     const int prow = (int)(r0 + (int64_t)(c + PF) * WKC);
-                    for (int g = 0; g < gA; ++g) tma_prefetch_2d(&tmD, n1_0 + g * 32, prow);
-                    for (int g = 0; g < gB; ++g) tma_prefetch_2d(&tmH, g * 32, prow);
+                    if (inf) {
+                        for (int g = 0; g < gA; ++g) tma_prefetch_2d_hint(&tmD, n1_0 + g * 32, prow, pol);
+                        for (int g = 0; g < gB; ++g) tma_prefetch_2d_hint(&tmH, g * 32, prow, pol);
+                    } else {
+                        for (int g = 0; g < gA; ++g) tma_prefetch_2d(&tmD, n1_0 + g * 32, prow);
+                        for (int g = 0; g < gB; ++g) tma_prefetch_2d(&tmH, g * 32, prow);
+                    }
                 }
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], (uint32_t)hi_bytes);
                 unsigned char* st = dyn + s * stage_bytes;
                 const int row = (int)(r0 + (int64_t)c * WKC);
+                if (inf) {
 #pragma unroll
-                for (int g = 0; g < gA; ++g) tma_load_2d(st + g * GRP, &tmD, n1_0 + g * 32, row, &full[s]);
-                for (int g = 0; g < gB; ++g) tma_load_2d(st + a_bytes + g * GRP, &tmH, g * 32, row, &full[s]);
+                    for (int g = 0; g < gA; ++g) tma_load_2d_hint(st + g * GRP, &tmD, n1_0 + g * 32, row, &full[s], pol);
+                    for (int g = 0; g < gB; ++g) tma_load_2d_hint(st + a_bytes + g * GRP, &tmH, g * 32, row, &full[s], pol);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < gA; ++g) tma_load_2d(st + g * GRP, &tmD, n1_0 + g * 32, row, &full[s]);
+                    for (int g = 0; g < gB; ++g) tma_load_2d(st + a_bytes + g * GRP, &tmH, g * 32, row, &full[s]);
+                }
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
@@ -348,6 +367,7 @@ int dppo_tc2_wgrad_multi(dppo_ctx* ctx, int n, const float* const* Dm, const int
     jobs.n = n;
     jobs.M = M;
     jobs.rn_hi = DPPO_DBG(ctx->tc_debug, 1024) ? 1 : 0;
+    jobs.in_first = (ctx->row_sweep >> 4) & 1;
     int cta = 0, max_stage = 0;
     for (int j = 0; j < n; ++j) {
         if (!dppo_tc2_wgrad_supported(M, N1[j], N2[j])) DPPO_FAIL(ctx, "tc2_wgrad: unsupported shape M=%lld N1=%d N2=%d", (long long)M, N1[j], N2[j]);

@@ -88,6 +88,14 @@ int dppo_count_launches(dppo_ctx* ctx, int64_t n);   /* add n: launches replayed
 /* Kernel-variant switches used by tests and bench.py for A/B measurements:
  *   "tensor_cores" 1 (default): CTA-pair (cta_group::2) persistent 3xTF32 tcgen05 GEMMs + tcgen05 weight gradients where
  *                  the shape allows (rows >= 1024, K % 16 == 0, N % 256 == 0 or N == 128); 0: FP32 FFMA GEMMs everywhere
+ *   "row_sweep"    bit mask, default 31: L2 reuse along the layer chain of an optimiser step / the pre-update pass.  1: consecutive
+ *                  GEMM launches alternate the direction of their row sweep (a launch starts with the rows its predecessor wrote
+ *                  last, which are still in the L2); 2: the head kernels sweep against the GEMM before them; 4: the head kernel's
+ *                  d3 stores are plain instead of streaming; 8: inputs that are dead after the launch are read with the L2
+ *                  evict-first hint; 16: the same for the operands of the weight-gradient launch.  0 = every launch ascending,
+ *                  no hints (A/B).  Forward outputs do not depend on the mask; masks 1 and 2 re-order fp32
+ *                  partial sums of the gradient (deterministic for a fixed mask)
+ *   "head_prefetch" 0 (default): off; n > 0: the role-split head kernel prefetches its rows n warp iterations ahead into the L2
  *   "gae_variant"  0 (default): pipelined TMA-staged GAE kernel (T >= 128; chunked loads, stores overlap them) or the
  *                  single-barrier TMA kernel when the layout allows, 1: register-staged, 2: single-barrier TMA
  *   "gae_inputs_settled" 0 (default): plain launch -- the GAE kernel starts after its stream predecessor has completed and
