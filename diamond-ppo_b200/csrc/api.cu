@@ -50,6 +50,7 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->tc_debug = 0;
     c->row_sweep = 31;
     c->head_prefetch = 0;
+    c->tc_prefetch = 0;
     c->draw_base = nullptr;
     c->rows_dev = nullptr;
     c->launch_count = 0;
@@ -71,6 +72,7 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
     if (!ctx || !name) return 1;
     if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value != 0 ? 3 : 0; return 0; }
     if (!strcmp(name, "row_sweep")) { ctx->row_sweep = value & 31; return 0; }
+    if (!strcmp(name, "tc_prefetch")) { ctx->tc_prefetch = value & 7; return 0; }
     if (!strcmp(name, "head_prefetch")) { ctx->head_prefetch = value < 0 ? 0 : value > 8 ? 8 : value; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
     if (!strcmp(name, "tc_debug")) {

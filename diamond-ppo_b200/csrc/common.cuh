@@ -22,6 +22,8 @@ struct dppo_ctx {
                                           // GEMM / head-kernel inputs are read with the L2 evict-first hint, bit 4: so are the operands of
                                           // the weight-gradient launch.  Bits 2-4 do not change any result; bits 0 / 1 re-order the fp32
                                           // partial sums of the bias gradients / the head kernel's accumulators (forward outputs unchanged)
+    int tc_prefetch;                      // software L2 prefetch, bit mask: 1 forward GEMMs / 2 dgrad GEMMs (next tile's activations), 4 weight
+                                          // gradient (operand chunks 8 ahead); default 0: every one of them measured slower in the graph replay (gemm_tc3.cu)
     int head_prefetch;                    // role-split head kernel: L2 prefetch distance in warp iterations (0: off)
     int tc_debug;                         // timing-experiment switches; only honoured by builds with -DDPPO_TIMING_SWITCHES (see DPPO_DBG)
     const unsigned long long* draw_base;  // optional device counter added to every sampling draw counter (CUDA-graph replay of rollouts)

@@ -58,6 +58,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const bool in_first = (rev & 2) != 0;                // inputs are read with the L2 evict-first hint (dppo_tc3_gemm)
+    const bool no_pf = (rev & 4) != 0;                   // no L2 prefetch of the next tile's activations (the default, see dppo_tc3_gemm)
     rev &= 1;
     const int half_n = n_tile / 2;                       // weight rows held by each CTA
     const int b_half = half_n * KC * 4;                  // bytes of one image (hi or lo) of this CTA's weight rows
@@ -119,7 +120,7 @@ tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (i + 1 < n_my) { int nt, nh; tile_of(i + 1, nt, nh); next_m = nt / n_tiles; }
                 for (int c = 0; c < chunks; ++c) {
                     // pull the next tile's activations into L2 while this tile computes
-                    if (next_m >= 0 && next_m != m_pair) {
+                    if (!no_pf && next_m >= 0 && next_m != m_pair) {
                         if (in_first) tma_prefetch_2d_hint(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM, pol);
                         else tma_prefetch_2d(&tmA, c * KC, next_m * 2 * BM + (int)rank * BM);
                     }
@@ -382,7 +383,11 @@ bool dppo_tc3_gemm_supported(int64_t M, int N, int K)
 // rev != 0: the tiles are visited from the last rows to the first.  Consecutive launches of a layer chain alternate their sweep
 // direction (api.cu), so that a launch starts with the rows its predecessor wrote LAST -- the part of the activations that is still
 // in the L2 -- instead of the rows that were evicted first (an ascending sweep over 67-134 MB after an ascending sweep is the
-// worst case of an LRU-like cache: nothing is ever hit).
+// worst case of an LRU-like cache: nothing is ever hit).  rev & 2: the A operand is read with the L2 evict-first hint.
+// The L2 prefetch of the NEXT tile's activations (one box per chunk while the current tile computes; round 1) is off by default
+// (tc_prefetch): in-situ DRAM counters showed the prefetched lines being fetched twice -- dgrad3 read 206 MB against 169 MB
+// without it (profiles/r4e_prefetch_ab.md) -- and the optimiser step is 1.4 % faster without (2.7 % with the weight-gradient
+// kernel's chunk prefetch off as well).
 int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigned char* Wimg, const float* bias, const float* Hact,
                   int ldh, float* C, int ldc, float* colsum, int64_t M, int N, int K, int rev, cudaStream_t st)
 {
@@ -401,6 +406,7 @@ int dppo_tc3_gemm(dppo_ctx* ctx, int epi, const float* A, int lda, const unsigne
     const size_t smem = (size_t)stages * (2 * A_IMG + n_tile * KC * 4) + (size_t)N_EPI * STG_BLK * (epi == DPPO_EPI_TANH_BWD ? 2 : 1) + 1024;
     int grid, tail_halves;
     tc3_plan(ctx, M, N, &grid, &tail_halves);
+    if (!(ctx->tc_prefetch & (epi == DPPO_EPI_TANH_BWD ? 2 : 1))) rev |= 4;
     if (epi == DPPO_EPI_TANH_BWD && colsum != nullptr && (N / n_tile > 1 || tail_halves == 2) &&
         cudaMemsetAsync(colsum + (size_t)grid * N, 0, (size_t)4 * grid * N * sizeof(float), st) != cudaSuccess)
         DPPO_FAIL(ctx, "tc3_gemm: cudaMemsetAsync(colsum) failed");

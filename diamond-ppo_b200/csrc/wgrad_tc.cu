@@ -47,6 +47,7 @@ struct WgradJobs {
     int smem_bytes;            // dynamic shared memory of the launch (each job derives its own stage count from it)
     int64_t M;
     int rn_hi;                 // A/B: store a round-to-nearest hi image instead of using the raw chunk as hi
+    int prefetch;              // L2 prefetch of the operand chunks PF ahead (tc_prefetch bit 2)
     int in_first;              // operands are read with the L2 evict-first hint (row_sweep bit 4): every row is read once per n1 block
 };
 
@@ -104,7 +105,8 @@ tc2_wgrad_kernel(const __grid_constant__ WgradJobs jobs)
             constexpr int PF = 8;                                       // chunks of L2 prefetch distance
             const bool inf = jobs.in_first != 0;
             const uint64_t pol = l2_policy_evict_first();
-            for (int c = 0; c < PF && c < chunks; ++c) {
+            const bool pf_on = jobs.prefetch != 0;
+            for (int c = 0; pf_on && c < PF && c < chunks; ++c) {
                 const int row = (int)(r0 + (int64_t)c * WKC);
                 if (inf) {
                     for (int g = 0; g < gA; ++g) tma_prefetch_2d_hint(&tmD, n1_0 + g * 32, row, pol);
@@ -115,7 +117,7 @@ tc2_wgrad_kernel(const __grid_constant__ WgradJobs jobs)
                 }
             }
             for (int c = 0; c < chunks; ++c) {
-                if (c + PF < chunks) {
+                if (pf_on && c + PF < chunks) {
                     const int prow = (int)(r0 + (int64_t)(c + PF) * WKC);
                     if (inf) {
                         for (int g = 0; g < gA; ++g) tma_prefetch_2d_hint(&tmD, n1_0 + g * 32, prow, pol);
@@ -368,6 +370,7 @@ int dppo_tc2_wgrad_multi(dppo_ctx* ctx, int n, const float* const* Dm, const int
     jobs.M = M;
     jobs.rn_hi = DPPO_DBG(ctx->tc_debug, 1024) ? 1 : 0;
     jobs.in_first = (ctx->row_sweep >> 4) & 1;
+    jobs.prefetch = (ctx->tc_prefetch >> 2) & 1;
     int cta = 0, max_stage = 0;
     for (int j = 0; j < n; ++j) {
         if (!dppo_tc2_wgrad_supported(M, N1[j], N2[j])) DPPO_FAIL(ctx, "tc2_wgrad: unsupported shape M=%lld N1=%d N2=%d", (long long)M, N1[j], N2[j]);

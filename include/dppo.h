@@ -95,6 +95,10 @@ int dppo_count_launches(dppo_ctx* ctx, int64_t n);   /* add n: launches replayed
  *                  evict-first hint; 16: the same for the operands of the weight-gradient launch.  0 = every launch ascending,
  *                  no hints (A/B).  Forward outputs do not depend on the mask; masks 1 and 2 re-order fp32
  *                  partial sums of the gradient (deterministic for a fixed mask)
+ *   "tc_prefetch"  bit mask, default 0: software L2 prefetch ahead of the TMA loads (kept for A/B).  1: forward GEMMs and 2: dgrad
+ *                  GEMMs prefetch the next tile's activations while the current tile computes, 4: the weight-gradient kernel
+ *                  prefetches its operand chunks 8 chunks ahead.  All three measured slower inside the optimiser step (the
+ *                  in-situ DRAM counters show prefetched lines being fetched twice)
  *   "head_prefetch" 0 (default): off; n > 0: the role-split head kernel prefetches its rows n warp iterations ahead into the L2
  *   "gae_variant"  0 (default): pipelined TMA-staged GAE kernel (T >= 128; chunked loads, stores overlap them) or the
  *                  single-barrier TMA kernel when the layout allows, 1: register-staged, 2: single-barrier TMA
