@@ -29,9 +29,11 @@ T, N_ENVS, D, H, A, E, MB = 128, 4096, 64, 256, 4, 4, 8
 FLOP_PER_SAMPLE_UPDATE = 1_252_864          # 2*(3F - D*H), F = D*H + 3H^2 + H*A + H
 FLOP_PER_SAMPLE_PREPASS = 723_968           # 2*(F + Fc)
 GAE_BYTES_PER_ELEM = 28                     # 5 fp32 reads + 2 fp32 writes
-# dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full,
-# profiles/r1f_kernels.csv): 67.7 MB read + 16.5 MB written before the kernel ends (the rest of the 67 MB output is still in L2)
-GEMM_DRAM_TRAFFIC = 84.2e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc3_gemm_kernel launch at this shape (ncu --set full, cold caches,
+# profiles/r4i_kernels.csv): 67.8 MB read + 10.4 MB written before the kernel ends (the rest of the 67 MB output is still in L2;
+# round 1, with the next-tile L2 prefetch: 84.2 MB).  In situ (caches not flushed between the launches of an optimiser step) the same
+# launch reads 6-11 MB from DRAM -- its input is its predecessor's output (profiles/r4d_insitu_traffic.md).
+GEMM_DRAM_TRAFFIC = 78.1e6
 # one gae_pipe_kernel launch on a cold buffer set (profiles/r1f_gae_kernels.csv): 10.5 MB read; the 4.2 MB of advantages / returns are
 # still in L2 when the kernel ends (dram__bytes_write.sum = 0) and reach DRAM by eviction as the benchmark cycles its 20 buffer sets
 GAE_DRAM_TRAFFIC = 10.5e6
