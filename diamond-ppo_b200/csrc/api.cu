@@ -49,7 +49,6 @@ extern "C" int dppo_create(dppo_ctx** out, int device)
     c->gae_inputs_settled = 0;
     c->tc_debug = 0;
     c->row_sweep = 31;
-    c->head_prefetch = 0;
     c->tc_prefetch = 0;
     c->draw_base = nullptr;
     c->rows_dev = nullptr;
@@ -73,7 +72,6 @@ extern "C" int dppo_set_option(dppo_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "tensor_cores")) { ctx->use_tensor_cores = value != 0 ? 3 : 0; return 0; }
     if (!strcmp(name, "row_sweep")) { ctx->row_sweep = value & 31; return 0; }
     if (!strcmp(name, "tc_prefetch")) { ctx->tc_prefetch = value & 7; return 0; }
-    if (!strcmp(name, "head_prefetch")) { ctx->head_prefetch = value < 0 ? 0 : value > 8 ? 8 : value; return 0; }
     if (!strcmp(name, "gae_variant")) { ctx->gae_variant = value; return 0; }
     if (!strcmp(name, "tc_debug")) {
 #ifdef DPPO_TIMING_SWITCHES
@@ -381,7 +379,7 @@ extern "C" int dppo_mlp_grad_minibatch(dppo_ctx* ctx, const dppo_mlp_desc* d, co
     ha.M = M; ha.H = H; ha.A = A;
     ha.clip = hy->ppo_clip; ha.vw = hy->value_loss_weight; ha.beta = hy->entropy_beta; ha.inv_m = inv_m;
     ha.partials = w.hp; ha.partial_stride = w.head_stride;
-    ha.rev = (sweep >> 1) & 1; ha.keep_d3 = (sweep >> 2) & 1; ha.h3_first = (sweep >> 3) & 1; ha.pfd = ctx->head_prefetch;
+    ha.rev = (sweep >> 1) & 1; ha.keep_d3 = (sweep >> 2) & 1; ha.h3_first = (sweep >> 3) & 1;
     if (launch_head_train_kernel(ctx, ha, d->continuous, w.head_blocks, st)) return 1;
 
     // backward (ppo.py:283): dgrad chain with the tanh' factors and bias-gradient column sums fused

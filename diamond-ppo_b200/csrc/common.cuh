@@ -24,7 +24,6 @@ struct dppo_ctx {
                                           // partial sums of the bias gradients / the head kernel's accumulators (forward outputs unchanged)
     int tc_prefetch;                      // software L2 prefetch, bit mask: 1 forward GEMMs / 2 dgrad GEMMs (next tile's activations), 4 weight
                                           // gradient (operand chunks 8 ahead); default 0: every one of them measured slower in the graph replay (gemm_tc3.cu)
-    int head_prefetch;                    // role-split head kernel: L2 prefetch distance in warp iterations (0: off)
     int tc_debug;                         // timing-experiment switches; only honoured by builds with -DDPPO_TIMING_SWITCHES (see DPPO_DBG)
     const unsigned long long* draw_base;  // optional device counter added to every sampling draw counter (CUDA-graph replay of rollouts)
     const int* rows_dev;                  // optional DEVICE row count: while set, the forward kernels (gather, GEMMs, head evaluation) process
@@ -93,6 +92,21 @@ static inline cudaError_t dppo_launch_pdl(dppo_ctx* ctx, void (*kern)(KArgs...),
                                           Args&&... args)
 {
     return dppo_launch_pdl_if(DPPO_DBG(ctx->tc_debug, 512), kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+
+// L2 eviction-priority hint for data that is dead after this read (row_sweep bit 3 / 4): at the end of a launch the L2 should hold
+// the launch's OUTPUT, which the next launch starts with, not a mix of output and consumed input.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_l2_hint(const float4* p, uint64_t policy)
+{
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

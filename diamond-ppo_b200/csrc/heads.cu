@@ -379,18 +379,6 @@ __device__ __forceinline__ float4 one_minus_sq4(const float4& h)                
 // 76.6 -> 54.1 us per launch, 268 MB = 76 % of the HBM peak).
 // Same per-element arithmetic; only the order of the reductions differs.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_l2_hint(const float4* p, uint64_t policy)
-{
-    float4 v;
-    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ uint64_t l2_evict_first_policy()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 constexpr int SPLIT_WARPS = 10;              // warps per CTA (two CTAs per SM at <= 96 registers)
 constexpr int SPLIT_NA = 8;                  // actor warps (an actor row costs ~4x a critic row); the other warps take the critic role
 template <bool CONT, int G>
@@ -411,7 +399,7 @@ head_train_split_kernel(HeadTrainArgs a)
     __syncthreads();
     float* tails = s_acc + (NA * AM + NC) * H;
     float* tail = tails + warp * (H + 16);
-    const uint64_t pol = l2_evict_first_policy();
+    const uint64_t pol = l2_policy_evict_first();
     const bool h3_first = a.h3_first != 0;
 
     if (warp < NA) {
@@ -437,11 +425,6 @@ head_train_split_kernel(HeadTrainArgs a)
         for (int b = blockIdx.x * NA + warp; b < nb; b += gridDim.x * NA) {
             const int mb = (a.rev ? nb - 1 - b : b) * 2;
             const bool ok1 = mb + 1 < Mi;
-            if (a.pfd > 0) {    // L2 prefetch of the actor halves of the row pair a.pfd iterations ahead (4 G lanes per row, one 128-byte line each)
-                const int bp = b + a.pfd * (int)gridDim.x * NA;
-                const int pm = (a.rev ? nb - 1 - bp : bp) * 2 + (lane >> 4);
-                if (bp < nb && pm < Mi && (lane & 15) < 4 * G) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h3 + (int64_t)pm * (2 * H) + (lane & 15) * 32));
-            }
             float4 ha[2][G];
             {
                 const float4* h0 = reinterpret_cast<const float4*>(a.h3 + (int64_t)mb * (2 * H));
@@ -606,11 +589,6 @@ head_train_split_kernel(HeadTrainArgs a)
         const int nb = (Mi + 3) >> 2;                            // blocks of four rows, same sweep direction as the actor warps
         for (int b = blockIdx.x * NC + cw; b < nb; b += gridDim.x * NC) {
             const int mb = (a.rev ? nb - 1 - b : b) * 4;
-            if (a.pfd > 0) {    // L2 prefetch of the critic halves of the four rows a.pfd iterations ahead (8 lanes per row, 128 B each)
-                const int bp = b + a.pfd * (int)gridDim.x * NC;
-                const int pm = (a.rev ? nb - 1 - bp : bp) * 4 + (lane >> 3);
-                if (bp < nb && pm < Mi && (lane & 7) < 4 * G) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h3 + (int64_t)pm * (2 * H) + H + (lane & 7) * 32));
-            }
             float4 hc[4][G];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {

@@ -21,7 +21,6 @@ struct HeadTrainArgs {
     int partial_stride;
     int rev;                  // role-split kernel: rows are visited from the last to the first (L2 reuse, gemm_tc3.cu dppo_tc3_gemm)
     int h3_first;             // role-split kernel: h3 (never read again) is loaded with the L2 evict-first hint
-    int pfd;                  // role-split kernel: L2 prefetch of h3 this many warp iterations ahead (0: off)
     int keep_d3;              // role-split kernel: plain instead of streaming (evict-first) stores of d3, which the next launch reads
 };
 

@@ -712,7 +712,7 @@ extern "C" int dppo_rnn_grad_minibatch(dppo_ctx* ctx, const dppo_rnn_desc* d, co
     ha.M = M; ha.H = H; ha.A = A;
     ha.clip = hy->ppo_clip; ha.vw = hy->value_loss_weight; ha.beta = hy->entropy_beta; ha.inv_m = inv_m;
     ha.partials = w.hp; ha.partial_stride = w.head_stride;
-    ha.rev = 0; ha.keep_d3 = 0; ha.h3_first = 0; ha.pfd = 0;
+    ha.rev = 0; ha.keep_d3 = 0; ha.h3_first = 0;
     if (launch_head_train_kernel(ctx, ha, 0, w.head_blocks, st)) return 1;
 
     // d(loss)/d(h_t): rows of the minibatch, zero for every other (t, env)

@@ -42,14 +42,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
-// L2 eviction-priority hints.  A launch of the layer chain streams its INPUT once (dead for the cache afterwards) while its OUTPUT is what
-// the next launch starts with, so inputs are read "evict first": at the end of the launch the L2 holds output lines, not a mix.
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+// TMA loads / prefetches with an L2 eviction-priority hint (policy: common.cuh l2_policy_evict_first)
 __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar, uint64_t policy)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"

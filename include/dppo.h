@@ -99,7 +99,6 @@ int dppo_count_launches(dppo_ctx* ctx, int64_t n);   /* add n: launches replayed
  *                  GEMMs prefetch the next tile's activations while the current tile computes, 4: the weight-gradient kernel
  *                  prefetches its operand chunks 8 chunks ahead.  All three measured slower inside the optimiser step (the
  *                  in-situ DRAM counters show prefetched lines being fetched twice)
- *   "head_prefetch" 0 (default): off; n > 0: the role-split head kernel prefetches its rows n warp iterations ahead into the L2
  *   "gae_variant"  0 (default): pipelined TMA-staged GAE kernel (T >= 128; chunked loads, stores overlap them) or the
  *                  single-barrier TMA kernel when the layout allows, 1: register-staged, 2: single-barrier TMA
  *   "gae_inputs_settled" 0 (default): plain launch -- the GAE kernel starts after its stream predecessor has completed and
