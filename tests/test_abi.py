@@ -26,6 +26,22 @@ def test_library_exports_every_header_symbol():
     assert lib.dppo_version() == 100
 
 
+def test_every_option_of_dppo_set_option_is_documented_in_the_header():
+    """dppo_set_option is the ABI's one stringly-typed entry point: every option name api.cu accepts must be described in the
+    comment above its declaration in include/dppo.h (and nothing is documented that the library does not accept)."""
+    api = open(os.path.join(ROOT, "diamond-ppo_b200", "csrc", "api.cu")).read()
+    body = api[api.index('extern "C" int dppo_set_option'):]
+    body = body[:body.index("\n}\n")]
+    accepted = set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', body))
+    assert {"tensor_cores", "row_sweep", "tc_prefetch", "gae_variant", "gae_inputs_settled"} <= accepted
+    hdr = open(os.path.join(ROOT, "include", "dppo.h")).read()
+    doc = hdr[:hdr.index("int dppo_set_option(")]
+    doc = doc[doc.rindex("/*"):]
+    documented = set(re.findall(r'^ \*   "([a-z_0-9]+)"', doc, flags=re.M))
+    # "tc_debug" exists only in timing builds (-DDPPO_TIMING_SWITCHES) and is rejected by the release library
+    assert documented == accepted - {"tc_debug"}, (sorted(documented), sorted(accepted))
+
+
 def test_only_sm100a_code_is_embedded():
     import subprocess
     from diamond import _native as N
